@@ -1,0 +1,112 @@
+"""ctypes binding of libbdet.so (include/bdet.h).  No CPU fallback: a missing library is an error."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbdet.so")
+
+BDET_OK = 0
+PAIR_IOU, PAIR_IOA, PAIR_INTER, PAIR_GIOU = 0, 1, 2, 3
+SCORE_RAW, SCORE_SIGMOID, SCORE_FCOS = 0, 1, 2
+MAX_LEVELS = 8
+
+vp = c_void_p
+ip = POINTER(c_int)
+fp = POINTER(c_float)
+dp = POINTER(c_double)
+lp = POINTER(c_int64)
+
+# name -> (restype, argtypes); mirrors include/bdet.h one to one (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "bdet_abi_version": (c_int, []),
+    "bdet_last_error": (c_char_p, []),
+    "bdet_device_info": (c_int, [ip, ip, ip]),
+    "bdet_anchors_grid": (c_int, [vp, c_int, ip, dp, dp, ip, fp, lp, vp]),
+    "bdet_points_grid": (c_int, [vp, c_int, ip, dp, dp, c_int, c_int, lp, vp]),
+    "bdet_pairwise": (c_int, [vp, c_int, c_int, vp, c_int, c_int, vp, c_int, vp]),
+    "bdet_pairwise_batched": (c_int, [vp, c_int, c_int64, vp, c_int, vp, c_int, c_int64, c_int, vp, c_int64,
+                                      c_int, c_int, vp]),
+    "bdet_box_center": (c_int, [vp, c_int, c_int, vp, vp]),
+    "bdet_point_distance": (c_int, [vp, c_int, vp, c_int, vp, vp]),
+    "bdet_match_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "bdet_match": (c_int, [vp, c_int64, vp, c_int, c_int, c_int, fp, ip, c_int, c_int, vp, vp, vp, c_size_t, vp]),
+    "bdet_match_rows": (c_int, [vp, c_int, c_int, vp, vp, vp]),
+    "bdet_box_encode": (c_int, [vp, vp, c_int, vp, c_int, fp, fp, vp, vp]),
+    "bdet_box_decode": (c_int, [vp, vp, c_int, c_int, fp, fp, vp, c_int, vp, c_int, c_int, vp]),
+    "bdet_sum_encode": (c_int, [vp, vp, c_int, fp, fp, vp, vp]),
+    "bdet_sum_decode": (c_int, [vp, vp, c_int, fp, fp, vp, c_int, vp]),
+    "bdet_point_encode": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
+    "bdet_point_decode": (c_int, [vp, vp, c_int, c_int, vp, vp, c_int, c_int, vp]),
+    "bdet_assign_targets_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "bdet_assign_targets": (c_int, [vp, c_int, vp, c_int, vp, c_int, fp, ip, c_int, c_int, c_int, fp, fp,
+                                    vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "bdet_topk": (c_int, [vp, lp, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_score_filter_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),
+    "bdet_score_filter_topk": (c_int, [vp, vp, c_int, lp, c_int, c_float, c_int, c_int, vp, vp, vp, vp,
+                                       c_size_t, vp]),
+    "bdet_scores": (c_int, [vp, vp, c_int, c_int64, c_int, vp, vp]),
+    "bdet_nms_workspace": (c_size_t, [c_int, c_int]),
+    "bdet_nms": (c_int, [vp, vp, vp, c_int, vp, c_int, c_int, c_float, c_int, vp, c_int, vp, vp, c_size_t, vp]),
+    "bdet_boxes_scale_clip": (c_int, [vp, c_int, c_float, c_float, c_float, c_float, vp]),
+    "bdet_boxes_filter_by_size": (c_int, [vp, c_int, c_float, c_float, vp, vp]),
+    "bdet_roi_assign_levels": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+    "bdet_roi_align_fwd": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, vp, vp]),
+    "bdet_roi_align_bwd": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, vp, c_int, vp]),
+}
+
+
+class BdetError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbdet error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libbdet.so (built by ``basedet_b200.build``).  Raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libbdet.so not found at %s: run `python -m basedet_b200.build` (nvcc, sm_100a). "
+            "basedet_b200 has no CPU or PyTorch fallback." % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:  # TODO(round1): remove once every entry point is implemented
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bdet_abi_version() != 1:
+        raise RuntimeError("libbdet.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != BDET_OK:
+        raise BdetError(rc, load().bdet_last_error().decode("utf-8", "replace"))
+
+
+def farr(values):
+    return (c_float * len(values))(*[float(v) for v in values])
+
+
+def iarr(values):
+    return (c_int * len(values))(*[int(v) for v in values])
+
+
+def darr(values):
+    return (c_double * len(values))(*[float(v) for v in values])
+
+
+def larr(values):
+    return (c_int64 * len(values))(*[int(v) for v in values])

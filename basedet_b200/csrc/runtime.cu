@@ -1,0 +1,73 @@
+// Error reporting, device queries and small host-side helpers shared by all entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include <limits>
+
+#include "common.cuh"
+
+namespace bdet {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+int make_match_cfg(MatchCfg* cfg, const float* thresholds_host, const int* labels_host, int n_labels) {
+  if (n_labels < 1 || n_labels > BDET_MAX_MATCH_LABELS)
+    return set_error(BDET_EINVAL, "matcher: n_labels must be in [1, %d]", BDET_MAX_MATCH_LABELS);
+  if (!labels_host || (n_labels > 1 && !thresholds_host))
+    return set_error(BDET_EINVAL, "matcher: thresholds and labels are not matched");
+  // layers/common/matcher.py:23: thresholds must be non-decreasing
+  for (int k = 0; k + 2 < n_labels; ++k)
+    if (!(thresholds_host[k] <= thresholds_host[k + 1]))
+      return set_error(BDET_EINVAL, "matcher: thresholds must be sorted (low <= high)");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->n = n_labels;
+  cfg->thr[0] = -std::numeric_limits<float>::infinity();
+  for (int k = 0; k + 1 < n_labels; ++k) cfg->thr[k + 1] = thresholds_host[k];
+  cfg->thr[n_labels] = std::numeric_limits<float>::infinity();
+  for (int k = 0; k < n_labels; ++k) cfg->lab[k] = labels_host[k];
+  return BDET_OK;
+}
+
+}  // namespace bdet
+
+extern "C" {
+
+int bdet_abi_version(void) { return BDET_ABI_VERSION; }
+
+const char* bdet_last_error(void) { return bdet::g_err; }
+
+int bdet_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host) {
+  int dev = 0;
+  BDET_CUDA(cudaGetDevice(&dev));
+  int n = 0, maj = 0, min = 0;
+  BDET_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  BDET_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  BDET_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count_host) *sm_count_host = n;
+  if (cc_major_host) *cc_major_host = maj;
+  if (cc_minor_host) *cc_minor_host = min;
+  return BDET_OK;
+}
+
+}  // extern "C"

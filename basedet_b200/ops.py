@@ -1,0 +1,333 @@
+"""Functional host layer: torch tensors in, raw device pointers into libbdet.so, torch tensors out.
+
+PyTorch is used for device memory and streams only; every arithmetic result comes from the CUDA
+library.  CPU tensors are rejected -- there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, darr, farr, iarr, larr
+
+_VP = ctypes.c_void_p
+
+
+def as_tensor(x):
+    """Tensor adapter: torch.Tensor, anything with __dlpack__ (MegEngine >= 1.9 tensors, cupy), or
+    __cuda_array_interface__ (numba / cupy / MegEngine through a one-line shim)."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "__dlpack__"):
+        return torch.from_dlpack(x)
+    if hasattr(x, "__cuda_array_interface__"):
+        return torch.as_tensor(x, device="cuda")
+    raise TypeError("expected a device tensor (torch / DLPack / __cuda_array_interface__), got %r" % type(x))
+
+
+def _dev(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device: basedet_b200 has no CPU path" % name)
+    return t
+
+
+def _f32(t, name="tensor"):
+    t = _dev(as_tensor(t), name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t
+
+
+def _f32c(t, name="tensor"):
+    return _f32(t, name).contiguous()
+
+
+def _i32c(t, name="tensor"):
+    t = _dev(as_tensor(t), name)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def _rows(t, name="boxes"):
+    """(N, >=4) fp32 view -> (tensor, ld): keeps row-strided views such as gt[:, :4] without a copy."""
+    t = _f32(t, name)
+    assert t.ndim == 2 and t.shape[1] >= 4
+    if t.shape[0] <= 1 or (t.stride(1) == 1 and t.stride(0) >= t.shape[1]):
+        return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 4))
+    t = t.contiguous()
+    return t, t.shape[1]
+
+
+def _p(t):
+    return _VP(t.data_ptr()) if t is not None else None
+
+
+def _stream(t=None):
+    dev = t.device if t is not None else None
+    return _VP(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _guard(t):
+    return torch.cuda.device(t.device)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- anchors
+def anchors_grid(sizes, strides, shifts, base_anchors, device):
+    """All levels in one launch.  base_anchors: list (per level) of (n_base, 4) float arrays (host)."""
+    lib = _lib.load()
+    n = len(sizes)
+    counts = [int(h) * int(w) * len(b) for (h, w), b in zip(sizes, base_anchors)]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    out = torch.empty((offs[-1], 4), dtype=torch.float32, device=device)
+    hw = [int(v) for hw_ in sizes for v in hw_]
+    base_flat = [float(v) for b in base_anchors for row in b for v in row]
+    with _guard(out):
+        check(lib.bdet_anchors_grid(_p(out), n, iarr(hw), darr(strides), darr(shifts),
+                                    iarr([len(b) for b in base_anchors]), farr(base_flat), larr(offs[:-1]),
+                                    _stream(out)))
+    return [out[offs[i]:offs[i + 1]] for i in range(n)]
+
+
+def points_grid(sizes, strides, shifts, num_anchors, mode, device):
+    lib = _lib.load()
+    n = len(sizes)
+    rep = num_anchors if mode == 0 else 1
+    counts = [int(h) * int(w) * rep for (h, w) in sizes]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    out = torch.empty((offs[-1], 2), dtype=torch.float32, device=device)
+    hw = [int(v) for hw_ in sizes for v in hw_]
+    with _guard(out):
+        check(lib.bdet_points_grid(_p(out), n, iarr(hw), darr(strides), darr(shifts), int(num_anchors), int(mode),
+                                   larr(offs[:-1]), _stream(out)))
+    return [out[offs[i]:offs[i + 1]] for i in range(n)]
+
+
+# ----------------------------------------------------------------------------- pairwise
+def pairwise(boxes1, boxes2, mode=_lib.PAIR_IOU):
+    lib = _lib.load()
+    b1, ld1 = _rows(boxes1, "boxes1")
+    b2, ld2 = _rows(boxes2, "boxes2")
+    N, M = b1.shape[0], b2.shape[0]
+    out = torch.empty((N, M), dtype=torch.float32, device=b1.device)
+    with _guard(out):
+        check(lib.bdet_pairwise(_p(b1), ld1, N, _p(b2), ld2, M, _p(out), mode, _stream(out)))
+    return out
+
+
+def pairwise_batched(gt, num_gt, anchors, mode=_lib.PAIR_IOU, out=None):
+    """gt (B, Gmax, >=4) contiguous, num_gt (B,) int32 or None, anchors (A, 4) shared -> (B, Gmax, A).
+    Rows >= num_gt[b] are left untouched."""
+    lib = _lib.load()
+    gt = _f32c(gt, "gt")
+    anchors = _f32c(anchors, "anchors")
+    B, Gmax, ld = gt.shape
+    A = anchors.shape[0]
+    if out is None:
+        out = torch.empty((B, Gmax, A), dtype=torch.float32, device=gt.device)
+    n1 = _i32c(num_gt, "num_gt") if num_gt is not None else None
+    with _guard(out):
+        check(lib.bdet_pairwise_batched(_p(gt), ld, Gmax * ld, _p(n1), Gmax, _p(anchors), 4, 0, A, _p(out),
+                                        Gmax * A, B, mode, _stream(out)))
+    return out
+
+
+def box_center(boxes):
+    lib = _lib.load()
+    b, ld = _rows(boxes)
+    out = torch.empty((b.shape[0], 2), dtype=torch.float32, device=b.device)
+    with _guard(out):
+        check(lib.bdet_box_center(_p(b), ld, b.shape[0], _p(out), _stream(out)))
+    return out
+
+
+def point_distance(p1, p2):
+    lib = _lib.load()
+    p1, p2 = _f32c(p1), _f32c(p2)
+    out = torch.empty((p1.shape[0], p2.shape[0]), dtype=torch.float32, device=p1.device)
+    with _guard(out):
+        check(lib.bdet_point_distance(_p(p1), p1.shape[0], _p(p2), p2.shape[0], _p(out), _stream(out)))
+    return out
+
+
+# ----------------------------------------------------------------------------- matcher
+def match(matrix, thresholds, labels, allow_low_quality=False, num_g=None):
+    """matrix (G, A) or (B, Gmax, A).  Returns (match_idx, labels) int32 of shape (A,) / (B, A)."""
+    lib = _lib.load()
+    m = _f32c(matrix, "matrix")
+    squeeze = m.ndim == 2
+    if squeeze:
+        m = m.unsqueeze(0)
+    B, G, A = m.shape
+    idx = torch.empty((B, A), dtype=torch.int32, device=m.device)
+    lab = torch.empty((B, A), dtype=torch.int32, device=m.device)
+    ws_bytes = lib.bdet_match_workspace(G, A, B)
+    ws = _workspace(ws_bytes, m.device)
+    gd = _i32c(num_g) if num_g is not None else None
+    with _guard(m):
+        check(lib.bdet_match(_p(m), G * A, _p(gd), G, A, B, farr(thresholds), iarr(labels), len(labels),
+                             int(bool(allow_low_quality)), _p(idx), _p(lab), _p(ws), ws.numel(), _stream(m)))
+    if squeeze:
+        return idx[0], lab[0]
+    return idx, lab
+
+
+def match_rows(matrix):
+    lib = _lib.load()
+    m = _f32c(matrix, "matrix")
+    R, G = m.shape
+    mx = torch.empty((R,), dtype=torch.float32, device=m.device)
+    am = torch.empty((R,), dtype=torch.int32, device=m.device)
+    with _guard(m):
+        check(lib.bdet_match_rows(_p(m), R, G, _p(mx), _p(am), _stream(m)))
+    return mx, am
+
+
+# ----------------------------------------------------------------------------- coders
+def box_encode(bbox, gt, mean, std, gather_idx=None):
+    lib = _lib.load()
+    bbox = _f32c(bbox, "bbox")
+    N = bbox.shape[0]
+    if gather_idx is not None:
+        g, ld = _rows(gt, "gt")
+        gi = _i32c(gather_idx)
+    else:
+        g, ld, gi = _f32c(gt, "gt"), 4, None
+        assert g.shape == bbox.shape
+    out = torch.empty((N, 4), dtype=torch.float32, device=bbox.device)
+    with _guard(out):
+        check(lib.bdet_box_encode(_p(bbox), _p(g), ld, _p(gi), N, farr(mean), farr(std), _p(out), _stream(out)))
+    return out
+
+
+def box_decode(anchors, deltas, mean, std, writeback=False, sel_idx=None, sel_div=1):
+    """deltas must be fp32 contiguous for the in-place write-back to reach the caller's tensor."""
+    lib = _lib.load()
+    anchors = _f32c(anchors, "anchors")
+    d = _f32(deltas, "deltas")
+    if not d.is_contiguous():
+        d = d.contiguous()
+    N = anchors.shape[0]
+    k = d.shape[1] // 4
+    assert d.shape[0] == N and d.shape[1] == 4 * k
+    if sel_idx is not None:
+        si = _i32c(sel_idx)
+        out = torch.empty((si.numel(), 4), dtype=torch.float32, device=anchors.device)
+        nsel = si.numel()
+    else:
+        si, nsel = None, 0
+        out = torch.empty((N, 4 * k), dtype=torch.float32, device=anchors.device)
+    with _guard(out):
+        check(lib.bdet_box_decode(_p(anchors), _p(d), N, k, farr(mean), farr(std), _p(out), int(bool(writeback)),
+                                  _p(si), nsel, int(sel_div), _stream(out)))
+    return out
+
+
+def sum_encode(anchors, gt, mean, std):
+    lib = _lib.load()
+    a, g = _f32c(anchors), _f32c(gt)
+    out = torch.empty_like(a)
+    with _guard(out):
+        check(lib.bdet_sum_encode(_p(a), _p(g), a.shape[0], farr(mean), farr(std), _p(out), _stream(out)))
+    return out
+
+
+def sum_decode(anchors, deltas, mean, std, writeback=False):
+    lib = _lib.load()
+    a = _f32c(anchors)
+    d = _f32(deltas)
+    if not d.is_contiguous():
+        d = d.contiguous()
+    out = torch.empty_like(a)
+    with _guard(out):
+        check(lib.bdet_sum_decode(_p(a), _p(d), a.shape[0], farr(mean), farr(std), _p(out), int(bool(writeback)),
+                                  _stream(out)))
+    return out
+
+
+def point_encode(points, gt):
+    """points (A, 2), gt (G, >=4) -> (G, A, 4)."""
+    lib = _lib.load()
+    p = _f32c(points)
+    g, ld = _rows(gt, "gt")
+    out = torch.empty((g.shape[0], p.shape[0], 4), dtype=torch.float32, device=p.device)
+    with _guard(out):
+        check(lib.bdet_point_encode(_p(p), p.shape[0], _p(g), ld, g.shape[0], _p(out), _stream(out)))
+    return out
+
+
+def point_decode(points, deltas, sel_idx=None, sel_div=1):
+    lib = _lib.load()
+    p, d = _f32c(points), _f32c(deltas)
+    N, k = p.shape[0], d.shape[1] // 4
+    if sel_idx is not None:
+        si = _i32c(sel_idx)
+        out = torch.empty((si.numel(), 4), dtype=torch.float32, device=p.device)
+        nsel = si.numel()
+    else:
+        si, nsel = None, 0
+        out = torch.empty_like(d)
+    with _guard(out):
+        check(lib.bdet_point_decode(_p(p), _p(d), N, k, _p(out), _p(si), nsel, int(sel_div), _stream(out)))
+    return out
+
+
+def boxes_scale_clip(boxes, scale_w, scale_h, clip_w=-1.0, clip_h=-1.0):
+    """In place on a contiguous fp32 (N, 4) tensor."""
+    lib = _lib.load()
+    assert boxes.is_cuda and boxes.dtype == torch.float32 and boxes.is_contiguous()
+    with _guard(boxes):
+        check(lib.bdet_boxes_scale_clip(_p(boxes), boxes.shape[0], float(scale_w), float(scale_h), float(clip_w),
+                                        float(clip_h), _stream(boxes)))
+    return boxes
+
+
+def boxes_filter_by_size(boxes, size0=0.0, size1=0.0):
+    lib = _lib.load()
+    b = _f32c(boxes)
+    keep = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
+    with _guard(b):
+        check(lib.bdet_boxes_filter_by_size(_p(b), b.shape[0], float(size0), float(size1), _p(keep), _stream(b)))
+    return keep.bool()
+
+
+# ----------------------------------------------------------------------------- fused target assignment
+class AssignPlan:
+    """Pre-allocated outputs + workspace for bdet_assign_targets (reused across steps)."""
+
+    def __init__(self, A, Gmax, B, device):
+        lib = _lib.load()
+        self.A, self.Gmax, self.B = A, Gmax, B
+        self.labels = torch.empty((B, A), dtype=torch.int32, device=device)
+        self.idx = torch.empty((B, A), dtype=torch.int32, device=device)
+        self.offsets = torch.empty((B, A, 4), dtype=torch.float32, device=device)
+        self.ws = _workspace(lib.bdet_assign_targets_workspace(Gmax, A, B), device)
+
+
+def assign_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_low_quality=True, apply_class=True,
+                   mean=(0, 0, 0, 0), std=(1, 1, 1, 1), plan=None):
+    """anchors (A,4); gt_boxes (B,Gmax,5); num_gt (B,) -> (labels (B,A), match_idx (B,A), offsets (B,A,4))."""
+    lib = _lib.load()
+    anchors = _f32c(anchors, "anchors")
+    gt = _f32c(gt_boxes, "gt_boxes")
+    assert gt.ndim == 3 and gt.shape[2] == 5, "gt_boxes must be (B, Gmax, 5)"
+    B, Gmax, _ = gt.shape
+    A = anchors.shape[0]
+    ng = _i32c(num_gt, "num_gt")
+    if plan is None:
+        plan = AssignPlan(A, Gmax, B, anchors.device)
+    assert (plan.A, plan.Gmax, plan.B) == (A, Gmax, B)
+    with _guard(anchors):
+        check(lib.bdet_assign_targets(_p(anchors), A, _p(gt), Gmax, _p(ng), B, farr(thresholds), iarr(labels),
+                                      len(labels), int(bool(allow_low_quality)), int(bool(apply_class)),
+                                      farr(mean), farr(std), _p(plan.labels), _p(plan.idx), _p(plan.offsets),
+                                      _p(plan.ws), plan.ws.numel(), _stream(anchors)))
+    return plan.labels, plan.idx, plan.offsets

@@ -1,0 +1,206 @@
+/*
+ * bdet.h -- C ABI of libbdet.so: B200 (sm_100a) box-op hot path for BaseDet.
+ *
+ * The reference (megvii-research/basedet) has NO FFI boundary today: its box ops are
+ * thin Python over megengine.functional.  Each entry point below names
+ * the reference Python interface (file:line) whose arithmetic it replaces; the drop-in
+ * Python layer in basedet_b200/{structures,layers} keeps those signatures and calls
+ * these functions through ctypes (INTEGRATION.md shows the binding a maintainer adds).
+ *
+ * Conventions
+ *   - every pointer is a RAW DEVICE pointer unless the parameter name ends in `_host`;
+ *   - fp32 values, int32 indices / labels, row-major, contiguous unless an `ld` is given;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
+ *     synchronise, allocate, or keep global state; the caller owns all buffers;
+ *   - variable-length results return their count through a device int32*;
+ *   - functions return BDET_OK or a negative BDET_E* code; bdet_last_error() gives the
+ *     thread-local message;
+ *   - there is no CPU fallback and no other backend: without an sm_100 device the
+ *     launches fail and the error is reported.
+ */
+#ifndef BDET_H_
+#define BDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDET_ABI_VERSION 1
+
+#define BDET_OK 0
+#define BDET_EINVAL (-1)       /* bad argument (mirrors the reference's Python asserts) */
+#define BDET_ECUDA (-2)        /* CUDA runtime / launch error */
+#define BDET_EWORKSPACE (-3)   /* workspace too small */
+#define BDET_EUNSUPPORTED (-4) /* size outside what the kernels cover */
+
+#define BDET_MAX_LEVELS 8
+#define BDET_MAX_MATCH_LABELS 8
+
+typedef void* bdet_stream_t;
+
+int bdet_abi_version(void);
+const char* bdet_last_error(void);
+/* SM count / compute capability of the current device (host query, no launch). */
+int bdet_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ------------------------------------------------------------------ a1/a2: anchors
+ * DefaultAnchorGenerator.generate_anchors_by_features  layers/common/anchor_generator.py:111-122
+ * create_anchor_grid                                   layers/common/anchor_generator.py:23-30
+ * All levels in one launch.  Level l writes H*W*n_base[l] boxes at out + 4*out_offset[l]
+ * (offsets in boxes), order (h, w, base).  x = fp32(shift + w*stride) evaluated in fp64.
+ * base_host: concatenated (sum n_base, 4) fp32 base anchors (host memory, <= 64 rows). */
+int bdet_anchors_grid(float* out, int n_levels, const int* hw_host /*2*n_levels: H,W*/,
+                      const double* stride_host, const double* shift_host, const int* n_base_host,
+                      const float* base_host, const int64_t* out_offset_host, bdet_stream_t stream);
+
+/* AnchorPointGenerator (mode 0)  layers/common/anchor_generator.py:152-165  (x,y) repeated num_anchors
+ * FastPointGenerator   (mode 1)  layers/common/anchor_generator.py:175-182  (i*stride, j*stride), (w,h) mesh quirk kept */
+int bdet_points_grid(float* out, int n_levels, const int* hw_host, const double* stride_host,
+                     const double* shift_host, int num_anchors, int mode,
+                     const int64_t* out_offset_host /*in points*/, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a3/a4: pairwise box ops
+ * box_iou  structures/op_patch.py:33-97      (mode BDET_PAIR_IOU)
+ * box_ioa  structures/op_patch.py:169-227    (mode BDET_PAIR_IOA)
+ * Boxes.intersection structures/boxes.py:114-130 (BDET_PAIR_INTER); Boxes.giou :74-95 (BDET_PAIR_GIOU)
+ * boxes1: (N, >=4) with row stride ld1 floats; boxes2: (M, >=4) with row stride ld2 floats.
+ * out: (N, M) row-major.  Batched form: batch b reads boxes1 + b*bs1, boxes2 + b*bs2 (bs2 = 0 shares
+ * boxes2), writes out + b*bs_out, and uses n1_dev[b] rows when n1_dev != NULL (rows >= n1_dev[b] untouched). */
+#define BDET_PAIR_IOU 0
+#define BDET_PAIR_IOA 1
+#define BDET_PAIR_INTER 2
+#define BDET_PAIR_GIOU 3
+int bdet_pairwise(const float* boxes1, int ld1, int N, const float* boxes2, int ld2, int M, float* out,
+                  int mode, bdet_stream_t stream);
+int bdet_pairwise_batched(const float* boxes1, int ld1, int64_t bs1, const int* n1_dev, int N,
+                          const float* boxes2, int ld2, int64_t bs2, int M, float* out, int64_t bs_out,
+                          int B, int mode, bdet_stream_t stream);
+/* box_center structures/op_patch.py:100-130: (N,4) -> (N,2);  point_distance :133-166: (N,2)x(M,2) -> (N,M) */
+int bdet_box_center(const float* boxes, int ld, int N, float* out, bdet_stream_t stream);
+int bdet_point_distance(const float* p1, int N, const float* p2, int M, float* out, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a5: Matcher
+ * Matcher.__call__  layers/common/matcher.py:31-51
+ * matrix (G, A) fp32 [batched: (B, Gmax, A) with g_dev[b] valid rows, NULL -> Gmax].
+ * thresholds_host: n_labels-1 user thresholds (the +-inf the constructor adds are implied);
+ * labels_host: n_labels ints.  Outputs match_idx (B,A) int32 = first argmax over G, labels (B,A) int32.
+ * Single pass over the matrix + a fix-up that re-reads only the row segments holding a row maximum. */
+size_t bdet_match_workspace(int Gmax, int A, int B);
+int bdet_match(const float* matrix, int64_t batch_stride, const int* g_dev, int Gmax, int A, int B,
+               const float* thresholds_host, const int* labels_host, int n_labels, int allow_low_quality,
+               int* match_idx, int* labels, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* (R, G) layout used by RCNN.get_ground_truth  layers/head/rcnn.py:113-116: max / first argmax over axis 1.
+ * One warp per row, warp-shuffle argmax. */
+int bdet_match_rows(const float* matrix, int R, int G, float* max_out, int* argmax_out, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a7-a9: coders
+ * BoxCoder.encode structures/boxcoder.py:61-73; BoxCoder.decode :75-98
+ * encode: t = ((delta(bbox, gt)) - mean) / std.  If gather_idx != NULL, gt row = gt[gather_idx[i]] with
+ * row stride gt_ld floats (fuses `gt_boxes[match_indices]`, models/det/retinanet.py:220-224). */
+int bdet_box_encode(const float* bbox, const float* gt, int gt_ld, const int* gather_idx, int N,
+                    const float* mean_host, const float* std_host, float* out, bdet_stream_t stream);
+/* decode: anchors (N,4), deltas (N,4k) -> out (N,4k).  writeback != 0 stores deltas*std+mean back into
+ * `deltas` like the reference's in-place update (boxcoder.py:76-77).
+ * If sel_idx != NULL (n_sel entries): out (n_sel,4) = decode(anchors[sel_idx[i]/sel_div], deltas[...]) --
+ * the decode-then-gather of models/det/retinanet.py:194-196 without decoding the other 99 %. */
+int bdet_box_decode(const float* anchors, float* deltas, int N, int k, const float* mean_host,
+                    const float* std_host, float* out, int writeback, const int* sel_idx, int n_sel,
+                    int sel_div, bdet_stream_t stream);
+/* SumBoxCoder structures/boxcoder.py:115-127 */
+int bdet_sum_encode(const float* anchors, const float* gt, int N, const float* mean_host,
+                    const float* std_host, float* out, bdet_stream_t stream);
+int bdet_sum_decode(const float* anchors, float* deltas, int N, const float* mean_host,
+                    const float* std_host, float* out, int writeback, bdet_stream_t stream);
+/* PointCoder structures/boxcoder.py:132-141.  encode: points (A,2), gt (G,>=4, ld) -> (G,A,4);
+ * decode: points (N,2), deltas (N,4k) -> (N,4k); sel_idx as in bdet_box_decode. */
+int bdet_point_encode(const float* points, int A, const float* gt, int gt_ld, int G, float* out,
+                      bdet_stream_t stream);
+int bdet_point_decode(const float* points, const float* deltas, int N, int k, float* out,
+                      const int* sel_idx, int n_sel, int sel_div, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ fused target assignment
+ * RetinaNet.get_ground_truth  models/det/retinanet.py:211-232 (and RPN.get_ground_truth rpn.py:215-226
+ * up to, not including, sample_labels): IoU (G,A) -> Matcher -> labels[fg]=class -> BoxCoder.encode,
+ * for all B images, WITHOUT materialising the (G,A) matrix.  Results are bit-identical to the
+ * bdet_pairwise + bdet_match + bdet_box_encode sequence.
+ * anchors (A,4) shared; gt (B,Gmax,5) rows [x1,y1,x2,y2,class]; num_gt_dev (B) int32.
+ * apply_class != 0: labels==1 become int32(gt class) (retinanet.py:222-223); 0: raw matcher labels (RPN).
+ * Outputs: labels (B,A) int32, match_idx (B,A) int32, offsets (B,A,4) fp32.
+ * Images with num_gt == 0 (the reference raises there): labels = label of IoU 0, idx 0, offsets 0. */
+size_t bdet_assign_targets_workspace(int Gmax, int A, int B);
+int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, const int* num_gt_dev, int B,
+                        const float* thresholds_host, const int* labels_host, int n_labels,
+                        int allow_low_quality, int apply_class, const float* mean_host,
+                        const float* std_host, int* labels, int* match_idx, float* offsets,
+                        void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a10: score filter + top-k
+ * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
+ * Segmented: segment s covers scores[seg_offset[s] .. seg_offset[s+1]).  For each segment writes
+ * min(k, n_s) (value, index-within-segment) pairs sorted by (value desc, index asc) at
+ * out_* + s*k, and the count at out_count[s].  Radix select on (value, index) keys + bitonic sort. */
+size_t bdet_topk_workspace(int64_t total, int n_seg, int k);
+int bdet_topk(const float* scores, const int64_t* seg_offset_host, int n_seg, int k, float* out_vals,
+              int* out_idx, int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* sigmoid -> score > thr -> top-k of models/det/retinanet.py:181-191 (mode BDET_SCORE_SIGMOID) and
+ * sqrt(sigmoid(cls)*sigmoid(ctr)) of models/det/fcos.py:194-202 (mode BDET_SCORE_FCOS; ctrness has one
+ * value per C logits).  logits are flat per segment; index = flat index within the segment
+ * (label = idx % C, box = idx / C).  Outputs as bdet_topk.  BDET_SCORE_RAW treats logits as scores. */
+#define BDET_SCORE_RAW 0
+#define BDET_SCORE_SIGMOID 1
+#define BDET_SCORE_FCOS 2
+size_t bdet_score_filter_topk_workspace(int64_t total, int n_seg, int k);
+int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_offset_host,
+                           int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
+                           int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* F.sigmoid / fcos score as a plain elementwise op (so tests can feed bit-identical scores to the oracle). */
+int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int mode, float* out,
+                bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a11: class-aware batched NMS
+ * batched_nms  layers/common/post_processing.py:17-47  ->  F.vision.nms
+ * boxes (B,Nmax,4), scores (B,Nmax), idxs (B,Nmax) int32 or fp32 (idxs_is_float; NULL = single class),
+ * n_dev (B) valid counts (NULL -> Nmax).  The class offset `idxs*(max(boxes)+1)` is applied in fp32 exactly
+ * as the reference does.  keep (B, max_out_cap) int32 = ORIGINAL indices of kept boxes in score-descending
+ * order; keep_count (B).  max_output <= 0 means unlimited (cap = Nmax). */
+size_t bdet_nms_workspace(int Nmax, int B);
+int bdet_nms(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
+             int Nmax, int B, float iou_thresh, int max_output, int* keep, int keep_ld, int* keep_count,
+             void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a12: Boxes.scale / clip / filter_by_size
+ * structures/boxes.py:193-212, :152-177, :132-150.  boxes (N,4) in place: x*=sw, y*=sh then clip to
+ * [0,clip_w]x[0,clip_h] (clip skipped when clip_w < 0).  keep_mask (N) uint8 optional: (w>0)&(h>0) style. */
+int bdet_boxes_scale_clip(float* boxes, int N, float scale_w, float scale_h, float clip_w, float clip_h,
+                          bdet_stream_t stream);
+int bdet_boxes_filter_by_size(const float* boxes, int N, float size0, float size1, uint8_t* keep_mask,
+                              bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ a13/a14: ROI pooling
+ * assign_rois  layers/common/roi_pool.py:12-25: level = clamp(floor(4 + log(sqrt(area)/224)/ln2), lo, hi) - lo */
+int bdet_roi_assign_levels(const float* rois, int K, int min_level, int max_level, int* levels,
+                           bdet_stream_t stream);
+/* roi_pool -> F.nn.roi_align(mode="average", aligned=True)  layers/common/roi_pool.py:35-78
+ * All FPN levels in one launch, output in ORIGINAL roi order (the reference's dummy-roi / argsort glue
+ * :28-31,:74-76 is not needed).  feats_host: n_levels device pointers to (B,C,H_l,W_l) fp32 NCHW;
+ * hw_host: H_l,W_l; scale_host: spatial scale (1/stride) per level; rois (K,5) [batch,x1,y1,x2,y2];
+ * levels (K) int32 (NULL -> all level 0).  out (K,C,PH,PW). */
+int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, const int* hw_host,
+                       const float* scale_host, int B, int C, const float* rois, const int* levels, int K,
+                       int PH, int PW, int sample_h, int sample_w, int aligned, float* out,
+                       bdet_stream_t stream);
+/* Backward w.r.t. the features (rois carry no gradient, roi_pool.py:56).  dfeats must be zero-initialised
+ * by the caller (or pass zero_init != 0 to have the library clear them on `stream` first).
+ * Accumulates each ROI's footprint in shared memory and flushes it once with red.global.add. */
+int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, const float* scale_host,
+                       int B, int C, const float* rois, const int* levels, int K, int PH, int PW,
+                       int sample_h, int sample_w, int aligned, const float* dout, int zero_init,
+                       bdet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDET_H_ */

@@ -1,0 +1,737 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy fp32 restatement of BaseDet's box-op hot path.
+
+Every function follows the cited reference lines *in operation order*, one fp32
+rounding per arithmetic op (numpy float32 arrays never contract to FMA).  All
+``path:line`` citations are relative to the reference tree (megvii-research/basedet).
+
+MegEngine itself (``megengine.functional``) is not available offline, so the
+semantics of its leaf ops are restated from its published behaviour and are
+flagged ``ASSUMED`` below; DESIGN.md lists which of them are pinned by the
+reference's own tests.
+
+  ASSUMED-1  Elemwise MAX / MIN are ``x>y?x:y`` / ``x<y?x:y``  (so max(NaN, 0) = 0).
+  ASSUMED-2  argmax returns the FIRST (lowest) index among equal maxima.
+  ASSUMED-3  argsort / topk(descending) order is (value desc, index asc), i.e. stable.
+  ASSUMED-4  cond_take returns flat indices in ascending order (int32).
+  ASSUMED-5  F.vision.nms: IoU = inter / (Sa + Sb - inter), suppress iff IoU > thresh,
+             greedy in score-descending order, truncated to max_output.
+  ASSUMED-6  F.nn.roi_align(aligned=True): offset 0.5, zero padding for taps outside
+             the map (no clamping), lerp written as a + (b - a) * t, average = sum / S^2.
+  ASSUMED-7  F.arange(start, stop, step) = fp32(start + i * step) evaluated in float64.
+"""
+import math
+
+import numpy as np
+
+f32 = np.float32
+_ZERO = f32(0.0)
+
+
+# --------------------------------------------------------------------------- leaf ops
+def emax(x, y):
+    """MegDNN Elemwise MAX (ASSUMED-1)."""
+    return np.where(x > y, x, y).astype(f32)
+
+
+def emin(x, y):
+    """MegDNN Elemwise MIN (ASSUMED-1)."""
+    return np.where(x < y, x, y).astype(f32)
+
+
+def arange_f32(start, stop, step):
+    """megengine.functional.arange (ASSUMED-7)."""
+    num = int(math.ceil((stop - start) / step))
+    num = max(num, 0)
+    return (start + np.arange(num, dtype=np.float64) * step).astype(f32)
+
+
+def meshgrid(x, y):
+    """basedet/layers/common/function.py:47-54."""
+    assert x.ndim == 1 and y.ndim == 1
+    shape = (y.shape[0], x.shape[0])
+    return np.broadcast_to(x, shape), np.broadcast_to(y.reshape(-1, 1), shape)
+
+
+def cond_take(mask, x):
+    """F.cond_take (ASSUMED-4): (values, flat ascending int32 indices)."""
+    idx = np.flatnonzero(mask.reshape(-1)).astype(np.int32)
+    return x.reshape(-1)[idx], idx
+
+
+def argsort_desc(scores):
+    """Stable descending argsort: (score desc, index asc) (ASSUMED-3)."""
+    scores = np.asarray(scores, dtype=f32)
+    # -0.0 and +0.0 compare equal; NaN-free inputs assumed.
+    return np.argsort(-scores, kind="stable").astype(np.int32)
+
+
+def topk_desc(scores, k):
+    """F.topk(scores, k, descending=True) -> (values, int32 indices), sorted (ASSUMED-3).
+
+    ``k`` is clamped to ``len(scores)`` (reference relies on MegEngine doing so at
+    RPN P6, basedet/models/det/rpn.py:155 with 819 < 1000).
+    """
+    order = argsort_desc(scores)[: min(int(k), len(scores))]
+    return np.asarray(scores, dtype=f32)[order], order
+
+
+# --------------------------------------------------------------------------- anchors
+def generate_base_anchors(scales, ratios):
+    """basedet/layers/common/anchor_generator.py:99-109 (float64 math, fp32 result :95).
+
+    ``scales`` / ``ratios`` are first rounded to fp32 then widened again, exactly as
+    ``np.array(..., dtype=np.float32)`` (:73-74) followed by ``.tolist()`` (:83) does.
+    """
+    scales = np.array(scales, dtype=f32).tolist()
+    ratios = np.array(ratios, dtype=f32).tolist()
+    out = []
+    areas = [s ** 2.0 for s in scales]
+    for area in areas:
+        for ratio in ratios:
+            w = math.sqrt(area / ratio)
+            h = ratio * w
+            out.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+    return np.array(out, dtype=f32).reshape(-1, 4)
+
+
+def create_anchor_grid(featmap_size, offsets, stride):
+    """basedet/layers/common/anchor_generator.py:23-30.
+
+    ``featmap_size`` is (H, W); the reference's step_x/step_y naming swap (:24) is
+    neutralised by ``meshgrid(grid_y, grid_x)`` (:29): x varies along W, y along H.
+    """
+    step_x, step_y = featmap_size
+    shift = offsets * stride
+    grid_x = arange_f32(shift, step_x * stride + shift, stride)
+    grid_y = arange_f32(shift, step_y * stride + shift, stride)
+    grids_x, grids_y = meshgrid(grid_y, grid_x)
+    return grids_x.reshape(-1), grids_y.reshape(-1)
+
+
+def default_anchors(sizes, anchor_scales, anchor_ratios, strides, offset):
+    """DefaultAnchorGenerator.generate_anchors_by_features, anchor_generator.py:86-122."""
+    n = len(strides)
+    scales = list(anchor_scales) * n if len(anchor_scales) == 1 else list(anchor_scales)
+    ratios = list(anchor_ratios) * n if len(anchor_ratios) == 1 else list(anchor_ratios)
+    assert len(scales) == n and len(ratios) == n and len(sizes) == n
+    out = []
+    for size, stride, sc, ra in zip(sizes, strides, scales, ratios):
+        base = generate_base_anchors(sc, ra)
+        gx, gy = create_anchor_grid(size, offset, stride)
+        grids = np.stack([gx, gy, gx, gy], axis=1).astype(f32)
+        out.append((grids.reshape(-1, 1, 4) + base.reshape(1, -1, 4)).reshape(-1, 4).astype(f32))
+    return out
+
+
+def anchor_points(sizes, num_anchors, strides, offset):
+    """AnchorPointGenerator.generate_anchors_by_features, anchor_generator.py:152-165."""
+    out = []
+    for size, stride in zip(sizes, strides):
+        gx, gy = create_anchor_grid(size, offset, stride)
+        grids = np.stack([gx, gy], axis=1).astype(f32)
+        out.append(np.repeat(grids[:, None, :], num_anchors, axis=1).reshape(-1, 2))
+    return out
+
+
+def fast_points(sizes, strides):
+    """FastPointGenerator.__call__, anchor_generator.py:175-182.
+
+    Quirk kept: ``meshgrid(arange(h), arange(w))`` yields a (w, h) mesh, so the
+    output row j*h + i holds (i*stride, j*stride) with i < h, j < w.
+    """
+    out = []
+    for (h, w), stride in zip(sizes, strides):
+        gx, gy = meshgrid(np.arange(h, dtype=f32), np.arange(w, dtype=f32))
+        grids = np.stack((gx, gy), axis=-1).reshape(-1, 2).astype(f32)
+        out.append((grids * f32(stride)).astype(f32))
+    return out
+
+
+# --------------------------------------------------------------------------- pairwise box ops
+def _pair_inter(b1, b2):
+    """Shared front half of IOU / IOA subgraphs, op_patch.py:50-61 / :187-197."""
+    b1 = np.asarray(b1, dtype=f32)[:, None, :]
+    b2 = np.asarray(b2, dtype=f32)[None, :, :]
+    iw = emin(b1[..., 2], b2[..., 2]) - emax(b1[..., 0], b2[..., 0])
+    ih = emin(b1[..., 3], b2[..., 3]) - emax(b1[..., 1], b2[..., 1])
+    iw = emax(iw, _ZERO)
+    ih = emax(ih, _ZERO)
+    return (iw * ih).astype(f32), b1, b2
+
+
+def box_iou(boxes1, boxes2):
+    """basedet/structures/op_patch.py:33-97 (IOU subgraph) -> (N, M) fp32."""
+    inter, b1, b2 = _pair_inter(boxes1, boxes2)
+    a1 = (b1[..., 2] - b1[..., 0]) * (b1[..., 3] - b1[..., 1])
+    a2 = (b2[..., 2] - b2[..., 0]) * (b2[..., 3] - b2[..., 1])
+    union = (a1 + a2).astype(f32)
+    union = (union - inter).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = (inter / union).astype(f32)
+    return emax(iou, _ZERO)
+
+
+def box_ioa(boxes1, boxes2):
+    """basedet/structures/op_patch.py:169-227 (IOA subgraph): inter / area(boxes2)."""
+    inter, _, b2 = _pair_inter(boxes1, boxes2)
+    a2 = (b2[..., 2] - b2[..., 0]) * (b2[..., 3] - b2[..., 1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ioa = (inter / a2).astype(f32)
+    return emax(ioa, _ZERO)
+
+
+def box_intersection(boxes1, boxes2):
+    """Boxes.intersection, basedet/structures/boxes.py:114-130."""
+    return _pair_inter(boxes1, boxes2)[0]
+
+
+def box_giou(boxes1, boxes2):
+    """Boxes.giou, basedet/structures/boxes.py:74-95 (iou NOT clamped)."""
+    b1 = np.asarray(boxes1, dtype=f32)
+    b2 = np.asarray(boxes2, dtype=f32)
+    inter = box_intersection(b1, b2)
+    a1 = ((b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1]))[:, None]
+    a2 = ((b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1]))[None, :]
+    union = ((a1 + a2).astype(f32) - inter).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = (inter / union).astype(f32)
+        e1, e2 = b1[:, None, :], b2[None, :, :]
+        lt = np.minimum(e1[..., :2], e2[..., :2])
+        rb = np.maximum(e1[..., 2:], e2[..., 2:])
+        wh = np.maximum((rb - lt).astype(f32), _ZERO)  # F.clip(lower=0)
+        area = (wh[..., 0] * wh[..., 1]).astype(f32)
+        return (iou - ((area - union).astype(f32) / area).astype(f32)).astype(f32)
+
+
+def box_center(boxes):
+    """basedet/structures/op_patch.py:100-113: (tl + br) / 2."""
+    b = np.asarray(boxes, dtype=f32)
+    return ((b[:, :2] + b[:, -2:]).astype(f32) / f32(2)).astype(f32)
+
+
+def point_distance(p1, p2):
+    """basedet/structures/op_patch.py:133-149: pow(sum(pow(diff, 2)), 0.5)."""
+    p1 = np.asarray(p1, dtype=f32)[:, None, :]
+    p2 = np.asarray(p2, dtype=f32)
+    diff = (p1 - p2).astype(f32)
+    sq = (diff * diff).astype(f32)  # pow(x, 2) == x*x exactly in IEEE
+    s = (sq[..., 0] + sq[..., 1]).astype(f32)
+    return np.sqrt(s).astype(f32)  # pow(x, 0.5): sqrt restated (ulp-level, tolerance-tested)
+
+
+# --------------------------------------------------------------------------- Boxes helpers
+def boxes_clip(boxes, sizes):
+    """Boxes.clip, basedet/structures/boxes.py:152-177; sizes = (h, w)."""
+    h, w = (f32(sizes[0]), f32(sizes[1]))
+    b = np.asarray(boxes, dtype=f32)
+    out = np.empty_like(b)
+    out[:, 0] = np.minimum(np.maximum(b[:, 0], _ZERO), w)
+    out[:, 1] = np.minimum(np.maximum(b[:, 1], _ZERO), h)
+    out[:, 2] = np.minimum(np.maximum(b[:, 2], _ZERO), w)
+    out[:, 3] = np.minimum(np.maximum(b[:, 3], _ZERO), h)
+    return out
+
+
+def boxes_scale(boxes, scale_ratios):
+    """Boxes.scale, basedet/structures/boxes.py:193-212; ratios = (scale_h, scale_w)."""
+    sh, sw = f32(scale_ratios[0]), f32(scale_ratios[1])
+    return (np.asarray(boxes, dtype=f32) * np.array([sw, sh, sw, sh], dtype=f32)).astype(f32)
+
+
+def boxes_filter_by_size(boxes, sizes=0):
+    """Boxes.filter_by_size, basedet/structures/boxes.py:132-150 (keeps the h/w name swap)."""
+    if isinstance(sizes, (int, float)):
+        sizes = (sizes, sizes)
+    b = np.asarray(boxes, dtype=f32)
+    h, w = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    return (w > f32(sizes[0])) & (h > f32(sizes[1]))
+
+
+# --------------------------------------------------------------------------- coders
+def _ltrb_to_cs(b):
+    """BoxCoder._box_ltrb_to_cs_opr, basedet/structures/boxcoder.py:44-59."""
+    w = (b[:, 2] - b[:, 0]).astype(f32)
+    h = (b[:, 3] - b[:, 1]).astype(f32)
+    cx = (b[:, 0] + (f32(0.5) * w).astype(f32)).astype(f32)
+    cy = (b[:, 1] + (f32(0.5) * h).astype(f32)).astype(f32)
+    return w, h, cx, cy
+
+
+def boxcoder_encode(bbox, gt, mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """BoxCoder.encode, basedet/structures/boxcoder.py:61-73 (true divide by std)."""
+    bbox = np.asarray(bbox, dtype=f32)
+    gt = np.asarray(gt, dtype=f32)
+    bw, bh, bcx, bcy = _ltrb_to_cs(bbox)
+    gw, gh, gcx, gcy = _ltrb_to_cs(gt)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dx = ((gcx - bcx).astype(f32) / bw).astype(f32)
+        dy = ((gcy - bcy).astype(f32) / bh).astype(f32)
+        dw = np.log((gw / bw).astype(f32)).astype(f32)
+        dh = np.log((gh / bh).astype(f32)).astype(f32)
+        t = np.stack([dx, dy, dw, dh], axis=1)
+        t = (t - np.asarray(mean, dtype=f32).reshape(1, 4)).astype(f32)
+        t = (t / np.asarray(std, dtype=f32).reshape(1, 4)).astype(f32)
+    return t
+
+
+def boxcoder_decode(anchors, deltas, mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """BoxCoder.decode, basedet/structures/boxcoder.py:75-98 -> (boxes (N,4k), rescaled deltas).
+
+    The reference rescales ``deltas`` IN PLACE (:76-77); the rescaled array is
+    returned second so tests can check the write-back.  No clamp on dw/dh.
+    """
+    anchors = np.asarray(anchors, dtype=f32)
+    d = np.asarray(deltas, dtype=f32)
+    k = d.shape[1] // 4
+    d = (d * np.tile(np.asarray(std, dtype=f32), k).reshape(1, -1)).astype(f32)
+    d = (d + np.tile(np.asarray(mean, dtype=f32), k).reshape(1, -1)).astype(f32)
+    aw, ah, acx, acy = [v[:, None] for v in _ltrb_to_cs(anchors)]
+    with np.errstate(over="ignore", invalid="ignore"):
+        pcx = (acx + (d[:, 0::4] * aw).astype(f32)).astype(f32)
+        pcy = (acy + (d[:, 1::4] * ah).astype(f32)).astype(f32)
+        pw = (aw * np.exp(d[:, 2::4]).astype(f32)).astype(f32)
+        ph = (ah * np.exp(d[:, 3::4]).astype(f32)).astype(f32)
+        half_w = (f32(0.5) * pw).astype(f32)
+        half_h = (f32(0.5) * ph).astype(f32)
+        x1 = (pcx - half_w).astype(f32)
+        y1 = (pcy - half_h).astype(f32)
+        x2 = (pcx + half_w).astype(f32)
+        y2 = (pcy + half_h).astype(f32)
+    box = np.stack([x1, y1, x2, y2], axis=2).reshape(d.shape[0], -1).astype(f32)
+    return box, d
+
+
+def sumcoder_encode(anchors, gt, mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """SumBoxCoder.encode, basedet/structures/boxcoder.py:115-120."""
+    t = (np.asarray(gt, dtype=f32) - np.asarray(anchors, dtype=f32)).astype(f32)
+    t = (t - np.asarray(mean, dtype=f32).reshape(1, 4)).astype(f32)
+    return (t / np.asarray(std, dtype=f32).reshape(1, 4)).astype(f32)
+
+
+def sumcoder_decode(anchors, deltas, mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """SumBoxCoder.decode, basedet/structures/boxcoder.py:122-127."""
+    d = (np.asarray(deltas, dtype=f32) * np.asarray(std, dtype=f32).reshape(1, 4)).astype(f32)
+    d = (d + np.asarray(mean, dtype=f32).reshape(1, 4)).astype(f32)
+    return (np.asarray(anchors, dtype=f32) + d).astype(f32), d
+
+
+def pointcoder_encode(point, gt):
+    """PointCoder.encode, basedet/structures/boxcoder.py:132-133 (broadcasting concat)."""
+    point = np.asarray(point, dtype=f32)
+    gt = np.asarray(gt, dtype=f32)
+    lt = (point - gt[..., :2]).astype(f32)
+    rb = (gt[..., 2:] - point).astype(f32)
+    return np.concatenate([lt, rb], axis=-1).astype(f32)
+
+
+def pointcoder_decode(anchors, deltas):
+    """PointCoder.decode, basedet/structures/boxcoder.py:135-141."""
+    a = np.asarray(anchors, dtype=f32)
+    d = np.asarray(deltas, dtype=f32)
+    out = np.stack(
+        [
+            a[:, 0:1] - d[:, 0::4],
+            a[:, 1:2] - d[:, 1::4],
+            a[:, 0:1] + d[:, 2::4],
+            a[:, 1:2] + d[:, 3::4],
+        ],
+        axis=2,
+    )
+    return out.reshape(d.shape).astype(f32)
+
+
+# --------------------------------------------------------------------------- box_convert
+def box_convert(boxes, mode="xywh2xyxy"):
+    """BoxConverter.convert, basedet/structures/box_convert.py:51-82 ((N,4) boxes)."""
+    src, dst = mode.lower().split("2")
+    b = np.asarray(boxes, dtype=f32)
+    if src == dst:
+        return b
+    if src == "xyxy":
+        b = np.concatenate([b[:, :2], b[:, 2:3] - b[:, 0:1], b[:, 3:4] - b[:, 1:2]], axis=1)
+    elif src == "xcycwh":
+        x = b[:, 0:1] - (b[:, 2:3] / f32(2)).astype(f32)
+        y = b[:, 1:2] - (b[:, 3:4] / f32(2)).astype(f32)
+        b = np.concatenate([x, y, b[:, 2:]], axis=1)
+    elif src != "xywh":
+        raise NotImplementedError(src)
+    b = b.astype(f32)
+    if dst == "xyxy":
+        b = np.concatenate([b[:, :2], b[:, 0:1] + b[:, 2:3], b[:, 1:2] + b[:, 3:4]], axis=1)
+    elif dst == "xcycwh":
+        xc = b[:, 0:1] + (b[:, 2:3] / f32(2)).astype(f32)
+        yc = b[:, 1:2] + (b[:, 3:4] / f32(2)).astype(f32)
+        b = np.concatenate([xc, yc, b[:, 2:]], axis=1)
+    return b.astype(f32)
+
+
+# --------------------------------------------------------------------------- Matcher
+def matcher(matrix, thresholds, labels, allow_low_quality_matches=False):
+    """Matcher.__call__, basedet/layers/common/matcher.py:31-51.
+
+    ``thresholds`` are the *user* thresholds (without the +-inf the constructor adds, :24-25).
+    Returns (match_indices int32 (A,), labels int32 (A,)).  NaN-free matrix assumed.
+    """
+    matrix = np.asarray(matrix, dtype=f32)
+    assert matrix.ndim == 2
+    assert len(thresholds) + 1 == len(labels)
+    thr = [-float("inf")] + [float(t) for t in thresholds] + [float("inf")]
+    max_scores = matrix.max(axis=0)
+    match_indices = np.argmax(matrix, axis=0).astype(np.int32)  # ASSUMED-2
+    out = np.full(match_indices.shape, -1, dtype=np.int32)
+    for label, low, high in zip(labels, thr[:-1], thr[1:]):
+        # python-float thresholds become fp32 scalars when compared with an fp32 tensor
+        mask = (max_scores >= f32(low)) & (max_scores < f32(high))
+        out[mask] = label
+    if allow_low_quality_matches:
+        mask = (matrix == matrix.max(axis=1, keepdims=True)).sum(axis=0) > 0
+        out[mask] = 1
+    return match_indices, out
+
+
+def matcher_rows(matrix):
+    """RCNN layout (R, G): max / argmax over axis 1, basedet/layers/head/rcnn.py:113-116."""
+    matrix = np.asarray(matrix, dtype=f32)
+    return matrix.max(axis=1), np.argmax(matrix, axis=1).astype(np.int32)
+
+
+def retinanet_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_lq,
+                      mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """RetinaNet.get_ground_truth, basedet/models/det/retinanet.py:211-232.
+
+    anchors (A,4); gt_boxes (B,Gmax,5) rows [x1,y1,x2,y2,class]; num_gt (B,).
+    Returns labels (B,A) int32 (class ids for fg, 0 bg, -1 ignore), offsets (B,A,4),
+    plus match_indices (B,A) for diagnostics.
+    """
+    lab_l, off_l, idx_l = [], [], []
+    for g, n in zip(gt_boxes, num_gt):
+        g = np.asarray(g, dtype=f32)[: int(n)]
+        overlaps = box_iou(g[:, :4], anchors)
+        idx, lab = matcher(overlaps, thresholds, labels, allow_lq)
+        matched = g[idx]
+        fg = lab == 1
+        lab[fg] = matched[fg, 4].astype(np.int32)
+        off_l.append(boxcoder_encode(anchors, matched[:, :4], mean, std))
+        lab_l.append(lab)
+        idx_l.append(idx)
+    return np.stack(lab_l), np.stack(off_l), np.stack(idx_l)
+
+
+# --------------------------------------------------------------------------- score filter + top-k
+def sigmoid_f32(x):
+    """F.sigmoid in fp32: 1 / (1 + exp(-x)) (ulp-level differences vs CUDA expected)."""
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(over="ignore"):
+        return (f32(1) / (f32(1) + np.exp(-x).astype(f32)).astype(f32)).astype(f32)
+
+
+def filter_topk_scores(scores_flat, cls_threshold, topk=1000):
+    """Score filter + top-k on a GIVEN fp32 score vector.
+
+    basedet/models/det/retinanet.py:185-191 / fcos.py:196-202:
+    cand = ascending flat idx with score > thr; keep = cand[topk_desc(scores[cand])].
+    Returns (keep_idx int32 sorted by score desc, scores[keep_idx]); empty if no candidate.
+    """
+    scores_flat = np.asarray(scores_flat, dtype=f32).reshape(-1)
+    _, keep = cond_take(scores_flat > f32(cls_threshold), scores_flat)
+    if keep.size == 0:
+        return keep, scores_flat[keep]
+    k = min(keep.shape[0], topk)
+    _, top = topk_desc(scores_flat[keep], k)
+    keep = keep[top]
+    return keep, scores_flat[keep]
+
+
+def retinanet_level_select(logits, offsets, anchors, cls_threshold, topk=1000,
+                           mean=(0, 0, 0, 0), std=(1, 1, 1, 1), scores=None):
+    """One iteration of the level loop of RetinaNet.inference, retinanet.py:181-196.
+
+    logits (HWA, C); offsets (HWA, 4); anchors (HWA, 4).  ``scores`` may be supplied
+    (bit-identical score tensor); otherwise sigmoid_f32(logits).
+    Returns (boxes (k,4), scores (k,), labels (k,) int32, keep_idx (k,) int32) or None.
+    """
+    num_classes = logits.shape[-1]
+    s = sigmoid_f32(logits).reshape(-1) if scores is None else np.asarray(scores, f32).reshape(-1)
+    keep, sc = filter_topk_scores(s, cls_threshold, topk)
+    if keep.size == 0:
+        return None
+    boxes, _ = boxcoder_decode(anchors, np.asarray(offsets, f32).reshape(-1, 4), mean, std)
+    return boxes[keep // num_classes], sc, (keep % num_classes).astype(np.int32), keep
+
+
+def fcos_scores(logits, ctrness):
+    """basedet/models/det/fcos.py:194: sqrt(sigmoid(cls) * sigmoid(ctr)), (HW,C)*(HW,1)."""
+    return np.sqrt((sigmoid_f32(logits) * sigmoid_f32(ctrness)).astype(f32)).astype(f32)
+
+
+# --------------------------------------------------------------------------- NMS
+def nms(boxes, scores, iou_thresh, max_output=None):
+    """megengine.functional.vision.nms (ASSUMED-3, ASSUMED-5).
+
+    Returns original indices of kept boxes in score-descending order (int32).
+    """
+    boxes = np.asarray(boxes, dtype=f32)
+    scores = np.asarray(scores, dtype=f32)
+    n = boxes.shape[0]
+    order = argsort_desc(scores)
+    b = boxes[order]
+    area = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])).astype(f32)
+    removed = np.zeros(n, dtype=bool)
+    thr = f32(iou_thresh)
+    keep = []
+    for i in range(n):
+        if removed[i]:
+            continue
+        keep.append(i)
+        if max_output is not None and len(keep) >= max_output:
+            break
+        r = b[i + 1:]
+        left = np.maximum(b[i, 0], r[:, 0])
+        right = np.minimum(b[i, 2], r[:, 2])
+        top = np.maximum(b[i, 1], r[:, 1])
+        bottom = np.minimum(b[i, 3], r[:, 3])
+        w = np.maximum((right - left).astype(f32), _ZERO)
+        h = np.maximum((bottom - top).astype(f32), _ZERO)
+        inter = (w * h).astype(f32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            iou = (inter / ((area[i] + area[i + 1:]).astype(f32) - inter).astype(f32)).astype(f32)
+        removed[i + 1:] |= iou > thr
+    return order[np.asarray(keep, dtype=np.int64)].astype(np.int32)
+
+
+def nms_offset_boxes(boxes, idxs):
+    """The class-offset trick, basedet/layers/common/post_processing.py:44-46 (fp32)."""
+    boxes = np.asarray(boxes, dtype=f32)
+    idxs = np.asarray(idxs)
+    max_coordinate = boxes.max()
+    offsets = (idxs.astype(f32) * (max_coordinate + f32(1)).astype(f32)).astype(f32)
+    return (boxes + offsets.reshape(-1, 1)).astype(f32)
+
+
+def batched_nms(boxes, scores, idxs, iou_thresh, max_output=None):
+    """basedet/layers/common/post_processing.py:17-47."""
+    boxes = np.asarray(boxes, dtype=f32)
+    scores = np.asarray(scores, dtype=f32)
+    idxs = np.asarray(idxs)
+    assert boxes.ndim == 2 and boxes.shape[1] == 4, "the expected shape of boxes is (N, 4)"
+    assert scores.ndim == 1, "the expected shape of scores is (N,)"
+    assert idxs.ndim == 1, "the expected shape of idxs is (N,)"
+    assert boxes.shape[0] == scores.shape[0] == idxs.shape[0], \
+        "number of boxes, scores and idxs are not matched"
+    if boxes.shape[0] == 0:
+        return np.zeros((0,), dtype=np.int32)
+    return nms(nms_offset_boxes(boxes, idxs), scores, iou_thresh, max_output)
+
+
+def py_cpu_nms(dets, thresh):
+    """Restatement of the reference's own numpy helper, post_processing.py:106-132.
+
+    (tests additionally ast-extract the ORIGINAL function when /root/reference exists.)
+    """
+    dets = np.asarray(dets)
+    x1, y1, x2, y2 = [np.ascontiguousarray(dets[:, i]) for i in range(4)]
+    areas = (x2 - x1) * (y2 - y1)
+    order = dets[:, 4].argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(i)
+        order = order[1:]
+        xx1, yy1 = np.maximum(x1[i], x1[order]), np.maximum(y1[i], y1[order])
+        xx2, yy2 = np.minimum(x2[i], x2[order]), np.minimum(y2[i], y2[order])
+        inter = np.maximum(xx2 - xx1, 0) * np.maximum(yy2 - yy1, 0)
+        iou = inter / np.maximum(areas[i] + areas[order] - inter, 1e-5)
+        order = order[iou <= thresh]
+    return keep
+
+
+def post_processing(boxes, box_scores, box_labels, img_info, iou_threshold,
+                    max_detections_per_image=None):
+    """basedet/layers/common/post_processing.py:78-103 -> (boxes, scores, labels, keep)."""
+    boxes = np.asarray(boxes, dtype=f32)
+    img_info = np.asarray(img_info, dtype=f32)
+    keep = batched_nms(boxes, box_scores, box_labels, iou_threshold, max_detections_per_image)
+    kb = boxes[keep]
+    scale_ratios = (img_info[0, 2] / img_info[0, 0], img_info[0, 3] / img_info[0, 1])
+    kb = boxes_scale(kb, scale_ratios)
+    kb = boxes_clip(kb, img_info[0, 2:4])
+    return kb, np.asarray(box_scores, f32)[keep], np.asarray(box_labels)[keep], keep
+
+
+def retinanet_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_threshold=0.05,
+                          iou_threshold=0.5, max_dets=100, topk=1000, scores_list=None):
+    """RetinaNet.inference minus the network, retinanet.py:172-209 (single image)."""
+    tb, ts, tl = [], [], []
+    for lvl, (lg, of, an) in enumerate(zip(logits_list, offsets_list, anchors_list)):
+        sc = None if scores_list is None else scores_list[lvl]
+        r = retinanet_level_select(lg, of, an, cls_threshold, topk, scores=sc)
+        if r is None:
+            continue
+        tb.append(r[0]); ts.append(r[1]); tl.append(r[2])
+    if not tb:
+        e = np.zeros((0,), dtype=f32)
+        return e.reshape(0, 4), e, e.astype(np.int32), e.astype(np.int32)
+    return post_processing(np.concatenate(tb), np.concatenate(ts), np.concatenate(tl),
+                           img_info, iou_threshold, max_dets)
+
+
+# --------------------------------------------------------------------------- ROI pooling
+def assign_levels(rois, strides):
+    """assign_rois without the dummy rows, basedet/layers/common/roi_pool.py:12-25 -> int32 (K,)."""
+    rois = np.asarray(rois, dtype=f32)
+    min_level, max_level = int(math.log2(strides[0])), int(math.log2(strides[-1]))
+    box_area = ((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2])).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lvl = np.floor(
+            (f32(4) + (np.log((np.sqrt(box_area).astype(f32) / f32(224)).astype(f32)).astype(f32)
+                       / f32(math.log(2))).astype(f32)).astype(f32)
+        )
+        # float -> int32 of NaN / -inf: x86 cvttss2si yields INT_MIN; the clamp makes it min_level.
+        lvl = np.where(np.isfinite(lvl), lvl, -1e9)
+    lvl = np.clip(lvl, -2 ** 31, 2 ** 31 - 1).astype(np.int64)
+    lvl = np.minimum(lvl, max_level)
+    lvl = np.maximum(lvl, min_level)
+    return (lvl - min_level).astype(np.int32)
+
+
+def _bilinear_setup(h, w, height, width):
+    h0 = np.floor(h).astype(np.int64)
+    w0 = np.floor(w).astype(np.int64)
+    return h0, w0, h0 + 1, w0 + 1, (h - h0.astype(f32)).astype(f32), (w - w0.astype(f32)).astype(f32)
+
+
+def roi_align(feat, rois, pool_shape, spatial_scale, sample_points=2, aligned=True):
+    """megengine.functional.nn.roi_align(mode="average") (ASSUMED-6), MegDNN roi_align order.
+
+    feat (B,C,H,W) fp32; rois (K,5) [batch, x1, y1, x2, y2] -> (K,C,PH,PW).
+    """
+    feat = np.asarray(feat, dtype=f32)
+    rois = np.asarray(rois, dtype=f32)
+    if isinstance(pool_shape, int):
+        pool_shape = (pool_shape, pool_shape)
+    ph_n, pw_n = pool_shape
+    if isinstance(sample_points, int):
+        sample_points = (sample_points, sample_points)
+    sh, sw = sample_points
+    _, C, H, W = feat.shape
+    K = rois.shape[0]
+    scale = f32(spatial_scale)
+    offset = f32(0.5) if aligned else f32(0.0)
+    out = np.zeros((K, C, ph_n, pw_n), dtype=f32)
+    ph = np.arange(ph_n, dtype=f32).reshape(-1, 1)
+    pw = np.arange(pw_n, dtype=f32).reshape(1, -1)
+    for k in range(K):
+        n = int(rois[k, 0])
+        fm = feat[n]
+        start_w = (rois[k, 1] * scale - offset).astype(f32)
+        start_h = (rois[k, 2] * scale - offset).astype(f32)
+        end_w = (rois[k, 3] * scale - offset).astype(f32)
+        end_h = (rois[k, 4] * scale - offset).astype(f32)
+        roi_w = np.maximum((end_w - start_w).astype(f32), _ZERO)
+        roi_h = np.maximum((end_h - start_h).astype(f32), _ZERO)
+        bin_h = (roi_h / f32(ph_n)).astype(f32)
+        bin_w = (roi_w / f32(pw_n)).astype(f32)
+        acc = np.zeros((C, ph_n, pw_n), dtype=f32)
+        for iy in range(sh):
+            for ix in range(sw):
+                fy = (f32(iy + 0.5) / f32(sh)).astype(f32)
+                fx = (f32(ix + 0.5) / f32(sw)).astype(f32)
+                hc = (start_h + (bin_h * (ph + fy).astype(f32)).astype(f32)).astype(f32)
+                wc = (start_w + (bin_w * (pw + fx).astype(f32)).astype(f32)).astype(f32)
+                hc = np.broadcast_to(hc, (ph_n, pw_n))
+                wc = np.broadcast_to(wc, (ph_n, pw_n))
+                h0, w0, h1, w1, lh, lw = _bilinear_setup(hc, wc, H, W)
+
+                def tap(hh, ww):
+                    ok = (hh >= 0) & (hh < H) & (ww >= 0) & (ww < W)
+                    v = fm[:, np.clip(hh, 0, H - 1), np.clip(ww, 0, W - 1)]
+                    return np.where(ok[None], v, _ZERO).astype(f32)
+
+                tl, tr, bl, br = tap(h0, w0), tap(h0, w1), tap(h1, w0), tap(h1, w1)
+                top = (tl + ((tr - tl).astype(f32) * lw[None]).astype(f32)).astype(f32)
+                bot = (bl + ((br - bl).astype(f32) * lw[None]).astype(f32)).astype(f32)
+                val = (top + ((bot - top).astype(f32) * lh[None]).astype(f32)).astype(f32)
+                acc = (acc + val).astype(f32)
+        out[k] = (acc / f32(sh * sw)).astype(f32)
+    return out
+
+
+def roi_align_backward(dout, feat_shape, rois, pool_shape, spatial_scale, sample_points=2,
+                       aligned=True, accumulate=np.float64):
+    """Gradient of roi_align w.r.t. feat (ASSUMED-6; reference test-suite never pins it).
+
+    Each of the S^2 samples of a bin passes dout/S^2 to its 4 taps with the bilinear weights
+    (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw; out-of-range taps are dropped.
+    ``accumulate``: dtype of the accumulation buffer (float64 = order-independent reference).
+    """
+    dout = np.asarray(dout, dtype=f32)
+    rois = np.asarray(rois, dtype=f32)
+    if isinstance(pool_shape, int):
+        pool_shape = (pool_shape, pool_shape)
+    ph_n, pw_n = pool_shape
+    if isinstance(sample_points, int):
+        sample_points = (sample_points, sample_points)
+    sh, sw = sample_points
+    B, C, H, W = feat_shape
+    grad = np.zeros((B, C, H * W), dtype=accumulate)
+    scale = f32(spatial_scale)
+    offset = f32(0.5) if aligned else f32(0.0)
+    ph = np.arange(ph_n, dtype=f32).reshape(-1, 1)
+    pw = np.arange(pw_n, dtype=f32).reshape(1, -1)
+    for k in range(rois.shape[0]):
+        n = int(rois[k, 0])
+        start_w = (rois[k, 1] * scale - offset).astype(f32)
+        start_h = (rois[k, 2] * scale - offset).astype(f32)
+        end_w = (rois[k, 3] * scale - offset).astype(f32)
+        end_h = (rois[k, 4] * scale - offset).astype(f32)
+        roi_w = np.maximum((end_w - start_w).astype(f32), _ZERO)
+        roi_h = np.maximum((end_h - start_h).astype(f32), _ZERO)
+        bin_h = (roi_h / f32(ph_n)).astype(f32)
+        bin_w = (roi_w / f32(pw_n)).astype(f32)
+        g = (dout[k] / f32(sh * sw)).astype(f32)  # (C, PH, PW)
+        for iy in range(sh):
+            for ix in range(sw):
+                fy = (f32(iy + 0.5) / f32(sh)).astype(f32)
+                fx = (f32(ix + 0.5) / f32(sw)).astype(f32)
+                hc = np.broadcast_to((start_h + (bin_h * (ph + fy).astype(f32)).astype(f32)).astype(f32),
+                                     (ph_n, pw_n))
+                wc = np.broadcast_to((start_w + (bin_w * (pw + fx).astype(f32)).astype(f32)).astype(f32),
+                                     (ph_n, pw_n))
+                h0, w0, h1, w1, lh, lw = _bilinear_setup(hc, wc, H, W)
+                one = f32(1)
+                for hh, ww, wt in (
+                    (h0, w0, ((one - lh) * (one - lw)).astype(f32)),
+                    (h0, w1, ((one - lh) * lw).astype(f32)),
+                    (h1, w0, (lh * (one - lw)).astype(f32)),
+                    (h1, w1, (lh * lw).astype(f32)),
+                ):
+                    ok = (hh >= 0) & (hh < H) & (ww >= 0) & (ww < W)
+                    if not ok.any():
+                        continue
+                    flat = (hh * W + ww)[ok]
+                    contrib = (g[:, ok] * wt[ok][None]).astype(f32)
+                    for c in range(C):
+                        np.add.at(grad[n, c], flat, contrib[c].astype(accumulate))
+    return grad.reshape(B, C, H, W)
+
+
+def roi_pool(features, rois, strides, pool_shape, pooler_type="roi_align"):
+    """basedet/layers/common/roi_pool.py:35-78 ("roi_align" branch only).
+
+    Follows the reference literally: dummy ROI per level (:28-31), per-level pooling,
+    argsort re-ordering, dummies dropped (:74-76).
+    """
+    assert pooler_type == "roi_align"
+    assert len(strides) == len(features)
+    rois = np.asarray(rois, dtype=f32)
+    num_fms = len(strides)
+    lvl = np.concatenate([assign_levels(rois, strides), np.arange(num_fms, dtype=np.int32)])
+    rois_d = np.concatenate([rois, np.zeros((num_fms, rois.shape[-1]), dtype=f32)])
+    pool_list, inds_list = [], []
+    for i, (feat, stride) in enumerate(zip(features, strides)):
+        inds = np.flatnonzero(lvl == i)
+        pool_list.append(roi_align(feat, rois_d[inds], pool_shape, 1.0 / stride, 2, True))
+        inds_list.append(inds)
+    fm_order = np.argsort(np.concatenate(inds_list), kind="stable")
+    pooled = np.concatenate(pool_list, axis=0)
+    return pooled[fm_order][:-num_fms]
