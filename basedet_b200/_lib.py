@@ -80,9 +80,7 @@ def load():
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name, None)
-        if fn is None:  # TODO(round1): remove once every entry point is implemented
-            continue
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
     if lib.bdet_abi_version() != 1:

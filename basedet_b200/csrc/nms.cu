@@ -1,0 +1,365 @@
+// a11: class-aware batched NMS.
+// Reference: basedet/layers/common/post_processing.py:17-47 (batched_nms: offset trick) -> F.vision.nms
+// (MegEngine NMSKeep: argsort by score, 64-bit overlap masks, serial sweep; oracle ASSUMED-3/5).
+//
+// Per image (all B images in the same launches):
+//   1. sort  : (score desc, index asc) via unique 64-bit keys; one CTA + shared-memory bitonic network for
+//              N <= 16384, tiled global bitonic network above that.  The same pass applies the reference's
+//              fp32 class offset  boxes + idxs * (max(boxes) + 1)  and gathers the boxes in sorted order.
+//   2. mask  : 64x64 tiles of the upper triangle; a warp takes a row box, its lanes two column boxes each,
+//              two __ballot_sync build the 64-bit suppression word (IoU > thr, IEEE division as the reference).
+//   3. sweep : per image, warp 0 resolves one 64-box block at a time from the diagonal words held in registers
+//              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' masks into the
+//              shared-memory `removed` bitmap; stops at max_output.
+// Rated in pair tests/s (issue bound), not HBM GB/s.
+#include "common.cuh"
+#include "sortnet.cuh"
+
+namespace bdet {
+
+constexpr int kSmallSortMax = 16384;
+constexpr int kSortTile = 4096;
+
+struct NmsArgs {
+  const float* boxes;   // (B, Nmax, 4)
+  const float* scores;  // (B, Nmax)
+  const void* idxs;     // (B, Nmax) int32 / fp32 or nullptr
+  const int* n_dev;     // (B) or nullptr
+  int idxs_is_float, Nmax, nwords, P;
+  float thr;
+  int max_out, keep_ld;
+  int* order;           // (B, Nmax)
+  float4* sboxes;       // (B, Nmax)
+  uint32_t* maxc;       // (B) order-encoded max coordinate (large path)
+  uint64_t* keys;       // (B, P) (large path)
+  uint64_t* mask;       // (B, Nmax, nwords)
+  int* keep;
+  int* keep_count;
+};
+
+__device__ __forceinline__ int nms_n(const NmsArgs& p, int b) { return p.n_dev ? max(0, min(p.n_dev[b], p.Nmax)) : p.Nmax; }
+
+__device__ __forceinline__ float class_offset(const NmsArgs& p, long long i, float maxc) {
+  if (!p.idxs) return 0.f;
+  float c = p.idxs_is_float ? __ldg(reinterpret_cast<const float*>(p.idxs) + i)
+                            : (float)__ldg(reinterpret_cast<const int*>(p.idxs) + i);
+  return c * (maxc + 1.f);  // post_processing.py:45: idxs * (max_coordinate + 1)
+}
+
+__device__ __forceinline__ float4 shifted_box(const NmsArgs& p, long long i, float maxc) {
+  float4 bx = ldg4(p.boxes + i * 4);
+  if (p.idxs) {
+    float off = class_offset(p, i, maxc);
+    bx.x += off;  // post_processing.py:46: boxes + offsets.reshape(-1, 1)
+    bx.y += off;
+    bx.z += off;
+    bx.w += off;
+  }
+  return bx;
+}
+
+// ---- small path: one CTA per image does max-reduce, key generation, sort, gather ----------------------
+__global__ void __launch_bounds__(1024) nms_sort_small_kernel(const NmsArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(raw);
+  __shared__ uint32_t smax;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = nms_n(p, b);
+  if (n == 0) return;
+  const long long base = (long long)b * p.Nmax;
+  if (t == 0) smax = 0u;
+  __syncthreads();
+  float mc = 0.f;
+  if (p.idxs) {
+    float m = -CUDART_INF_F;
+    for (int i = t; i < n; i += 1024) {
+      float4 bx = ldg4(p.boxes + (base + i) * 4);
+      m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+    }
+    uint32_t w = __reduce_max_sync(0xffffffffu, f2ord(m));
+    if ((t & 31) == 0) atomicMax(&smax, w);
+    __syncthreads();
+    mc = ord2f(smax);
+  }
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = t; i < P; i += 1024) keys[i] = i < n ? make_key(__ldg(p.scores + base + i), (uint32_t)i) : ~0ull;
+  bitonic_sort_smem(keys, P);
+  for (int i = t; i < n; i += 1024) {
+    int src = (int)(uint32_t)keys[i];
+    p.order[base + i] = src;
+    p.sboxes[base + i] = shifted_box(p, base + src, mc);
+  }
+}
+
+// ---- large path ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nms_maxcoord_kernel(const NmsArgs p) {
+  const int b = blockIdx.y;
+  const int n = nms_n(p, b);
+  const long long base = (long long)b * p.Nmax;
+  float m = -CUDART_INF_F;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    float4 bx = ldg4(p.boxes + (base + i) * 4);
+    m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  }
+  uint32_t w = __reduce_max_sync(0xffffffffu, f2ord(m));
+  if ((threadIdx.x & 31) == 0) atomicMax(&p.maxc[b], w);
+}
+
+__global__ void __launch_bounds__(1024) nms_tile_sort_kernel(const NmsArgs p) {
+  __shared__ uint64_t a[kSortTile];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int n = nms_n(p, b);
+  const long long tb = (long long)blockIdx.x * kSortTile;
+  const long long base = (long long)b * p.Nmax;
+  uint64_t* keys = p.keys + (long long)b * p.P;
+  for (int i = t; i < kSortTile; i += 1024) {
+    long long g = tb + i;
+    a[i] = g < n ? make_key(__ldg(p.scores + base + g), (uint32_t)g) : ~0ull;
+  }
+  for (int size = 2; size <= kSortTile; size <<= 1) bitonic_merge_tail_smem(a, kSortTile, tb, size, size >> 1);
+  for (int i = t; i < kSortTile; i += 1024) keys[tb + i] = a[i];
+}
+
+__global__ void __launch_bounds__(256) nms_global_step_kernel(const NmsArgs p, long long size, long long stride) {
+  const int b = blockIdx.y;
+  uint64_t* keys = p.keys + (long long)b * p.P;
+  long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= (p.P >> 1)) return;
+  long long lo = 2 * i - (i & (stride - 1));
+  long long hi = lo + stride;
+  bool up = ((lo & size) == 0);
+  uint64_t x = keys[lo], y = keys[hi];
+  if ((x > y) == up) {
+    keys[lo] = y;
+    keys[hi] = x;
+  }
+}
+
+__global__ void __launch_bounds__(1024) nms_tile_tail_kernel(const NmsArgs p, long long size) {
+  __shared__ uint64_t a[kSortTile];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const long long tb = (long long)blockIdx.x * kSortTile;
+  uint64_t* keys = p.keys + (long long)b * p.P;
+  for (int i = t; i < kSortTile; i += 1024) a[i] = keys[tb + i];
+  bitonic_merge_tail_smem(a, kSortTile, tb, size, kSortTile >> 1);
+  for (int i = t; i < kSortTile; i += 1024) keys[tb + i] = a[i];
+}
+
+__global__ void __launch_bounds__(256) nms_gather_kernel(const NmsArgs p) {
+  const int b = blockIdx.y;
+  const int n = nms_n(p, b);
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const long long base = (long long)b * p.Nmax;
+  int src = (int)(uint32_t)p.keys[(long long)b * p.P + i];
+  float mc = p.idxs ? ord2f(p.maxc[b]) : 0.f;
+  p.order[base + i] = src;
+  p.sboxes[base + i] = shifted_box(p, base + src, mc);
+}
+
+// ---- suppression mask ----------------------------------------------------------------------------------
+// oracle ASSUMED-5: IoU = inter / (Sa + Sb - inter); suppress iff IoU > thr.  inter == 0 can only exceed a
+// negative threshold, so the division is skipped for it when thr >= 0.
+__device__ __forceinline__ bool nms_overlap(float4 a, float sa, float4 b, float sb, float thr) {
+  float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
+  float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
+  float inter = w * h;
+  if (!(inter > 0.f) && thr >= 0.f) return false;
+  return __fdiv_rn(inter, (sa + sb) - inter) > thr;
+}
+
+__global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p) {
+  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+  if (cb < rb) return;
+  const int n = nms_n(p, b);
+  if (rb * 64 >= n || cb * 64 >= n) return;
+  __shared__ float4 srow[64];
+  __shared__ float sarea[64];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float4* sb = p.sboxes + (long long)b * p.Nmax;
+  if (t < 64) {
+    int i = rb * 64 + t;
+    float4 bx = i < n ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    srow[t] = bx;
+    sarea[t] = box_area(bx);
+  }
+  const int c0 = cb * 64 + lane, c1 = c0 + 32;
+  const float4 b0 = c0 < n ? sb[c0] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b1 = c1 < n ? sb[c1] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float a0 = box_area(b0), a1 = box_area(b1);
+  __syncthreads();
+  uint64_t* mrow = p.mask + ((long long)b * p.Nmax + rb * 64) * p.nwords + cb;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int lr = warp * 8 + r;
+    const int i = rb * 64 + lr;
+    if (i >= n) break;  // warp-uniform
+    const float4 a = srow[lr];
+    const float sa = sarea[lr];
+    bool p0 = (c0 < n) && (c0 > i) && nms_overlap(a, sa, b0, a0, p.thr);
+    bool p1 = (c1 < n) && (c1 > i) && nms_overlap(a, sa, b1, a1, p.thr);
+    uint32_t lo = __ballot_sync(0xffffffffu, p0);
+    uint32_t hi = __ballot_sync(0xffffffffu, p1);
+    if (lane == 0) mrow[(long long)lr * p.nwords] = ((uint64_t)hi << 32) | lo;
+  }
+}
+
+// ---- sweep -----------------------------------------------------------------------------------------------
+constexpr int kSweepThreads = 256;
+
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // nwords
+  __shared__ int skept[64];
+  __shared__ int snk;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const int n = nms_n(p, b);
+  const int nblk = (n + 63) >> 6;
+  const long long base = (long long)b * p.Nmax;
+  const uint64_t* mask = p.mask + base * p.nwords;
+  const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
+  for (int w = t; w < nblk; w += kSweepThreads) remv[w] = 0ull;
+  int count = 0;
+  for (int blk = 0; blk < nblk && count < max_out; ++blk) {
+    __syncthreads();
+    if (t < 32) {
+      const int r0 = blk * 64 + lane, r1 = r0 + 32;
+      const uint64_t d0 = r0 < n ? mask[(long long)r0 * p.nwords + blk] : 0ull;
+      const uint64_t d1 = r1 < n ? mask[(long long)r1 * p.nwords + blk] : 0ull;
+      const int nv = min(64, n - blk * 64);
+      const uint64_t valid = nv >= 64 ? ~0ull : ((1ull << nv) - 1ull);
+      uint64_t cand = ~remv[blk] & valid;
+      int nk = 0;
+      while (cand != 0ull && count + nk < max_out) {
+        const int i = __ffsll((long long)cand) - 1;
+        if (lane == 0) skept[nk] = i;
+        ++nk;
+        const uint64_t mine = (i < 32) ? d0 : d1;
+        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)mine, i & 31);
+        const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(mine >> 32), i & 31);
+        cand &= ~(((uint64_t)hi << 32) | lo);
+        cand &= ~(1ull << i);
+      }
+      if (lane == 0) snk = nk;
+    }
+    __syncthreads();
+    const int nk = snk;
+    if (t < nk) p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + blk * 64 + skept[t]];
+    count += nk;
+    if (count >= max_out || nk == 0) continue;
+    for (int w = blk + 1 + t; w < nblk; w += kSweepThreads) {
+      uint64_t acc = remv[w];
+      for (int q = 0; q < nk; ++q) acc |= mask[(long long)(blk * 64 + skept[q]) * p.nwords + w];
+      remv[w] = acc;
+    }
+  }
+  if (t == 0) p.keep_count[b] = count;
+}
+
+struct NmsWs {
+  size_t order, sboxes, maxc, keys, mask, total;
+};
+static NmsWs nms_ws(int Nmax, int B) {
+  NmsWs w;
+  const size_t nwords = (size_t)(Nmax + 63) / 64;
+  size_t o = 0;
+  w.order = o;
+  o += align_up((size_t)B * Nmax * 4, 256);
+  w.sboxes = o;
+  o += align_up((size_t)B * Nmax * 16, 256);
+  w.maxc = o;
+  o += align_up((size_t)B * 4, 256);
+  w.keys = o;
+  if (Nmax > kSmallSortMax) o += align_up((size_t)B * next_pow2(Nmax) * 8, 256);
+  w.mask = o;
+  o += (size_t)B * Nmax * nwords * 8;
+  w.total = o + 256;
+  return w;
+}
+
+}  // namespace bdet
+
+using namespace bdet;
+
+extern "C" size_t bdet_nms_workspace(int Nmax, int B) {
+  if (Nmax <= 0 || B <= 0) return 16;
+  return nms_ws(Nmax, B).total;
+}
+
+extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
+                        int Nmax, int B, float iou_thresh, int max_output, int* keep, int keep_ld, int* keep_count,
+                        void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  BDET_REQUIRE(Nmax >= 0 && B >= 0 && keep_ld >= 0, "negative size");
+  if (B == 0) return BDET_OK;
+  BDET_REQUIRE(keep_count, "null keep_count");
+  cudaStream_t st = as_stream(stream);
+  if (Nmax == 0 || keep_ld == 0) {
+    BDET_CUDA(cudaMemsetAsync(keep_count, 0, (size_t)B * 4, st));
+    return BDET_OK;
+  }
+  BDET_REQUIRE(boxes && scores && keep, "null argument");
+  BDET_REQUIRE(aligned16(boxes), "boxes must be 16-byte aligned");
+  BDET_REQUIRE(B <= 65535, "B > 65535");
+  if (Nmax > (1 << 22)) return set_error(BDET_EUNSUPPORTED, "bdet_nms: Nmax > 2^22");
+  NmsWs w = nms_ws(Nmax, B);
+  if (!workspace || workspace_bytes < w.total)
+    return set_error(BDET_EWORKSPACE, "bdet_nms: workspace needs %zu bytes", w.total);
+  BDET_REQUIRE(aligned16(workspace), "workspace must be 16-byte aligned");
+  char* ws = reinterpret_cast<char*>(workspace);
+  NmsArgs a;
+  a.boxes = boxes;
+  a.scores = scores;
+  a.idxs = idxs;
+  a.n_dev = n_dev;
+  a.idxs_is_float = idxs_is_float;
+  a.Nmax = Nmax;
+  a.nwords = (Nmax + 63) / 64;
+  a.P = next_pow2(Nmax < 2 ? 2 : Nmax);
+  a.thr = iou_thresh;
+  a.max_out = max_output;
+  a.keep_ld = keep_ld;
+  a.order = reinterpret_cast<int*>(ws + w.order);
+  a.sboxes = reinterpret_cast<float4*>(ws + w.sboxes);
+  a.maxc = reinterpret_cast<uint32_t*>(ws + w.maxc);
+  a.keys = reinterpret_cast<uint64_t*>(ws + w.keys);
+  a.mask = reinterpret_cast<uint64_t*>(ws + w.mask);
+  a.keep = keep;
+  a.keep_count = keep_count;
+
+  if (Nmax <= kSmallSortMax) {
+    size_t smem = (size_t)a.P * 8;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      BDET_CUDA(cudaFuncSetAttribute(nms_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    nms_sort_small_kernel<<<B, 1024, smem, st>>>(a);
+  } else {
+    if (a.P < kSortTile) a.P = kSortTile;
+    BDET_CUDA(cudaMemsetAsync(a.maxc, 0, (size_t)B * 4, st));
+    if (idxs) nms_maxcoord_kernel<<<dim3(min(ceil_div(Nmax, 256), 64), B), 256, 0, st>>>(a);
+    const int tiles = a.P / kSortTile;
+    nms_tile_sort_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a);
+    for (long long size = 2ll * kSortTile; size <= a.P; size <<= 1) {
+      for (long long stride = size >> 1; stride >= kSortTile; stride >>= 1)
+        nms_global_step_kernel<<<dim3(ceil_div(a.P / 2, 256), B), 256, 0, st>>>(a, size, stride);
+      nms_tile_tail_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a, size);
+    }
+    nms_gather_kernel<<<dim3(ceil_div(Nmax, 256), B), 256, 0, st>>>(a);
+  }
+  BDET_LAUNCH_CHECK();
+  const int nblk = a.nwords;
+  if (nblk > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_nms: too many 64-box blocks");
+  nms_mask_kernel<<<dim3(nblk, nblk, B), 256, 0, st>>>(a);
+  BDET_LAUNCH_CHECK();
+  size_t sweep_smem = (size_t)a.nwords * 8;
+  static thread_local size_t sweep_configured = 0;
+  if (sweep_smem > 48 * 1024 && sweep_smem > sweep_configured) {
+    BDET_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+    sweep_configured = sweep_smem;
+  }
+  nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}

@@ -1,0 +1,337 @@
+// a13/a14: multi-level ROIAlign forward / backward and FPN level assignment.
+// Reference: basedet/layers/common/roi_pool.py:12-78 -> F.nn.roi_align(mode="average", sample_points=2,
+// aligned=True); MegDNN roi_align semantics restated in oracle ASSUMED-6 (zero padding for taps outside the map,
+// lerp as a + (b - a) * t, average = sum / S^2).
+//
+// forward : one CTA per ROI.  The S*P sample coordinates per axis (floor index, fraction) are computed once
+//           into shared memory; threads then walk the (channel, bin) outputs in memory order, so the 49-float
+//           output rows are written fully coalesced and the 16 taps of a bin hit L1/L2 (the ROI footprint is a
+//           few KB per channel).  All levels in one launch; output directly in the original ROI order.
+// backward: one CTA per ROI accumulates the ROI footprint of a channel chunk in shared memory
+//           (shared atomics), then flushes each touched pixel once with red.global.add.f32, coalesced along x:
+//           <= footprint reds per (roi, channel) instead of 16 * P^2 scattered global atomics.
+#include "common.cuh"
+
+namespace bdet {
+
+constexpr int kRoiThreads = 256;
+constexpr int kMaxSamples = 256;  // P * S per axis
+
+struct RoiLevels {
+  const float* feat[BDET_MAX_LEVELS];
+  float* dfeat[BDET_MAX_LEVELS];
+  int H[BDET_MAX_LEVELS], W[BDET_MAX_LEVELS];
+  float scale[BDET_MAX_LEVELS];
+  int n_levels;
+};
+
+struct RoiArgs {
+  RoiLevels lv;
+  const float* rois;   // (K, 5)
+  const int* levels;   // (K) or nullptr
+  const float* dout;   // backward
+  float* out;          // forward
+  int B, C, K, PH, PW, SH, SW;
+  float offset;
+  int bwd_cap;         // floats of shared accumulation buffer (backward)
+};
+
+struct SampleTab {
+  int i0[kMaxSamples];
+  float frac[kMaxSamples];
+};
+
+// sample coordinate table for one axis: coord = start + bin * (p + (i + 0.5) / S)
+__device__ __forceinline__ void fill_axis(SampleTab& tab, int P, int S, float start, float bin) {
+  for (int s = threadIdx.x; s < P * S; s += kRoiThreads) {
+    int pidx = s / S, i = s - pidx * S;
+    float f = __fdiv_rn((float)i + 0.5f, (float)S);
+    float c = start + bin * ((float)pidx + f);
+    float fl = floorf(c);
+    tab.i0[s] = (int)fl;
+    tab.frac[s] = c - fl;
+  }
+}
+
+struct RoiGeom {
+  int n, lvl, H, W;
+  float start_w, start_h, bin_w, bin_h;
+  bool valid;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const RoiArgs& p, int k) {
+  RoiGeom g;
+  const float* r = p.rois + (long long)k * 5;
+  g.n = (int)__ldg(r);
+  g.lvl = p.levels ? __ldg(p.levels + k) : 0;
+  g.valid = g.n >= 0 && g.n < p.B && g.lvl >= 0 && g.lvl < p.lv.n_levels;
+  if (!g.valid) g.lvl = 0;
+  g.H = p.lv.H[g.lvl];
+  g.W = p.lv.W[g.lvl];
+  const float sc = p.lv.scale[g.lvl];
+  g.start_w = __ldg(r + 1) * sc - p.offset;
+  g.start_h = __ldg(r + 2) * sc - p.offset;
+  float end_w = __ldg(r + 3) * sc - p.offset;
+  float end_h = __ldg(r + 4) * sc - p.offset;
+  float roi_w = fmaxf(end_w - g.start_w, 0.f);
+  float roi_h = fmaxf(end_h - g.start_h, 0.f);
+  g.bin_h = __fdiv_rn(roi_h, (float)p.PH);
+  g.bin_w = __fdiv_rn(roi_w, (float)p.PW);
+  return g;
+}
+
+template <int TPH, int TPW, int TS>
+__global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArgs p) {
+  __shared__ SampleTab ty, tx;
+  const int k = blockIdx.x, t = threadIdx.x;
+  const int PH = TPH ? TPH : p.PH, PW = TPW ? TPW : p.PW, SH = TS ? TS : p.SH, SW = TS ? TS : p.SW;
+  const RoiGeom g = roi_geom(p, k);
+  float* out = p.out + (long long)k * p.C * PH * PW;
+  const int total = p.C * PH * PW;
+  if (!g.valid) {  // out-of-range batch / level index: defined as zeros (the reference would read out of bounds)
+    for (int o = t; o < total; o += kRoiThreads) out[o] = 0.f;
+    return;
+  }
+  fill_axis(ty, PH, SH, g.start_h, g.bin_h);
+  fill_axis(tx, PW, SW, g.start_w, g.bin_w);
+  __syncthreads();
+  const int H = g.H, W = g.W;
+  const float* feat = p.lv.feat[g.lvl] + (long long)g.n * p.C * H * W;
+  const float inv_cnt = (float)(SH * SW);
+  const int bins = PH * PW;
+  for (int o = t; o < total; o += kRoiThreads) {
+    const int c = o / bins, bin = o - c * bins;
+    const int ph = bin / PW, pw = bin - ph * PW;
+    const float* f = feat + (long long)c * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < (TS ? TS : 1); ++iy) {
+      for (int iy2 = 0; iy2 < (TS ? 1 : SH); ++iy2) {
+        const int sy = ph * SH + (TS ? iy : iy2);
+        const int y0 = ty.i0[sy], y1 = y0 + 1;
+        const float ly = ty.frac[sy];
+        const bool y0ok = y0 >= 0 && y0 < H, y1ok = y1 >= 0 && y1 < H;
+#pragma unroll
+        for (int ix = 0; ix < (TS ? TS : 1); ++ix) {
+          for (int ix2 = 0; ix2 < (TS ? 1 : SW); ++ix2) {
+            const int sx = pw * SW + (TS ? ix : ix2);
+            const int x0 = tx.i0[sx], x1 = x0 + 1;
+            const float lx = tx.frac[sx];
+            const bool x0ok = x0 >= 0 && x0 < W, x1ok = x1 >= 0 && x1 < W;
+            const float tl = (y0ok && x0ok) ? __ldg(f + y0 * W + x0) : 0.f;
+            const float tr = (y0ok && x1ok) ? __ldg(f + y0 * W + x1) : 0.f;
+            const float bl = (y1ok && x0ok) ? __ldg(f + y1 * W + x0) : 0.f;
+            const float br = (y1ok && x1ok) ? __ldg(f + y1 * W + x1) : 0.f;
+            const float top = tl + (tr - tl) * lx;
+            const float bot = bl + (br - bl) * lx;
+            acc += top + (bot - top) * ly;
+          }
+        }
+      }
+    }
+    out[o] = __fdiv_rn(acc, inv_cnt);
+  }
+}
+
+// Backward.  Shared accumulation buffer covers rows [fy0, fy0+fh) x cols [fx0, fx0+fw) of the level map for a
+// chunk of channels; taps outside the map were zero-padded in the forward pass and receive nothing.
+__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
+  extern __shared__ __align__(16) float sacc[];
+  __shared__ SampleTab ty, tx;
+  __shared__ int sbox[4];
+  const int k = blockIdx.x, t = threadIdx.x;
+  const int PH = p.PH, PW = p.PW, SH = p.SH, SW = p.SW;
+  const RoiGeom g = roi_geom(p, k);
+  if (!g.valid) return;
+  fill_axis(ty, PH, SH, g.start_h, g.bin_h);
+  fill_axis(tx, PW, SW, g.start_w, g.bin_w);
+  __syncthreads();
+  const int H = g.H, W = g.W;
+  if (t == 0) {
+    // sample coordinates are monotone along each axis: first / last sample bound the footprint
+    int y_lo = max(ty.i0[0], 0), y_hi = min(ty.i0[PH * SH - 1] + 1, H - 1);
+    int x_lo = max(tx.i0[0], 0), x_hi = min(tx.i0[PW * SW - 1] + 1, W - 1);
+    sbox[0] = y_lo;
+    sbox[1] = x_lo;
+    sbox[2] = y_hi - y_lo + 1;
+    sbox[3] = x_hi - x_lo + 1;
+  }
+  __syncthreads();
+  const int fy0 = sbox[0], fx0 = sbox[1], fh = sbox[2], fw = sbox[3];
+  if (fh <= 0 || fw <= 0) return;  // ROI entirely outside the map
+  const int bins = PH * PW;
+  const float cnt = (float)(SH * SW);
+  float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
+  const float* dout = p.dout + (long long)k * p.C * bins;
+  const long long area = (long long)fh * fw;
+  const bool use_smem = area <= p.bwd_cap;
+  const int chunk = use_smem ? (int)min((long long)p.C, (long long)p.bwd_cap / area) : p.C;
+
+  for (int c0 = 0; c0 < p.C; c0 += chunk) {
+    const int nc = min(chunk, p.C - c0);
+    if (use_smem) {
+      for (int i = t; i < nc * (int)area; i += kRoiThreads) sacc[i] = 0.f;
+      __syncthreads();
+    }
+    for (int o = t; o < nc * bins; o += kRoiThreads) {
+      const int cl = o / bins, bin = o - cl * bins;
+      const int ph = bin / PW, pw = bin - ph * PW;
+      const float gval = __fdiv_rn(__ldg(dout + (long long)(c0 + cl) * bins + bin), cnt);
+      float* gacc = dfeat + (long long)(c0 + cl) * H * W;
+      float* lacc = sacc + (long long)cl * area;
+      for (int iy = 0; iy < SH; ++iy) {
+        const int sy = ph * SH + iy;
+        const int y0 = ty.i0[sy], y1 = y0 + 1;
+        const float ly = ty.frac[sy];
+        const bool y0ok = y0 >= 0 && y0 < H, y1ok = y1 >= 0 && y1 < H;
+        for (int ix = 0; ix < SW; ++ix) {
+          const int sx = pw * SW + ix;
+          const int x0 = tx.i0[sx], x1 = x0 + 1;
+          const float lx = tx.frac[sx];
+          const bool x0ok = x0 >= 0 && x0 < W, x1ok = x1 >= 0 && x1 < W;
+          const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx;
+          const float w10 = ly * (1.f - lx), w11 = ly * lx;
+          if (use_smem) {
+            if (y0ok && x0ok) atomicAdd(lacc + (y0 - fy0) * fw + (x0 - fx0), gval * w00);
+            if (y0ok && x1ok) atomicAdd(lacc + (y0 - fy0) * fw + (x1 - fx0), gval * w01);
+            if (y1ok && x0ok) atomicAdd(lacc + (y1 - fy0) * fw + (x0 - fx0), gval * w10);
+            if (y1ok && x1ok) atomicAdd(lacc + (y1 - fy0) * fw + (x1 - fx0), gval * w11);
+          } else {
+            if (y0ok && x0ok) atomicAdd(gacc + y0 * W + x0, gval * w00);
+            if (y0ok && x1ok) atomicAdd(gacc + y0 * W + x1, gval * w01);
+            if (y1ok && x0ok) atomicAdd(gacc + y1 * W + x0, gval * w10);
+            if (y1ok && x1ok) atomicAdd(gacc + y1 * W + x1, gval * w11);
+          }
+        }
+      }
+    }
+    if (use_smem) {
+      __syncthreads();
+      for (int i = t; i < nc * (int)area; i += kRoiThreads) {
+        const float v = sacc[i];
+        if (v != 0.f) {
+          const int cl = i / (int)area, rem = i - cl * (int)area;
+          const int yy = rem / fw, xx = rem - yy * fw;
+          atomicAdd(dfeat + ((long long)(c0 + cl) * H + (fy0 + yy)) * W + (fx0 + xx), v);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// assign_rois, roi_pool.py:19-25: clamp(floor(4 + log(sqrt(area) / 224) / ln 2), lo, hi) - lo
+__global__ void __launch_bounds__(256) roi_assign_levels_kernel(const float* __restrict__ rois, int K, int lo, int hi, float ln2,
+                                                                int* __restrict__ levels) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float* r = rois + (long long)k * 5;
+  float area = (__ldg(r + 3) - __ldg(r + 1)) * (__ldg(r + 4) - __ldg(r + 2));
+  float v = floorf(4.f + __fdiv_rn(logf(__fdiv_rn(sqrtf(area), 224.f)), ln2));
+  // float -> int32 of NaN / -inf on the reference's x86 path is INT_MIN; the clamp then yields `lo`
+  int l = (v == v && v > -2.0e9f) ? (v < 2.0e9f ? (int)v : 0x7fffffff) : (int)0x80000000;
+  l = max(min(l, hi), lo);
+  levels[k] = l - lo;
+}
+
+static int fill_roi_args(RoiArgs* a, const void* const* feats, bool bwd, int n_levels, const int* hw, const float* scale, int B,
+                         int C, const float* rois, const int* levels, int K, int PH, int PW, int sh, int sw, int aligned) {
+  if (n_levels < 1 || n_levels > BDET_MAX_LEVELS) return set_error(BDET_EINVAL, "roi_align: n_levels must be in [1, %d]", BDET_MAX_LEVELS);
+  if (PH < 1 || PW < 1 || sh < 1 || sw < 1) return set_error(BDET_EINVAL, "roi_align: pool shape / sample points must be >= 1");
+  if (PH * sh > kMaxSamples || PW * sw > kMaxSamples) return set_error(BDET_EUNSUPPORTED, "roi_align: more than %d samples per axis", kMaxSamples);
+  if (B < 0 || C < 0 || K < 0) return set_error(BDET_EINVAL, "roi_align: negative size");
+  a->lv.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!feats[l]) return set_error(BDET_EINVAL, "roi_align: null feature pointer");
+    if (bwd) {
+      a->lv.dfeat[l] = reinterpret_cast<float*>(const_cast<void*>(feats[l]));
+      a->lv.feat[l] = nullptr;
+    } else {
+      a->lv.feat[l] = reinterpret_cast<const float*>(feats[l]);
+      a->lv.dfeat[l] = nullptr;
+    }
+    a->lv.H[l] = hw[2 * l];
+    a->lv.W[l] = hw[2 * l + 1];
+    a->lv.scale[l] = scale[l];
+    if (a->lv.H[l] < 1 || a->lv.W[l] < 1) return set_error(BDET_EINVAL, "roi_align: empty feature map");
+  }
+  a->rois = rois;
+  a->levels = levels;
+  a->B = B;
+  a->C = C;
+  a->K = K;
+  a->PH = PH;
+  a->PW = PW;
+  a->SH = sh;
+  a->SW = sw;
+  a->offset = aligned ? 0.5f : 0.f;
+  a->dout = nullptr;
+  a->out = nullptr;
+  a->bwd_cap = 0;
+  return BDET_OK;
+}
+
+}  // namespace bdet
+
+using namespace bdet;
+
+extern "C" int bdet_roi_assign_levels(const float* rois, int K, int min_level, int max_level, int* levels,
+                                      bdet_stream_t stream) {
+  BDET_REQUIRE(K >= 0 && min_level <= max_level, "bad arguments");
+  if (K == 0) return BDET_OK;
+  BDET_REQUIRE(rois && levels, "null argument");
+  roi_assign_levels_kernel<<<ceil_div(K, 256), 256, 0, as_stream(stream)>>>(rois, K, min_level, max_level, (float)0.6931471805599453,
+                                                                          levels);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, const int* hw_host,
+                                  const float* scale_host, int B, int C, const float* rois, const int* levels, int K,
+                                  int PH, int PW, int sample_h, int sample_w, int aligned, float* out,
+                                  bdet_stream_t stream) {
+  BDET_REQUIRE(feats_host && hw_host && scale_host, "null argument");
+  RoiArgs a;
+  int rc = fill_roi_args(&a, reinterpret_cast<const void* const*>(feats_host), false, n_levels, hw_host, scale_host, B, C, rois,
+                         levels, K, PH, PW, sample_h, sample_w, aligned);
+  if (rc) return rc;
+  if (K == 0 || C == 0) return BDET_OK;
+  BDET_REQUIRE(rois && out, "null argument");
+  a.out = out;
+  cudaStream_t st = as_stream(stream);
+  if (PH == 7 && PW == 7 && sample_h == 2 && sample_w == 2)
+    roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a);
+  else
+    roi_align_fwd_kernel<0, 0, 0><<<K, kRoiThreads, 0, st>>>(a);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, const float* scale_host,
+                                  int B, int C, const float* rois, const int* levels, int K, int PH, int PW,
+                                  int sample_h, int sample_w, int aligned, const float* dout, int zero_init,
+                                  bdet_stream_t stream) {
+  BDET_REQUIRE(dfeats_host && hw_host && scale_host, "null argument");
+  RoiArgs a;
+  int rc = fill_roi_args(&a, reinterpret_cast<const void* const*>(dfeats_host), true, n_levels, hw_host, scale_host, B, C, rois,
+                         levels, K, PH, PW, sample_h, sample_w, aligned);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (zero_init) {
+    for (int l = 0; l < n_levels; ++l)
+      BDET_CUDA(cudaMemsetAsync(dfeats_host[l], 0, (size_t)B * C * hw_host[2 * l] * hw_host[2 * l + 1] * 4, st));
+  }
+  if (K == 0 || C == 0) return BDET_OK;
+  BDET_REQUIRE(rois && dout, "null argument");
+  a.dout = dout;
+  const int smem = 64 * 1024;
+  a.bwd_cap = smem / 4;
+  static thread_local bool configured = false;
+  if (!configured) {
+    BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}

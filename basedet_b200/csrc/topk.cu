@@ -1,0 +1,435 @@
+// a10: score filter + per-level top-k.
+// Reference: basedet/models/det/retinanet.py:181-191 (sigmoid -> non_zeros(score > thr) -> F.topk desc),
+//            basedet/models/det/fcos.py:194-202 (sqrt(sigmoid(cls)*sigmoid(ctr))), basedet/models/det/rpn.py:155.
+//
+// Order contract (oracle ASSUMED-3): results sorted by (score desc, flat index asc).  Every element gets
+// the UNIQUE 64-bit key  (~ord(score) << 32) | index, so "top-k sorted" == "the k smallest keys, ascending";
+// a radix select finds the k-th key, a shared-memory bitonic network sorts the <= k survivors.
+//
+//   stage 1 (score_filter_kernel, HBM-read bound: 4 B/logit, grid-wide): 128-bit logit loads, a raw-logit
+//           pre-filter (monotonicity of sigmoid) rejects ~99 % of the elements with one compare; survivors get the
+//           exact fp32 score, the `> thr` test, and are appended (warp-aggregated atomics) as keys.
+//   stage 2 (select_sort_kernel, one CTA per segment): MSB-first 8-bit radix select over the candidates with
+//           early exit + small-bucket buffering in shared memory, then bitonic sort and write-out.
+#include <limits>
+
+#include "common.cuh"
+#include "sortnet.cuh"
+
+namespace bdet {
+
+constexpr int kSelThreads = 1024;
+constexpr int kBufCap = 4096;  // candidate keys buffered in shared memory once a radix bucket is this small
+constexpr int kMaxK = 16384;
+
+struct RawSrc {
+  const float* s;
+  __device__ __forceinline__ uint64_t key(int i) const { return make_key(__ldg(s + i), (uint32_t)i); }
+};
+struct KeySrc {
+  const uint64_t* k;
+  __device__ __forceinline__ uint64_t key(int i) const { return k[i]; }
+};
+
+// warp-aggregated shared-memory histogram increment
+__device__ __forceinline__ void hist_add(int* hist, int bin, bool active) {
+  uint32_t act = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  uint32_t peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+}
+
+// warp-aggregated append; returns the slot for this lane (or -1)
+__device__ __forceinline__ int append_slot(int* counter, bool active) {
+  uint32_t act = __ballot_sync(0xffffffffu, active);
+  if (act == 0) return -1;
+  int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(act) - 1) base = atomicAdd(counter, __popc(act));
+  base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
+  return active ? base + __popc(act & ((1u << lane) - 1u)) : -1;
+}
+
+struct SelSmem {
+  int hist[256];
+  int scan[256];
+  int nbuf;
+  int nsel;
+  int bin, below, cnt;
+};
+
+// k-th smallest key (1 <= k <= n), keys unique.
+template <class Src>
+__device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint64_t* buf) {
+  const int t = threadIdx.x;
+  uint64_t prefix = 0, mask = 0;
+  int krem = k;
+  bool buffered = false;
+  for (int d = 7; d >= 0; --d) {
+    const int shift = 8 * d;
+    if (t < 256) sm.hist[t] = 0;
+    __syncthreads();
+    const int m = buffered ? sm.nbuf : n;
+    for (int i0 = 0; i0 < m; i0 += kSelThreads) {
+      int i = i0 + t;
+      bool in = i < m;
+      uint64_t key = in ? (buffered ? buf[i] : src.key(i)) : 0;
+      bool act = in && ((key & mask) == prefix);
+      hist_add(sm.hist, (int)((key >> shift) & 255), act);
+    }
+    __syncthreads();
+    // inclusive scan of the 256 bins (8 warps)
+    if (t < 256) {
+      int v = sm.hist[t];
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, v, s);
+        if ((t & 31) >= s) v += o;
+      }
+      sm.scan[t] = v;
+    }
+    __syncthreads();
+    if (t < 256) {
+      int add = 0;
+      for (int w = 0; w < (t >> 5); ++w) add += sm.scan[w * 32 + 31];
+      int incl = sm.scan[t] + add;
+      int excl = incl - sm.hist[t];
+      if (excl < krem && krem <= incl) {
+        sm.bin = t;
+        sm.below = excl;
+        sm.cnt = sm.hist[t];
+      }
+    }
+    __syncthreads();
+    const int bin = sm.bin, cnt = sm.cnt;
+    krem -= sm.below;
+    prefix |= (uint64_t)bin << shift;
+    mask |= (uint64_t)255 << shift;
+    if (krem == cnt) return prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);  // whole bucket selected
+    if (!buffered && cnt <= kBufCap) {
+      if (t == 0) sm.nbuf = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+        int i = i0 + t;
+        uint64_t key = i < n ? src.key(i) : 0;
+        bool act = i < n && ((key & mask) == prefix);
+        int slot = append_slot(&sm.nbuf, act);
+        if (act) buf[slot] = key;
+      }
+      buffered = true;
+    }
+    __syncthreads();
+  }
+  return prefix;
+}
+
+struct SelArgs {
+  const float* scores;        // RAW source (may be nullptr)
+  const uint64_t* keys;       // candidate keys (filter path)
+  const int* cand_count;      // per segment candidate count (filter path) or nullptr
+  const long long* seg_off;   // device (n_seg + 1)
+  float* out_vals;
+  int* out_idx;
+  int* out_count;
+  int k, P;                   // P = pow2 >= k
+};
+
+template <bool RAW>
+__global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(raw);  // P
+  uint64_t* buf = sortbuf + p.P;                          // kBufCap
+  __shared__ SelSmem sm;
+  const int s = blockIdx.x, t = threadIdx.x;
+  const long long off = p.seg_off[s];
+  const int n = RAW ? (int)(p.seg_off[s + 1] - off) : p.cand_count[s];
+  const int k = min(p.k, n);
+  if (t == 0) {
+    p.out_count[s] = k;
+    sm.nsel = 0;
+  }
+  if (k == 0) return;
+  RawSrc rs{p.scores + off};
+  KeySrc ks{p.keys + off};
+  uint64_t T = ~0ull;
+  if (n > k) T = RAW ? radix_select(rs, n, k, sm, buf) : radix_select(ks, n, k, sm, buf);
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    int i = i0 + t;
+    uint64_t key = i < n ? (RAW ? rs.key(i) : ks.key(i)) : ~0ull;
+    bool act = i < n && key <= T;
+    int slot = append_slot(&sm.nsel, act);
+    if (act) sortbuf[slot] = key;
+  }
+  for (int i = k + t; i < p.P; i += kSelThreads) sortbuf[i] = ~0ull;
+  bitonic_sort_smem(sortbuf, p.P);
+  for (int i = t; i < k; i += kSelThreads) {
+    uint64_t key = sortbuf[i];
+    uint32_t idx = (uint32_t)key;
+    p.out_idx[(long long)s * p.k + i] = (int)idx;
+    p.out_vals[(long long)s * p.k + i] = RAW ? __ldg(p.scores + off + idx) : key_score(key);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ stage 1
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+
+struct FilterArgs {
+  const float* logits;
+  const float* ctr;           // FCOS: one per C logits, indexed (off + i) / C
+  const long long* seg_off;   // device (n_seg + 1)
+  const int* tile_start;      // device (n_seg + 1): prefix of per-segment tile counts
+  uint64_t* keys;
+  int* cand_count;
+  float* scores_out;          // optional dense score output (bdet_scores)
+  int n_seg, C, mode;
+  float thr, pre;             // pre: raw-logit pre-filter (sigmoid mode)
+};
+
+constexpr int kFiltThreads = 256;
+constexpr int kFiltVec = 4;                               // float4 per thread per tile
+constexpr int kFiltTile = kFiltThreads * kFiltVec * 4;    // 4096 elements
+
+__device__ __forceinline__ bool eval_score(const FilterArgs& p, float x, long long gi, float& s) {
+  if (p.mode == BDET_SCORE_SIGMOID) {
+    if (!(x > p.pre)) return false;
+    s = sigmoid_f(x);
+  } else if (p.mode == BDET_SCORE_FCOS) {
+    // fcos.py:194: sqrt(sigmoid(cls) * sigmoid(ctr)); score <= sqrt(sigmoid(cls)) so the same pre-filter on
+    // sigmoid(cls) > thr^2 holds (p.pre = logit(thr^2) - margin)
+    if (!(x > p.pre)) return false;
+    float sc = sigmoid_f(__ldg(p.ctr + gi / p.C));
+    s = sqrtf(sigmoid_f(x) * sc);
+  } else {
+    s = x;
+  }
+  return s > p.thr;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p) {
+  // tile -> segment (CTA-uniform binary search)
+  int lo = 0, hi = p.n_seg;
+  const int tile = blockIdx.x;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (p.tile_start[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int s = lo;
+  const long long off = p.seg_off[s];
+  const int n = (int)(p.seg_off[s + 1] - off);
+  const int e0 = (tile - p.tile_start[s]) * kFiltTile;
+  const float* src = p.logits + off;
+  uint64_t* keys = p.keys + off;
+  int* counter = p.cand_count + s;
+  const int t = threadIdx.x;
+  if (VEC) {
+    float4 v[kFiltVec];
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) {
+      int e = e0 + (j * kFiltThreads + t) * 4;
+      v[j] = (e + 3 < n) ? __ldcs(reinterpret_cast<const float4*>(src + e)) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      if (e < n && e + 3 >= n) {  // ragged tail of the segment
+        float tmp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmp[q] = (e + q < n) ? __ldg(src + e + q) : -CUDART_INF_F;
+        v[j] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) {
+      int e = e0 + (j * kFiltThreads + t) * 4;
+      float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float sc = 0.f;
+        bool pass = (e + q < n) && eval_score(p, x[q], off + e + q, sc);
+        int slot = append_slot(counter, pass);
+        if (pass) keys[slot] = make_key(sc, (uint32_t)(e + q));
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < kFiltVec * 4; ++j) {
+      int e = e0 + j * kFiltThreads + t;
+      float x = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
+      float sc = 0.f;
+      bool pass = (e < n) && eval_score(p, x, off + e, sc);
+      int slot = append_slot(counter, pass);
+      if (pass) keys[slot] = make_key(sc, (uint32_t)e);
+    }
+  }
+}
+
+// Dense scores (so tests can hand bit-identical scores to the oracle).
+__global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ logits, const float* __restrict__ ctr, int C, long long n,
+                                                     int mode, float* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = __ldg(logits + i), s;
+  if (mode == BDET_SCORE_SIGMOID) s = sigmoid_f(x);
+  else if (mode == BDET_SCORE_FCOS) s = sqrtf(sigmoid_f(x) * sigmoid_f(__ldg(ctr + i / C)));
+  else s = x;
+  out[i] = s;
+}
+
+struct TopkWs {
+  long long* seg_off;
+  int* tile_start;
+  int* cand_count;
+  uint64_t* keys;
+  size_t bytes;
+};
+static TopkWs carve_ws(void* base, int64_t total, int n_seg, bool with_keys) {
+  TopkWs w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t o = 0;
+  w.seg_off = reinterpret_cast<long long*>(p + o);
+  o += align_up((size_t)(n_seg + 1) * 8, 256);
+  w.tile_start = reinterpret_cast<int*>(p + o);
+  o += align_up((size_t)(n_seg + 1) * 4, 256);
+  w.cand_count = reinterpret_cast<int*>(p + o);
+  o += align_up((size_t)n_seg * 4, 256);
+  w.keys = reinterpret_cast<uint64_t*>(p + o);
+  if (with_keys) o += align_up((size_t)total * 8, 256);
+  w.bytes = o + 256;
+  return w;
+}
+
+template <bool RAW>
+static int launch_select(const SelArgs& a, int n_seg, cudaStream_t st) {
+  size_t smem = (size_t)(a.P + kBufCap) * 8;
+  static thread_local size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[RAW]) {
+    BDET_CUDA(cudaFuncSetAttribute(select_sort_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[RAW] = smem;
+  }
+  select_sort_kernel<RAW><<<n_seg, kSelThreads, smem, st>>>(a);
+  return BDET_OK;
+}
+
+}  // namespace bdet
+
+using namespace bdet;
+
+extern "C" size_t bdet_topk_workspace(int64_t total, int n_seg, int k) {
+  (void)k;
+  return carve_ws(nullptr, total, n_seg < 1 ? 1 : n_seg, false).bytes;
+}
+
+extern "C" size_t bdet_score_filter_topk_workspace(int64_t total, int n_seg, int k) {
+  (void)k;
+  return carve_ws(nullptr, total < 0 ? 0 : total, n_seg < 1 ? 1 : n_seg, true).bytes;
+}
+
+static int check_segments(const int64_t* seg, int n_seg, const char* who) {
+  for (int s = 0; s < n_seg; ++s) {
+    if (seg[s + 1] < seg[s]) return set_error(BDET_EINVAL, "%s: segment offsets must be non-decreasing", who);
+    if (seg[s + 1] - seg[s] > 0x7fffffffLL) return set_error(BDET_EUNSUPPORTED, "%s: segment longer than 2^31-1", who);
+  }
+  return BDET_OK;
+}
+
+extern "C" int bdet_topk(const float* scores, const int64_t* seg_offset_host, int n_seg, int k, float* out_vals,
+                         int* out_idx, int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  BDET_REQUIRE(n_seg >= 0 && k >= 0, "negative size");
+  if (n_seg == 0) return BDET_OK;
+  BDET_REQUIRE(seg_offset_host && out_count, "null argument");
+  BDET_REQUIRE(k == 0 || (out_vals && out_idx), "null output");
+  if (k > kMaxK) return set_error(BDET_EUNSUPPORTED, "bdet_topk: k > %d", kMaxK);
+  int rc = check_segments(seg_offset_host, n_seg, "bdet_topk");
+  if (rc) return rc;
+  const int64_t total = seg_offset_host[n_seg];
+  BDET_REQUIRE(total == 0 || scores, "null scores");
+  TopkWs w = carve_ws(workspace, total, n_seg, false);
+  if (!workspace || workspace_bytes < w.bytes) return set_error(BDET_EWORKSPACE, "bdet_topk: workspace needs %zu bytes", w.bytes);
+  BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  BDET_CUDA(cudaMemcpyAsync(w.seg_off, seg_offset_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+  SelArgs a{scores, nullptr, nullptr, w.seg_off, out_vals, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
+  rc = launch_select<true>(a, n_seg, st);
+  if (rc) return rc;
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_offset_host,
+                                      int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
+                                      int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  BDET_REQUIRE(n_seg >= 0 && k >= 0 && C >= 1, "bad size");
+  BDET_REQUIRE(mode >= BDET_SCORE_RAW && mode <= BDET_SCORE_FCOS, "unknown mode");
+  BDET_REQUIRE(mode != BDET_SCORE_FCOS || ctrness, "FCOS mode needs ctrness");
+  if (n_seg == 0) return BDET_OK;
+  BDET_REQUIRE(seg_offset_host && out_count, "null argument");
+  BDET_REQUIRE(k == 0 || (out_scores && out_idx), "null output");
+  if (k > kMaxK) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: k > %d", kMaxK);
+  int rc = check_segments(seg_offset_host, n_seg, "bdet_score_filter_topk");
+  if (rc) return rc;
+  const int64_t total = seg_offset_host[n_seg];
+  BDET_REQUIRE(total == 0 || logits, "null logits");
+  TopkWs w = carve_ws(workspace, total, n_seg, true);
+  if (!workspace || workspace_bytes < w.bytes)
+    return set_error(BDET_EWORKSPACE, "bdet_score_filter_topk: workspace needs %zu bytes", w.bytes);
+  BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  // tile table (host) -> device
+  static thread_local int tile_host[4096];
+  if (n_seg + 1 > 4096) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: more than 4095 segments");
+  bool vec = aligned16(logits);
+  tile_host[0] = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    int64_t n = seg_offset_host[s + 1] - seg_offset_host[s];
+    tile_host[s + 1] = tile_host[s] + ceil_div(n, kFiltTile);
+    if (seg_offset_host[s] % 4 != 0) vec = false;
+  }
+  const int tiles = tile_host[n_seg];
+  BDET_CUDA(cudaMemcpyAsync(w.seg_off, seg_offset_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+  BDET_CUDA(cudaMemcpyAsync(w.tile_start, tile_host, (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+  BDET_CUDA(cudaMemsetAsync(w.cand_count, 0, (size_t)n_seg * 4, st));
+  FilterArgs f;
+  f.logits = logits;
+  f.ctr = ctrness;
+  f.seg_off = w.seg_off;
+  f.tile_start = w.tile_start;
+  f.keys = w.keys;
+  f.cand_count = w.cand_count;
+  f.scores_out = nullptr;
+  f.n_seg = n_seg;
+  f.C = C;
+  f.mode = mode;
+  f.thr = threshold;
+  // raw-logit pre-filter: sigmoid(x) > q  needs  x > logit(q); keep a safety margin for fp32 rounding.
+  f.pre = -std::numeric_limits<float>::infinity();
+  if (mode != BDET_SCORE_RAW) {
+    double q = mode == BDET_SCORE_FCOS ? (double)threshold * (double)threshold : (double)threshold;
+    if (threshold > 0.f && q < 1.0) {
+      double l = log(q / (1.0 - q));
+      f.pre = (float)(l - 1e-3 * (fabs(l) > 1.0 ? fabs(l) : 1.0));
+    } else if (q >= 1.0) {
+      f.pre = std::numeric_limits<float>::infinity();  // nothing can pass
+    }
+  }
+  if (tiles > 0) {
+    if (vec)
+      score_filter_kernel<true><<<tiles, kFiltThreads, 0, st>>>(f);
+    else
+      score_filter_kernel<false><<<tiles, kFiltThreads, 0, st>>>(f);
+  }
+  SelArgs a{nullptr, w.keys, w.cand_count, w.seg_off, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
+  rc = launch_select<false>(a, n_seg, st);
+  if (rc) return rc;
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int mode, float* out,
+                           bdet_stream_t stream) {
+  BDET_REQUIRE(n >= 0 && C >= 1, "bad size");
+  BDET_REQUIRE(mode >= BDET_SCORE_RAW && mode <= BDET_SCORE_FCOS, "unknown mode");
+  BDET_REQUIRE(mode != BDET_SCORE_FCOS || ctrness, "FCOS mode needs ctrness");
+  if (n == 0) return BDET_OK;
+  BDET_REQUIRE(logits && out, "null argument");
+  scores_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(logits, ctrness, C, n, mode, out);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}

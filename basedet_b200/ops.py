@@ -331,3 +331,147 @@ def assign_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_low_qual
                                       farr(mean), farr(std), _p(plan.labels), _p(plan.idx), _p(plan.offsets),
                                       _p(plan.ws), plan.ws.numel(), _stream(anchors)))
     return plan.labels, plan.idx, plan.offsets
+
+
+# ----------------------------------------------------------------------------- score filter + top-k
+def _seg_offsets(seg_lengths):
+    offs = [0]
+    for n in seg_lengths:
+        offs.append(offs[-1] + int(n))
+    return offs
+
+
+def topk_segments(scores, seg_lengths, k):
+    """scores: flat fp32 tensor holding the segments back to back.  Returns (vals (S,k), idx (S,k), count (S,)):
+    per segment the min(k, n_s) largest scores sorted by (score desc, index asc); idx is within the segment."""
+    lib = _lib.load()
+    s = _f32c(scores, "scores").reshape(-1)
+    offs = _seg_offsets(seg_lengths)
+    assert offs[-1] == s.numel()
+    S = len(seg_lengths)
+    vals = torch.empty((S, k), dtype=torch.float32, device=s.device)
+    idx = torch.empty((S, k), dtype=torch.int32, device=s.device)
+    cnt = torch.empty((S,), dtype=torch.int32, device=s.device)
+    ws = _workspace(lib.bdet_topk_workspace(offs[-1], S, k), s.device)
+    with _guard(s):
+        check(lib.bdet_topk(_p(s), larr(offs), S, int(k), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(s)))
+    return vals, idx, cnt
+
+
+def score_filter_topk(logits, seg_lengths, threshold, k, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1,
+                      workspace=None):
+    """Fused score -> (score > threshold) -> top-k per segment (retinanet.py:181-191 / fcos.py:194-202).
+    logits flat fp32 (segments back to back); ctrness (FCOS) has one value per `num_classes` logits.
+    Returns (scores (S,k), idx (S,k) flat index within the segment, count (S,))."""
+    lib = _lib.load()
+    lg = _f32c(logits, "logits").reshape(-1)
+    offs = _seg_offsets(seg_lengths)
+    assert offs[-1] == lg.numel()
+    S = len(seg_lengths)
+    ct = _f32c(ctrness, "ctrness").reshape(-1) if ctrness is not None else None
+    vals = torch.empty((S, k), dtype=torch.float32, device=lg.device)
+    idx = torch.empty((S, k), dtype=torch.int32, device=lg.device)
+    cnt = torch.empty((S,), dtype=torch.int32, device=lg.device)
+    need = lib.bdet_score_filter_topk_workspace(offs[-1], S, k)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, lg.device)
+    with _guard(lg):
+        check(lib.bdet_score_filter_topk(_p(lg), _p(ct), int(num_classes), larr(offs), S, float(threshold), int(k),
+                                         int(mode), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(lg)))
+    return vals, idx, cnt
+
+
+def scores(logits, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1):
+    lib = _lib.load()
+    lg = _f32c(logits, "logits")
+    ct = _f32c(ctrness, "ctrness").reshape(-1) if ctrness is not None else None
+    out = torch.empty_like(lg)
+    with _guard(lg):
+        check(lib.bdet_scores(_p(lg), _p(ct), int(num_classes), lg.numel(), int(mode), _p(out), _stream(lg)))
+    return out
+
+
+# ----------------------------------------------------------------------------- NMS
+def nms_batched(boxes, scores_, idxs, iou_thresh, max_output=None, num=None, workspace=None):
+    """boxes (B,Nmax,4), scores (B,Nmax), idxs (B,Nmax) int32/fp32 or None, num (B,) int32 or None.
+    Returns (keep (B,cap) int32 original indices in score-descending order, keep_count (B,) int32)."""
+    lib = _lib.load()
+    b = _f32c(boxes, "boxes")
+    s = _f32c(scores_, "scores")
+    assert b.ndim == 3 and b.shape[2] == 4 and s.shape == b.shape[:2]
+    B, Nmax = s.shape
+    if idxs is not None:
+        ix = _dev(as_tensor(idxs), "idxs")
+        is_float = ix.dtype.is_floating_point
+        ix = ix.float().contiguous() if is_float else ix.to(torch.int32).contiguous()
+        assert ix.shape == s.shape
+    else:
+        ix, is_float = None, False
+    cap = Nmax if not max_output or max_output <= 0 else min(int(max_output), Nmax)
+    keep = torch.empty((B, max(cap, 1)), dtype=torch.int32, device=b.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=b.device)
+    nd = _i32c(num) if num is not None else None
+    need = lib.bdet_nms_workspace(Nmax, B)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, b.device)
+    with _guard(b):
+        check(lib.bdet_nms(_p(b), _p(s), _p(ix), int(is_float), _p(nd), Nmax, B, float(iou_thresh),
+                           int(max_output) if max_output else 0, _p(keep), cap, _p(cnt), _p(ws), ws.numel(), _stream(b)))
+    return keep, cnt
+
+
+# ----------------------------------------------------------------------------- ROI pooling
+def roi_assign_levels(rois, min_level, max_level):
+    lib = _lib.load()
+    r = _f32c(rois, "rois")
+    out = torch.empty((r.shape[0],), dtype=torch.int32, device=r.device)
+    with _guard(r):
+        check(lib.bdet_roi_assign_levels(_p(r), r.shape[0], int(min_level), int(max_level), _p(out), _stream(r)))
+    return out
+
+
+def _level_args(features):
+    n = len(features)
+    ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in features])
+    hw = [int(v) for f in features for v in f.shape[-2:]]
+    return n, ptrs, iarr(hw)
+
+
+def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True):
+    """features: list of (B,C,H_l,W_l) fp32 contiguous; rois (K,5); levels (K,) int32 or None -> (K,C,PH,PW)."""
+    lib = _lib.load()
+    feats = [_f32c(f, "feature") for f in features]
+    B, C = feats[0].shape[:2]
+    for f in feats:
+        assert f.ndim == 4 and f.shape[0] == B and f.shape[1] == C
+    r = _f32c(rois, "rois")
+    assert r.ndim == 2 and r.shape[1] == 5
+    K = r.shape[0]
+    lv = _i32c(levels) if levels is not None else None
+    PH, PW = pool_shape
+    out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=r.device)
+    n, ptrs, hw = _level_args(feats)
+    with _guard(r):
+        check(lib.bdet_roi_align_fwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
+                                     int(sample_points[1]), int(bool(aligned)), _p(out), _stream(r)))
+    return out
+
+
+def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True,
+                  dfeats=None):
+    """Gradient w.r.t. the features.  dfeats (list) are accumulated into if given (must be pre-zeroed by the
+    caller), otherwise allocated and cleared by the library."""
+    lib = _lib.load()
+    d = _f32c(dout, "dout")
+    r = _f32c(rois, "rois")
+    K = r.shape[0]
+    lv = _i32c(levels) if levels is not None else None
+    zero_init = dfeats is None
+    if dfeats is None:
+        dfeats = [torch.empty(tuple(s), dtype=torch.float32, device=d.device) for s in feature_shapes]
+    B, C = dfeats[0].shape[:2]
+    PH, PW = pool_shape
+    assert d.shape == (K, C, PH, PW)
+    n, ptrs, hw = _level_args(dfeats)
+    with _guard(d):
+        check(lib.bdet_roi_align_bwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
+                                     int(sample_points[1]), int(bool(aligned)), _p(d), int(zero_init), _stream(d)))
+    return dfeats
