@@ -37,6 +37,7 @@ SIGNATURES = {
     "bdet_sum_encode": (c_int, [vp, vp, c_int, fp, fp, vp, vp]),
     "bdet_sum_decode": (c_int, [vp, vp, c_int, fp, fp, vp, c_int, vp]),
     "bdet_point_encode": (c_int, [vp, c_int, vp, c_int, c_int, vp, vp]),
+    "bdet_point_encode_rows": (c_int, [vp, vp, c_int, c_int, vp, vp]),
     "bdet_point_decode": (c_int, [vp, vp, c_int, c_int, vp, vp, c_int, c_int, vp]),
     "bdet_assign_targets_workspace": (c_size_t, [c_int, c_int, c_int]),
     "bdet_assign_targets": (c_int, [vp, c_int, vp, c_int, vp, c_int, fp, ip, c_int, c_int, c_int, fp, fp,
@@ -56,6 +57,14 @@ SIGNATURES = {
                                    c_int, c_int, c_int, vp, vp]),
     "bdet_roi_align_bwd": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
                                    c_int, c_int, c_int, vp, c_int, vp]),
+    "bdet_box_props": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+    "bdet_box_convert": (c_int, [vp, c_int, c_int, c_int, vp, vp]),
+    "bdet_cond_take_workspace": (c_size_t, [c_int64]),
+    "bdet_cond_take": (c_int, [vp, vp, c_int64, vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_count_labels": (c_int, [vp, c_int, c_int, vp, vp]),
+    "bdet_profile_begin": (c_int, []),
+    "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),
+    "bdet_profile_end": (c_int, []),
 }
 
 

@@ -105,7 +105,7 @@ extern "C" int bdet_anchors_grid(float* out, int n_levels, const int* hw_host, c
   if (rc) return rc;
   long long total = p.start[n_levels];
   if (total == 0) return BDET_OK;
-  anchors_grid_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(out), p);
+  BDET_KERNEL("anchors_grid_kernel", as_stream(stream), anchors_grid_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(out), p));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -122,7 +122,7 @@ extern "C" int bdet_points_grid(float* out, int n_levels, const int* hw_host, co
   if (rc) return rc;
   long long total = p.start[n_levels];
   if (total == 0) return BDET_OK;
-  points_grid_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(out), p, mode);
+  BDET_KERNEL("points_grid_kernel", as_stream(stream), points_grid_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(out), p, mode));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

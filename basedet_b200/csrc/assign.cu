@@ -296,17 +296,17 @@ extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt,
   }
   dim3 grid(a.tiles, B);
   if (apt == 2) {
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {
       BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    assign_main_kernel<2><<<grid, kAT, smem, st>>>(a);
-    if (a.allow_lq) assign_lq_kernel<2><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a);
+    BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<2><<<grid, kAT, smem, st>>>(a));
+    if (a.allow_lq) BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<2><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a));
   } else {
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {
       BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    assign_main_kernel<1><<<grid, kAT, smem, st>>>(a);
-    if (a.allow_lq) assign_lq_kernel<1><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a);
+    BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<1><<<grid, kAT, smem, st>>>(a));
+    if (a.allow_lq) BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<1><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a));
   }
   BDET_LAUNCH_CHECK();
   return BDET_OK;

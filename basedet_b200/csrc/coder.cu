@@ -90,6 +90,16 @@ __global__ void __launch_bounds__(256) point_encode_kernel(const float2* __restr
   out[i] = make_float4(p.x - b.x, p.y - b.y, b.z - p.x, b.w - p.y);
 }
 
+// PointCoder.encode on matched rows (models/det/fcos.py:268): out[a] = [p_a - gt_a[:2], gt_a[2:] - p_a]
+__global__ void __launch_bounds__(256) point_encode_rows_kernel(const float2* __restrict__ pts, const float* __restrict__ gt, int gt_ld, int N,
+                                                                float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float2 p = __ldg(pts + i);
+  float4 b = load_box<false>(gt, i, gt_ld);
+  out[i] = make_float4(p.x - b.x, p.y - b.y, b.z - p.x, b.w - p.y);
+}
+
 // PointCoder.decode, boxcoder.py:135-141
 __global__ void __launch_bounds__(256) point_decode_kernel(const float2* __restrict__ pts, const float4* __restrict__ deltas, long long total,
                                                            int k, float4* __restrict__ out, const int* __restrict__ sel, int sel_div) {
@@ -148,9 +158,9 @@ extern "C" int bdet_box_encode(const float* bbox, const float* gt, int gt_ld, co
   BDET_REQUIRE(bbox && gt && out, "null argument");
   BDET_REQUIRE(aligned16(bbox) && aligned16(out), "bbox/out must be 16-byte aligned");
   BDET_REQUIRE(gt_ld != 4 || gather_idx || aligned16(gt), "gt must be 16-byte aligned");
-  box_encode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(bbox), gt, gt_ld, gather_idx, N,
+  BDET_KERNEL("box_encode_kernel", as_stream(stream), box_encode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(bbox), gt, gt_ld, gather_idx, N,
                                                                      to_vec4(mean_host, 0.f), to_vec4(std_host, 1.f),
-                                                                     reinterpret_cast<float4*>(out));
+                                                                     reinterpret_cast<float4*>(out)));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -164,9 +174,9 @@ extern "C" int bdet_box_decode(const float* anchors, float* deltas, int N, int k
   if (total == 0) return BDET_OK;
   BDET_REQUIRE(anchors && deltas && out, "null argument");
   BDET_REQUIRE(aligned16(anchors) && aligned16(deltas) && aligned16(out), "anchors/deltas/out must be 16-byte aligned");
-  box_decode_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+  BDET_KERNEL("box_decode_kernel", as_stream(stream), box_decode_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(anchors), reinterpret_cast<float4*>(deltas), total, k, to_vec4(mean_host, 0.f),
-      to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out), sel_idx ? 0 : writeback, sel_idx, sel_div);
+      to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out), sel_idx ? 0 : writeback, sel_idx, sel_div));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -177,9 +187,9 @@ extern "C" int bdet_sum_encode(const float* anchors, const float* gt, int N, con
   if (N == 0) return BDET_OK;
   BDET_REQUIRE(anchors && gt && out, "null argument");
   BDET_REQUIRE(aligned16(anchors) && aligned16(gt) && aligned16(out), "pointers must be 16-byte aligned");
-  sum_encode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(anchors),
+  BDET_KERNEL("sum_encode_kernel", as_stream(stream), sum_encode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(anchors),
                                                                      reinterpret_cast<const float4*>(gt), N, to_vec4(mean_host, 0.f),
-                                                                     to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out));
+                                                                     to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out)));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -190,9 +200,9 @@ extern "C" int bdet_sum_decode(const float* anchors, float* deltas, int N, const
   if (N == 0) return BDET_OK;
   BDET_REQUIRE(anchors && deltas && out, "null argument");
   BDET_REQUIRE(aligned16(anchors) && aligned16(deltas) && aligned16(out), "pointers must be 16-byte aligned");
-  sum_decode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(anchors),
+  BDET_KERNEL("sum_decode_kernel", as_stream(stream), sum_decode_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(anchors),
                                                                      reinterpret_cast<float4*>(deltas), N, to_vec4(mean_host, 0.f),
-                                                                     to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out), writeback);
+                                                                     to_vec4(std_host, 1.f), reinterpret_cast<float4*>(out), writeback));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -203,8 +213,21 @@ extern "C" int bdet_point_encode(const float* points, int A, const float* gt, in
   if (A == 0 || G == 0) return BDET_OK;
   BDET_REQUIRE(points && gt && out, "null argument");
   BDET_REQUIRE(aligned16(out) && (reinterpret_cast<uintptr_t>(points) & 7u) == 0, "alignment");
-  point_encode_kernel<<<ceil_div((int64_t)A * G, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(points), A, gt, gt_ld,
-                                                                                  G, reinterpret_cast<float4*>(out));
+  BDET_KERNEL("point_encode_kernel", as_stream(stream), point_encode_kernel<<<ceil_div((int64_t)A * G, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(points), A, gt, gt_ld,
+                                                                                  G, reinterpret_cast<float4*>(out)));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_point_encode_rows(const float* points, const float* gt, int gt_ld, int N, float* out,
+                                      bdet_stream_t stream) {
+  BDET_REQUIRE(N >= 0 && gt_ld >= 4, "bad shape");
+  if (N == 0) return BDET_OK;
+  BDET_REQUIRE(points && gt && out, "null argument");
+  BDET_REQUIRE(aligned16(out) && (reinterpret_cast<uintptr_t>(points) & 7u) == 0, "alignment");
+  BDET_KERNEL("point_encode_rows_kernel", as_stream(stream),
+              point_encode_rows_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(points), gt, gt_ld, N,
+                                                                                        reinterpret_cast<float4*>(out)));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -217,9 +240,9 @@ extern "C" int bdet_point_decode(const float* points, const float* deltas, int N
   if (total == 0) return BDET_OK;
   BDET_REQUIRE(points && deltas && out, "null argument");
   BDET_REQUIRE(aligned16(deltas) && aligned16(out) && (reinterpret_cast<uintptr_t>(points) & 7u) == 0, "alignment");
-  point_decode_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(points),
+  BDET_KERNEL("point_decode_kernel", as_stream(stream), point_decode_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(points),
                                                                            reinterpret_cast<const float4*>(deltas), total, k,
-                                                                           reinterpret_cast<float4*>(out), sel_idx, sel_div);
+                                                                           reinterpret_cast<float4*>(out), sel_idx, sel_div));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -229,7 +252,7 @@ extern "C" int bdet_boxes_scale_clip(float* boxes, int N, float scale_w, float s
   BDET_REQUIRE(N >= 0, "bad shape");
   if (N == 0) return BDET_OK;
   BDET_REQUIRE(boxes && aligned16(boxes), "boxes must be a 16-byte aligned device pointer");
-  scale_clip_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(boxes), N, scale_w, scale_h, clip_w, clip_h);
+  BDET_KERNEL("scale_clip_kernel", as_stream(stream), scale_clip_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(boxes), N, scale_w, scale_h, clip_w, clip_h));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -239,7 +262,7 @@ extern "C" int bdet_boxes_filter_by_size(const float* boxes, int N, float size0,
   BDET_REQUIRE(N >= 0, "bad shape");
   if (N == 0) return BDET_OK;
   BDET_REQUIRE(boxes && keep_mask && aligned16(boxes), "boxes must be a 16-byte aligned device pointer");
-  filter_by_size_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(boxes), N, size0, size1, keep_mask);
+  BDET_KERNEL("filter_by_size_kernel", as_stream(stream), filter_by_size_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(boxes), N, size0, size1, keep_mask));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

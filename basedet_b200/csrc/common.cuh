@@ -32,6 +32,16 @@ int sm_count();
       return ::bdet::set_error(BDET_ECUDA, "%s: %s", __func__, cudaGetErrorString(e__)); \
   } while (0)
 
+// Measurement hooks (bdet_profile_*): bracket a named kernel launch with an event pair when profiling is on.
+void prof_pre(cudaStream_t st, const char* name);
+void prof_post(cudaStream_t st);
+#define BDET_KERNEL(name, st, ...) \
+  do {                             \
+    ::bdet::prof_pre(st, name);    \
+    __VA_ARGS__;                   \
+    ::bdet::prof_post(st);         \
+  } while (0)
+
 static inline cudaStream_t as_stream(bdet_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

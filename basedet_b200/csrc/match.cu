@@ -172,8 +172,8 @@ template <int CPT>
 static void launch_match(const MatchArgs& a, int B, cudaStream_t st) {
   dim3 grid(a.tiles, B);
   size_t smem = (size_t)max(a.Gmax, 1) * 4;
-  match_colmax_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a);
-  if (a.allow_lq) match_lq_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a);
+  BDET_KERNEL("match_colmax_kernel", st, match_colmax_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a));
+  if (a.allow_lq) BDET_KERNEL("match_lq_kernel", st, match_lq_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a));
 }
 
 }  // namespace bdet
@@ -232,7 +232,7 @@ extern "C" int bdet_match_rows(const float* matrix, int R, int G, float* max_out
   BDET_REQUIRE(R >= 0 && G >= 1, "need G >= 1");
   if (R == 0) return BDET_OK;
   BDET_REQUIRE(matrix && argmax_out, "null argument");
-  match_rows_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(matrix, R, G, max_out, argmax_out);
+  BDET_KERNEL("match_rows_kernel", as_stream(stream), match_rows_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(matrix, R, G, max_out, argmax_out));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

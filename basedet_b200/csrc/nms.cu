@@ -329,37 +329,31 @@ extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idx
 
   if (Nmax <= kSmallSortMax) {
     size_t smem = (size_t)a.P * 8;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024)
       BDET_CUDA(cudaFuncSetAttribute(nms_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    nms_sort_small_kernel<<<B, 1024, smem, st>>>(a);
+    BDET_KERNEL("nms_sort_small_kernel", st, nms_sort_small_kernel<<<B, 1024, smem, st>>>(a));
   } else {
     if (a.P < kSortTile) a.P = kSortTile;
     BDET_CUDA(cudaMemsetAsync(a.maxc, 0, (size_t)B * 4, st));
-    if (idxs) nms_maxcoord_kernel<<<dim3(min(ceil_div(Nmax, 256), 64), B), 256, 0, st>>>(a);
+    if (idxs) BDET_KERNEL("nms_maxcoord_kernel", st, nms_maxcoord_kernel<<<dim3(min(ceil_div(Nmax, 256), 64), B), 256, 0, st>>>(a));
     const int tiles = a.P / kSortTile;
-    nms_tile_sort_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a);
+    BDET_KERNEL("nms_tile_sort_kernel", st, nms_tile_sort_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a));
     for (long long size = 2ll * kSortTile; size <= a.P; size <<= 1) {
       for (long long stride = size >> 1; stride >= kSortTile; stride >>= 1)
-        nms_global_step_kernel<<<dim3(ceil_div(a.P / 2, 256), B), 256, 0, st>>>(a, size, stride);
-      nms_tile_tail_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a, size);
+        BDET_KERNEL("nms_global_step_kernel", st, nms_global_step_kernel<<<dim3(ceil_div(a.P / 2, 256), B), 256, 0, st>>>(a, size, stride));
+      BDET_KERNEL("nms_tile_tail_kernel", st, nms_tile_tail_kernel<<<dim3(tiles, B), 1024, 0, st>>>(a, size));
     }
-    nms_gather_kernel<<<dim3(ceil_div(Nmax, 256), B), 256, 0, st>>>(a);
+    BDET_KERNEL("nms_gather_kernel", st, nms_gather_kernel<<<dim3(ceil_div(Nmax, 256), B), 256, 0, st>>>(a));
   }
   BDET_LAUNCH_CHECK();
   const int nblk = a.nwords;
   if (nblk > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_nms: too many 64-box blocks");
-  nms_mask_kernel<<<dim3(nblk, nblk, B), 256, 0, st>>>(a);
+  BDET_KERNEL("nms_mask_kernel", st, nms_mask_kernel<<<dim3(nblk, nblk, B), 256, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   size_t sweep_smem = (size_t)a.nwords * 8;
-  static thread_local size_t sweep_configured = 0;
-  if (sweep_smem > 48 * 1024 && sweep_smem > sweep_configured) {
+  if (sweep_smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
-    sweep_configured = sweep_smem;
-  }
-  nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a);
+  BDET_KERNEL("nms_sweep_kernel", st, nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

@@ -144,9 +144,9 @@ static int launch_pairwise(const PairArgs& a0, int B, cudaStream_t st) {
   size_t smem = (size_t)a.rows_per_cta * 20;
   const bool vec2 = (a.ld2 == 4) && aligned16(a.b2) && (a.bs2 % 4 == 0);
   if (vec2)
-    pairwise_kernel<MODE, CPT, true><<<grid, kPairThreads, smem, st>>>(a);
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, true><<<grid, kPairThreads, smem, st>>>(a));
   else
-    pairwise_kernel<MODE, CPT, false><<<grid, kPairThreads, smem, st>>>(a);
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, false><<<grid, kPairThreads, smem, st>>>(a));
   return BDET_OK;
 }
 
@@ -203,7 +203,7 @@ extern "C" int bdet_box_center(const float* boxes, int ld, int N, float* out, bd
   BDET_REQUIRE(N >= 0 && ld >= 4, "bad shape");
   if (N == 0) return BDET_OK;
   BDET_REQUIRE(boxes && out, "null argument");
-  box_center_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(boxes, ld, N, reinterpret_cast<float2*>(out));
+  BDET_KERNEL("box_center_kernel", as_stream(stream), box_center_kernel<<<ceil_div(N, 256), 256, 0, as_stream(stream)>>>(boxes, ld, N, reinterpret_cast<float2*>(out)));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -212,8 +212,8 @@ extern "C" int bdet_point_distance(const float* p1, int N, const float* p2, int 
   BDET_REQUIRE(N >= 0 && M >= 0, "bad shape");
   if (N == 0 || M == 0) return BDET_OK;
   BDET_REQUIRE(p1 && p2 && out, "null argument");
-  point_distance_kernel<<<ceil_div((int64_t)N * M, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float2*>(p1), N, reinterpret_cast<const float2*>(p2), M, out);
+  BDET_KERNEL("point_distance_kernel", as_stream(stream), point_distance_kernel<<<ceil_div((int64_t)N * M, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(p1), N, reinterpret_cast<const float2*>(p2), M, out));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

@@ -280,8 +280,8 @@ extern "C" int bdet_roi_assign_levels(const float* rois, int K, int min_level, i
   BDET_REQUIRE(K >= 0 && min_level <= max_level, "bad arguments");
   if (K == 0) return BDET_OK;
   BDET_REQUIRE(rois && levels, "null argument");
-  roi_assign_levels_kernel<<<ceil_div(K, 256), 256, 0, as_stream(stream)>>>(rois, K, min_level, max_level, (float)0.6931471805599453,
-                                                                          levels);
+  BDET_KERNEL("roi_assign_levels_kernel", as_stream(stream), roi_assign_levels_kernel<<<ceil_div(K, 256), 256, 0, as_stream(stream)>>>(rois, K, min_level, max_level, (float)0.6931471805599453,
+                                                                          levels));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -300,9 +300,9 @@ extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, 
   a.out = out;
   cudaStream_t st = as_stream(stream);
   if (PH == 7 && PW == 7 && sample_h == 2 && sample_w == 2)
-    roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a);
+    BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a));
   else
-    roi_align_fwd_kernel<0, 0, 0><<<K, kRoiThreads, 0, st>>>(a);
+    BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<0, 0, 0><<<K, kRoiThreads, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
@@ -326,12 +326,8 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
   a.dout = dout;
   const int smem = 64 * 1024;
   a.bwd_cap = smem / 4;
-  static thread_local bool configured = false;
-  if (!configured) {
-    BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a);
+  BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <limits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -49,9 +50,67 @@ int make_match_cfg(MatchCfg* cfg, const float* thresholds_host, const int* label
   return BDET_OK;
 }
 
+struct ProfPair {
+  cudaEvent_t a, b;
+  const char* name;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfPair>* g_prof = nullptr;
+
+void prof_pre(cudaStream_t st, const char* name) {
+  if (!g_prof_on) return;
+  ProfPair p;
+  p.name = name;
+  if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+  cudaEventRecord(p.a, st);
+  g_prof->push_back(p);
+}
+
+void prof_post(cudaStream_t st) {
+  if (!g_prof_on || g_prof->empty()) return;
+  cudaEventRecord(g_prof->back().b, st);
+}
+
 }  // namespace bdet
 
 extern "C" {
+
+int bdet_profile_begin(void) {
+  if (!bdet::g_prof) bdet::g_prof = new std::vector<bdet::ProfPair>();
+  bdet_profile_end();
+  bdet::g_prof_on = true;
+  return BDET_OK;
+}
+
+int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_host) {
+  float total = 0.f;
+  int n = 0;
+  if (bdet::g_prof) {
+    for (auto& p : *bdet::g_prof) {
+      if (name && strcmp(name, p.name) != 0) continue;
+      BDET_CUDA(cudaEventSynchronize(p.b));
+      float ms = 0.f;
+      BDET_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+      total += ms;
+      ++n;
+    }
+  }
+  if (total_ms_host) *total_ms_host = total;
+  if (launches_host) *launches_host = n;
+  return BDET_OK;
+}
+
+int bdet_profile_end(void) {
+  bdet::g_prof_on = false;
+  if (bdet::g_prof) {
+    for (auto& p : *bdet::g_prof) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+    }
+    bdet::g_prof->clear();
+  }
+  return BDET_OK;
+}
 
 int bdet_abi_version(void) { return BDET_ABI_VERSION; }
 

@@ -299,12 +299,9 @@ static TopkWs carve_ws(void* base, int64_t total, int n_seg, bool with_keys) {
 template <bool RAW>
 static int launch_select(const SelArgs& a, int n_seg, cudaStream_t st) {
   size_t smem = (size_t)(a.P + kBufCap) * 8;
-  static thread_local size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[RAW]) {
+  if (smem > 40 * 1024)  // static shared memory (SelSmem) counts against the 48 KB default limit too
     BDET_CUDA(cudaFuncSetAttribute(select_sort_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[RAW] = smem;
-  }
-  select_sort_kernel<RAW><<<n_seg, kSelThreads, smem, st>>>(a);
+  BDET_KERNEL("select_sort_kernel", st, select_sort_kernel<RAW><<<n_seg, kSelThreads, smem, st>>>(a));
   return BDET_OK;
 }
 
@@ -411,9 +408,9 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
   }
   if (tiles > 0) {
     if (vec)
-      score_filter_kernel<true><<<tiles, kFiltThreads, 0, st>>>(f);
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<tiles, kFiltThreads, 0, st>>>(f));
     else
-      score_filter_kernel<false><<<tiles, kFiltThreads, 0, st>>>(f);
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false><<<tiles, kFiltThreads, 0, st>>>(f));
   }
   SelArgs a{nullptr, w.keys, w.cand_count, w.seg_off, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
   rc = launch_select<false>(a, n_seg, st);
@@ -429,7 +426,7 @@ extern "C" int bdet_scores(const float* logits, const float* ctrness, int C, int
   BDET_REQUIRE(mode != BDET_SCORE_FCOS || ctrness, "FCOS mode needs ctrness");
   if (n == 0) return BDET_OK;
   BDET_REQUIRE(logits && out, "null argument");
-  scores_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(logits, ctrness, C, n, mode, out);
+  BDET_KERNEL("scores_kernel", as_stream(stream), scores_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(logits, ctrness, C, n, mode, out));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

@@ -77,8 +77,9 @@ def _workspace(nbytes, device):
 
 
 # ----------------------------------------------------------------------------- anchors
-def anchors_grid(sizes, strides, shifts, base_anchors, device):
-    """All levels in one launch.  base_anchors: list (per level) of (n_base, 4) float arrays (host)."""
+def anchors_grid(sizes, strides, shifts, base_anchors, device, flat=False):
+    """All levels in one launch.  base_anchors: list (per level) of (n_base, 4) float arrays (host).
+    Returns the per-level list (views of one buffer), or that (sum, 4) buffer itself when ``flat``."""
     lib = _lib.load()
     n = len(sizes)
     counts = [int(h) * int(w) * len(b) for (h, w), b in zip(sizes, base_anchors)]
@@ -92,6 +93,8 @@ def anchors_grid(sizes, strides, shifts, base_anchors, device):
         check(lib.bdet_anchors_grid(_p(out), n, iarr(hw), darr(strides), darr(shifts),
                                     iarr([len(b) for b in base_anchors]), farr(base_flat), larr(offs[:-1]),
                                     _stream(out)))
+    if flat:
+        return out
     return [out[offs[i]:offs[i + 1]] for i in range(n)]
 
 
@@ -261,6 +264,18 @@ def point_encode(points, gt):
     out = torch.empty((g.shape[0], p.shape[0], 4), dtype=torch.float32, device=p.device)
     with _guard(out):
         check(lib.bdet_point_encode(_p(p), p.shape[0], _p(g), ld, g.shape[0], _p(out), _stream(out)))
+    return out
+
+
+def point_encode_rows(points, gt):
+    """points (N, 2), gt (N, >=4) -> (N, 4): row a against gt row a."""
+    lib = _lib.load()
+    p = _f32c(points)
+    g, ld = _rows(gt, "gt")
+    assert g.shape[0] == p.shape[0]
+    out = torch.empty((p.shape[0], 4), dtype=torch.float32, device=p.device)
+    with _guard(out):
+        check(lib.bdet_point_encode_rows(_p(p), _p(g), ld, p.shape[0], _p(out), _stream(out)))
     return out
 
 
@@ -475,3 +490,72 @@ def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample
         check(lib.bdet_roi_align_bwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
                                      int(sample_points[1]), int(bool(aligned)), _p(d), int(zero_init), _stream(d)))
     return dfeats
+
+
+# ----------------------------------------------------------------------------- small Boxes / glue ops
+def box_props(boxes, mode):
+    """mode 0 width, 1 height, 2 area (structures/boxes.py:36-52)."""
+    lib = _lib.load()
+    b, ld = _rows(boxes)
+    out = torch.empty((b.shape[0],), dtype=torch.float32, device=b.device)
+    with _guard(b):
+        check(lib.bdet_box_props(_p(b), ld, b.shape[0], int(mode), _p(out), _stream(b)))
+    return out
+
+
+def box_convert(boxes, from_mode, to_mode):
+    lib = _lib.load()
+    b = _f32c(boxes)
+    out = torch.empty_like(b)
+    with _guard(b):
+        check(lib.bdet_box_convert(_p(b), b.shape[0], int(from_mode), int(to_mode), _p(out), _stream(b)))
+    return out
+
+
+def cond_take(x, mask=None):
+    """F.cond_take(mask, x) -> (values, ascending int32 flat indices).  mask None means x != 0.
+    The variable-length result needs the count on the host: one D2H read, as in the reference API."""
+    lib = _lib.load()
+    xf = _f32c(x, "x").reshape(-1)
+    n = xf.numel()
+    m = None
+    if mask is not None:
+        m = _dev(as_tensor(mask), "mask").reshape(-1).to(torch.uint8).contiguous()
+        assert m.numel() == n
+    vals = torch.empty((n,), dtype=torch.float32, device=xf.device)
+    idx = torch.empty((n,), dtype=torch.int32, device=xf.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=xf.device)
+    ws = _workspace(lib.bdet_cond_take_workspace(n), xf.device)
+    with _guard(xf):
+        check(lib.bdet_cond_take(_p(xf), _p(m), n, _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(xf)))
+    k = int(cnt.item())
+    return vals[:k], idx[:k]
+
+
+def count_labels(labels):
+    """labels (B, A) int32 -> (B, 3) int32 counts of (label < 0, label == 0, label > 0)."""
+    lib = _lib.load()
+    lab = _i32c(labels, "labels")
+    if lab.ndim == 1:
+        lab = lab.unsqueeze(0)
+    B, A = lab.shape
+    out = torch.empty((B, 3), dtype=torch.int32, device=lab.device)
+    with _guard(lab):
+        check(lib.bdet_count_labels(_p(lab), A, B, _p(out), _stream(lab)))
+    return out
+
+
+# ----------------------------------------------------------------------------- measurement hooks
+def profile_begin():
+    check(_lib.load().bdet_profile_begin())
+
+
+def profile_collect(name=None):
+    """(total_ms, launches) of the named kernel since profile_begin() (None = all kernels)."""
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    check(_lib.load().bdet_profile_collect(name.encode() if name else None, ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
+
+
+def profile_end():
+    check(_lib.load().bdet_profile_end())

@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 box-op hot path (contract in the task statement).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU restatement of the reference path
+
+Workload (BASELINE.json configs[1]): RetinaNet training target assignment, batch 16 per GPU, 800x800 input ->
+A = 120 087 anchors, G = 100 GT boxes per image.  One "step" = anchor generation + pairwise IoU + max-IoU Matcher
+(thresholds .4/.5, low-quality matches) + class labels + BoxCoder.encode for the 16 images of one GPU.
+Images are sharded across ranks (weak scaling, no collective on the data path).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "box-op images/sec (IoU+match+NMS+ROIAlign) @1/2/4/8 B200; % of HBM roofline"
+UNIT = "images/s"
+IMAGES_PER_GPU = 16
+NUM_GT = 100
+IMG_HW = (800, 800)
+THRESHOLDS, LABELS, ALLOW_LQ = [0.4, 0.5], [0, -1, 1], True
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        rows = [s for (t, s) in self.samples if t0 <= t <= t1] or [s for (_, s) in self.samples]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- workload
+def make_inputs(rank):
+    from basedet_b200 import workloads as W
+    gt, ng = W.target_assign_batch(IMAGES_PER_GPU, NUM_GT, IMG_HW[0], IMG_HW[1], seed0=100 + rank * IMAGES_PER_GPU)
+    sizes = W.retinanet_level_sizes(*IMG_HW)
+    return gt, ng, sizes
+
+
+def algorithmic_bytes(A, B, G, path):
+    """Per-step HBM bytes of the dominant kernel (DESIGN.md 'Roofline accounting')."""
+    if path == "fused":
+        # assign_main_kernel: anchors read once (16 B), labels + idx + offsets written per image (24 B), GT rows
+        return A * 16 + B * (A * 24 + G * 20)
+    # pairwise_kernel: the (G, A) fp32 matrix written once per image + box reads
+    return B * (4 * G * A + 16 * G) + 16 * A
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from basedet_b200 import _lib, ops
+    from basedet_b200.layers import DefaultAnchorGenerator
+    from basedet_b200 import workloads as W
+
+    _lib.load()
+    gt_np, ng_np, sizes = make_inputs(rank)
+    B, G = gt_np.shape[0], gt_np.shape[1]
+    gen = DefaultAnchorGenerator(W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, W.RETINANET_OFFSET)
+    A = sum(h * w * 9 for h, w in sizes)
+    gt_d = torch.from_numpy(gt_np).to(dev)
+    ng_d = torch.from_numpy(ng_np).to(dev)
+    plan = ops.AssignPlan(A, G, B, dev)
+    iou_buf = torch.empty((B, G, A), dtype=torch.float32, device=dev) if args.path == "materialised" else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(gt, ng):
+        anchors = gen.generate_all_level_anchors(sizes, dev)  # regenerated every step, as retinanet.py:116 does
+        if args.path == "fused":
+            return ops.assign_targets(anchors, gt, ng, THRESHOLDS, LABELS, ALLOW_LQ, True, plan=plan)
+        ops.pairwise_batched(gt, ng, anchors, out=iou_buf)
+        idx, lab = ops.match(iou_buf, THRESHOLDS, LABELS, ALLOW_LQ, num_g=ng)
+        offs = []
+        for b in range(B):  # BoxCoder.encode(anchors, gt[match_indices]) per image, as the reference loop does
+            offs.append(ops.box_encode(anchors, gt[b, :, :4], (0, 0, 0, 0), (1, 1, 1, 1), gather_idx=idx[b]))
+        return lab, idx, offs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step(gt_d, ng_d)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- timed region: device-resident inputs, per-step CUDA events, L2 flushed between steps (outside the events)
+    ops.profile_begin()
+    evs = []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(gt_d, ng_d)
+        e.record()
+        evs.append((s, e))
+    barrier()
+    t1 = time.perf_counter()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    dom = "assign_main_kernel" if args.path == "fused" else "pairwise_kernel"
+    dom_ms, dom_n = ops.profile_collect(dom)
+    _, launches = ops.profile_collect(None)
+    ops.profile_end()
+    # keep the same load running until the clock sampler has seen >= 0.5 s of it
+    t_tail = time.perf_counter()
+    while time.perf_counter() - t0 < 0.6:
+        step(gt_d, ng_d)
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t0, t_end) if sampler else None
+
+    # ---- end-to-end: host (pinned) gt -> H2D -> step -> label census -> D2H, every step
+    gt_h = torch.from_numpy(gt_np).pin_memory()
+    ng_h = torch.from_numpy(ng_np).pin_memory()
+    gt_in, ng_in = torch.empty_like(gt_d), torch.empty_like(ng_d)
+    res_h = torch.empty((args.steps, B, 3), dtype=torch.int32).pin_memory()
+    for i in range(3):
+        gt_in.copy_(gt_h, non_blocking=True)
+        ng_in.copy_(ng_h, non_blocking=True)
+        lab = step(gt_in, ng_in)[0]
+        res_h[0].copy_(ops.count_labels(lab), non_blocking=True)
+    barrier()
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        gt_in.copy_(gt_h, non_blocking=True)
+        ng_in.copy_(ng_h, non_blocking=True)
+        lab = step(gt_in, ng_in)[0]
+        res_h[i].copy_(ops.count_labels(lab), non_blocking=True)
+    barrier()
+    te1 = time.perf_counter()
+    e2e_s = te1 - te0
+    num_fg = int(res_h[-1, :, 2].sum())
+
+    # ---- max over ranks
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    total_images = IMAGES_PER_GPU * world * args.steps
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        abytes = algorithmic_bytes(A, B, G, args.path)
+        achieved = abytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_n else None
+        out = {
+            "metric": METRIC, "value": total_images / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: RetinaNet target assignment, batch %d per GPU, A=%d anchors (800x800), G=%d GT: "
+                            "anchors_grid + IoU + Matcher(.4/.5, low-quality) + class labels + BoxCoder.encode" % (B, A, G),
+                "path": args.path, "images_per_gpu": B, "anchors": A, "gt_per_image": G,
+                "sharding": "images across ranks, no collective on the data path",
+                "l2": "256 MB memset between timed steps (outside the per-step CUDA event pairs)",
+                "timing": "sum of per-step CUDA event intervals on the launching stream, max over ranks",
+            },
+            "e2e": {"value": total_images / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(gt_np.nbytes + ng_np.nbytes), "d2h_bytes_per_step": int(B * 3 * 4),
+                    "note": "pinned host gt -> H2D -> step -> per-image label census (num_fg normaliser) -> D2H; "
+                            "wall clock between device syncs; labels/offsets stay on the GPU as in the reference's loss",
+                    "num_fg_last_step": num_fg},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms / max(dom_n, 1),
+                         "launches_timed": dom_n, "peak_source": peak_src},
+            "clocks": clocks,
+            "wall_ms_timed_region_incl_flush": (t1 - t0) * 1e3,
+        }
+        out["cpu_baseline"] = cpu_baseline(gt_np, ng_np, sizes)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_step(anchors_host_fn, gt, ng):
+    from oracle import ref_ops as R
+    anchors = anchors_host_fn()
+    return R.retinanet_targets(anchors, gt, ng, THRESHOLDS, LABELS, ALLOW_LQ)
+
+
+def _anchors_fn(sizes):
+    from basedet_b200 import workloads as W
+    from oracle import ref_ops as R
+    return lambda: np.concatenate(R.default_anchors(sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES,
+                                                    W.RETINANET_OFFSET))
+
+
+def cpu_baseline(gt_np, ng_np, sizes, budget_s=12.0):
+    """Oracle (numpy restatement of the reference's MegEngine op sequence) timed on the host cores: bounded sample."""
+    fn = _anchors_fn(sizes)
+    n_img, t0 = 0, time.perf_counter()
+    while True:
+        b = n_img % gt_np.shape[0]
+        cpu_step(fn, gt_np[b:b + 1], ng_np[b:b + 1])
+        n_img += 1
+        if time.perf_counter() - t0 > budget_s or n_img >= 64:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n_img / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d images of the same workload, one at a time (numpy fp32 restatement of the reference's op "
+                      "sequence; MegEngine itself is not installable offline); host has %d cores" % (n_img, os.cpu_count())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    gt_np, ng_np, sizes = make_inputs(0)
+    fn = _anchors_fn(sizes)
+    for i in range(max(args.warmup, 1)):
+        cpu_step(fn, gt_np[:1], ng_np[:1])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        b = i % gt_np.shape[0]
+        cpu_step(fn, gt_np[b:b + 1], ng_np[b:b + 1])  # bounded sample: ONE image of the batch per step
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    A = sum(h * w * 9 for h, w in sizes)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: RetinaNet target assignment, A=%d anchors, G=%d GT; each step = 1 image "
+                               "(bounded sample of the batch-16 step)" % (A, NUM_GT), "path": "cpu-oracle"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "1 image per step; numpy fp32 restatement of the reference's MegEngine op sequence "
+                                   "(MegEngine not installable offline; reference is pure Python over it)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--path", default="fused", choices=["fused", "materialised"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,8 @@ int bdet_sum_decode(const float* anchors, float* deltas, int N, const float* mea
  * decode: points (N,2), deltas (N,4k) -> (N,4k); sel_idx as in bdet_box_decode. */
 int bdet_point_encode(const float* points, int A, const float* gt, int gt_ld, int G, float* out,
                       bdet_stream_t stream);
+/* row-wise form used after matching (models/det/fcos.py:268): points (N,2), gt (N,>=4, ld) -> (N,4) */
+int bdet_point_encode_rows(const float* points, const float* gt, int gt_ld, int N, float* out, bdet_stream_t stream);
 int bdet_point_decode(const float* points, const float* deltas, int N, int k, float* out,
                       const int* sel_idx, int n_sel, int sel_div, bdet_stream_t stream);
 
@@ -199,6 +201,29 @@ int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_ho
                        int B, int C, const float* rois, const int* levels, int K, int PH, int PW,
                        int sample_h, int sample_w, int aligned, const float* dout, int zero_init,
                        bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ small Boxes / glue ops
+ * Boxes.width / height / area  structures/boxes.py:36-52 (mode 0 / 1 / 2) -> out (N) */
+int bdet_box_props(const float* boxes, int ld, int N, int mode, float* out, bdet_stream_t stream);
+/* BoxConverter.convert  structures/box_convert.py:51-82; modes BoxMode XYXY=0, XYWH=1, XcYcWH=2; (N,4) -> (N,4) */
+int bdet_box_convert(const float* boxes, int N, int from_mode, int to_mode, float* out, bdet_stream_t stream);
+/* non_zeros -> F.cond_take(mask != 0, x)  layers/common/function.py:19-23: ordered stream compaction.
+ * x (n) fp32; mask (n) uint8 or NULL (then the mask is x != 0).  out_vals / out_idx (n) receive the selected
+ * values and their ascending flat indices; count_dev (1) the number selected. */
+size_t bdet_cond_take_workspace(int64_t n);
+int bdet_cond_take(const float* x, const uint8_t* mask, int64_t n, float* out_vals, int* out_idx, int* count_dev,
+                   void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* Per-image label census: counts (B,3) = #(label < 0), #(label == 0), #(label > 0); the `num_fg` normaliser of
+ * models/det/retinanet.py:142-146 and the sampling counts of models/det/rpn.py:232-236. */
+int bdet_count_labels(const int* labels, int A, int B, int* counts, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ measurement hooks (bench.py only)
+ * While profiling is on, every named kernel launch inside the library is bracketed by a CUDA event pair on the
+ * launching stream.  bdet_profile_collect synchronises those events and returns the summed duration and the
+ * number of launches whose kernel name matches `name` (NULL = all).  Off by default; thread-local. */
+int bdet_profile_begin(void);
+int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_host);
+int bdet_profile_end(void);
 
 #ifdef __cplusplus
 }
