@@ -24,13 +24,13 @@ SIGNATURES = {
     "bdet_device_info": (c_int, [ip, ip, ip]),
     "bdet_anchors_grid": (c_int, [vp, c_int, ip, dp, dp, ip, fp, lp, vp]),
     "bdet_points_grid": (c_int, [vp, c_int, ip, dp, dp, c_int, c_int, lp, vp]),
-    "bdet_pairwise": (c_int, [vp, c_int, c_int, vp, c_int, c_int, vp, c_int, vp]),
-    "bdet_pairwise_batched": (c_int, [vp, c_int, c_int64, vp, c_int, vp, c_int, c_int64, c_int, vp, c_int64,
+    "bdet_pairwise": (c_int, [vp, c_int, c_int, vp, c_int, c_int, vp, c_int64, c_int, vp]),
+    "bdet_pairwise_batched": (c_int, [vp, c_int, c_int64, vp, c_int, vp, c_int, c_int64, c_int, vp, c_int64, c_int64,
                                       c_int, c_int, vp]),
     "bdet_box_center": (c_int, [vp, c_int, c_int, vp, vp]),
     "bdet_point_distance": (c_int, [vp, c_int, vp, c_int, vp, vp]),
     "bdet_match_workspace": (c_size_t, [c_int, c_int, c_int]),
-    "bdet_match": (c_int, [vp, c_int64, vp, c_int, c_int, c_int, fp, ip, c_int, c_int, vp, vp, vp, c_size_t, vp]),
+    "bdet_match": (c_int, [vp, c_int64, c_int64, vp, c_int, c_int, c_int, fp, ip, c_int, c_int, vp, vp, vp, c_size_t, vp]),
     "bdet_match_rows": (c_int, [vp, c_int, c_int, vp, vp, vp]),
     "bdet_box_encode": (c_int, [vp, vp, c_int, vp, c_int, fp, fp, vp, vp]),
     "bdet_box_decode": (c_int, [vp, vp, c_int, c_int, fp, fp, vp, c_int, vp, c_int, c_int, vp]),
@@ -62,6 +62,7 @@ SIGNATURES = {
     "bdet_cond_take_workspace": (c_size_t, [c_int64]),
     "bdet_cond_take": (c_int, [vp, vp, c_int64, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_count_labels": (c_int, [vp, c_int, c_int, vp, vp]),
+    "bdet_bw_probe": (c_int, [vp, vp, c_size_t, c_int, c_int, vp]),
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),
     "bdet_profile_end": (c_int, []),

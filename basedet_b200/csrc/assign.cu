@@ -4,20 +4,25 @@
 //   structures/op_patch.py:33-97 (box_iou), layers/common/matcher.py:31-51 (Matcher),
 //   structures/boxcoder.py:61-73 (BoxCoder.encode); RPN uses the same sequence (models/det/rpn.py:215-226).
 //
-// Data flow per CTA (kAPT*256 consecutive anchors of one image):
-//   anchors: one 128-bit load each, kept in registers; GT boxes (+area, class) staged in shared memory;
-//   the CTA reduces the bounding box of its anchors and keeps only the GTs that can intersect it
-//   (ascending order, so "first argmax" survives); every other (g, anchor) pair has IoU exactly +0 and
-//   can never win a strict '>' against the running maximum that starts at (0, index 0).
-//   Row maxima (needed by allow_low_quality_matches) are folded per warp with redux.sync and kept in
-//   shared memory; the CTA publishes only its non-zero row maxima.
-//   Kernel 2 re-evaluates a (g, CTA) segment only where the CTA's maximum equals the global row maximum.
+// assign_main_kernel -- one CTA = 8 warps x 64 consecutive anchors of one image:
+//   * anchors: one 128-bit load each, kept in registers; GT boxes (+area, class) staged in shared memory;
+//   * every WARP reduces the bounding box of its 64 anchors (4 redux.sync) and walks the GT list 32 at a time:
+//     lane l tests GT g0+l against the warp box, one __ballot_sync gives the survivors, and the warp visits only
+//     the set bits (ascending g, so "first argmax" survives).  Every skipped (g, anchor) pair has IoU exactly +0
+//     and can never win the strict '>' against the running maximum, which starts at (0, index 0);
+//   * row maxima (needed by allow_low_quality_matches) are folded per warp with redux.sync into a shared-memory
+//     table; the CTA publishes its table (transposed, (B, G, tiles)) and atomicMax-es the global row maxima.
+// assign_lq_kernel -- one CTA per (image, GT): finds the tiles whose maximum equals the row maximum and
+//   re-evaluates only those 512-anchor segments (matcher.py:47-49), including rows whose maximum is 0.
 // HBM traffic: 16 B/anchor read + 24 B/anchor written (labels, indices, offsets) per image.
 #include "common.cuh"
 
 namespace bdet {
 
-constexpr int kAT = 256;
+constexpr int kAT = 256;                   // threads per CTA
+constexpr int kAPW = 64;                   // anchors per warp (2 per lane)
+constexpr int kATile = (kAT / 32) * kAPW;  // 512 anchors per CTA
+constexpr int kLqThreads = 128;
 
 struct AssignArgs {
   const float* anchors;
@@ -27,212 +32,161 @@ struct AssignArgs {
   int* idx;
   float* offsets;
   uint32_t* rowmax;  // (B, Gmax) fp32 bits (IoU >= 0, so uint order == float order); zero-initialised
-  int* blk_count;    // (B, tiles)
-  uint2* blk_list;   // (B, tiles, Gmax): (g, local max bits)
-  int A, Gmax, tiles, allow_lq, apply_class;
+  uint32_t* blkmax;  // (B, Gmax, tiles)
+  int A, Gmax, tiles, allow_lq, apply_class, unit_coder;
   MatchCfg cfg;
   Vec4 mean, stdv;
 };
 
-struct AssignSmem {
-  float4* box;
-  float* area;
-  float* cls;
-  uint32_t* rmax;
-  int* list;
-};
-__device__ __forceinline__ AssignSmem carve(unsigned char* raw, int Gmax) {
-  AssignSmem s;
-  s.box = reinterpret_cast<float4*>(raw);
-  s.area = reinterpret_cast<float*>(s.box + Gmax);
-  s.cls = s.area + Gmax;
-  s.rmax = reinterpret_cast<uint32_t*>(s.cls + Gmax);
-  s.list = reinterpret_cast<int*>(s.rmax + Gmax);
-  return s;
-}
-
-template <int APT>
 __global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
   extern __shared__ __align__(16) unsigned char raw[];
-  AssignSmem s = carve(raw, p.Gmax);
-  __shared__ uint32_t sred[4];
-  __shared__ float sbb[4];
-  __shared__ int scount, spub;
-  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  float4* sbox = reinterpret_cast<float4*>(raw);
+  float* sarea = reinterpret_cast<float*>(sbox + p.Gmax);
+  float* scls = sarea + p.Gmax;
+  uint32_t* srmax = reinterpret_cast<uint32_t*>(scls + p.Gmax);  // (8 warps, Gmax): each warp visits a GT at most once
+  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int G = min(p.num_gt[b], p.Gmax);
 
-  if (t < 4) sred[t] = (t < 2) ? 0xffffffffu : 0u;
-  if (t == 0) spub = 0;
   const float* gt = p.gt + (long long)b * p.Gmax * 5;
   for (int g = t; g < G; g += kAT) {
     const float* r = gt + g * 5;
     float4 bx = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-    s.box[g] = bx;
-    s.area[g] = box_area(bx);
-    s.cls[g] = __ldg(r + 4);
-    s.rmax[g] = 0u;
+    sbox[g] = bx;
+    sarea[g] = box_area(bx);
+    scls[g] = __ldg(r + 4);
   }
-  float4 an[APT];
-  float aa[APT];
-  bool ok[APT];
+  if (p.allow_lq)
+    for (int i = t; i < (kAT / 32) * p.Gmax; i += kAT) srmax[i] = 0u;
+  // this lane's two anchors: consecutive runs of 32 inside the warp's 64
+  const long long c0 = (long long)tile * kATile + warp * kAPW + lane;
+  const long long c1 = c0 + 32;
+  const bool ok0 = c0 < p.A, ok1 = c1 < p.A;
+  const float4 an0 = ok0 ? ldg4(p.anchors + c0 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 an1 = ok1 ? ldg4(p.anchors + c1 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float aa0 = box_area(an0), aa1 = box_area(an1);
+  // warp bounding box (NaN coordinates are ignored by fmin/fmax; such anchors give IoU 0 against everything)
   float mnx = CUDART_INF_F, mny = CUDART_INF_F, mxx = -CUDART_INF_F, mxy = -CUDART_INF_F;
-  const long long col0 = (long long)tile * (kAT * APT) + t;
-#pragma unroll
-  for (int j = 0; j < APT; ++j) {
-    long long c = col0 + j * kAT;
-    ok[j] = c < p.A;
-    an[j] = ok[j] ? ldg4(p.anchors + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    aa[j] = box_area(an[j]);
-    if (ok[j]) {
-      mnx = fminf(mnx, an[j].x);
-      mny = fminf(mny, an[j].y);
-      mxx = fmaxf(mxx, an[j].z);
-      mxy = fmaxf(mxy, an[j].w);
-    }
+  if (ok0) {
+    mnx = an0.x;
+    mny = an0.y;
+    mxx = an0.z;
+    mxy = an0.w;
   }
-  __syncthreads();
-  {
-    uint32_t r0 = __reduce_min_sync(0xffffffffu, f2ord(mnx));
-    uint32_t r1 = __reduce_min_sync(0xffffffffu, f2ord(mny));
-    uint32_t r2 = __reduce_max_sync(0xffffffffu, f2ord(mxx));
-    uint32_t r3 = __reduce_max_sync(0xffffffffu, f2ord(mxy));
-    if (lane == 0) {
-      atomicMin(&sred[0], r0);
-      atomicMin(&sred[1], r1);
-      atomicMax(&sred[2], r2);
-      atomicMax(&sred[3], r3);
-    }
+  if (ok1) {
+    mnx = fminf(mnx, an1.x);
+    mny = fminf(mny, an1.y);
+    mxx = fmaxf(mxx, an1.z);
+    mxy = fmaxf(mxy, an1.w);
   }
+  const float bb0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(mnx)));
+  const float bb1 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(mny)));
+  const float bb2 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(mxx)));
+  const float bb3 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(mxy)));
   __syncthreads();
-  if (t < 4) sbb[t] = ord2f(sred[t]);
-  __syncthreads();
-  // Order-preserving compaction of the GTs that can overlap this CTA's anchors (warp 0).
-  if (t < 32) {
-    const float bb0 = sbb[0], bb1 = sbb[1], bb2 = sbb[2], bb3 = sbb[3];
-    int n = 0;
-    for (int g0 = 0; g0 < G; g0 += 32) {
-      int g = g0 + lane;
-      bool live = false;
-      if (g < G) {
-        float4 a = s.box[g];
-        live = !(a.z <= bb0 || a.x >= bb2 || a.w <= bb1 || a.y >= bb3);  // NaN GT -> live
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, live);
-      if (live) s.list[n + __popc(mask & ((1u << lane) - 1u))] = g;
-      n += __popc(mask);
-    }
-    if (lane == 0) scount = n;
-  }
-  __syncthreads();
-  const int n_live = scount;
 
-  // Running (max, first argmax) over G.  All IoUs are >= +0 and never NaN, so the state after the
-  // (possibly skipped) row 0 is at least (0, 0); skipped rows are exact zeros and cannot win '>'.
-  float best[APT];
-  int bidx[APT];
-#pragma unroll
-  for (int j = 0; j < APT; ++j) {
-    best[j] = 0.f;
-    bidx[j] = 0;
-  }
-  for (int i = 0; i < n_live; ++i) {
-    const int g = s.list[i];
-    const float4 a = s.box[g];
-    const float ga = s.area[g];
-    float rv = 0.f;
-#pragma unroll
-    for (int j = 0; j < APT; ++j) {
-      float v = ok[j] ? iou_pair(a, ga, an[j], aa[j]) : 0.f;
-      if (v > best[j]) {
-        best[j] = v;
-        bidx[j] = g;
-      }
-      rv = fmaxf(rv, v);
+  // Running (max, first argmax) over G.  All IoUs are >= +0 and never NaN, so the state after the (possibly
+  // skipped) row 0 is at least (0, 0); skipped rows are exact zeros and cannot win '>'.
+  float best0 = 0.f, best1 = 0.f;
+  int bi0 = 0, bi1 = 0;
+  for (int g0 = 0; g0 < G; g0 += 32) {
+    const int gl = g0 + lane;
+    bool live = false;
+    if (gl < G) {
+      const float4 a = sbox[gl];
+      live = !(a.z <= bb0 || a.x >= bb2 || a.w <= bb1 || a.y >= bb3);  // NaN GT -> live (evaluated, gives 0)
     }
-    if (p.allow_lq && __any_sync(0xffffffffu, rv > 0.f)) {
-      uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(rv));
-      if (lane == 0) atomicMax(&s.rmax[g], w);
+    uint32_t m = __ballot_sync(0xffffffffu, live);
+    while (m) {
+      const int g = g0 + __ffs(m) - 1;
+      m &= m - 1;
+      const float4 a = sbox[g];
+      const float ga = sarea[g];
+      const float v0 = iou_pair(a, ga, an0, aa0);  // out-of-range lanes hold a zero-size anchor: IoU 0 with anything
+      const float v1 = iou_pair(a, ga, an1, aa1);
+      if (v0 > best0) {
+        best0 = v0;
+        bi0 = g;
+      }
+      if (v1 > best1) {
+        best1 = v1;
+        bi1 = g;
+      }
+      if (p.allow_lq) {
+        const float rv = fmaxf(v0, v1);
+        if (__any_sync(0xffffffffu, rv > 0.f)) {
+          const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(rv));
+          if (lane == 0) srmax[warp * p.Gmax + g] = w;
+        }
+      }
     }
   }
 
 #pragma unroll
-  for (int j = 0; j < APT; ++j) {
-    if (!ok[j]) continue;
-    long long o = (long long)b * p.A + col0 + j * kAT;
-    int label = threshold_label(p.cfg, best[j]);
+  for (int j = 0; j < 2; ++j) {
+    const bool ok = j ? ok1 : ok0;
+    if (!ok) continue;
+    const long long o = (long long)b * p.A + (j ? c1 : c0);
+    const float best = j ? best1 : best0;
+    const int bi = j ? bi1 : bi0;
+    int label = threshold_label(p.cfg, best);
     float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
     if (G > 0) {
-      if (p.apply_class && label == 1) label = (int)s.cls[bidx[j]];  // retinanet.py:222-223 astype("int32")
-      off = encode_box(an[j], s.box[bidx[j]], p.mean, p.stdv);
+      if (p.apply_class && label == 1) label = (int)scls[bi];  // retinanet.py:222-223 astype("int32")
+      off = p.unit_coder ? encode_box<true>(j ? an1 : an0, sbox[bi], p.mean, p.stdv)
+                         : encode_box<false>(j ? an1 : an0, sbox[bi], p.mean, p.stdv);
     }
     p.labels[o] = label;
-    p.idx[o] = bidx[j];
+    p.idx[o] = bi;
     reinterpret_cast<float4*>(p.offsets)[o] = off;
   }
 
   if (p.allow_lq) {
     __syncthreads();
-    uint2* lst = p.blk_list + ((long long)b * p.tiles + tile) * p.Gmax;
+    uint32_t* bm = p.blkmax + (long long)b * p.Gmax * p.tiles + tile;
     for (int g = t; g < G; g += kAT) {
-      uint32_t u = s.rmax[g];
-      if (u) {
-        atomicMax(&p.rowmax[(long long)b * p.Gmax + g], u);
-        lst[atomicAdd(&spub, 1)] = make_uint2((uint32_t)g, u);
-      }
+      uint32_t u = 0u;
+#pragma unroll
+      for (int w = 0; w < kAT / 32; ++w) u = max(u, srmax[w * p.Gmax + g]);
+      bm[(long long)g * p.tiles] = u;
+      if (u) atomicMax(&p.rowmax[(long long)b * p.Gmax + g], u);
     }
-    __syncthreads();
-    if (t == 0) p.blk_count[(long long)b * p.tiles + tile] = spub;
   }
 }
 
-// allow_low_quality_matches, matcher.py:47-49: every anchor whose IoU with g equals the row maximum of g
-// gets label 1 (then the class of ITS OWN matched GT, retinanet.py:222-223) -- including rows whose
-// maximum is 0, where every zero-IoU anchor qualifies.
-template <int APT>
-__global__ void __launch_bounds__(kAT) assign_lq_kernel(const AssignArgs p) {
-  extern __shared__ __align__(16) unsigned char raw[];
-  int* hit = reinterpret_cast<int*>(raw);  // Gmax
+// allow_low_quality_matches, matcher.py:47-49: every anchor whose IoU with g equals the row maximum of g gets
+// label 1 (then the class of ITS OWN matched GT, retinanet.py:222-223).
+__global__ void __launch_bounds__(kLqThreads) assign_lq_kernel(const AssignArgs p) {
+  extern __shared__ int stiles[];  // tiles
   __shared__ int nhit;
-  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+  const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const int G = min(p.num_gt[b], p.Gmax);
+  if (g >= G) return;
   if (t == 0) nhit = 0;
   __syncthreads();
-  const uint32_t* rm = p.rowmax + (long long)b * p.Gmax;
-  const uint2* lst = p.blk_list + ((long long)b * p.tiles + tile) * p.Gmax;
-  const int n = p.blk_count[(long long)b * p.tiles + tile];
-  for (int i = t; i < n; i += kAT) {
-    uint2 e = lst[i];
-    if (e.y == rm[e.x]) hit[atomicAdd(&nhit, 1)] = (int)e.x;
-  }
-  for (int g = t; g < G; g += kAT)
-    if (rm[g] == 0u) hit[atomicAdd(&nhit, 1)] = g;  // zero-maximum rows never appear in a CTA list
+  const uint32_t rm = p.rowmax[(long long)b * p.Gmax + g];
+  const uint32_t* bm = p.blkmax + ((long long)b * p.Gmax + g) * p.tiles;
+  for (int i = t; i < p.tiles; i += kLqThreads)
+    if (bm[i] == rm) stiles[atomicAdd(&nhit, 1)] = i;  // rm == 0: every tile (all their zero-IoU anchors qualify)
   __syncthreads();
   const int nh = nhit;
   if (nh == 0) return;
-  const float* gt = p.gt + (long long)b * p.Gmax * 5;
-  const long long col0 = (long long)tile * (kAT * APT) + t;
-#pragma unroll
-  for (int j = 0; j < APT; ++j) {
-    long long c = col0 + j * kAT;
-    if (c >= p.A) continue;
-    float4 an = ldg4(p.anchors + c * 4);
-    float aa = box_area(an);
-    bool lq = false;
-    for (int i = 0; i < nh; ++i) {
-      const float* r = gt + hit[i] * 5;
-      float4 a = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-      float v = iou_pair(a, box_area(a), an, aa);
-      lq |= (__float_as_uint(v) == rm[hit[i]]);
-    }
-    if (lq) {
-      long long o = (long long)b * p.A + c;
-      p.labels[o] = p.apply_class ? (int)__ldg(gt + p.idx[o] * 5 + 4) : 1;
+  const float* r = p.gt + ((long long)b * p.Gmax + g) * 5;
+  const float4 a = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+  const float ga = box_area(a);
+  const float* gtb = p.gt + (long long)b * p.Gmax * 5;
+  for (int h = 0; h < nh; ++h) {
+    const long long base = (long long)stiles[h] * kATile;
+    for (int i = t; i < kATile; i += kLqThreads) {
+      const long long c = base + i;
+      if (c >= p.A) break;
+      const float4 an = ldg4(p.anchors + c * 4);
+      const float v = iou_pair(a, ga, an, box_area(an));
+      if (__float_as_uint(v) == rm) {
+        const long long o = (long long)b * p.A + c;
+        p.labels[o] = p.apply_class ? (int)__ldg(gtb + p.idx[o] * 5 + 4) : 1;
+      }
     }
   }
-}
-
-static int assign_apt(int A, int B) {
-  return ((long long)ceil_div(A, kAT * 2) * B >= (long long)sm_count() * 4) ? 2 : 1;
 }
 
 }  // namespace bdet
@@ -241,8 +195,8 @@ using namespace bdet;
 
 extern "C" size_t bdet_assign_targets_workspace(int Gmax, int A, int B) {
   if (Gmax <= 0 || A <= 0 || B <= 0) return 16;
-  int tiles = ceil_div(A, kAT * assign_apt(A, B));
-  return align_up((size_t)B * Gmax * 4, 256) + align_up((size_t)B * tiles * 4, 256) + (size_t)B * tiles * Gmax * 8 + 256;
+  const int tiles = ceil_div(A, kATile);
+  return align_up((size_t)B * Gmax * 4, 256) + (size_t)B * Gmax * tiles * 4 + 256;
 }
 
 extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, const int* num_gt_dev, int B,
@@ -258,10 +212,9 @@ extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt,
   BDET_REQUIRE(anchors && labels && match_idx && offsets && num_gt_dev, "null argument");
   BDET_REQUIRE(Gmax == 0 || gt, "null gt");
   BDET_REQUIRE(aligned16(anchors) && aligned16(offsets), "anchors/offsets must be 16-byte aligned");
-  BDET_REQUIRE(B <= 65535, "B > 65535");
-  const size_t smem = (size_t)max(Gmax, 1) * 32;
-  if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_assign_targets: Gmax > 6400 does not fit shared memory");
-  const int apt = assign_apt(A, B);
+  BDET_REQUIRE(B <= 65535 && Gmax <= 65535, "B / Gmax > 65535");
+  const size_t smem = (size_t)max(Gmax, 1) * (24 + 4 * (kAT / 32));
+  if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_assign_targets: Gmax > 3600 does not fit shared memory");
   a.anchors = anchors;
   a.gt = gt;
   a.num_gt = num_gt_dev;
@@ -270,43 +223,36 @@ extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt,
   a.offsets = offsets;
   a.A = A;
   a.Gmax = Gmax;
-  a.tiles = ceil_div(A, kAT * apt);
+  a.tiles = ceil_div(A, kATile);
   a.allow_lq = (allow_low_quality != 0 && Gmax > 0) ? 1 : 0;
   a.apply_class = apply_class != 0;
+  a.unit_coder = 1;
   for (int i = 0; i < 4; ++i) {
     a.mean.v[i] = mean_host ? mean_host[i] : 0.f;
     a.stdv.v[i] = std_host ? std_host[i] : 1.f;
+    if (a.mean.v[i] != 0.f || a.stdv.v[i] != 1.f) a.unit_coder = 0;  // (t - 0) / 1 == t bit for bit
   }
   a.rowmax = nullptr;
-  a.blk_count = nullptr;
-  a.blk_list = nullptr;
+  a.blkmax = nullptr;
   cudaStream_t st = as_stream(stream);
   if (a.allow_lq) {
     const size_t need = bdet_assign_targets_workspace(Gmax, A, B);
     if (!workspace || workspace_bytes < need)
       return set_error(BDET_EWORKSPACE, "bdet_assign_targets: workspace needs %zu bytes", need);
-    BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
+    BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 3u) == 0, "workspace must be 4-byte aligned");
     char* w = reinterpret_cast<char*>(workspace);
     a.rowmax = reinterpret_cast<uint32_t*>(w);
-    w += align_up((size_t)B * Gmax * 4, 256);
-    a.blk_count = reinterpret_cast<int*>(w);
-    w += align_up((size_t)B * a.tiles * 4, 256);
-    a.blk_list = reinterpret_cast<uint2*>(w);
+    a.blkmax = reinterpret_cast<uint32_t*>(w + align_up((size_t)B * Gmax * 4, 256));
     BDET_CUDA(cudaMemsetAsync(a.rowmax, 0, (size_t)B * Gmax * 4, st));
   }
-  dim3 grid(a.tiles, B);
-  if (apt == 2) {
-    if (smem > 40 * 1024) {
-      BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<2><<<grid, kAT, smem, st>>>(a));
-    if (a.allow_lq) BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<2><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a));
-  } else {
-    if (smem > 40 * 1024) {
-      BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<1><<<grid, kAT, smem, st>>>(a));
-    if (a.allow_lq) BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<1><<<grid, kAT, (size_t)max(Gmax, 1) * 4, st>>>(a));
+  if (smem > 40 * 1024)
+    BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<<<dim3(a.tiles, B), kAT, smem, st>>>(a));
+  if (a.allow_lq) {
+    const size_t lq_smem = (size_t)a.tiles * 4;
+    if (lq_smem > 40 * 1024)
+      BDET_CUDA(cudaFuncSetAttribute(assign_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem));
+    BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<<<dim3(Gmax, B), kLqThreads, lq_smem, st>>>(a));
   }
   BDET_LAUNCH_CHECK();
   return BDET_OK;

@@ -107,6 +107,9 @@ struct Vec4 {
 };
 
 // BoxCoder._box_ltrb_to_cs_opr + encode, structures/boxcoder.py:44-73.
+// kUnit: mean == 0 and std == 1, where (t - 0) / 1 == t bit for bit (only the sign of a zero could differ:
+// -0 - 0 = -0, -0 / 1 = -0), so the four subtractions and IEEE divisions are skipped.
+template <bool kUnit = false>
 __device__ __forceinline__ float4 encode_box(float4 b, float4 g, const Vec4& mean, const Vec4& stdv) {
   float bw = b.z - b.x, bh = b.w - b.y;
   float bcx = b.x + 0.5f * bw, bcy = b.y + 0.5f * bh;
@@ -116,6 +119,7 @@ __device__ __forceinline__ float4 encode_box(float4 b, float4 g, const Vec4& mea
   float dy = __fdiv_rn(gcy - bcy, bh);
   float dw = logf(__fdiv_rn(gw, bw));
   float dh = logf(__fdiv_rn(gh, bh));
+  if (kUnit) return make_float4(dx, dy, dw, dh);
   float4 t;
   t.x = __fdiv_rn(dx - mean.v[0], stdv.v[0]);
   t.y = __fdiv_rn(dy - mean.v[1], stdv.v[1]);

@@ -7,8 +7,8 @@
 //       (max, first argmax) for its columns while walking the G rows; per row the warp folds its
 //       values with one redux.sync and keeps a CTA-local row maximum in shared memory;
 //       at the end the CTA publishes its row maxima (global atomicMax + a per-CTA copy).
-//   kernel 2 (low-quality fix-up): a CTA re-reads a row segment only if its local maximum equals the
-//       global row maximum -- G segments in total instead of a second full pass.
+//   kernel 2 (low-quality fix-up): one CTA per (image, row) re-reads a column segment only if that segment's
+//       maximum equals the row maximum -- ~G segments in total instead of a second full pass.
 // (R, G) layout of RCNN (layers/head/rcnn.py:113-116): one warp per row, warp-shuffle argmax.
 #include "common.cuh"
 
@@ -32,13 +32,13 @@ static MatchPlan match_plan(int A, int B) {
 
 struct MatchArgs {
   const float* m;
-  long long bs;
+  long long bs, ld;
   const int* g_dev;
   int Gmax, A, tiles, allow_lq;
   int* idx;
   int* labels;
   uint32_t* rowmax;  // (B, Gmax)   order-encoded, zero-initialised
-  uint32_t* blkmax;  // (B, tiles, Gmax)
+  uint32_t* blkmax;  // (B, Gmax, tiles)
   MatchCfg cfg;
 };
 
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kMatchThreads) match_colmax_kernel(const Match
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int j = 0; j < CPT; ++j)
-        v[u][j] = (g0 + u < G && ok[j]) ? __ldcs(base + (long long)(g0 + u) * p.A + j * kMatchThreads) : -CUDART_INF_F;
+        v[u][j] = (g0 + u < G && ok[j]) ? __ldcs(base + (long long)(g0 + u) * p.ld + j * kMatchThreads) : -CUDART_INF_F;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (g0 + u < G) {  // uniform across the CTA
@@ -100,38 +100,40 @@ __global__ void __launch_bounds__(kMatchThreads) match_colmax_kernel(const Match
   }
   if (p.allow_lq) {
     __syncthreads();
-    uint32_t* bm = p.blkmax + ((long long)b * p.tiles + tile) * p.Gmax;
+    uint32_t* bm = p.blkmax + (long long)b * p.Gmax * p.tiles + tile;  // (B, Gmax, tiles): row-contiguous for kernel 2
     for (int g = t; g < G; g += kMatchThreads) {
       uint32_t u = srow[g];
-      bm[g] = u;
+      bm[(long long)g * p.tiles] = u;
       atomicMax(&p.rowmax[(long long)b * p.Gmax + g], u);
     }
   }
 }
 
+// Low-quality fix-up, matcher.py:47-49: labels[(matrix == rowmax).sum(0) > 0] = 1.
+// One CTA per (image, row): finds the column tiles whose maximum equals the row maximum (float compare, so
+// -0 == +0 as in the reference) and re-reads only those segments of the row.
+constexpr int kLqThreads = 128;
 template <int CPT>
-__global__ void __launch_bounds__(kMatchThreads) match_lq_kernel(const MatchArgs p) {
-  extern __shared__ int slist[];
-  __shared__ int scount;
-  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+__global__ void __launch_bounds__(kLqThreads) match_lq_kernel(const MatchArgs p) {
+  extern __shared__ int stiles[];
+  __shared__ int nhit;
+  const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const int G = p.g_dev ? min(p.g_dev[b], p.Gmax) : p.Gmax;
-  if (t == 0) scount = 0;
+  if (g >= G) return;
+  if (t == 0) nhit = 0;
   __syncthreads();
-  const uint32_t* bm = p.blkmax + ((long long)b * p.tiles + tile) * p.Gmax;
-  const uint32_t* rm = p.rowmax + (long long)b * p.Gmax;
-  for (int g = t; g < G; g += kMatchThreads)
-    if (ord2f(bm[g]) == ord2f(rm[g])) slist[atomicAdd(&scount, 1)] = g;
+  const float target = ord2f(p.rowmax[(long long)b * p.Gmax + g]);
+  const uint32_t* bm = p.blkmax + ((long long)b * p.Gmax + g) * p.tiles;
+  for (int i = t; i < p.tiles; i += kLqThreads)
+    if (ord2f(bm[i]) == target) stiles[atomicAdd(&nhit, 1)] = i;
   __syncthreads();
-  const int n = scount;
-  const long long col0 = (long long)tile * (kMatchThreads * CPT) + t;
-  for (int i = 0; i < n; ++i) {
-    const int g = slist[i];
-    const float target = ord2f(rm[g]);
-    const float* row = p.m + b * p.bs + (long long)g * p.A;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      long long c = col0 + j * kMatchThreads;
-      // matcher.py:48-49: labels[(matrix == rowmax).sum(0) > 0] = 1
+  const int nh = nhit;
+  const float* row = p.m + b * p.bs + (long long)g * p.ld;
+  constexpr int kCols = kMatchThreads * CPT;
+  for (int h = 0; h < nh; ++h) {
+    const long long base = (long long)stiles[h] * kCols;
+    for (int i = t; i < kCols; i += kLqThreads) {
+      const long long c = base + i;
       if (c < p.A && __ldg(row + c) == target) p.labels[(long long)b * p.A + c] = 1;
     }
   }
@@ -173,7 +175,8 @@ static void launch_match(const MatchArgs& a, int B, cudaStream_t st) {
   dim3 grid(a.tiles, B);
   size_t smem = (size_t)max(a.Gmax, 1) * 4;
   BDET_KERNEL("match_colmax_kernel", st, match_colmax_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a));
-  if (a.allow_lq) BDET_KERNEL("match_lq_kernel", st, match_lq_kernel<CPT><<<grid, kMatchThreads, smem, st>>>(a));
+  if (a.allow_lq)
+    BDET_KERNEL("match_lq_kernel", st, match_lq_kernel<CPT><<<dim3(a.Gmax, B), kLqThreads, (size_t)a.tiles * 4, st>>>(a));
 }
 
 }  // namespace bdet
@@ -186,7 +189,7 @@ extern "C" size_t bdet_match_workspace(int Gmax, int A, int B) {
   return align_up((size_t)B * Gmax * 4, 256) + (size_t)B * pl.tiles * Gmax * 4 + 256;
 }
 
-extern "C" int bdet_match(const float* matrix, int64_t batch_stride, const int* g_dev, int Gmax, int A, int B,
+extern "C" int bdet_match(const float* matrix, int64_t ld, int64_t batch_stride, const int* g_dev, int Gmax, int A, int B,
                           const float* thresholds_host, const int* labels_host, int n_labels, int allow_low_quality,
                           int* match_idx, int* labels, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(Gmax >= 0 && A >= 0 && B >= 0, "negative size");
@@ -196,10 +199,13 @@ extern "C" int bdet_match(const float* matrix, int64_t batch_stride, const int* 
   if (A == 0 || B == 0) return BDET_OK;
   BDET_REQUIRE(match_idx && labels, "null output");
   BDET_REQUIRE(Gmax == 0 || matrix, "null matrix");
+  BDET_REQUIRE(ld >= A, "row stride smaller than A");
   BDET_REQUIRE(Gmax <= 12000, "Gmax too large for the shared-memory row table");
+  BDET_REQUIRE(A <= 10000 * kMatchThreads, "A too large for the tile table");
   MatchPlan pl = match_plan(A, B);
   a.m = matrix;
   a.bs = batch_stride;
+  a.ld = ld;
   a.g_dev = g_dev;
   a.Gmax = Gmax;
   a.A = A;

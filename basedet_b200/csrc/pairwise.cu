@@ -42,9 +42,12 @@ struct PairArgs {
   const int* n1;  // per-batch valid rows (device) or nullptr
   long long bs1, bs2, bs_out;
   int ld1, ld2, N, M, rows_per_cta;
+  long long ldo;  // output row stride in floats (>= M)
 };
 
-template <int MODE, int CPT, bool VEC2>
+// VECO: the thread owns 4 CONSECUTIVE columns and writes one 128-bit store per row (needs ldo % 4 == 0 and a
+// 16-byte aligned output; scalar 4-byte stores top out near 3.5 TB/s on B200, 128-bit stores reach the copy peak).
+template <int MODE, int CPT, bool VEC2, bool VECO>
 __global__ void __launch_bounds__(kPairThreads) pairwise_kernel(const PairArgs p) {
   extern __shared__ float4 smem4[];
   const int b = blockIdx.z;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(kPairThreads) pairwise_kernel(const PairArgs p
   float mnx = CUDART_INF_F, mny = CUDART_INF_F, mxx = -CUDART_INF_F, mxy = -CUDART_INF_F;
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
-    long long c = col0 + j * kPairThreads + t;
+    long long c = VECO ? (col0 + 4 * t + j) : (col0 + j * kPairThreads + t);
     ok[j] = c < p.M;
     bx[j] = ok[j] ? load_box<VEC2>(b2, c, p.ld2) : make_float4(0.f, 0.f, 0.f, 0.f);
     ar[j] = box_area(bx[j]);
@@ -106,9 +109,9 @@ __global__ void __launch_bounds__(kPairThreads) pairwise_kernel(const PairArgs p
   }
   const float bb0 = sbb[0], bb1 = sbb[1], bb2 = sbb[2], bb3 = sbb[3];
 
-  float* orow = out + (long long)row0 * p.M + col0 + t;
+  float* orow = out + (long long)row0 * p.ldo + col0 + (VECO ? 4 * t : t);
 #pragma unroll 2
-  for (int r = 0; r < rows; ++r, orow += p.M) {
+  for (int r = 0; r < rows; ++r, orow += p.ldo) {
     const float4 a = sbox[r];
     float v[CPT];
     bool live = true;
@@ -122,9 +125,14 @@ __global__ void __launch_bounds__(kPairThreads) pairwise_kernel(const PairArgs p
 #pragma unroll
       for (int j = 0; j < CPT; ++j) v[j] = 0.f;
     }
+    if (VECO) {
+      // columns >= M of the last quad land in the row padding (ldo is a multiple of 4)
+      if (ok[0]) *reinterpret_cast<float4*>(orow) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < CPT; ++j)
-      if (ok[j]) orow[j * kPairThreads] = v[j];
+      for (int j = 0; j < CPT; ++j)
+        if (ok[j]) orow[j * kPairThreads] = v[j];
+    }
   }
 }
 
@@ -143,10 +151,16 @@ static int launch_pairwise(const PairArgs& a0, int B, cudaStream_t st) {
   dim3 grid(col_tiles, row_tiles, B);
   size_t smem = (size_t)a.rows_per_cta * 20;
   const bool vec2 = (a.ld2 == 4) && aligned16(a.b2) && (a.bs2 % 4 == 0);
-  if (vec2)
-    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, true><<<grid, kPairThreads, smem, st>>>(a));
+  const bool veco = (a.ldo % 4 == 0) && aligned16(a.out) && (a.bs_out % 4 == 0) && a.ldo >= (long long)(a.M + 3) / 4 * 4;
+  static_assert(CPT == 4, "the 128-bit store path writes CPT == 4 columns");
+  if (vec2 && veco)
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, true, true><<<grid, kPairThreads, smem, st>>>(a));
+  else if (vec2)
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, true, false><<<grid, kPairThreads, smem, st>>>(a));
+  else if (veco)
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, false, true><<<grid, kPairThreads, smem, st>>>(a));
   else
-    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, false><<<grid, kPairThreads, smem, st>>>(a));
+    BDET_KERNEL("pairwise_kernel", st, pairwise_kernel<MODE, CPT, false, false><<<grid, kPairThreads, smem, st>>>(a));
   return BDET_OK;
 }
 
@@ -174,14 +188,15 @@ __global__ void __launch_bounds__(256) point_distance_kernel(const float2* __res
 using namespace bdet;
 
 extern "C" int bdet_pairwise_batched(const float* boxes1, int ld1, int64_t bs1, const int* n1_dev, int N,
-                                     const float* boxes2, int ld2, int64_t bs2, int M, float* out, int64_t bs_out,
-                                     int B, int mode, bdet_stream_t stream) {
+                                     const float* boxes2, int ld2, int64_t bs2, int M, float* out, int64_t ldo,
+                                     int64_t bs_out, int B, int mode, bdet_stream_t stream) {
   BDET_REQUIRE(N >= 0 && M >= 0 && B >= 0, "negative size");
   BDET_REQUIRE(ld1 >= 4 && ld2 >= 4, "boxes must have >= 4 columns");
   BDET_REQUIRE(mode >= BDET_PAIR_IOU && mode <= BDET_PAIR_GIOU, "unknown mode");
   if (N == 0 || M == 0 || B == 0) return BDET_OK;
   BDET_REQUIRE(boxes1 && boxes2 && out, "null argument");
-  PairArgs a{boxes1, boxes2, out, n1_dev, bs1, bs2, bs_out, ld1, ld2, N, M, 0};
+  BDET_REQUIRE(ldo >= M, "output row stride smaller than M");
+  PairArgs a{boxes1, boxes2, out, n1_dev, bs1, bs2, bs_out, ld1, ld2, N, M, 0, ldo};
   int rc;
   switch (mode) {
     case BDET_PAIR_IOU: rc = launch_pairwise<BDET_PAIR_IOU>(a, B, as_stream(stream)); break;
@@ -195,8 +210,8 @@ extern "C" int bdet_pairwise_batched(const float* boxes1, int ld1, int64_t bs1, 
 }
 
 extern "C" int bdet_pairwise(const float* boxes1, int ld1, int N, const float* boxes2, int ld2, int M, float* out,
-                             int mode, bdet_stream_t stream) {
-  return bdet_pairwise_batched(boxes1, ld1, 0, nullptr, N, boxes2, ld2, 0, M, out, 0, 1, mode, stream);
+                             int64_t ldo, int mode, bdet_stream_t stream) {
+  return bdet_pairwise_batched(boxes1, ld1, 0, nullptr, N, boxes2, ld2, 0, M, out, ldo, 0, 1, mode, stream);
 }
 
 extern "C" int bdet_box_center(const float* boxes, int ld, int N, float* out, bdet_stream_t stream) {

@@ -71,19 +71,25 @@ class DefaultAnchorGenerator(BaseAnchorGenerator):
                 base_anchors.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
         return base_anchors
 
+    def _plan(self, sizes):
+        key = tuple(tuple(int(v) for v in s) for s in sizes)
+        plans = self.__dict__.setdefault("_plans", {})
+        if key not in plans:
+            shifts = [self.offset * s for s in self.strides]
+            plans[key] = ops.AnchorPlan(key, self.strides, shifts, self.base_anchors)
+        return plans[key]
+
     def generate_anchors_by_features(self, sizes, device):
         assert len(sizes) == self.num_features, (
             "input features expected {}, got {}".format(self.num_features, len(sizes))
         )
-        shifts = [self.offset * s for s in self.strides]
-        return ops.anchors_grid(sizes, self.strides, shifts, self.base_anchors, device)
+        return ops.anchors_grid(None, None, None, None, device, plan=self._plan(sizes))
 
     def generate_all_level_anchors(self, sizes, device):
         """Extension: the level-concatenated (sum, 4) anchors (``F.concat(anchors_list)``, retinanet.py:128) with
         no extra copy -- the per-level tensors are views of this buffer."""
         assert len(sizes) == self.num_features
-        shifts = [self.offset * s for s in self.strides]
-        return ops.anchors_grid(sizes, self.strides, shifts, self.base_anchors, device, flat=True)
+        return ops.anchors_grid(None, None, None, None, device, flat=True, plan=self._plan(sizes))
 
 
 class AnchorPointGenerator(BaseAnchorGenerator):

@@ -77,25 +77,37 @@ def _workspace(nbytes, device):
 
 
 # ----------------------------------------------------------------------------- anchors
-def anchors_grid(sizes, strides, shifts, base_anchors, device, flat=False):
+class AnchorPlan:
+    """Host-side arguments of bdet_anchors_grid, built once per (feature sizes, generator) and reused every step
+    (the reference regenerates anchors every forward, retinanet.py:116; only the launch should cost)."""
+
+    def __init__(self, sizes, strides, shifts, base_anchors):
+        self.n = len(sizes)
+        counts = [int(h) * int(w) * len(b) for (h, w), b in zip(sizes, base_anchors)]
+        self.offs = [0]
+        for c in counts:
+            self.offs.append(self.offs[-1] + c)
+        self.hw = iarr([int(v) for hw_ in sizes for v in hw_])
+        self.strides = darr(strides)
+        self.shifts = darr(shifts)
+        self.n_base = iarr([len(b) for b in base_anchors])
+        self.base = farr([float(v) for b in base_anchors for row in b for v in row])
+        self.out_off = larr(self.offs[:-1])
+
+
+def anchors_grid(sizes, strides, shifts, base_anchors, device, flat=False, plan=None):
     """All levels in one launch.  base_anchors: list (per level) of (n_base, 4) float arrays (host).
     Returns the per-level list (views of one buffer), or that (sum, 4) buffer itself when ``flat``."""
     lib = _lib.load()
-    n = len(sizes)
-    counts = [int(h) * int(w) * len(b) for (h, w), b in zip(sizes, base_anchors)]
-    offs = [0]
-    for c in counts:
-        offs.append(offs[-1] + c)
-    out = torch.empty((offs[-1], 4), dtype=torch.float32, device=device)
-    hw = [int(v) for hw_ in sizes for v in hw_]
-    base_flat = [float(v) for b in base_anchors for row in b for v in row]
+    if plan is None:
+        plan = AnchorPlan(sizes, strides, shifts, base_anchors)
+    out = torch.empty((plan.offs[-1], 4), dtype=torch.float32, device=device)
     with _guard(out):
-        check(lib.bdet_anchors_grid(_p(out), n, iarr(hw), darr(strides), darr(shifts),
-                                    iarr([len(b) for b in base_anchors]), farr(base_flat), larr(offs[:-1]),
-                                    _stream(out)))
+        check(lib.bdet_anchors_grid(_p(out), plan.n, plan.hw, plan.strides, plan.shifts, plan.n_base, plan.base,
+                                    plan.out_off, _stream(out)))
     if flat:
         return out
-    return [out[offs[i]:offs[i + 1]] for i in range(n)]
+    return [out[plan.offs[i]:plan.offs[i + 1]] for i in range(plan.n)]
 
 
 def points_grid(sizes, strides, shifts, num_anchors, mode, device):
@@ -115,31 +127,41 @@ def points_grid(sizes, strides, shifts, num_anchors, mode, device):
 
 
 # ----------------------------------------------------------------------------- pairwise
+def _padded_rows(shape_prefix, M, device):
+    """(..., M) fp32 view whose rows start 16-byte aligned (row stride rounded up to 4 floats): lets the kernels
+    use 128-bit stores / loads.  Returns (view, row stride)."""
+    ldo = (M + 3) // 4 * 4
+    buf = torch.empty(tuple(shape_prefix) + (ldo,), dtype=torch.float32, device=device)
+    return buf[..., :M], ldo
+
+
 def pairwise(boxes1, boxes2, mode=_lib.PAIR_IOU):
+    """(N, >=4) x (M, >=4) -> (N, M).  The result is a view of a row-padded buffer when M % 4 != 0."""
     lib = _lib.load()
     b1, ld1 = _rows(boxes1, "boxes1")
     b2, ld2 = _rows(boxes2, "boxes2")
     N, M = b1.shape[0], b2.shape[0]
-    out = torch.empty((N, M), dtype=torch.float32, device=b1.device)
+    out, ldo = _padded_rows((N,), M, b1.device)
     with _guard(out):
-        check(lib.bdet_pairwise(_p(b1), ld1, N, _p(b2), ld2, M, _p(out), mode, _stream(out)))
+        check(lib.bdet_pairwise(_p(b1), ld1, N, _p(b2), ld2, M, _p(out), ldo, mode, _stream(out)))
     return out
 
 
 def pairwise_batched(gt, num_gt, anchors, mode=_lib.PAIR_IOU, out=None):
     """gt (B, Gmax, >=4) contiguous, num_gt (B,) int32 or None, anchors (A, 4) shared -> (B, Gmax, A).
-    Rows >= num_gt[b] are left untouched."""
+    Rows >= num_gt[b] are left untouched.  ``out`` may be a view made by ``_padded_rows``."""
     lib = _lib.load()
     gt = _f32c(gt, "gt")
     anchors = _f32c(anchors, "anchors")
     B, Gmax, ld = gt.shape
     A = anchors.shape[0]
     if out is None:
-        out = torch.empty((B, Gmax, A), dtype=torch.float32, device=gt.device)
+        out, _ = _padded_rows((B, Gmax), A, gt.device)
+    assert out.shape == (B, Gmax, A) and out.stride(2) == 1 and out.stride(0) == Gmax * out.stride(1)
     n1 = _i32c(num_gt, "num_gt") if num_gt is not None else None
     with _guard(out):
         check(lib.bdet_pairwise_batched(_p(gt), ld, Gmax * ld, _p(n1), Gmax, _p(anchors), 4, 0, A, _p(out),
-                                        Gmax * A, B, mode, _stream(out)))
+                                        out.stride(1), out.stride(0), B, mode, _stream(out)))
     return out
 
 
@@ -163,20 +185,25 @@ def point_distance(p1, p2):
 
 # ----------------------------------------------------------------------------- matcher
 def match(matrix, thresholds, labels, allow_low_quality=False, num_g=None):
-    """matrix (G, A) or (B, Gmax, A).  Returns (match_idx, labels) int32 of shape (A,) / (B, A)."""
+    """matrix (G, A) or (B, Gmax, A), rows may be padded (stride >= A).  Returns (match_idx, labels) int32 of shape
+    (A,) / (B, A)."""
     lib = _lib.load()
-    m = _f32c(matrix, "matrix")
+    m = _f32(matrix, "matrix")
     squeeze = m.ndim == 2
     if squeeze:
         m = m.unsqueeze(0)
     B, G, A = m.shape
+    if not (m.stride(2) == 1 and m.stride(1) >= A and (B == 1 or m.stride(0) >= G * m.stride(1))) and m.numel():
+        m = m.contiguous()
+    ld = m.stride(1) if G > 1 else max(A, 1)
+    bs = m.stride(0) if B > 1 else G * ld
     idx = torch.empty((B, A), dtype=torch.int32, device=m.device)
     lab = torch.empty((B, A), dtype=torch.int32, device=m.device)
     ws_bytes = lib.bdet_match_workspace(G, A, B)
     ws = _workspace(ws_bytes, m.device)
     gd = _i32c(num_g) if num_g is not None else None
     with _guard(m):
-        check(lib.bdet_match(_p(m), G * A, _p(gd), G, A, B, farr(thresholds), iarr(labels), len(labels),
+        check(lib.bdet_match(_p(m), ld, bs, _p(gd), G, A, B, farr(thresholds), iarr(labels), len(labels),
                              int(bool(allow_low_quality)), _p(idx), _p(lab), _p(ws), ws.numel(), _stream(m)))
     if squeeze:
         return idx[0], lab[0]

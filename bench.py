@@ -126,7 +126,7 @@ def run_b200(args):
     gt_d = torch.from_numpy(gt_np).to(dev)
     ng_d = torch.from_numpy(ng_np).to(dev)
     plan = ops.AssignPlan(A, G, B, dev)
-    iou_buf = torch.empty((B, G, A), dtype=torch.float32, device=dev) if args.path == "materialised" else None
+    iou_buf = ops._padded_rows((B, G), A, dev)[0] if args.path == "materialised" else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(gt, ng):

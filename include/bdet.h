@@ -67,29 +67,30 @@ int bdet_points_grid(float* out, int n_levels, const int* hw_host, const double*
  * box_ioa  structures/op_patch.py:169-227    (mode BDET_PAIR_IOA)
  * Boxes.intersection structures/boxes.py:114-130 (BDET_PAIR_INTER); Boxes.giou :74-95 (BDET_PAIR_GIOU)
  * boxes1: (N, >=4) with row stride ld1 floats; boxes2: (M, >=4) with row stride ld2 floats.
- * out: (N, M) row-major.  Batched form: batch b reads boxes1 + b*bs1, boxes2 + b*bs2 (bs2 = 0 shares
+ * out: (N, M) with row stride ldo >= M floats.  When ldo is a multiple of 4 (rows padded to 16 bytes) and out is
+ * 16-byte aligned the kernel writes 128-bit stores (up to 3 padding floats per row may be written).  Batched form: batch b reads boxes1 + b*bs1, boxes2 + b*bs2 (bs2 = 0 shares
  * boxes2), writes out + b*bs_out, and uses n1_dev[b] rows when n1_dev != NULL (rows >= n1_dev[b] untouched). */
 #define BDET_PAIR_IOU 0
 #define BDET_PAIR_IOA 1
 #define BDET_PAIR_INTER 2
 #define BDET_PAIR_GIOU 3
 int bdet_pairwise(const float* boxes1, int ld1, int N, const float* boxes2, int ld2, int M, float* out,
-                  int mode, bdet_stream_t stream);
+                  int64_t ldo, int mode, bdet_stream_t stream);
 int bdet_pairwise_batched(const float* boxes1, int ld1, int64_t bs1, const int* n1_dev, int N,
-                          const float* boxes2, int ld2, int64_t bs2, int M, float* out, int64_t bs_out,
-                          int B, int mode, bdet_stream_t stream);
+                          const float* boxes2, int ld2, int64_t bs2, int M, float* out, int64_t ldo,
+                          int64_t bs_out, int B, int mode, bdet_stream_t stream);
 /* box_center structures/op_patch.py:100-130: (N,4) -> (N,2);  point_distance :133-166: (N,2)x(M,2) -> (N,M) */
 int bdet_box_center(const float* boxes, int ld, int N, float* out, bdet_stream_t stream);
 int bdet_point_distance(const float* p1, int N, const float* p2, int M, float* out, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ a5: Matcher
  * Matcher.__call__  layers/common/matcher.py:31-51
- * matrix (G, A) fp32 [batched: (B, Gmax, A) with g_dev[b] valid rows, NULL -> Gmax].
+ * matrix (G, A) fp32 with row stride ld >= A [batched: (B, Gmax, A) with g_dev[b] valid rows, NULL -> Gmax].
  * thresholds_host: n_labels-1 user thresholds (the +-inf the constructor adds are implied);
  * labels_host: n_labels ints.  Outputs match_idx (B,A) int32 = first argmax over G, labels (B,A) int32.
  * Single pass over the matrix + a fix-up that re-reads only the row segments holding a row maximum. */
 size_t bdet_match_workspace(int Gmax, int A, int B);
-int bdet_match(const float* matrix, int64_t batch_stride, const int* g_dev, int Gmax, int A, int B,
+int bdet_match(const float* matrix, int64_t ld, int64_t batch_stride, const int* g_dev, int Gmax, int A, int B,
                const float* thresholds_host, const int* labels_host, int n_labels, int allow_low_quality,
                int* match_idx, int* labels, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 /* (R, G) layout used by RCNN.get_ground_truth  layers/head/rcnn.py:113-116: max / first argmax over axis 1.
@@ -221,6 +222,9 @@ int bdet_count_labels(const int* labels, int A, int B, int* counts, bdet_stream_
  * While profiling is on, every named kernel launch inside the library is bracketed by a CUDA event pair on the
  * launching stream.  bdet_profile_collect synchronises those events and returns the summed duration and the
  * number of launches whose kernel name matches `name` (NULL = all).  Off by default; thread-local. */
+/* Streaming probe: mode 0 write-only (st.v4), 1 read-only (ld.v4), 2 copy, 3 cudaMemsetAsync -- the device's
+ * write / read / copy HBM ceilings that the kernels' achieved GB/s are put next to (profiles/). */
+int bdet_bw_probe(void* dst, const void* src, size_t bytes, int mode, int ctas_per_sm, bdet_stream_t stream);
 int bdet_profile_begin(void);
 int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_host);
 int bdet_profile_end(void);

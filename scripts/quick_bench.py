@@ -29,7 +29,7 @@ gt_d, ng_d = T(gt), T(ng)
 print("A", A)
 res = {}
 res["anchors_grid_ms"] = timeit(lambda: ops.anchors_grid(sizes, W.RETINANET_STRIDES, [4, 8, 16, 32, 64], base, dev), flush=flush)
-iou = torch.empty((B, 100, A), dtype=torch.float32, device=dev)
+iou = ops._padded_rows((B, 100), A, dev)[0]
 res["iou_b16_ms"] = timeit(lambda: ops.pairwise_batched(gt_d, ng_d, anchors, out=iou), flush=flush)
 by = B * 100 * A * 4
 print("iou GB/s (median)", by / res["iou_b16_ms"][0] / 1e6)
@@ -43,7 +43,7 @@ res["assign_fused_b16_ms"] = timeit(lambda: ops.assign_targets(anchors, gt_d, ng
 res["assign_fused_nolq_b16_ms"] = timeit(lambda: ops.assign_targets(anchors, gt_d, ng_d, [0.4, 0.5], [0, -1, 1], False, True, plan=plan), flush=flush)
 print("fused img/s", B / res["assign_fused_b16_ms"][0] * 1e3, "bytes-based GB/s", B * A * 40 / res["assign_fused_b16_ms"][0] / 1e6)
 # single image variants
-iou1 = torch.empty((1, 100, A), dtype=torch.float32, device=dev)
+iou1 = ops._padded_rows((1, 100), A, dev)[0]
 res["iou_b1_ms"] = timeit(lambda: ops.pairwise_batched(gt_d[:1], ng_d[:1], anchors, out=iou1), flush=flush)
 res["match_b1_ms"] = timeit(lambda: ops.match(iou1, [0.4, 0.5], [0, -1, 1], True, num_g=ng_d[:1]), flush=flush)
 plan1 = ops.AssignPlan(A, 100, 1, dev)
@@ -61,3 +61,17 @@ res["cpu_oracle_iou_s"], res["cpu_oracle_match_s"] = t1 - t0, t2 - t1
 print(json.dumps(res, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/quick_bench.json", "w"), indent=1)
+# per-kernel breakdown via the library's event hooks
+ops.profile_begin()
+for _ in range(20):
+    flush.zero_()
+    ops.assign_targets(anchors, gt_d, ng_d, [0.4, 0.5], [0, -1, 1], True, True, plan=plan)
+    flush.zero_()
+    ops.pairwise_batched(gt_d, ng_d, anchors, out=iou)
+    flush.zero_()
+    ops.match(iou, [0.4, 0.5], [0, -1, 1], True, num_g=ng_d)
+torch.cuda.synchronize()
+for k in ("assign_main_kernel", "assign_lq_kernel", "pairwise_kernel", "match_colmax_kernel", "match_lq_kernel"):
+    ms, n = ops.profile_collect(k)
+    print("kernel %-22s avg %.2f us over %d launches" % (k, ms / max(n, 1) * 1e3, n))
+ops.profile_end()
