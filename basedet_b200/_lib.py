@@ -43,10 +43,14 @@ SIGNATURES = {
     "bdet_assign_targets": (c_int, [vp, c_int, vp, c_int, vp, c_int, fp, ip, c_int, c_int, c_int, fp, fp,
                                     vp, vp, vp, vp, c_size_t, vp]),
     "bdet_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),
-    "bdet_topk": (c_int, [vp, lp, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_topk": (c_int, [vp, lp, lp, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_score_filter_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),
-    "bdet_score_filter_topk": (c_int, [vp, vp, c_int, lp, c_int, c_float, c_int, c_int, vp, vp, vp, vp,
+    "bdet_score_filter_topk": (c_int, [vp, vp, c_int, lp, lp, lp, c_int, c_float, c_int, c_int, vp, vp, vp, vp,
                                        c_size_t, vp]),
+    "bdet_select_decode": (c_int, [POINTER(vp), POINTER(vp), ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,
+                                   fp, fp, vp, c_int, vp, vp, vp, vp, vp]),
+    "bdet_finalize_detections": (c_int, [vp, vp, vp, c_int, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp,
+                                         vp]),
     "bdet_scores": (c_int, [vp, vp, c_int, c_int64, c_int, vp, vp]),
     "bdet_nms_workspace": (c_size_t, [c_int, c_int]),
     "bdet_nms": (c_int, [vp, vp, vp, c_int, vp, c_int, c_int, c_float, c_int, vp, c_int, vp, vp, c_size_t, vp]),

@@ -1,0 +1,233 @@
+// Batched glue between top-k, NMS and the final detections (the per-image / per-level Python loops of the reference):
+//   select_decode_kernel : models/det/retinanet.py:193-196 / fcos.py:204-207 (label = idx % C, box = decode(...)[idx // C])
+//                          models/det/rpn.py:149-171 (decode, top-k gather, level ids, clip -> filter_by_size mask)
+//                          + level concat of layers/common/post_processing.py:63-67 / rpn.py:163-165
+//   finalize_kernel      : layers/common/post_processing.py:96-101 (gather kept, scale to the original image, clip)
+//                          and rpn.py:179-183 (rois = [batch, x1, y1, x2, y2])
+// Only the <= k selected candidates per (image, level) are decoded -- the reference decodes every anchor and then
+// gathers.  One CTA per image keeps the reference's ordering (levels in order, score-descending inside).
+#include "common.cuh"
+
+namespace bdet {
+
+constexpr int kDetThreads = 1024;
+
+struct SelectArgs {
+  const float* anchors[BDET_MAX_LEVELS];  // (n_l, 4) boxes or (n_l, 2) points
+  const float* deltas[BDET_MAX_LEVELS];   // (B, n_l, 4)
+  int n_l[BDET_MAX_LEVELS];
+  int L, B, k, div, coder, label_mode, filter;
+  const int* topk_idx;     // (B, L, k) flat index within the (image, level) segment
+  const float* topk_val;   // (B, L, k)
+  const int* topk_cnt;     // (B, L)
+  const float* im_info;    // (B, info_ld): [h, w, ...] used by the size filter
+  int info_ld;
+  Vec4 mean, stdv;
+  float* boxes;   // (B, L*k, 4)
+  float* scores;  // (B, L*k)
+  void* labels;   // (B, L*k) int32 (label_mode 0) or fp32 level ids (label_mode 1)
+  int* count;     // (B)
+};
+
+__device__ __forceinline__ float4 decode_one(const SelectArgs& p, int l, int b, int a) {
+  const float4 d = ldg4(p.deltas[l] + ((long long)b * p.n_l[l] + a) * 4);
+  if (p.coder == 1) {  // PointCoder.decode, structures/boxcoder.py:135-141
+    const float2 pt = __ldg(reinterpret_cast<const float2*>(p.anchors[l]) + a);
+    return make_float4(pt.x - d.x, pt.y - d.y, pt.x + d.z, pt.y + d.w);
+  }
+  const float4 an = ldg4(p.anchors[l] + (long long)a * 4);  // BoxCoder.decode, structures/boxcoder.py:75-98
+  const float dx = d.x * p.stdv.v[0] + p.mean.v[0], dy = d.y * p.stdv.v[1] + p.mean.v[1];
+  const float dw = d.z * p.stdv.v[2] + p.mean.v[2], dh = d.w * p.stdv.v[3] + p.mean.v[3];
+  const float aw = an.z - an.x, ah = an.w - an.y;
+  const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+  const float pcx = acx + dx * aw, pcy = acy + dy * ah;
+  const float pw = aw * expf(dw), ph = ah * expf(dh);
+  const float hw = 0.5f * pw, hh = 0.5f * ph;
+  return make_float4(pcx - hw, pcy - hh, pcx + hw, pcy + hh);
+}
+
+__global__ void __launch_bounds__(kDetThreads) select_decode_kernel(const SelectArgs p) {
+  __shared__ int warp_cnt[kDetThreads / 32];
+  __shared__ int sbase;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long cap = (long long)p.L * p.k;
+  float4* ob = reinterpret_cast<float4*>(p.boxes) + b * cap;
+  float* os = p.scores + b * cap;
+  if (t == 0) sbase = 0;
+  __syncthreads();
+  float ih = 0.f, iw = 0.f;
+  if (p.filter) {
+    ih = __ldg(p.im_info + (long long)b * p.info_ld);
+    iw = __ldg(p.im_info + (long long)b * p.info_ld + 1);
+  }
+  for (int l = 0; l < p.L; ++l) {
+    const int seg = b * p.L + l;
+    const int cnt = min(p.topk_cnt[seg], p.k);
+    for (int j0 = 0; j0 < cnt; j0 += kDetThreads) {
+      const int j = j0 + t;
+      bool keep = j < cnt;
+      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      int idx = 0;
+      if (keep) {
+        idx = __ldg(p.topk_idx + (long long)seg * p.k + j);
+        bx = decode_one(p, l, b, idx / p.div);
+        if (p.filter) {
+          // rpn.py:168-169: Boxes(proposals).clip(im_info[:2]).filter_by_size(): (h > 0) & (w > 0) of the CLIPPED
+          // box; the proposal itself keeps its un-clipped coordinates
+          const float x1 = fminf(fmaxf(bx.x, 0.f), iw), y1 = fminf(fmaxf(bx.y, 0.f), ih);
+          const float x2 = fminf(fmaxf(bx.z, 0.f), iw), y2 = fminf(fmaxf(bx.w, 0.f), ih);
+          keep = (y2 - y1 > 0.f) && (x2 - x1 > 0.f);
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) warp_cnt[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < kDetThreads / 32; ++w) {
+        const int c = warp_cnt[w];
+        if (w < warp) before += c;
+        total += c;
+      }
+      const int base = sbase;
+      if (keep) {
+        const long long o = base + before + __popc(bal & ((1u << lane) - 1u));
+        ob[o] = bx;
+        os[o] = __ldg(p.topk_val + (long long)seg * p.k + j);
+        if (p.label_mode == 0)
+          reinterpret_cast<int*>(p.labels)[b * cap + o] = idx % p.div;   // retinanet.py:194
+        else
+          reinterpret_cast<float*>(p.labels)[b * cap + o] = (float)l;    // rpn.py:160 F.full_like(scores, level)
+      }
+      __syncthreads();
+      if (t == 0) sbase = base + total;
+      __syncthreads();
+    }
+  }
+  if (t == 0) p.count[b] = sbase;
+}
+
+struct FinalArgs {
+  const float* boxes;   // (B, N, 4)
+  const float* scores;  // (B, N)
+  const void* labels;   // (B, N) int32 / fp32
+  const int* keep;      // (B, keep_ld)
+  const int* keep_count;
+  const float* im_info;  // (B, info_ld) [h, w, orig_h, orig_w, ...] or NULL
+  int info_ld, N, keep_ld, max_out, mode, labels_float, B;
+  float* out;  // mode 0: (B, max_out, 6) [x1,y1,x2,y2,score,label]; mode 1: (B, max_out, 5) [batch,x1,y1,x2,y2]
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs p) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.max_out) return;
+  const int cnt = min(p.keep_count[b], p.max_out);
+  const int row = p.mode == 0 ? 6 : 5;
+  float* o = p.out + ((long long)b * p.max_out + j) * row;
+  if (j >= cnt) {
+    for (int q = 0; q < row; ++q) o[q] = 0.f;
+    return;
+  }
+  const int src = p.keep[(long long)b * p.keep_ld + j];
+  float4 bx = ldg4(p.boxes + ((long long)b * p.N + src) * 4);
+  if (p.mode == 0) {
+    if (p.im_info) {
+      const float* info = p.im_info + (long long)b * p.info_ld;
+      // post_processing.py:99-101: scale ratios (orig / resized) then clip to the original image
+      const float sh = __fdiv_rn(info[2], info[0]), sw = __fdiv_rn(info[3], info[1]);
+      bx.x *= sw;
+      bx.y *= sh;
+      bx.z *= sw;
+      bx.w *= sh;
+      const float ch = info[2], cw = info[3];
+      bx.x = fminf(fmaxf(bx.x, 0.f), cw);
+      bx.y = fminf(fmaxf(bx.y, 0.f), ch);
+      bx.z = fminf(fmaxf(bx.z, 0.f), cw);
+      bx.w = fminf(fmaxf(bx.w, 0.f), ch);
+    }
+    o[0] = bx.x;
+    o[1] = bx.y;
+    o[2] = bx.z;
+    o[3] = bx.w;
+    o[4] = p.scores[(long long)b * p.N + src];
+    o[5] = p.labels_float ? reinterpret_cast<const float*>(p.labels)[(long long)b * p.N + src]
+                          : (float)reinterpret_cast<const int*>(p.labels)[(long long)b * p.N + src];
+  } else {
+    o[0] = (float)b;  // rpn.py:181-182: F.full((n, 1), bid) ++ proposals
+    o[1] = bx.x;
+    o[2] = bx.y;
+    o[3] = bx.z;
+    o[4] = bx.w;
+  }
+}
+
+}  // namespace bdet
+
+using namespace bdet;
+
+extern "C" int bdet_select_decode(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host, int L,
+                                  int B, int k, int div, int coder, int label_mode, const int* topk_idx,
+                                  const float* topk_val, const int* topk_cnt, const float* mean_host, const float* std_host,
+                                  const float* im_info, int info_ld, float* boxes, float* scores, void* labels, int* count,
+                                  bdet_stream_t stream) {
+  BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && k >= 0 && div >= 1, "bad sizes");
+  BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
+  BDET_REQUIRE(label_mode == 0 || label_mode == 1, "label_mode must be 0 (idx % div) or 1 (level id)");
+  if (B == 0) return BDET_OK;
+  BDET_REQUIRE(count, "null count");
+  cudaStream_t st = as_stream(stream);
+  if (k == 0) {
+    BDET_CUDA(cudaMemsetAsync(count, 0, (size_t)B * 4, st));
+    return BDET_OK;
+  }
+  BDET_REQUIRE(anchors_host && deltas_host && n_l_host && topk_idx && topk_val && topk_cnt && boxes && scores && labels,
+               "null argument");
+  BDET_REQUIRE(aligned16(boxes), "boxes must be 16-byte aligned");
+  BDET_REQUIRE(!im_info || info_ld >= 2, "im_info rows need at least [h, w]");
+  SelectArgs a;
+  for (int l = 0; l < L; ++l) {
+    BDET_REQUIRE(anchors_host[l] && deltas_host[l] && aligned16(deltas_host[l]), "null / unaligned level pointer");
+    a.anchors[l] = anchors_host[l];
+    a.deltas[l] = deltas_host[l];
+    a.n_l[l] = n_l_host[l];
+  }
+  a.L = L;
+  a.B = B;
+  a.k = k;
+  a.div = div;
+  a.coder = coder;
+  a.label_mode = label_mode;
+  a.filter = im_info != nullptr;
+  a.topk_idx = topk_idx;
+  a.topk_val = topk_val;
+  a.topk_cnt = topk_cnt;
+  a.im_info = im_info;
+  a.info_ld = info_ld;
+  for (int i = 0; i < 4; ++i) {
+    a.mean.v[i] = mean_host ? mean_host[i] : 0.f;
+    a.stdv.v[i] = std_host ? std_host[i] : 1.f;
+  }
+  a.boxes = boxes;
+  a.scores = scores;
+  a.labels = labels;
+  a.count = count;
+  BDET_KERNEL("select_decode_kernel", st, select_decode_kernel<<<B, kDetThreads, 0, st>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_finalize_detections(const float* boxes, const float* scores, const void* labels, int labels_is_float, int N,
+                                        const int* keep, int keep_ld, const int* keep_count, const float* im_info, int info_ld,
+                                        int B, int max_out, int mode, float* out, bdet_stream_t stream) {
+  BDET_REQUIRE(B >= 0 && max_out >= 0 && N >= 0 && (mode == 0 || mode == 1), "bad arguments");
+  if (B == 0 || max_out == 0) return BDET_OK;
+  BDET_REQUIRE(boxes && keep && keep_count && out && (mode == 1 || (scores && labels)), "null argument");
+  BDET_REQUIRE(aligned16(boxes), "boxes must be 16-byte aligned");
+  BDET_REQUIRE(!im_info || info_ld >= 4, "im_info rows need [h, w, orig_h, orig_w]");
+  BDET_REQUIRE(B <= 65535, "B > 65535");
+  FinalArgs a{boxes, scores, labels, keep, keep_count, im_info, info_ld, N, keep_ld, max_out, mode, labels_is_float, B, out};
+  BDET_KERNEL("finalize_kernel", as_stream(stream),
+              finalize_kernel<<<dim3(ceil_div(max_out, 256), B), 256, 0, as_stream(stream)>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}

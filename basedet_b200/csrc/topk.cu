@@ -22,6 +22,16 @@ constexpr int kSelThreads = 1024;
 constexpr int kBufCap = 4096;  // candidate keys buffered in shared memory once a radix bucket is this small
 constexpr int kMaxK = 16384;
 
+// One (image, level) segment.  Segments may live in different allocations: `start` is an element offset from the
+// base pointer handed to the entry point (any fp32 device address is base + 4*start for some start).
+struct SegDesc {
+  long long start;      // first element, relative to the scores / logits base pointer
+  long long key_off;    // first slot of this segment in the candidate-key buffer
+  long long ctr_start;  // FCOS: ctrness index of element 0
+  int len;
+  int tile_start;       // first filter tile of this segment
+};
+
 struct RawSrc {
   const float* s;
   __device__ __forceinline__ uint64_t key(int i) const { return make_key(__ldg(s + i), (uint32_t)i); }
@@ -127,7 +137,7 @@ struct SelArgs {
   const float* scores;        // RAW source (may be nullptr)
   const uint64_t* keys;       // candidate keys (filter path)
   const int* cand_count;      // per segment candidate count (filter path) or nullptr
-  const long long* seg_off;   // device (n_seg + 1)
+  const SegDesc* seg;         // device (n_seg + 1)
   float* out_vals;
   int* out_idx;
   int* out_count;
@@ -141,8 +151,8 @@ __global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs 
   uint64_t* buf = sortbuf + p.P;                          // kBufCap
   __shared__ SelSmem sm;
   const int s = blockIdx.x, t = threadIdx.x;
-  const long long off = p.seg_off[s];
-  const int n = RAW ? (int)(p.seg_off[s + 1] - off) : p.cand_count[s];
+  const long long off = RAW ? p.seg[s].start : p.seg[s].key_off;
+  const int n = RAW ? p.seg[s].len : p.cand_count[s];
   const int k = min(p.k, n);
   if (t == 0) {
     p.out_count[s] = k;
@@ -176,9 +186,8 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.f, 1.f 
 
 struct FilterArgs {
   const float* logits;
-  const float* ctr;           // FCOS: one per C logits, indexed (off + i) / C
-  const long long* seg_off;   // device (n_seg + 1)
-  const int* tile_start;      // device (n_seg + 1): prefix of per-segment tile counts
+  const float* ctr;           // FCOS: one value per C logits
+  const SegDesc* seg;         // device (n_seg + 1); seg[n_seg].tile_start = total tiles
   uint64_t* keys;
   int* cand_count;
   float* scores_out;          // optional dense score output (bdet_scores)
@@ -190,7 +199,7 @@ constexpr int kFiltThreads = 256;
 constexpr int kFiltVec = 4;                               // float4 per thread per tile
 constexpr int kFiltTile = kFiltThreads * kFiltVec * 4;    // 4096 elements
 
-__device__ __forceinline__ bool eval_score(const FilterArgs& p, float x, long long gi, float& s) {
+__device__ __forceinline__ bool eval_score(const FilterArgs& p, float x, long long ci, float& s) {
   if (p.mode == BDET_SCORE_SIGMOID) {
     if (!(x > p.pre)) return false;
     s = sigmoid_f(x);
@@ -198,7 +207,7 @@ __device__ __forceinline__ bool eval_score(const FilterArgs& p, float x, long lo
     // fcos.py:194: sqrt(sigmoid(cls) * sigmoid(ctr)); score <= sqrt(sigmoid(cls)) so the same pre-filter on
     // sigmoid(cls) > thr^2 holds (p.pre = logit(thr^2) - margin)
     if (!(x > p.pre)) return false;
-    float sc = sigmoid_f(__ldg(p.ctr + gi / p.C));
+    float sc = sigmoid_f(__ldg(p.ctr + ci));
     s = sqrtf(sigmoid_f(x) * sc);
   } else {
     s = x;
@@ -213,14 +222,15 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
   const int tile = blockIdx.x;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
-    if (p.tile_start[mid] <= tile) lo = mid; else hi = mid;
+    if (p.seg[mid].tile_start <= tile) lo = mid; else hi = mid;
   }
   const int s = lo;
-  const long long off = p.seg_off[s];
-  const int n = (int)(p.seg_off[s + 1] - off);
-  const int e0 = (tile - p.tile_start[s]) * kFiltTile;
-  const float* src = p.logits + off;
-  uint64_t* keys = p.keys + off;
+  const SegDesc sd = p.seg[s];
+  const int n = sd.len;
+  const int e0 = (tile - sd.tile_start) * kFiltTile;
+  const float* src = p.logits + sd.start;
+  const long long coff = sd.ctr_start;
+  uint64_t* keys = p.keys + sd.key_off;
   int* counter = p.cand_count + s;
   const int t = threadIdx.x;
   if (VEC) {
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float sc = 0.f;
-        bool pass = (e + q < n) && eval_score(p, x[q], off + e + q, sc);
+        bool pass = (e + q < n) && eval_score(p, x[q], coff + (e + q) / p.C, sc);
         int slot = append_slot(counter, pass);
         if (pass) keys[slot] = make_key(sc, (uint32_t)(e + q));
       }
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
       int e = e0 + j * kFiltThreads + t;
       float x = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
       float sc = 0.f;
-      bool pass = (e < n) && eval_score(p, x, off + e, sc);
+      bool pass = (e < n) && eval_score(p, x, coff + e / p.C, sc);
       int slot = append_slot(counter, pass);
       if (pass) keys[slot] = make_key(sc, (uint32_t)e);
     }
@@ -274,8 +284,7 @@ __global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ l
 }
 
 struct TopkWs {
-  long long* seg_off;
-  int* tile_start;
+  SegDesc* seg;
   int* cand_count;
   uint64_t* keys;
   size_t bytes;
@@ -284,16 +293,41 @@ static TopkWs carve_ws(void* base, int64_t total, int n_seg, bool with_keys) {
   TopkWs w;
   char* p = reinterpret_cast<char*>(base);
   size_t o = 0;
-  w.seg_off = reinterpret_cast<long long*>(p + o);
-  o += align_up((size_t)(n_seg + 1) * 8, 256);
-  w.tile_start = reinterpret_cast<int*>(p + o);
-  o += align_up((size_t)(n_seg + 1) * 4, 256);
+  w.seg = reinterpret_cast<SegDesc*>(p + o);
+  o += align_up((size_t)(n_seg + 1) * sizeof(SegDesc), 256);
   w.cand_count = reinterpret_cast<int*>(p + o);
   o += align_up((size_t)n_seg * 4, 256);
   w.keys = reinterpret_cast<uint64_t*>(p + o);
   if (with_keys) o += align_up((size_t)total * 8, 256);
   w.bytes = o + 256;
   return w;
+}
+
+constexpr int kMaxSeg = 4096;
+
+// Host-side descriptor table; returns total length (or -1 after set_error).
+static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t* len, const int64_t* ctr_start, int C,
+                              int n_seg, bool* vec_ok, const char* who) {
+  int64_t total = 0;
+  int tiles = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    if (len[s] < 0 || len[s] > 0x7fffffffLL) {
+      set_error(BDET_EINVAL, "%s: segment length out of range", who);
+      return -1;
+    }
+    host[s].start = start[s];
+    host[s].key_off = total;
+    host[s].ctr_start = ctr_start ? ctr_start[s] : start[s] / C;
+    host[s].len = (int)len[s];
+    host[s].tile_start = tiles;
+    if (start[s] % 4 != 0) *vec_ok = false;
+    total += len[s];
+    tiles += ceil_div(len[s], kFiltTile);
+  }
+  host[n_seg].start = host[n_seg].key_off = host[n_seg].ctr_start = 0;
+  host[n_seg].len = 0;
+  host[n_seg].tile_start = tiles;
+  return total;
 }
 
 template <bool RAW>
@@ -319,75 +353,61 @@ extern "C" size_t bdet_score_filter_topk_workspace(int64_t total, int n_seg, int
   return carve_ws(nullptr, total < 0 ? 0 : total, n_seg < 1 ? 1 : n_seg, true).bytes;
 }
 
-static int check_segments(const int64_t* seg, int n_seg, const char* who) {
-  for (int s = 0; s < n_seg; ++s) {
-    if (seg[s + 1] < seg[s]) return set_error(BDET_EINVAL, "%s: segment offsets must be non-decreasing", who);
-    if (seg[s + 1] - seg[s] > 0x7fffffffLL) return set_error(BDET_EUNSUPPORTED, "%s: segment longer than 2^31-1", who);
-  }
-  return BDET_OK;
-}
-
-extern "C" int bdet_topk(const float* scores, const int64_t* seg_offset_host, int n_seg, int k, float* out_vals,
-                         int* out_idx, int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+extern "C" int bdet_topk(const float* scores, const int64_t* seg_start_host, const int64_t* seg_len_host, int n_seg, int k,
+                         float* out_vals, int* out_idx, int* out_count, void* workspace, size_t workspace_bytes,
+                         bdet_stream_t stream) {
   BDET_REQUIRE(n_seg >= 0 && k >= 0, "negative size");
   if (n_seg == 0) return BDET_OK;
-  BDET_REQUIRE(seg_offset_host && out_count, "null argument");
+  BDET_REQUIRE(seg_start_host && seg_len_host && out_count, "null argument");
   BDET_REQUIRE(k == 0 || (out_vals && out_idx), "null output");
   if (k > kMaxK) return set_error(BDET_EUNSUPPORTED, "bdet_topk: k > %d", kMaxK);
-  int rc = check_segments(seg_offset_host, n_seg, "bdet_topk");
-  if (rc) return rc;
-  const int64_t total = seg_offset_host[n_seg];
+  if (n_seg > kMaxSeg) return set_error(BDET_EUNSUPPORTED, "bdet_topk: more than %d segments", kMaxSeg);
+  static thread_local SegDesc host[kMaxSeg + 1];
+  bool vec = true;
+  const int64_t total = build_segments(host, seg_start_host, seg_len_host, nullptr, 1, n_seg, &vec, "bdet_topk");
+  if (total < 0) return BDET_EINVAL;
   BDET_REQUIRE(total == 0 || scores, "null scores");
   TopkWs w = carve_ws(workspace, total, n_seg, false);
   if (!workspace || workspace_bytes < w.bytes) return set_error(BDET_EWORKSPACE, "bdet_topk: workspace needs %zu bytes", w.bytes);
   BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
   cudaStream_t st = as_stream(stream);
-  BDET_CUDA(cudaMemcpyAsync(w.seg_off, seg_offset_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
-  SelArgs a{scores, nullptr, nullptr, w.seg_off, out_vals, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
-  rc = launch_select<true>(a, n_seg, st);
+  BDET_CUDA(cudaMemcpyAsync(w.seg, host, (size_t)(n_seg + 1) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+  SelArgs a{scores, nullptr, nullptr, w.seg, out_vals, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
+  int rc = launch_select<true>(a, n_seg, st);
   if (rc) return rc;
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
 
-extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_offset_host,
-                                      int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
-                                      int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_start_host,
+                                      const int64_t* seg_len_host, const int64_t* ctr_start_host, int n_seg, float threshold,
+                                      int k, int mode, float* out_scores, int* out_idx, int* out_count, void* workspace,
+                                      size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(n_seg >= 0 && k >= 0 && C >= 1, "bad size");
   BDET_REQUIRE(mode >= BDET_SCORE_RAW && mode <= BDET_SCORE_FCOS, "unknown mode");
   BDET_REQUIRE(mode != BDET_SCORE_FCOS || ctrness, "FCOS mode needs ctrness");
   if (n_seg == 0) return BDET_OK;
-  BDET_REQUIRE(seg_offset_host && out_count, "null argument");
+  BDET_REQUIRE(seg_start_host && seg_len_host && out_count, "null argument");
   BDET_REQUIRE(k == 0 || (out_scores && out_idx), "null output");
   if (k > kMaxK) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: k > %d", kMaxK);
-  int rc = check_segments(seg_offset_host, n_seg, "bdet_score_filter_topk");
-  if (rc) return rc;
-  const int64_t total = seg_offset_host[n_seg];
+  if (n_seg > kMaxSeg) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: more than %d segments", kMaxSeg);
+  static thread_local SegDesc host[kMaxSeg + 1];
+  bool vec = aligned16(logits);
+  const int64_t total = build_segments(host, seg_start_host, seg_len_host, ctr_start_host, C, n_seg, &vec, "bdet_score_filter_topk");
+  if (total < 0) return BDET_EINVAL;
   BDET_REQUIRE(total == 0 || logits, "null logits");
   TopkWs w = carve_ws(workspace, total, n_seg, true);
   if (!workspace || workspace_bytes < w.bytes)
     return set_error(BDET_EWORKSPACE, "bdet_score_filter_topk: workspace needs %zu bytes", w.bytes);
   BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
   cudaStream_t st = as_stream(stream);
-  // tile table (host) -> device
-  static thread_local int tile_host[4096];
-  if (n_seg + 1 > 4096) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: more than 4095 segments");
-  bool vec = aligned16(logits);
-  tile_host[0] = 0;
-  for (int s = 0; s < n_seg; ++s) {
-    int64_t n = seg_offset_host[s + 1] - seg_offset_host[s];
-    tile_host[s + 1] = tile_host[s] + ceil_div(n, kFiltTile);
-    if (seg_offset_host[s] % 4 != 0) vec = false;
-  }
-  const int tiles = tile_host[n_seg];
-  BDET_CUDA(cudaMemcpyAsync(w.seg_off, seg_offset_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
-  BDET_CUDA(cudaMemcpyAsync(w.tile_start, tile_host, (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+  const int tiles = host[n_seg].tile_start;
+  BDET_CUDA(cudaMemcpyAsync(w.seg, host, (size_t)(n_seg + 1) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
   BDET_CUDA(cudaMemsetAsync(w.cand_count, 0, (size_t)n_seg * 4, st));
   FilterArgs f;
   f.logits = logits;
   f.ctr = ctrness;
-  f.seg_off = w.seg_off;
-  f.tile_start = w.tile_start;
+  f.seg = w.seg;
   f.keys = w.keys;
   f.cand_count = w.cand_count;
   f.scores_out = nullptr;
@@ -412,8 +432,8 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     else
       BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false><<<tiles, kFiltThreads, 0, st>>>(f));
   }
-  SelArgs a{nullptr, w.keys, w.cand_count, w.seg_off, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
-  rc = launch_select<false>(a, n_seg, st);
+  SelArgs a{nullptr, w.keys, w.cand_count, w.seg, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
+  int rc = launch_select<false>(a, n_seg, st);
   if (rc) return rc;
   BDET_LAUNCH_CHECK();
   return BDET_OK;

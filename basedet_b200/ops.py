@@ -376,27 +376,49 @@ def assign_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_low_qual
 
 
 # ----------------------------------------------------------------------------- score filter + top-k
-def _seg_offsets(seg_lengths):
-    offs = [0]
-    for n in seg_lengths:
-        offs.append(offs[-1] + int(n))
-    return offs
+def _segments(tensors, per_image_len=None):
+    """Describe (image, level) segments that live in several tensors as element offsets from one base pointer.
+
+    tensors: list of L fp32 CUDA tensors, each (B, n_l) contiguous (flattened trailing dims).  Segment s = b*L + l
+    (image-major) covers tensors[l][b].  Returns (base_tensor, starts, lens)."""
+    base = min(tensors, key=lambda t: t.data_ptr())
+    starts, lens = [], []
+    B = tensors[0].shape[0]
+    for b in range(B):
+        for t in tensors:
+            n = t[0].numel()
+            diff = t.data_ptr() - base.data_ptr()
+            assert diff % 4 == 0
+            starts.append(diff // 4 + b * n)
+            lens.append(n)
+    return base, starts, lens
 
 
 def topk_segments(scores, seg_lengths, k):
     """scores: flat fp32 tensor holding the segments back to back.  Returns (vals (S,k), idx (S,k), count (S,)):
     per segment the min(k, n_s) largest scores sorted by (score desc, index asc); idx is within the segment."""
-    lib = _lib.load()
     s = _f32c(scores, "scores").reshape(-1)
-    offs = _seg_offsets(seg_lengths)
-    assert offs[-1] == s.numel()
-    S = len(seg_lengths)
-    vals = torch.empty((S, k), dtype=torch.float32, device=s.device)
-    idx = torch.empty((S, k), dtype=torch.int32, device=s.device)
-    cnt = torch.empty((S,), dtype=torch.int32, device=s.device)
-    ws = _workspace(lib.bdet_topk_workspace(offs[-1], S, k), s.device)
-    with _guard(s):
-        check(lib.bdet_topk(_p(s), larr(offs), S, int(k), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(s)))
+    starts = [0]
+    for n in seg_lengths[:-1]:
+        starts.append(starts[-1] + int(n))
+    assert sum(int(n) for n in seg_lengths) == s.numel()
+    return topk_raw(s, starts if seg_lengths else [], list(seg_lengths), k)
+
+
+def topk_raw(base, starts, lens, k, out=None, workspace=None):
+    """Low-level form: segments given as element offsets from ``base`` (see ``_segments``)."""
+    lib = _lib.load()
+    S = len(lens)
+    dev = base.device
+    if out is None:
+        out = (torch.empty((S, k), dtype=torch.float32, device=dev), torch.empty((S, k), dtype=torch.int32, device=dev),
+               torch.empty((S,), dtype=torch.int32, device=dev))
+    vals, idx, cnt = out
+    need = lib.bdet_topk_workspace(sum(int(n) for n in lens), S, k)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+    with _guard(base):
+        check(lib.bdet_topk(_p(base), larr(starts), larr(lens), S, int(k), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(),
+                            _stream(base)))
     return vals, idx, cnt
 
 
@@ -405,20 +427,31 @@ def score_filter_topk(logits, seg_lengths, threshold, k, mode=_lib.SCORE_SIGMOID
     """Fused score -> (score > threshold) -> top-k per segment (retinanet.py:181-191 / fcos.py:194-202).
     logits flat fp32 (segments back to back); ctrness (FCOS) has one value per `num_classes` logits.
     Returns (scores (S,k), idx (S,k) flat index within the segment, count (S,))."""
-    lib = _lib.load()
     lg = _f32c(logits, "logits").reshape(-1)
-    offs = _seg_offsets(seg_lengths)
-    assert offs[-1] == lg.numel()
-    S = len(seg_lengths)
+    starts = [0]
+    for n in seg_lengths[:-1]:
+        starts.append(starts[-1] + int(n))
+    assert sum(int(n) for n in seg_lengths) == lg.numel()
     ct = _f32c(ctrness, "ctrness").reshape(-1) if ctrness is not None else None
-    vals = torch.empty((S, k), dtype=torch.float32, device=lg.device)
-    idx = torch.empty((S, k), dtype=torch.int32, device=lg.device)
-    cnt = torch.empty((S,), dtype=torch.int32, device=lg.device)
-    need = lib.bdet_score_filter_topk_workspace(offs[-1], S, k)
-    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, lg.device)
-    with _guard(lg):
-        check(lib.bdet_score_filter_topk(_p(lg), _p(ct), int(num_classes), larr(offs), S, float(threshold), int(k),
-                                         int(mode), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(lg)))
+    return score_filter_topk_raw(lg, starts if seg_lengths else [], list(seg_lengths), threshold, k, mode, ct, None,
+                                 num_classes, workspace=workspace)
+
+
+def score_filter_topk_raw(base, starts, lens, threshold, k, mode, ctr_base=None, ctr_starts=None, num_classes=1,
+                          out=None, workspace=None):
+    lib = _lib.load()
+    S = len(lens)
+    dev = base.device
+    if out is None:
+        out = (torch.empty((S, k), dtype=torch.float32, device=dev), torch.empty((S, k), dtype=torch.int32, device=dev),
+               torch.empty((S,), dtype=torch.int32, device=dev))
+    vals, idx, cnt = out
+    need = lib.bdet_score_filter_topk_workspace(sum(int(n) for n in lens), S, k)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+    with _guard(base):
+        check(lib.bdet_score_filter_topk(_p(base), _p(ctr_base), int(num_classes), larr(starts), larr(lens),
+                                         larr(ctr_starts) if ctr_starts is not None else None, S, float(threshold), int(k),
+                                         int(mode), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(base)))
     return vals, idx, cnt
 
 
@@ -429,6 +462,45 @@ def scores(logits, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1):
     out = torch.empty_like(lg)
     with _guard(lg):
         check(lib.bdet_scores(_p(lg), _p(ct), int(num_classes), lg.numel(), int(mode), _p(out), _stream(lg)))
+    return out
+
+
+def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0, 0, 0, 0), std=(1, 1, 1, 1), im_info=None):
+    """anchors: L tensors (n_l, 4|2); deltas: L tensors (B, n_l, 4); topk = (vals, idx, cnt) with segment s = b*L + l.
+    Returns boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k) [int32 or fp32 level ids], count (B,)."""
+    lib = _lib.load()
+    L = len(anchors)
+    anc = [_f32c(a) for a in anchors]
+    dl = [_f32c(d) for d in deltas]
+    B = dl[0].shape[0]
+    vals, idx, cnt = topk
+    dev = dl[0].device
+    boxes = torch.empty((B, L * k, 4), dtype=torch.float32, device=dev)
+    sc = torch.empty((B, L * k), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, L * k), dtype=torch.float32 if label_mode == 1 else torch.int32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    ap = (ctypes.c_void_p * L)(*[a.data_ptr() for a in anc])
+    dp_ = (ctypes.c_void_p * L)(*[d.data_ptr() for d in dl])
+    info = _f32c(im_info) if im_info is not None else None
+    with _guard(boxes):
+        check(lib.bdet_select_decode(ap, dp_, iarr([a.shape[0] for a in anc]), L, B, int(k), int(div), int(coder),
+                                     int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
+                                     info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels), _p(count),
+                                     _stream(boxes)))
+    return boxes, sc, labels, count
+
+
+def finalize_detections(boxes, scores_, labels, keep, keep_count, max_out, im_info=None, mode=0):
+    """mode 0 -> (B, max_out, 6) [x1,y1,x2,y2,score,label] scaled/clipped by im_info; mode 1 -> (B, max_out, 5) rois."""
+    lib = _lib.load()
+    B, N = boxes.shape[0], boxes.shape[1]
+    out = torch.empty((B, max_out, 6 if mode == 0 else 5), dtype=torch.float32, device=boxes.device)
+    info = _f32c(im_info) if im_info is not None else None
+    lf = labels is not None and labels.dtype.is_floating_point
+    with _guard(boxes):
+        check(lib.bdet_finalize_detections(_p(boxes), _p(scores_), _p(labels), int(lf), N, _p(keep), keep.shape[1],
+                                           _p(keep_count), _p(info), info.shape[1] if info is not None else 0, B,
+                                           int(max_out), int(mode), _p(out), _stream(boxes)))
     return out
 
 

@@ -1,0 +1,81 @@
+"""Batched pipelines: the per-image / per-level Python loops of the reference's callers, as a handful of launches.
+
+Each function states the reference call stack it replaces.  Results are per-image identical to
+running the reference's single-image code B times (the reference itself refuses multi-batch inference,
+models/det/retinanet.py:174).  All arithmetic happens in libbdet.so."""
+import math
+
+import torch
+
+from . import _lib, ops
+
+
+def retinanet_targets(anchors, gt_boxes, num_gt, thresholds=(0.4, 0.5), labels=(0, -1, 1), allow_low_quality=True,
+                      reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1), apply_class=True, plan=None):
+    """RetinaNet.get_ground_truth, models/det/retinanet.py:211-232 (apply_class=False: RPN.get_ground_truth up to
+    sample_labels, models/det/rpn.py:215-226).  -> labels (B,A) int32, offsets (B,A,4), match_indices (B,A)."""
+    lab, idx, off = ops.assign_targets(anchors, gt_boxes, num_gt, list(thresholds), list(labels), allow_low_quality,
+                                       apply_class, reg_mean, reg_std, plan=plan)
+    return lab, off, idx
+
+
+def _flat_levels(tensors):
+    return [t.reshape(t.shape[0], -1) for t in tensors]
+
+
+def dense_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_threshold=0.05, iou_threshold=0.5,
+                      max_detections=100, topk=1000, ctrness_list=None, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1)):
+    """RetinaNet.inference / FCOS.inference minus the network, for a whole batch.
+
+    models/det/retinanet.py:181-209 (ctrness_list None: sigmoid scores, BoxCoder) or models/det/fcos.py:191-221
+    (ctrness_list given: sqrt(sigmoid(cls)*sigmoid(ctr)), PointCoder) + layers/common/post_processing.py:50-103.
+    logits_list[l] (B, n_l, C); offsets_list[l] (B, n_l, 4); anchors_list[l] (n_l, 4) boxes or (n_l, 2) points;
+    img_info (B, >=4) rows [h, w, orig_h, orig_w].
+    Returns dets (B, max_detections, 6) rows [x1, y1, x2, y2, score, label] (zero padded) and counts (B,)."""
+    L = len(logits_list)
+    C = logits_list[0].shape[-1]
+    lg = [t.float().contiguous() for t in logits_list]
+    base, starts, lens = ops._segments(_flat_levels(lg))
+    if ctrness_list is not None:
+        ct = [t.float().contiguous() for t in ctrness_list]
+        cbase, cstarts, _ = ops._segments(_flat_levels(ct))
+        top = ops.score_filter_topk_raw(base, starts, lens, cls_threshold, topk, _lib.SCORE_FCOS, cbase, cstarts, C)
+        coder = 1
+    else:
+        top = ops.score_filter_topk_raw(base, starts, lens, cls_threshold, topk, _lib.SCORE_SIGMOID, None, None, C)
+        coder = 0
+    boxes, scores, labels, count = ops.select_decode(anchors_list, offsets_list, top, topk, C, coder, 0, reg_mean, reg_std)
+    keep, keep_cnt = ops.nms_batched(boxes, scores, labels, iou_threshold, max_detections, num=count)
+    dets = ops.finalize_detections(boxes, scores, labels, keep, keep_cnt, max_detections, img_info, mode=0)
+    return dets, keep_cnt
+
+
+def rpn_proposals(scores_list, offsets_list, anchors_list, im_info, prev_nms_topk=2000, post_nms_topk=1000,
+                  nms_threshold=0.7, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1)):
+    """RPN.find_top_rpn_proposals, models/det/rpn.py:134-186, for a whole batch.
+
+    scores_list[l] (B, n_l) objectness logits in (h, w, anchor) order; offsets_list[l] (B, n_l, 4); anchors_list[l]
+    (n_l, 4); im_info (B, >=2) rows [h, w, ...].  k is clamped to the level size.
+    Returns rois (B, post_nms_topk, 5) rows [batch, x1, y1, x2, y2] (zero padded) and counts (B,)."""
+    sc = [t.float().contiguous() for t in scores_list]
+    base, starts, lens = ops._segments(_flat_levels(sc))
+    top = ops.topk_raw(base, starts, lens, prev_nms_topk)
+    boxes, scores, levels, count = ops.select_decode(anchors_list, offsets_list, top, prev_nms_topk, 1, 0, 1, reg_mean,
+                                                     reg_std, im_info=im_info)
+    keep, keep_cnt = ops.nms_batched(boxes, scores, levels, nms_threshold, post_nms_topk, num=count)
+    rois = ops.finalize_detections(boxes, scores, levels, keep, keep_cnt, post_nms_topk, None, mode=1)
+    return rois, keep_cnt
+
+
+def roi_pool_forward_backward(features, rois, strides, pool_shape=(7, 7), dout=None):
+    """RCNN.forward's roi_pool (layers/head/rcnn.py:56 -> layers/common/roi_pool.py:35-78) and, if ``dout`` is
+    given, the gradient w.r.t. the features that MegEngine's autodiff would produce."""
+    levels = None
+    if len(strides) > 1:
+        levels = ops.roi_assign_levels(rois, int(math.log2(strides[0])), int(math.log2(strides[-1])))
+    scales = [1.0 / s for s in strides]
+    out = ops.roi_align_fwd(features, rois, levels, scales, pool_shape)
+    if dout is None:
+        return out
+    grads = ops.roi_align_bwd(dout, [tuple(f.shape) for f in features], rois, levels, scales, pool_shape)
+    return out, grads

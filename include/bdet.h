@@ -142,26 +142,48 @@ int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, 
 
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
- * Segmented: segment s covers scores[seg_offset[s] .. seg_offset[s+1]).  For each segment writes
- * min(k, n_s) (value, index-within-segment) pairs sorted by (value desc, index asc) at
- * out_* + s*k, and the count at out_count[s].  Radix select on (value, index) keys + bitonic sort. */
+ * Segmented: segment s covers scores[seg_start[s] .. seg_start[s] + seg_len[s]) (element offsets from `scores`;
+ * segments may lie in different allocations).  For each segment writes min(k, n_s) (value, index-within-segment)
+ * pairs sorted by (value desc, index asc) at out_* + s*k, and the count at out_count[s].
+ * Radix select on unique (value, index) keys + shared-memory bitonic sort; k <= 16384. */
 size_t bdet_topk_workspace(int64_t total, int n_seg, int k);
-int bdet_topk(const float* scores, const int64_t* seg_offset_host, int n_seg, int k, float* out_vals,
-              int* out_idx, int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+int bdet_topk(const float* scores, const int64_t* seg_start_host, const int64_t* seg_len_host, int n_seg, int k,
+              float* out_vals, int* out_idx, int* out_count, void* workspace, size_t workspace_bytes,
+              bdet_stream_t stream);
 /* sigmoid -> score > thr -> top-k of models/det/retinanet.py:181-191 (mode BDET_SCORE_SIGMOID) and
- * sqrt(sigmoid(cls)*sigmoid(ctr)) of models/det/fcos.py:194-202 (mode BDET_SCORE_FCOS; ctrness has one
- * value per C logits).  logits are flat per segment; index = flat index within the segment
- * (label = idx % C, box = idx / C).  Outputs as bdet_topk.  BDET_SCORE_RAW treats logits as scores. */
+ * sqrt(sigmoid(cls)*sigmoid(ctr)) of models/det/fcos.py:194-202 (mode BDET_SCORE_FCOS; ctrness has one value per C
+ * logits: element e of segment s uses ctrness[ctr_start[s] + e / C]; ctr_start_host NULL -> seg_start / C).
+ * index = flat index within the segment (label = idx % C, box = idx / C).  BDET_SCORE_RAW treats logits as scores. */
 #define BDET_SCORE_RAW 0
 #define BDET_SCORE_SIGMOID 1
 #define BDET_SCORE_FCOS 2
 size_t bdet_score_filter_topk_workspace(int64_t total, int n_seg, int k);
-int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_offset_host,
-                           int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
-                           int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_start_host,
+                           const int64_t* seg_len_host, const int64_t* ctr_start_host, int n_seg, float threshold,
+                           int k, int mode, float* out_scores, int* out_idx, int* out_count, void* workspace,
+                           size_t workspace_bytes, bdet_stream_t stream);
 /* F.sigmoid / fcos score as a plain elementwise op (so tests can feed bit-identical scores to the oracle). */
 int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int mode, float* out,
                 bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ batched glue: top-k -> boxes -> NMS -> detections
+ * bdet_select_decode: for image b, level l (in order) and each of its topk_cnt[b,l] selected flat indices idx:
+ *   box   = decode(anchors_l[idx / div], deltas_l[b, idx / div])     (coder 0 BoxCoder boxcoder.py:75-98, 1 PointCoder :135-141)
+ *   label = idx % div (label_mode 0, retinanet.py:194) or the level id as fp32 (label_mode 1, rpn.py:160)
+ *   im_info != NULL: drop candidates whose box, clipped to im_info[b, :2] = (h, w), has h <= 0 or w <= 0 (rpn.py:168-171)
+ * and writes them compacted, levels concatenated in order (post_processing.py:63-67 / rpn.py:163-165):
+ *   boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k), count (B).  anchors_host / deltas_host: L device pointers to
+ *   (n_l, 4|2) and (B, n_l, 4).  topk_* as written by bdet_topk / bdet_score_filter_topk with segment s = b*L + l. */
+int bdet_select_decode(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host, int L,
+                       int B, int k, int div, int coder, int label_mode, const int* topk_idx, const float* topk_val,
+                       const int* topk_cnt, const float* mean_host, const float* std_host, const float* im_info,
+                       int info_ld, float* boxes, float* scores, void* labels, int* count, bdet_stream_t stream);
+/* mode 0: post_processing.py:96-101 -- out (B, max_out, 6) = [box scaled by (orig/resized) and clipped to the original
+ *         image, score, label] for the kept indices (im_info (B, >=4) [h, w, orig_h, orig_w]; NULL = no scale/clip);
+ * mode 1: rpn.py:179-183 -- out (B, max_out, 5) = [batch index, x1, y1, x2, y2].  Rows >= keep_count[b] are zero. */
+int bdet_finalize_detections(const float* boxes, const float* scores, const void* labels, int labels_is_float, int N,
+                             const int* keep, int keep_ld, const int* keep_count, const float* im_info, int info_ld,
+                             int B, int max_out, int mode, float* out, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ a11: class-aware batched NMS
  * batched_nms  layers/common/post_processing.py:17-47  ->  F.vision.nms

@@ -167,25 +167,35 @@ void oracle_retinanet_targets(const float* anchors, int A, const float* gt5, int
 }
 
 /* F.vision.nms on boxes already sorted by score (ASSUMED-5): returns #kept, kept[] = sorted positions */
+typedef struct { const float* b; const float* area; uint8_t* removed; int i; float thr; } nms_ctx;
+static void nms_range(int lo, int hi, void* p) {
+  nms_ctx* c = (nms_ctx*)p;
+  const float* a = c->b + 4 * (size_t)c->i;
+  const int base = c->i + 1;
+  for (int jj = lo; jj < hi; ++jj) {
+    const int j = base + jj;
+    if (c->removed[j]) continue;
+    const float* q = c->b + 4 * (size_t)j;
+    float w = fmaxf(fminf(a[2], q[2]) - fmaxf(a[0], q[0]), 0.f);
+    float h = fmaxf(fminf(a[3], q[3]) - fmaxf(a[1], q[1]), 0.f);
+    float inter = w * h;
+    if (!(inter > 0.f) && c->thr >= 0.f) continue; /* 0 / x can only exceed a negative threshold */
+    float iou = inter / ((c->area[c->i] + c->area[j]) - inter);
+    if (iou > c->thr) c->removed[j] = 1;
+  }
+}
 int oracle_nms_sorted(const float* b, int n, float thr, int max_output, int* kept) {
-  uint8_t* removed = (uint8_t*)calloc((size_t)n, 1);
-  float* area = (float*)malloc(sizeof(float) * (size_t)n);
+  uint8_t* removed = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
+  float* area = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
   for (int i = 0; i < n; ++i) area[i] = (b[4 * i + 2] - b[4 * i]) * (b[4 * i + 3] - b[4 * i + 1]);
   int cnt = 0;
   for (int i = 0; i < n; ++i) {
     if (removed[i]) continue;
     kept[cnt++] = i;
     if (max_output > 0 && cnt >= max_output) break;
-    const float* a = b + 4 * (size_t)i;
-    for (int j = i + 1; j < n; ++j) {
-      if (removed[j]) continue;
-      const float* c = b + 4 * (size_t)j;
-      float w = fmaxf(fminf(a[2], c[2]) - fmaxf(a[0], c[0]), 0.f);
-      float h = fmaxf(fminf(a[3], c[3]) - fmaxf(a[1], c[1]), 0.f);
-      float inter = w * h;
-      float iou = inter / ((area[i] + area[j]) - inter);
-      if (iou > thr) removed[j] = 1;
-    }
+    nms_ctx c = {b, area, removed, i, thr};
+    const int rest = n - i - 1;
+    if (rest > 0) nms_range(0, rest, &c);
   }
   free(removed);
   free(area);
