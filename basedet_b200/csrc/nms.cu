@@ -11,6 +11,8 @@
 //   3. sweep : per image, warp 0 resolves one 64-box block at a time from the diagonal words held in registers
 //              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' masks into the
 //              shared-memory `removed` bitmap; stops at max_output.
+//   2+3 fused (nms_fused_kernel) when max_output x N is small (every detector config): the ballot words are built
+//              only for kept rows, block by block, and never leave the SM.
 // Rated in pair tests/s (issue bound), not HBM GB/s.
 #include "common.cuh"
 #include "sortnet.cuh"
@@ -257,6 +259,105 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs 
   if (t == 0) p.keep_count[b] = count;
 }
 
+// ---- keep-driven path: mask words only for KEPT rows, nothing in HBM ---------------------------------------
+// One CTA per image walks the sorted boxes 64 at a time:
+//   (c) the 64x64 diagonal words of the still-alive rows are built with ballots (2 rows per warp);
+//   (d) warp 0 resolves the block from those words (visiting only un-suppressed boxes), stopping at max_output;
+//   (f) every warp takes later 64-column words: its lanes hold two column boxes each, the kept rows' boxes are
+//       broadcast from shared memory, two ballots per kept row are ORed into the shared `removed` bitmap.
+// Pair tests: kept x N instead of N^2/2, and no N x N/64 mask in HBM.  Decisions are the same overlap predicate as
+// the mask kernel, so the keep list is identical.
+constexpr int kFusedThreads = 1024;
+
+__global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // nwords
+  __shared__ float4 srow[64];
+  __shared__ float sarea[64];
+  __shared__ uint64_t sdiag[64];
+  __shared__ int skept[64];
+  __shared__ int snk;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = nms_n(p, b);
+  const int nblk = (n + 63) >> 6;
+  const long long base = (long long)b * p.Nmax;
+  const float4* sb = p.sboxes + base;
+  const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
+  for (int w = t; w < nblk; w += kFusedThreads) remv[w] = 0ull;
+  int count = 0;
+  for (int blk = 0; blk < nblk && count < max_out; ++blk) {
+    __syncthreads();  // remv complete for this block; previous block's shared rows free
+    const int r0 = blk * 64;
+    const int nv = min(64, n - r0);
+    const uint64_t valid = nv >= 64 ? ~0ull : ((1ull << nv) - 1ull);
+    const uint64_t alive = ~remv[blk] & valid;
+    if (alive == 0ull) continue;  // CTA-uniform
+    if (t < 64) {
+      const float4 bx = t < nv ? sb[r0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+      srow[t] = bx;
+      sarea[t] = box_area(bx);
+      sdiag[t] = 0ull;
+    }
+    __syncthreads();
+    {  // (c) diagonal words: warp w -> rows w and w + 32
+      const float4 c0 = srow[lane], c1 = srow[lane + 32];
+      const float a0 = sarea[lane], a1 = sarea[lane + 32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = warp + 32 * h;
+        if (!((alive >> i) & 1ull)) continue;  // warp-uniform
+        const float4 a = srow[i];
+        const float sa = sarea[i];
+        const bool p0 = (lane > i) && (lane < nv) && nms_overlap(a, sa, c0, a0, p.thr);
+        const bool p1 = (lane + 32 > i) && (lane + 32 < nv) && nms_overlap(a, sa, c1, a1, p.thr);
+        const uint32_t lo = __ballot_sync(0xffffffffu, p0);
+        const uint32_t hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == 0) sdiag[i] = ((uint64_t)hi << 32) | lo;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // (d) serial resolve, all lanes redundantly (uniform)
+      uint64_t cand = alive;
+      int nk = 0;
+      while (cand != 0ull && count + nk < max_out) {
+        const int i = __ffsll((long long)cand) - 1;
+        if (lane == 0) skept[nk] = i;
+        ++nk;
+        cand &= ~sdiag[i];
+        cand &= ~(1ull << i);
+      }
+      if (lane == 0) snk = nk;
+    }
+    __syncthreads();
+    const int nk = snk;
+    if (t < nk) p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + r0 + skept[t]];
+    count += nk;
+    if (count >= max_out || nk == 0) continue;
+    // (f) OR the kept rows' masks into the later words
+    for (int w = blk + 1 + warp; w < nblk; w += kFusedThreads / 32) {
+      const uint64_t cur = remv[w];
+      if (cur == ~0ull) continue;
+      const int c0 = w * 64 + lane, c1 = c0 + 32;
+      const bool live0 = c0 < n && !((cur >> lane) & 1ull), live1 = c1 < n && !((cur >> (lane + 32)) & 1ull);
+      const float4 b0 = live0 ? sb[c0] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b1 = live1 ? sb[c1] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float a0 = box_area(b0), a1 = box_area(b1);
+      bool s0 = false, s1 = false;
+      for (int q = 0; q < nk; ++q) {
+        const int i = skept[q];
+        const float4 a = srow[i];
+        const float sa = sarea[i];
+        s0 = s0 || (live0 && nms_overlap(a, sa, b0, a0, p.thr));
+        s1 = s1 || (live1 && nms_overlap(a, sa, b1, a1, p.thr));
+      }
+      const uint32_t lo = __ballot_sync(0xffffffffu, s0);
+      const uint32_t hi = __ballot_sync(0xffffffffu, s1);
+      if (lane == 0) remv[w] = cur | ((uint64_t)hi << 32) | lo;
+    }
+  }
+  if (t == 0) p.keep_count[b] = count;
+}
+
 struct NmsWs {
   size_t order, sboxes, maxc, keys, mask, total;
 };
@@ -346,6 +447,16 @@ extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idx
     BDET_KERNEL("nms_gather_kernel", st, nms_gather_kernel<<<dim3(ceil_div(Nmax, 256), B), 256, 0, st>>>(a));
   }
   BDET_LAUNCH_CHECK();
+  // keep-driven single-CTA path when (boxes that can be kept) x N stays small; otherwise the full bitmask + sweep
+  const long long cap = max_output > 0 ? (long long)min(max_output, Nmax) : (long long)Nmax;
+  if (cap * (long long)Nmax <= (64ll << 20)) {
+    const size_t fsmem = (size_t)a.nwords * 8;
+    if (fsmem > 40 * 1024)
+      BDET_CUDA(cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    BDET_KERNEL("nms_fused_kernel", st, nms_fused_kernel<<<B, kFusedThreads, fsmem, st>>>(a));
+    BDET_LAUNCH_CHECK();
+    return BDET_OK;
+  }
   const int nblk = a.nwords;
   if (nblk > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_nms: too many 64-box blocks");
   BDET_KERNEL("nms_mask_kernel", st, nms_mask_kernel<<<dim3(nblk, nblk, B), 256, 0, st>>>(a));

@@ -41,12 +41,18 @@ struct KeySrc {
   __device__ __forceinline__ uint64_t key(int i) const { return k[i]; }
 };
 
-// warp-aggregated shared-memory histogram increment
+// Shared-memory histogram increment.  Score keys are concentrated (few exponents), so most warps hit ONE bin: that
+// case costs one atomic per warp; mixed warps fall back to per-lane shared atomics (__match_any_sync is far slower).
 __device__ __forceinline__ void hist_add(int* hist, int bin, bool active) {
-  uint32_t act = __ballot_sync(0xffffffffu, active);
-  if (!active) return;
-  uint32_t peers = __match_any_sync(act, bin);
-  if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+  const uint32_t act = __ballot_sync(0xffffffffu, active);
+  if (act == 0u) return;
+  const int leader = __ffs(act) - 1;
+  const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+  if (__all_sync(0xffffffffu, !active || bin == b0)) {
+    if ((threadIdx.x & 31) == leader) atomicAdd(&hist[b0], __popc(act));
+  } else if (active) {
+    atomicAdd(&hist[bin], 1);
+  }
 }
 
 // warp-aggregated append; returns the slot for this lane (or -1)
@@ -199,24 +205,30 @@ constexpr int kFiltThreads = 256;
 constexpr int kFiltVec = 4;                               // float4 per thread per tile
 constexpr int kFiltTile = kFiltThreads * kFiltVec * 4;    // 4096 elements
 
-__device__ __forceinline__ bool eval_score(const FilterArgs& p, float x, long long ci, float& s) {
+// Exact fp32 score of one candidate (same expressions as scores_kernel, so a dense bdet_scores tensor is bit-identical).
+__device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long long ci, float& s) {
   if (p.mode == BDET_SCORE_SIGMOID) {
-    if (!(x > p.pre)) return false;
     s = sigmoid_f(x);
   } else if (p.mode == BDET_SCORE_FCOS) {
-    // fcos.py:194: sqrt(sigmoid(cls) * sigmoid(ctr)); score <= sqrt(sigmoid(cls)) so the same pre-filter on
-    // sigmoid(cls) > thr^2 holds (p.pre = logit(thr^2) - margin)
-    if (!(x > p.pre)) return false;
-    float sc = sigmoid_f(__ldg(p.ctr + ci));
-    s = sqrtf(sigmoid_f(x) * sc);
+    s = sqrtf(sigmoid_f(x) * sigmoid_f(__ldg(p.ctr + ci)));  // fcos.py:194
   } else {
     s = x;
   }
   return s > p.thr;
 }
 
+constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresholds (FCOS); needs C >= 4096 / 159
+
+// HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
+// (monotonicity of sigmoid; for FCOS the bound is per position: sigmoid(x) * sigmoid(ctr) > thr^2  <=>
+// x > logit(thr^2 / sigmoid(ctr)), computed once per position into shared memory).  The ~1 % survivors get the exact
+// fp32 score and the `> thr` test, are staged in shared memory, and the CTA reserves its output range with a single
+// global atomic per tile (a per-candidate atomic on ~40 segment counters serialises in L2).
 template <bool VEC>
 __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p) {
+  __shared__ uint64_t skeys[kFiltTile];
+  __shared__ float spre[kPosTab];
+  __shared__ int scount, sbase;
   // tile -> segment (CTA-uniform binary search)
   int lo = 0, hi = p.n_seg;
   const int tile = blockIdx.x;
@@ -230,45 +242,78 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
   const int e0 = (tile - sd.tile_start) * kFiltTile;
   const float* src = p.logits + sd.start;
   const long long coff = sd.ctr_start;
-  uint64_t* keys = p.keys + sd.key_off;
-  int* counter = p.cand_count + s;
   const int t = threadIdx.x;
+  if (t == 0) scount = 0;
+  const int pos0 = e0 / p.C;
+  const bool use_tab = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
+  if (use_tab) {
+    const int npos = min((min(e0 + kFiltTile, n) - 1) / p.C - pos0 + 1, kPosTab);
+    for (int i = t; i < npos; i += kFiltThreads) {
+      const float sc = sigmoid_f(__ldg(p.ctr + coff + pos0 + i));
+      const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
+      float bound = CUDART_INF_F;
+      if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
+      else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: candidates are re-tested exactly
+      spre[i] = bound;
+    }
+  }
+  __syncthreads();
+
+  auto consider = [&](float x, int e, float bound) {
+    if (x > bound) {  // rare
+      float sc;
+      if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(&scount, 1)] = make_key(sc, (uint32_t)e);
+    }
+  };
   if (VEC) {
     float4 v[kFiltVec];
 #pragma unroll
     for (int j = 0; j < kFiltVec; ++j) {
-      int e = e0 + (j * kFiltThreads + t) * 4;
-      v[j] = (e + 3 < n) ? __ldcs(reinterpret_cast<const float4*>(src + e)) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-      if (e < n && e + 3 >= n) {  // ragged tail of the segment
-        float tmp[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmp[q] = (e + q < n) ? __ldg(src + e + q) : -CUDART_INF_F;
-        v[j] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+      const int e = e0 + (j * kFiltThreads + t) * 4;
+      const float ninf = -CUDART_INF_F;
+      if (e + 3 < n) {
+        v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
+      } else {  // ragged tail of the segment
+        v[j].x = e < n ? __ldg(src + e) : ninf;
+        v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
+        v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
+        v[j].w = ninf;
       }
     }
 #pragma unroll
     for (int j = 0; j < kFiltVec; ++j) {
-      int e = e0 + (j * kFiltThreads + t) * 4;
-      float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float sc = 0.f;
-        bool pass = (e + q < n) && eval_score(p, x[q], coff + (e + q) / p.C, sc);
-        int slot = append_slot(counter, pass);
-        if (pass) keys[slot] = make_key(sc, (uint32_t)(e + q));
+      const int e = e0 + (j * kFiltThreads + t) * 4;
+      float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
+      if (use_tab) {
+        // C % 4 == 0 is not required: each element looks up its own position
+        const int q0 = e / p.C - pos0;
+        const int r0 = e - (q0 + pos0) * p.C;
+        b0 = spre[min(q0, kPosTab - 1)];
+        b1 = spre[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
+        b2 = spre[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
+        b3 = spre[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
       }
+      consider(v[j].x, e, b0);
+      consider(v[j].y, e + 1, b1);
+      consider(v[j].z, e + 2, b2);
+      consider(v[j].w, e + 3, b3);
     }
   } else {
 #pragma unroll 4
     for (int j = 0; j < kFiltVec * 4; ++j) {
-      int e = e0 + j * kFiltThreads + t;
-      float x = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
-      float sc = 0.f;
-      bool pass = (e < n) && eval_score(p, x, coff + e / p.C, sc);
-      int slot = append_slot(counter, pass);
-      if (pass) keys[slot] = make_key(sc, (uint32_t)e);
+      const int e = e0 + j * kFiltThreads + t;
+      const float x = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
+      const float bound = use_tab ? spre[min(e / p.C - pos0, kPosTab - 1)] : p.pre;
+      consider(x, e, bound);
     }
   }
+  __syncthreads();
+  const int cnt = scount;
+  if (cnt == 0) return;
+  if (t == 0) sbase = atomicAdd(p.cand_count + s, cnt);
+  __syncthreads();
+  uint64_t* keys = p.keys + sd.key_off + sbase;
+  for (int i = t; i < cnt; i += kFiltThreads) keys[i] = skeys[i];
 }
 
 // Dense scores (so tests can hand bit-identical scores to the oracle).
