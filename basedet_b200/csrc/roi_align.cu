@@ -7,9 +7,10 @@
 //           into shared memory; threads then walk the (channel, bin) outputs in memory order, so the 49-float
 //           output rows are written fully coalesced and the 16 taps of a bin hit L1/L2 (the ROI footprint is a
 //           few KB per channel).  All levels in one launch; output directly in the original ROI order.
-// backward: one CTA per ROI accumulates the ROI footprint of a channel chunk in shared memory
-//           (shared atomics), then flushes each touched pixel once with red.global.add.f32, coalesced along x:
-//           <= footprint reds per (roi, channel) instead of 16 * P^2 scattered global atomics.
+// backward: (default, with workspace) atomics-free tile gather -- ROIs are binned per feature-map tile, one CTA
+//           accumulates its tile x channel chunk in shared memory and writes every dfeat element exactly once;
+//           (no workspace) scatter form: one CTA per ROI accumulates the ROI footprint in shared memory and
+//           flushes each touched pixel once with red.global.add.f32.
 #include "common.cuh"
 
 namespace bdet {
@@ -220,6 +221,236 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward, gather form (default).  The feature maps are cut into kTH x kTW pixel tiles; ROIs are binned per tile
+// (count -> scan -> fill); one CTA owns (tile, chunk of kCC channels), accumulates every ROI of its list into a
+// shared-memory tile and writes each dfeat element exactly once: no global atomics, no memset, deterministic.
+// Per pixel the contributing samples form a contiguous range along each axis (sample coordinates are monotone), so
+//   dfeat[y][x] += sum_{sy in R(y)} sum_{sx in C(x)}  (dout[ph(sy)][pw(sx)] / S^2) * (wy(sy, y) * wx(sx, x))
+// with the same products as the scatter form (oracle: g * ((1-ly)(1-lx)) ...); only the summation order differs.
+constexpr int kTH = 16, kTW = 32, kCC = 32;
+constexpr int kGatherThreads = 256;
+
+struct TileGrid {
+  int tiles_y[BDET_MAX_LEVELS], tiles_x[BDET_MAX_LEVELS];
+  int base[BDET_MAX_LEVELS + 1];  // first tile id of each level; base[n_levels] = total
+};
+
+struct BinArgs {
+  RoiArgs r;
+  TileGrid g;
+  int* count;   // (n_tiles)
+  int* offset;  // (n_tiles + 1)
+  int* fill;    // (n_tiles)
+  int* list;    // (cap)
+};
+
+// footprint rows / cols of ROI k on its level (same fp32 expressions as fill_axis), clipped to the map
+__device__ __forceinline__ bool roi_footprint(const RoiArgs& p, const RoiGeom& g, int& y_lo, int& y_hi, int& x_lo, int& x_hi) {
+  const float fy0 = __fdiv_rn(0.5f, (float)p.SH), fy1 = __fdiv_rn((float)(p.SH - 1) + 0.5f, (float)p.SH);
+  const float fx0 = __fdiv_rn(0.5f, (float)p.SW), fx1 = __fdiv_rn((float)(p.SW - 1) + 0.5f, (float)p.SW);
+  const float ya = g.start_h + g.bin_h * (0.f + fy0), yb = g.start_h + g.bin_h * ((float)(p.PH - 1) + fy1);
+  const float xa = g.start_w + g.bin_w * (0.f + fx0), xb = g.start_w + g.bin_w * ((float)(p.PW - 1) + fx1);
+  y_lo = max((int)floorf(ya), 0);
+  y_hi = min((int)floorf(yb) + 1, g.H - 1);
+  x_lo = max((int)floorf(xa), 0);
+  x_hi = min((int)floorf(xb) + 1, g.W - 1);
+  return y_lo <= y_hi && x_lo <= x_hi;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) roi_bin_kernel(const BinArgs b) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= b.r.K) return;
+  const RoiGeom g = roi_geom(b.r, k);
+  if (!g.valid) return;
+  int y_lo, y_hi, x_lo, x_hi;
+  if (!roi_footprint(b.r, g, y_lo, y_hi, x_lo, x_hi)) return;
+  const int tx_n = b.g.tiles_x[g.lvl], ty_n = b.g.tiles_y[g.lvl];
+  const int t0 = b.g.base[g.lvl] + g.n * ty_n * tx_n;
+  for (int ty = y_lo / kTH; ty <= y_hi / kTH; ++ty)
+    for (int tx = x_lo / kTW; tx <= x_hi / kTW; ++tx) {
+      const int tile = t0 + ty * tx_n + tx;
+      if (FILL)
+        b.list[b.offset[tile] + atomicAdd(&b.fill[tile], 1)] = k;
+      else
+        atomicAdd(&b.count[tile], 1);
+    }
+}
+
+__global__ void __launch_bounds__(1024) roi_bin_scan_kernel(const BinArgs b) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = b.g.base[b.r.lv.n_levels];
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    const int v = i < n ? b.count[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int add = carry;
+    for (int w = 0; w < warp; ++w) add += warp_tot[w];
+    if (i < n) {
+      b.offset[i] = add + incl - v;
+      b.fill[i] = 0;
+    }
+    __syncthreads();
+    if (t == 1023) carry = add + incl;
+    __syncthreads();
+  }
+  if (t == 0) b.offset[n] = carry;
+}
+
+struct GatherSmem {
+  int y_i0[kMaxSamples], x_i0[kMaxSamples];
+  float y_fr[kMaxSamples], x_fr[kMaxSamples];
+  int rlo[kTH], rhi[kTH], clo[kTW], chi[kTW];
+  int box[4];
+};
+
+__global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(const BinArgs b, int accumulate) {
+  extern __shared__ __align__(16) float gsm[];
+  float* acc = gsm;                        // kCC * kTH * kTW
+  float* sdout = gsm + kCC * kTH * kTW;    // kCC * PH * PW
+  __shared__ GatherSmem sm;
+  const RoiArgs& p = b.r;
+  const int tile = blockIdx.x, c0 = blockIdx.y * kCC, t = threadIdx.x;
+  const int nc = min(kCC, p.C - c0);
+  int l = 0;
+#pragma unroll
+  for (int q = 1; q < BDET_MAX_LEVELS; ++q)
+    if (q < p.lv.n_levels && tile >= b.g.base[q]) l = q;
+  const int H = p.lv.H[l], W = p.lv.W[l];
+  const int tx_n = b.g.tiles_x[l], ty_n = b.g.tiles_y[l];
+  int rel = tile - b.g.base[l];
+  const int n = rel / (ty_n * tx_n);
+  rel -= n * ty_n * tx_n;
+  const int y0t = (rel / tx_n) * kTH, x0t = (rel % tx_n) * kTW;
+  const int bins = p.PH * p.PW, NS_Y = p.PH * p.SH, NS_X = p.PW * p.SW;
+  const float cnt = (float)(p.SH * p.SW);
+  for (int i = t; i < kCC * kTH * kTW; i += kGatherThreads) acc[i] = 0.f;
+  const int beg = b.offset[tile], end = b.offset[tile + 1];
+  for (int e = beg; e < end; ++e) {
+    const int k = b.list[e];
+    const RoiGeom g = roi_geom(p, k);
+    __syncthreads();  // previous ROI's tables / sdout are free; acc zero-fill done
+    for (int s = t; s < NS_Y; s += kGatherThreads) {
+      const int pidx = s / p.SH, i = s - pidx * p.SH;
+      const float c = g.start_h + g.bin_h * ((float)pidx + __fdiv_rn((float)i + 0.5f, (float)p.SH));
+      const float fl = floorf(c);
+      sm.y_i0[s] = (int)fl;
+      sm.y_fr[s] = c - fl;
+    }
+    for (int s = t; s < NS_X; s += kGatherThreads) {
+      const int pidx = s / p.SW, i = s - pidx * p.SW;
+      const float c = g.start_w + g.bin_w * ((float)pidx + __fdiv_rn((float)i + 0.5f, (float)p.SW));
+      const float fl = floorf(c);
+      sm.x_i0[s] = (int)fl;
+      sm.x_fr[s] = c - fl;
+    }
+    const float* dk = p.dout + ((long long)k * p.C + c0) * bins;
+    for (int i = t; i < nc * bins; i += kGatherThreads) sdout[i] = __fdiv_rn(__ldg(dk + i), cnt);
+    __syncthreads();
+    // contiguous sample ranges feeding each tile row / column: i0 in {y - 1, y}
+    if (t < kTH) {
+      const int y = y0t + t;
+      int lo = NS_Y, hi = -1;
+      if (y < H)
+        for (int s = 0; s < NS_Y; ++s) {
+          const int i0 = sm.y_i0[s];
+          if (i0 == y || i0 + 1 == y) {
+            lo = min(lo, s);
+            hi = s;
+          }
+        }
+      sm.rlo[t] = lo;
+      sm.rhi[t] = hi;
+    } else if (t >= 32 && t < 32 + kTW) {
+      const int x = x0t + (t - 32);
+      int lo = NS_X, hi = -1;
+      if (x < W)
+        for (int s = 0; s < NS_X; ++s) {
+          const int i0 = sm.x_i0[s];
+          if (i0 == x || i0 + 1 == x) {
+            lo = min(lo, s);
+            hi = s;
+          }
+        }
+      sm.clo[t - 32] = lo;
+      sm.chi[t - 32] = hi;
+    }
+    if (t == 0) {  // footprint of this ROI inside the tile (tile-local coordinates)
+      const int y_lo = max(sm.y_i0[0], y0t), y_hi = min(sm.y_i0[NS_Y - 1] + 1, min(y0t + kTH, H) - 1);
+      const int x_lo = max(sm.x_i0[0], x0t), x_hi = min(sm.x_i0[NS_X - 1] + 1, min(x0t + kTW, W) - 1);
+      sm.box[0] = y_lo - y0t;
+      sm.box[1] = x_lo - x0t;
+      sm.box[2] = y_hi - y_lo + 1;
+      sm.box[3] = x_hi - x_lo + 1;
+    }
+    __syncthreads();
+    const int fr0 = sm.box[0], fc0 = sm.box[1], nr = sm.box[2], ncol = sm.box[3];
+    if (nr <= 0 || ncol <= 0) continue;  // CTA-uniform
+    const int per_c = nr * ncol;
+    for (int i = t; i < nc * per_c; i += kGatherThreads) {
+      const int c = i / per_c, rem = i - c * per_c;
+      const int r = fr0 + rem / ncol, x = fc0 + rem % ncol;
+      const int slo = sm.rlo[r], shi = sm.rhi[r], tlo = sm.clo[x], thi = sm.chi[x];
+      if (slo > shi || tlo > thi) continue;
+      const int gy = y0t + r, gx = x0t + x;
+      const float* dc = sdout + c * bins;
+      float sum = 0.f;
+      for (int sy = slo; sy <= shi; ++sy) {
+        const int iy0 = sm.y_i0[sy];
+        float wy;
+        if (iy0 == gy) wy = 1.f - sm.y_fr[sy];
+        else if (iy0 + 1 == gy) wy = sm.y_fr[sy];
+        else continue;
+        const float* drow = dc + (sy / p.SH) * p.PW;
+        for (int sx = tlo; sx <= thi; ++sx) {
+          const int ix0 = sm.x_i0[sx];
+          float wx;
+          if (ix0 == gx) wx = 1.f - sm.x_fr[sx];
+          else if (ix0 + 1 == gx) wx = sm.x_fr[sx];
+          else continue;
+          sum += drow[sx / p.SW] * (wy * wx);
+        }
+      }
+      acc[(c * kTH + r) * kTW + x] += sum;  // one thread per (c, r, x) within a ROI: no conflict
+    }
+  }
+  __syncthreads();
+  float* df = p.lv.dfeat[l] + ((long long)n * p.C + c0) * H * W;
+  for (int i = t; i < nc * kTH * kTW; i += kGatherThreads) {
+    const int c = i / (kTH * kTW), rem = i - c * (kTH * kTW);
+    const int y = y0t + rem / kTW, x = x0t + rem % kTW;
+    if (y < H && x < W) {
+      float* o = df + ((long long)c * H + y) * W + x;
+      *o = accumulate ? (*o + acc[i]) : acc[i];
+    }
+  }
+}
+
+static void make_tile_grid(TileGrid* g, int n_levels, const int* hw, int B, int* max_per_image) {
+  int base = 0, mx = 1;
+  for (int l = 0; l < n_levels; ++l) {
+    g->tiles_y[l] = (hw[2 * l] + kTH - 1) / kTH;
+    g->tiles_x[l] = (hw[2 * l + 1] + kTW - 1) / kTW;
+    g->base[l] = base;
+    base += B * g->tiles_y[l] * g->tiles_x[l];
+    mx = max(mx, g->tiles_y[l] * g->tiles_x[l]);
+  }
+  for (int l = n_levels; l <= BDET_MAX_LEVELS; ++l) g->base[l] = base;
+  if (max_per_image) *max_per_image = mx;
+}
+
 // assign_rois, roi_pool.py:19-25: clamp(floor(4 + log(sqrt(area) / 224) / ln 2), lo, hi) - lo
 __global__ void __launch_bounds__(256) roi_assign_levels_kernel(const float* __restrict__ rois, int K, int lo, int hi, float ln2,
                                                                 int* __restrict__ levels) {
@@ -307,23 +538,64 @@ extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, 
   return BDET_OK;
 }
 
+extern "C" size_t bdet_roi_align_bwd_workspace(int n_levels, const int* hw_host, int B, int K) {
+  if (n_levels < 1 || n_levels > BDET_MAX_LEVELS || !hw_host || B <= 0 || K <= 0) return 16;
+  TileGrid g;
+  int mx = 1;
+  make_tile_grid(&g, n_levels, hw_host, B, &mx);
+  const size_t n_tiles = (size_t)g.base[n_levels];
+  // a ROI can touch at most every tile of its (image, level) map
+  return align_up((n_tiles + 1) * 4, 256) * 3 + align_up((size_t)K * mx * 4, 256) + 256;
+}
+
 extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, const float* scale_host,
                                   int B, int C, const float* rois, const int* levels, int K, int PH, int PW,
-                                  int sample_h, int sample_w, int aligned, const float* dout, int zero_init,
-                                  bdet_stream_t stream) {
+                                  int sample_h, int sample_w, int aligned, const float* dout, int accumulate,
+                                  void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(dfeats_host && hw_host && scale_host, "null argument");
   RoiArgs a;
   int rc = fill_roi_args(&a, reinterpret_cast<const void* const*>(dfeats_host), true, n_levels, hw_host, scale_host, B, C, rois,
                          levels, K, PH, PW, sample_h, sample_w, aligned);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  if (zero_init) {
+  if (B == 0 || C == 0) return BDET_OK;
+  BDET_REQUIRE(K == 0 || (rois && dout), "null argument");
+  a.dout = dout;
+  if (workspace) {
+    // gather form: every dfeat element is written once (zero where no ROI reaches), no atomics
+    const size_t need = bdet_roi_align_bwd_workspace(n_levels, hw_host, B, K > 0 ? K : 1);
+    if (workspace_bytes < need) return set_error(BDET_EWORKSPACE, "bdet_roi_align_bwd: workspace needs %zu bytes", need);
+    BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 3u) == 0, "workspace must be 4-byte aligned");
+    BinArgs b;
+    b.r = a;
+    make_tile_grid(&b.g, n_levels, hw_host, B, nullptr);
+    const int n_tiles = b.g.base[n_levels];
+    char* w = reinterpret_cast<char*>(workspace);
+    const size_t seg = align_up(((size_t)n_tiles + 1) * 4, 256);
+    b.count = reinterpret_cast<int*>(w);
+    b.offset = reinterpret_cast<int*>(w + seg);
+    b.fill = reinterpret_cast<int*>(w + 2 * seg);
+    b.list = reinterpret_cast<int*>(w + 3 * seg);
+    BDET_CUDA(cudaMemsetAsync(b.count, 0, (size_t)n_tiles * 4, st));
+    if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<false><<<ceil_div(K, 256), 256, 0, st>>>(b));
+    BDET_KERNEL("roi_bin_scan_kernel", st, roi_bin_scan_kernel<<<1, 1024, 0, st>>>(b));
+    if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<true><<<ceil_div(K, 256), 256, 0, st>>>(b));
+    const size_t smem = ((size_t)kCC * kTH * kTW + (size_t)kCC * PH * PW) * 4;
+    if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large for the gather kernel");
+    BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int chunks = ceil_div(C, kCC);
+    if (chunks > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: too many channels");
+    BDET_KERNEL("roi_align_bwd_gather_kernel", st,
+                roi_align_bwd_gather_kernel<<<dim3(n_tiles, chunks), kGatherThreads, smem, st>>>(b, accumulate));
+    BDET_LAUNCH_CHECK();
+    return BDET_OK;
+  }
+  // scatter form (no workspace): shared-memory footprint accumulation + red.global.add flush
+  if (!accumulate) {
     for (int l = 0; l < n_levels; ++l)
       BDET_CUDA(cudaMemsetAsync(dfeats_host[l], 0, (size_t)B * C * hw_host[2 * l] * hw_host[2 * l + 1] * 4, st));
   }
-  if (K == 0 || C == 0) return BDET_OK;
-  BDET_REQUIRE(rois && dout, "null argument");
-  a.dout = dout;
+  if (K == 0) return BDET_OK;
   const int smem = 64 * 1024;
   a.bwd_cap = smem / 4;
   BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -225,95 +225,103 @@ constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresh
 // fp32 score and the `> thr` test, are staged in shared memory, and the CTA reserves its output range with a single
 // global atomic per tile (a per-candidate atomic on ~40 segment counters serialises in L2).
 template <bool VEC>
-__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p) {
+__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p, int total_tiles) {
   __shared__ uint64_t skeys[kFiltTile];
   __shared__ float spre[kPosTab];
   __shared__ int scount, sbase;
-  // tile -> segment (CTA-uniform binary search)
-  int lo = 0, hi = p.n_seg;
-  const int tile = blockIdx.x;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (p.seg[mid].tile_start <= tile) lo = mid; else hi = mid;
-  }
-  const int s = lo;
-  const SegDesc sd = p.seg[s];
-  const int n = sd.len;
-  const int e0 = (tile - sd.tile_start) * kFiltTile;
-  const float* src = p.logits + sd.start;
-  const long long coff = sd.ctr_start;
   const int t = threadIdx.x;
-  if (t == 0) scount = 0;
-  const int pos0 = e0 / p.C;
-  const bool use_tab = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
-  if (use_tab) {
-    const int npos = min((min(e0 + kFiltTile, n) - 1) / p.C - pos0 + 1, kPosTab);
-    for (int i = t; i < npos; i += kFiltThreads) {
-      const float sc = sigmoid_f(__ldg(p.ctr + coff + pos0 + i));
-      const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
-      float bound = CUDART_INF_F;
-      if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
-      else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: candidates are re-tested exactly
-      spre[i] = bound;
-    }
-  }
-  __syncthreads();
-
-  auto consider = [&](float x, int e, float bound) {
-    if (x > bound) {  // rare
-      float sc;
-      if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(&scount, 1)] = make_key(sc, (uint32_t)e);
-    }
-  };
-  if (VEC) {
+  // Persistent CTAs walk the tiles with a grid stride; the tile -> segment map only moves forward, so the search
+  // is one (cached) descriptor read per tile instead of a dependent binary search per CTA.
+  int s = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
+    const SegDesc sd = p.seg[s];
+    const int n = sd.len;
+    const int e0 = (tile - sd.tile_start) * kFiltTile;
+    const float* src = p.logits + sd.start;
+    const long long coff = sd.ctr_start;
+    // issue this tile's loads first; everything below overlaps with them
     float4 v[kFiltVec];
+    float sv[VEC ? 1 : kFiltVec * 4];
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < kFiltVec; ++j) {
-      const int e = e0 + (j * kFiltThreads + t) * 4;
-      const float ninf = -CUDART_INF_F;
-      if (e + 3 < n) {
-        v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
-      } else {  // ragged tail of the segment
-        v[j].x = e < n ? __ldg(src + e) : ninf;
-        v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
-        v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
-        v[j].w = ninf;
+      for (int j = 0; j < kFiltVec; ++j) {
+        const int e = e0 + (j * kFiltThreads + t) * 4;
+        const float ninf = -CUDART_INF_F;
+        if (e + 3 < n) {
+          v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
+        } else {  // ragged tail of the segment
+          v[j].x = e < n ? __ldg(src + e) : ninf;
+          v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
+          v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
+          v[j].w = ninf;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFiltVec * 4; ++j) {
+        const int e = e0 + j * kFiltThreads + t;
+        sv[j] = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
       }
     }
-#pragma unroll
-    for (int j = 0; j < kFiltVec; ++j) {
-      const int e = e0 + (j * kFiltThreads + t) * 4;
-      float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
-      if (use_tab) {
-        // C % 4 == 0 is not required: each element looks up its own position
-        const int q0 = e / p.C - pos0;
-        const int r0 = e - (q0 + pos0) * p.C;
-        b0 = spre[min(q0, kPosTab - 1)];
-        b1 = spre[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
-        b2 = spre[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
-        b3 = spre[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
+    if (t == 0) scount = 0;
+    const int pos0 = e0 / p.C;
+    const bool use_tab = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
+    if (use_tab) {
+      const int npos = min((min(e0 + kFiltTile, n) - 1) / p.C - pos0 + 1, kPosTab);
+      for (int i = t; i < npos; i += kFiltThreads) {
+        const float sc = sigmoid_f(__ldg(p.ctr + coff + pos0 + i));
+        const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
+        float bound = CUDART_INF_F;
+        if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
+        else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
+        spre[i] = bound;
       }
-      consider(v[j].x, e, b0);
-      consider(v[j].y, e + 1, b1);
-      consider(v[j].z, e + 2, b2);
-      consider(v[j].w, e + 3, b3);
     }
-  } else {
-#pragma unroll 4
-    for (int j = 0; j < kFiltVec * 4; ++j) {
-      const int e = e0 + j * kFiltThreads + t;
-      const float x = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
-      const float bound = use_tab ? spre[min(e / p.C - pos0, kPosTab - 1)] : p.pre;
-      consider(x, e, bound);
+    __syncthreads();
+
+    auto consider = [&](float x, int e, float bound) {
+      if (x > bound) {  // rare
+        float sc;
+        if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(&scount, 1)] = make_key(sc, (uint32_t)e);
+      }
+    };
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < kFiltVec; ++j) {
+        const int e = e0 + (j * kFiltThreads + t) * 4;
+        float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
+        if (use_tab) {
+          const int q0 = e / p.C - pos0;
+          const int r0 = e - (q0 + pos0) * p.C;
+          b0 = spre[min(q0, kPosTab - 1)];
+          b1 = spre[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
+          b2 = spre[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
+          b3 = spre[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
+        }
+        consider(v[j].x, e, b0);
+        consider(v[j].y, e + 1, b1);
+        consider(v[j].z, e + 2, b2);
+        consider(v[j].w, e + 3, b3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFiltVec * 4; ++j) {
+        const int e = e0 + j * kFiltThreads + t;
+        const float bound = use_tab ? spre[min(e / p.C - pos0, kPosTab - 1)] : p.pre;
+        consider(sv[j], e, bound);
+      }
     }
+    __syncthreads();
+    const int cnt = scount;
+    if (cnt > 0) {  // CTA-uniform
+      if (t == 0) sbase = atomicAdd(p.cand_count + s, cnt);
+      __syncthreads();
+      uint64_t* keys = p.keys + sd.key_off + sbase;
+      for (int i = t; i < cnt; i += kFiltThreads) keys[i] = skeys[i];
+    }
+    __syncthreads();  // skeys / scount are reused by the next tile
   }
-  __syncthreads();
-  const int cnt = scount;
-  if (cnt == 0) return;
-  if (t == 0) sbase = atomicAdd(p.cand_count + s, cnt);
-  __syncthreads();
-  uint64_t* keys = p.keys + sd.key_off + sbase;
-  for (int i = t; i < cnt; i += kFiltThreads) keys[i] = skeys[i];
 }
 
 // Dense scores (so tests can hand bit-identical scores to the oracle).
@@ -472,10 +480,11 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     }
   }
   if (tiles > 0) {
+    const int grid = min(tiles, sm_count() * 6);  // 6 resident CTAs / SM (33 KB of shared memory each)
     if (vec)
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<tiles, kFiltThreads, 0, st>>>(f));
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
     else
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false><<<tiles, kFiltThreads, 0, st>>>(f));
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
   }
   SelArgs a{nullptr, w.keys, w.cand_count, w.seg, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
   int rc = launch_select<false>(a, n_seg, st);

@@ -570,24 +570,29 @@ def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 
 
 
 def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True,
-                  dfeats=None):
-    """Gradient w.r.t. the features.  dfeats (list) are accumulated into if given (must be pre-zeroed by the
-    caller), otherwise allocated and cleared by the library."""
+                  dfeats=None, accumulate=False, gather=True, workspace=None):
+    """Gradient w.r.t. the features.  ``dfeats`` (list) are written (accumulate=False) or added to (True);
+    allocated when None.  gather=True uses the atomics-free tile-gather kernel, False the scatter kernel."""
     lib = _lib.load()
     d = _f32c(dout, "dout")
     r = _f32c(rois, "rois")
     K = r.shape[0]
     lv = _i32c(levels) if levels is not None else None
-    zero_init = dfeats is None
     if dfeats is None:
+        assert not accumulate
         dfeats = [torch.empty(tuple(s), dtype=torch.float32, device=d.device) for s in feature_shapes]
     B, C = dfeats[0].shape[:2]
     PH, PW = pool_shape
     assert d.shape == (K, C, PH, PW)
     n, ptrs, hw = _level_args(dfeats)
+    ws = None
+    if gather:
+        need = lib.bdet_roi_align_bwd_workspace(n, hw, B, max(K, 1))
+        ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, d.device)
     with _guard(d):
         check(lib.bdet_roi_align_bwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
-                                     int(sample_points[1]), int(bool(aligned)), _p(d), int(zero_init), _stream(d)))
+                                     int(sample_points[1]), int(bool(aligned)), _p(d), int(bool(accumulate)), _p(ws),
+                                     ws.numel() if ws is not None else 0, _stream(d)))
     return dfeats
 
 

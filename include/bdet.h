@@ -217,13 +217,17 @@ int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, const int* 
                        const float* scale_host, int B, int C, const float* rois, const int* levels, int K,
                        int PH, int PW, int sample_h, int sample_w, int aligned, float* out,
                        bdet_stream_t stream);
-/* Backward w.r.t. the features (rois carry no gradient, roi_pool.py:56).  dfeats must be zero-initialised
- * by the caller (or pass zero_init != 0 to have the library clear them on `stream` first).
- * Accumulates each ROI's footprint in shared memory and flushes it once with red.global.add. */
+/* Backward w.r.t. the features (rois carry no gradient, roi_pool.py:56).
+ * accumulate == 0: dfeats are OVERWRITTEN with the gradient (zeros where no ROI reaches); != 0: added to.
+ * With a workspace (bdet_roi_align_bwd_workspace bytes) the gather form runs: ROIs are binned per 16x32-pixel tile,
+ * one CTA accumulates its tile x 32-channel chunk in shared memory and writes every element exactly once -- no global
+ * atomics, no memset, deterministic.  workspace == NULL selects the scatter form (shared-memory footprint
+ * accumulation + red.global.add), which needs no workspace. */
+size_t bdet_roi_align_bwd_workspace(int n_levels, const int* hw_host, int B, int K);
 int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, const float* scale_host,
                        int B, int C, const float* rois, const int* levels, int K, int PH, int PW,
-                       int sample_h, int sample_w, int aligned, const float* dout, int zero_init,
-                       bdet_stream_t stream);
+                       int sample_h, int sample_w, int aligned, const float* dout, int accumulate,
+                       void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ small Boxes / glue ops
  * Boxes.width / height / area  structures/boxes.py:36-52 (mode 0 / 1 / 2) -> out (N) */

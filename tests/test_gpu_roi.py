@@ -75,28 +75,51 @@ def test_roi_align_generic_shapes(cuda, pool, samples):
     assert rel(out, ref) <= 1e-5
 
 
-def test_roi_align_backward(cuda):
+@pytest.mark.parametrize("gather", [True, False])
+def test_roi_align_backward(cuda, gather):
+    """gather=True: atomics-free tile-gather kernel; False: shared-memory scatter + red.global.add."""
     rng = np.random.default_rng(4)
-    B, C = 2, 6
+    B, C = 2, 38   # 38 channels: one full 32-channel chunk + a ragged one
     feats = _pyramid(rng, B, C, (160, 224))
     rois = W.make_rois(rng, 30, B, 160, 224, 6, 250)
     rois[0, 1:] = [-30, -20, 40, 50]
     rois[1, 1:] = [0, 0, 224, 160]           # whole image on the coarsest level
+    rois[2, 1:] = [300, 300, 340, 330]       # entirely outside the image: contributes nothing
     levels = R.assign_levels(rois, W.FRCNN_RCNN_STRIDES)
     dout = rng.normal(0, 1, (rois.shape[0], C, 7, 7)).astype(np.float32)
     scales = [1.0 / s for s in W.FRCNN_RCNN_STRIDES]
-    got = ops.roi_align_bwd(T(dout, cuda), [f.shape for f in feats], T(rois, cuda), T(levels, cuda), scales, (7, 7))
+    got = ops.roi_align_bwd(T(dout, cuda), [f.shape for f in feats], T(rois, cuda), T(levels, cuda), scales, (7, 7),
+                            gather=gather)
     for l, f in enumerate(feats):
         sel = levels == l
         ref = R.roi_align_backward(dout[sel], f.shape, rois[sel], (7, 7), scales[l])
         g = got[l].cpu().numpy()
         denom = max(np.abs(ref).max(), 1.0)
         assert np.max(np.abs(g - ref)) / denom <= 1e-5, l
+    # accumulate=True adds to what is already there
+    again = ops.roi_align_bwd(T(dout, cuda), None, T(rois, cuda), T(levels, cuda), scales, (7, 7), dfeats=[g.clone() for g in got],
+                              accumulate=True, gather=gather)
+    for a, g in zip(again, got):
+        assert torch.allclose(a, 2 * g, rtol=1e-5, atol=1e-5)
     # adjointness: <roi_align(x), dout> == <x, roi_align_bwd(dout)>
     out = ops.roi_align_fwd([T(f, cuda) for f in feats], T(rois, cuda), T(levels, cuda), scales, (7, 7))
     lhs = float((out.double() * T(dout, cuda).double()).sum())
     rhs = sum(float((T(f, cuda).double() * g.double()).sum()) for f, g in zip(feats, got))
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_roi_align_backward_gather_is_deterministic_and_generic(cuda):
+    rng = np.random.default_rng(7)
+    feat_shape = (2, 5, 45, 70)
+    rois = W.make_rois(rng, 40, 2, 45 * 4, 70 * 4, 6, 200)
+    dout = rng.normal(0, 1, (80, 5, 3, 5)).astype(np.float32)
+    a = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3))[0]
+    b = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3))[0]
+    assert torch.equal(a, b)
+    ref = R.roi_align_backward(dout, feat_shape, rois, (3, 5), 0.25, (1, 3))
+    assert np.max(np.abs(a.cpu().numpy() - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
+    empty = ops.roi_align_bwd(T(dout[:0], cuda), [feat_shape], T(rois[:0], cuda), None, [0.25], (3, 5), (1, 3))[0]
+    assert float(empty.abs().max()) == 0.0   # K = 0: the gradient is all zeros, still fully written
 
 
 def test_roi_align_backward_large_footprint_fallback(cuda):
@@ -105,6 +128,7 @@ def test_roi_align_backward_large_footprint_fallback(cuda):
     feat_shape = (1, 2, 160, 200)
     rois = np.array([[0, 0, 0, 199, 159], [0, 20, 30, 60, 90]], np.float32)
     dout = rng.normal(0, 1, (2, 2, 7, 7)).astype(np.float32)
-    got = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [1.0], (7, 7))[0].cpu().numpy()
     ref = R.roi_align_backward(dout, feat_shape, rois, (7, 7), 1.0)
-    assert np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
+    for gather in (False, True):
+        got = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [1.0], (7, 7), gather=gather)[0].cpu().numpy()
+        assert np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
