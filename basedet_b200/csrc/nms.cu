@@ -449,7 +449,7 @@ extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idx
   BDET_LAUNCH_CHECK();
   // keep-driven single-CTA path when (boxes that can be kept) x N stays small; otherwise the full bitmask + sweep
   const long long cap = max_output > 0 ? (long long)min(max_output, Nmax) : (long long)Nmax;
-  if (cap * (long long)Nmax <= (64ll << 20)) {
+  if (cap * (long long)Nmax <= (2ll << 20)) {  // e.g. 100 detections out of 5 000; RPN (1 000 of ~9 000) takes the mask path
     const size_t fsmem = (size_t)a.nwords * 8;
     if (fsmem > 40 * 1024)
       BDET_CUDA(cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
 // with the same products as the scatter form (oracle: g * ((1-ly)(1-lx)) ...); only the summation order differs.
 constexpr int kTH = 16, kTW = 32, kCC = 32;
 constexpr int kGatherThreads = 256;
+constexpr int kMaxList = 1024;
 
 struct TileGrid {
   int tiles_y[BDET_MAX_LEVELS], tiles_x[BDET_MAX_LEVELS];
@@ -338,8 +339,22 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
   const float cnt = (float)(p.SH * p.SW);
   for (int i = t; i < kCC * kTH * kTW; i += kGatherThreads) acc[i] = 0.f;
   const int beg = b.offset[tile], end = b.offset[tile + 1];
+  // The bin lists are filled with atomics (arbitrary order); visiting ROIs in ascending id makes the fp32 sums
+  // reproducible.  Rank sort in shared memory (ids are unique); longer lists stay in fill order.
+  __shared__ int sids[kMaxList];
+  const int nlist = end - beg;
+  const bool sorted = nlist <= kMaxList;
+  if (sorted) {
+    for (int i = t; i < nlist; i += kGatherThreads) {
+      const int id = b.list[beg + i];
+      int rank = 0;
+      for (int j = 0; j < nlist; ++j) rank += b.list[beg + j] < id;
+      sids[rank] = id;
+    }
+  }
+  __syncthreads();
   for (int e = beg; e < end; ++e) {
-    const int k = b.list[e];
+    const int k = sorted ? sids[e - beg] : b.list[e];
     const RoiGeom g = roi_geom(p, k);
     __syncthreads();  // previous ROI's tables / sdout are free; acc zero-fill done
     for (int s = t; s < NS_Y; s += kGatherThreads) {

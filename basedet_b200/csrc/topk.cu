@@ -21,6 +21,7 @@ namespace bdet {
 constexpr int kSelThreads = 1024;
 constexpr int kBufCap = 4096;  // candidate keys buffered in shared memory once a radix bucket is this small
 constexpr int kMaxK = 16384;
+constexpr int kSelUnroll = 8;
 
 // One (image, level) segment.  Segments may live in different allocations: `start` is an element offset from the
 // base pointer handed to the entry point (any fp32 device address is base + 4*start for some start).
@@ -86,12 +87,21 @@ __device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint
     if (t < 256) sm.hist[t] = 0;
     __syncthreads();
     const int m = buffered ? sm.nbuf : n;
-    for (int i0 = 0; i0 < m; i0 += kSelThreads) {
-      int i = i0 + t;
-      bool in = i < m;
-      uint64_t key = in ? (buffered ? buf[i] : src.key(i)) : 0;
-      bool act = in && ((key & mask) == prefix);
-      hist_add(sm.hist, (int)((key >> shift) & 255), act);
+    // kSelUnroll independent loads in flight per thread: a one-load-per-iteration sweep is pure L2 latency
+    for (int i0 = 0; i0 < m; i0 += kSelThreads * kSelUnroll) {
+      uint64_t key[kSelUnroll];
+      bool in[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int i = i0 + u * kSelThreads + t;
+        in[u] = i < m;
+        key[u] = in[u] ? (buffered ? buf[i] : src.key(i)) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const bool act = in[u] && ((key[u] & mask) == prefix);
+        hist_add(sm.hist, (int)((key[u] >> shift) & 255), act);
+      }
     }
     __syncthreads();
     // inclusive scan of the 256 bins (8 warps)
@@ -125,12 +135,20 @@ __device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint
     if (!buffered && cnt <= kBufCap) {
       if (t == 0) sm.nbuf = 0;
       __syncthreads();
-      for (int i0 = 0; i0 < n; i0 += kSelThreads) {
-        int i = i0 + t;
-        uint64_t key = i < n ? src.key(i) : 0;
-        bool act = i < n && ((key & mask) == prefix);
-        int slot = append_slot(&sm.nbuf, act);
-        if (act) buf[slot] = key;
+      for (int i0 = 0; i0 < n; i0 += kSelThreads * kSelUnroll) {
+        uint64_t key[kSelUnroll];
+#pragma unroll
+        for (int u = 0; u < kSelUnroll; ++u) {
+          const int i = i0 + u * kSelThreads + t;
+          key[u] = i < n ? src.key(i) : ~0ull;  // ~0 never matches a (prefix, mask) that selected a real bucket
+        }
+#pragma unroll
+        for (int u = 0; u < kSelUnroll; ++u) {
+          const int i = i0 + u * kSelThreads + t;
+          const bool act = i < n && ((key[u] & mask) == prefix);
+          const int slot = append_slot(&sm.nbuf, act);
+          if (act) buf[slot] = key[u];
+        }
       }
       buffered = true;
     }
@@ -170,12 +188,20 @@ __global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs 
   uint64_t T = ~0ull;
   if (n > k) T = RAW ? radix_select(rs, n, k, sm, buf) : radix_select(ks, n, k, sm, buf);
   __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
-    int i = i0 + t;
-    uint64_t key = i < n ? (RAW ? rs.key(i) : ks.key(i)) : ~0ull;
-    bool act = i < n && key <= T;
-    int slot = append_slot(&sm.nsel, act);
-    if (act) sortbuf[slot] = key;
+  for (int i0 = 0; i0 < n; i0 += kSelThreads * kSelUnroll) {
+    uint64_t key[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int i = i0 + u * kSelThreads + t;
+      key[u] = i < n ? (RAW ? rs.key(i) : ks.key(i)) : ~0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int i = i0 + u * kSelThreads + t;
+      const bool act = i < n && key[u] <= T;
+      const int slot = append_slot(&sm.nsel, act);
+      if (act) sortbuf[slot] = key[u];
+    }
   }
   for (int i = k + t; i < p.P; i += kSelThreads) sortbuf[i] = ~0ull;
   bitonic_sort_smem(sortbuf, p.P);

@@ -570,9 +570,10 @@ def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 
 
 
 def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True,
-                  dfeats=None, accumulate=False, gather=True, workspace=None):
+                  dfeats=None, accumulate=False, gather=False, workspace=None):
     """Gradient w.r.t. the features.  ``dfeats`` (list) are written (accumulate=False) or added to (True);
-    allocated when None.  gather=True uses the atomics-free tile-gather kernel, False the scatter kernel."""
+    allocated when None.  gather=False (default, currently the faster one) is the shared-memory scatter kernel;
+    gather=True the atomics-free, run-to-run deterministic tile-gather kernel."""
     lib = _lib.load()
     d = _f32c(dout, "dout")
     r = _f32c(rois, "rois")

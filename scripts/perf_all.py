@@ -114,7 +114,7 @@ run("c3_roi_fwd", lambda: pipelines.roi_pool_forward_backward(feats, rois, W.FRC
 dfe = [torch.empty_like(f) for f in feats]
 lv = ops.roi_assign_levels(rois, 2, 5)
 wsb = ops._workspace(_lib.load().bdet_roi_align_bwd_workspace(4, _lib.iarr([v for f in feats for v in f.shape[-2:]]), B3, K), dev)
-run("c3_roi_bwd_gather", lambda: ops.roi_align_bwd(dout, None, rois, lv, [1 / s for s in W.FRCNN_RCNN_STRIDES], (7, 7), dfeats=dfe, workspace=wsb),
+run("c3_roi_bwd_gather", lambda: ops.roi_align_bwd(dout, None, rois, lv, [1 / s for s in W.FRCNN_RCNN_STRIDES], (7, 7), dfeats=dfe, workspace=wsb, gather=True),
     {"roi_align_bwd_gather_kernel": K * Cn * 49 * 4 + pyr}, iters=5)
 run("c3_roi_bwd_scatter", lambda: ops.roi_align_bwd(dout, None, rois, lv, [1 / s for s in W.FRCNN_RCNN_STRIDES], (7, 7), dfeats=dfe, gather=False),
     {"roi_align_bwd_kernel": K * Cn * 49 * 4 + 2 * pyr}, iters=3)

@@ -113,12 +113,12 @@ def test_roi_align_backward_gather_is_deterministic_and_generic(cuda):
     feat_shape = (2, 5, 45, 70)
     rois = W.make_rois(rng, 40, 2, 45 * 4, 70 * 4, 6, 200)
     dout = rng.normal(0, 1, (80, 5, 3, 5)).astype(np.float32)
-    a = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3))[0]
-    b = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3))[0]
+    a = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3), gather=True)[0]
+    b = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], (3, 5), (1, 3), gather=True)[0]
     assert torch.equal(a, b)
     ref = R.roi_align_backward(dout, feat_shape, rois, (3, 5), 0.25, (1, 3))
     assert np.max(np.abs(a.cpu().numpy() - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
-    empty = ops.roi_align_bwd(T(dout[:0], cuda), [feat_shape], T(rois[:0], cuda), None, [0.25], (3, 5), (1, 3))[0]
+    empty = ops.roi_align_bwd(T(dout[:0], cuda), [feat_shape], T(rois[:0], cuda), None, [0.25], (3, 5), (1, 3), gather=True)[0]
     assert float(empty.abs().max()) == 0.0   # K = 0: the gradient is all zeros, still fully written
 
 
