@@ -310,20 +310,25 @@ __global__ void __launch_bounds__(1024) roi_bin_scan_kernel(const BinArgs b) {
   if (t == 0) b.offset[n] = carry;
 }
 
-struct GatherSmem {
-  int y_i0[kMaxSamples], x_i0[kMaxSamples];
-  float y_fr[kMaxSamples], x_fr[kMaxSamples];
-  int rlo[kTH], rhi[kTH], clo[kTW], chi[kTW];
-  int box[4];
-};
+// Per-axis weight of one sample coordinate c on pixel `pix`: the bilinear taps are floor(c) and floor(c) + 1.
+__device__ __forceinline__ float tap_weight(float c, int pix) {
+  const float fl = floorf(c);
+  const int i0 = (int)fl;
+  const float fr = c - fl;
+  return i0 == pix ? 1.f - fr : (i0 + 1 == pix ? fr : 0.f);
+}
 
 __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(const BinArgs b, int accumulate) {
   extern __shared__ __align__(16) float gsm[];
-  float* acc = gsm;                        // kCC * kTH * kTW
-  float* sdout = gsm + kCC * kTH * kTW;    // kCC * PH * PW
-  __shared__ GatherSmem sm;
   const RoiArgs& p = b.r;
-  const int tile = blockIdx.x, c0 = blockIdx.y * kCC, t = threadIdx.x;
+  const int PH = p.PH, PW = p.PW, bins = PH * PW;
+  float* acc = gsm;                          // kCC * kTH * kTW
+  float* sdout = acc + kCC * kTH * kTW;      // kCC * bins      (dout / S^2 of the current ROI)
+  float* wy = sdout + kCC * bins;            // kTH * PH        Wy[r][ph] = sum of the bin's sample weights on row r
+  float* wx = wy + kTH * PH;                 // kTW * PW
+  __shared__ int rlo[kTH], rhi[kTH], clo[kTW], chi[kTW];
+  __shared__ int sids[kMaxList];
+  const int tile = blockIdx.x, c0 = blockIdx.y * kCC, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nc = min(kCC, p.C - c0);
   int l = 0;
 #pragma unroll
@@ -335,13 +340,11 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
   const int n = rel / (ty_n * tx_n);
   rel -= n * ty_n * tx_n;
   const int y0t = (rel / tx_n) * kTH, x0t = (rel % tx_n) * kTW;
-  const int bins = p.PH * p.PW, NS_Y = p.PH * p.SH, NS_X = p.PW * p.SW;
   const float cnt = (float)(p.SH * p.SW);
   for (int i = t; i < kCC * kTH * kTW; i += kGatherThreads) acc[i] = 0.f;
   const int beg = b.offset[tile], end = b.offset[tile + 1];
   // The bin lists are filled with atomics (arbitrary order); visiting ROIs in ascending id makes the fp32 sums
   // reproducible.  Rank sort in shared memory (ids are unique); longer lists stay in fill order.
-  __shared__ int sids[kMaxList];
   const int nlist = end - beg;
   const bool sorted = nlist <= kMaxList;
   if (sorted) {
@@ -352,93 +355,82 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
       sids[rank] = id;
     }
   }
-  __syncthreads();
   for (int e = beg; e < end; ++e) {
+    __syncthreads();  // previous ROI's tables are free; (first iteration) acc zero-fill and sids are complete
     const int k = sorted ? sids[e - beg] : b.list[e];
     const RoiGeom g = roi_geom(p, k);
-    __syncthreads();  // previous ROI's tables / sdout are free; acc zero-fill done
-    for (int s = t; s < NS_Y; s += kGatherThreads) {
-      const int pidx = s / p.SH, i = s - pidx * p.SH;
-      const float c = g.start_h + g.bin_h * ((float)pidx + __fdiv_rn((float)i + 0.5f, (float)p.SH));
-      const float fl = floorf(c);
-      sm.y_i0[s] = (int)fl;
-      sm.y_fr[s] = c - fl;
-    }
-    for (int s = t; s < NS_X; s += kGatherThreads) {
-      const int pidx = s / p.SW, i = s - pidx * p.SW;
-      const float c = g.start_w + g.bin_w * ((float)pidx + __fdiv_rn((float)i + 0.5f, (float)p.SW));
-      const float fl = floorf(c);
-      sm.x_i0[s] = (int)fl;
-      sm.x_fr[s] = c - fl;
+    // rows: thread r < kTH builds Wy[r][:] and its non-zero bin range; columns: threads 32 .. 32 + kTW
+    if (t < kTH) {
+      const int y = y0t + t;
+      int lo = PH, hi = -1;
+      for (int ph = 0; ph < PH; ++ph) {
+        float w = 0.f;
+        if (y < H)
+          for (int iy = 0; iy < p.SH; ++iy)
+            w += tap_weight(g.start_h + g.bin_h * ((float)ph + __fdiv_rn((float)iy + 0.5f, (float)p.SH)), y);
+        wy[t * PH + ph] = w;
+        if (w != 0.f) {
+          lo = min(lo, ph);
+          hi = ph;
+        }
+      }
+      rlo[t] = lo;
+      rhi[t] = hi;
+    } else if (t >= 32 && t < 32 + kTW) {
+      const int xx = t - 32, x = x0t + xx;
+      int lo = PW, hi = -1;
+      for (int pw = 0; pw < PW; ++pw) {
+        float w = 0.f;
+        if (x < W)
+          for (int ix = 0; ix < p.SW; ++ix)
+            w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
+        wx[xx * PW + pw] = w;
+        if (w != 0.f) {
+          lo = min(lo, pw);
+          hi = pw;
+        }
+      }
+      clo[xx] = lo;
+      chi[xx] = hi;
     }
     const float* dk = p.dout + ((long long)k * p.C + c0) * bins;
     for (int i = t; i < nc * bins; i += kGatherThreads) sdout[i] = __fdiv_rn(__ldg(dk + i), cnt);
     __syncthreads();
-    // contiguous sample ranges feeding each tile row / column: i0 in {y - 1, y}
-    if (t < kTH) {
-      const int y = y0t + t;
-      int lo = NS_Y, hi = -1;
-      if (y < H)
-        for (int s = 0; s < NS_Y; ++s) {
-          const int i0 = sm.y_i0[s];
-          if (i0 == y || i0 + 1 == y) {
-            lo = min(lo, s);
-            hi = s;
-          }
-        }
-      sm.rlo[t] = lo;
-      sm.rhi[t] = hi;
-    } else if (t >= 32 && t < 32 + kTW) {
-      const int x = x0t + (t - 32);
-      int lo = NS_X, hi = -1;
-      if (x < W)
-        for (int s = 0; s < NS_X; ++s) {
-          const int i0 = sm.x_i0[s];
-          if (i0 == x || i0 + 1 == x) {
-            lo = min(lo, s);
-            hi = s;
-          }
-        }
-      sm.clo[t - 32] = lo;
-      sm.chi[t - 32] = hi;
-    }
-    if (t == 0) {  // footprint of this ROI inside the tile (tile-local coordinates)
-      const int y_lo = max(sm.y_i0[0], y0t), y_hi = min(sm.y_i0[NS_Y - 1] + 1, min(y0t + kTH, H) - 1);
-      const int x_lo = max(sm.x_i0[0], x0t), x_hi = min(sm.x_i0[NS_X - 1] + 1, min(x0t + kTW, W) - 1);
-      sm.box[0] = y_lo - y0t;
-      sm.box[1] = x_lo - x0t;
-      sm.box[2] = y_hi - y_lo + 1;
-      sm.box[3] = x_hi - x_lo + 1;
-    }
-    __syncthreads();
-    const int fr0 = sm.box[0], fc0 = sm.box[1], nr = sm.box[2], ncol = sm.box[3];
-    if (nr <= 0 || ncol <= 0) continue;  // CTA-uniform
-    const int per_c = nr * ncol;
-    for (int i = t; i < nc * per_c; i += kGatherThreads) {
-      const int c = i / per_c, rem = i - c * per_c;
-      const int r = fr0 + rem / ncol, x = fc0 + rem % ncol;
-      const int slo = sm.rlo[r], shi = sm.rhi[r], tlo = sm.clo[x], thi = sm.chi[x];
-      if (slo > shi || tlo > thi) continue;
-      const int gy = y0t + r, gx = x0t + x;
-      const float* dc = sdout + c * bins;
-      float sum = 0.f;
-      for (int sy = slo; sy <= shi; ++sy) {
-        const int iy0 = sm.y_i0[sy];
-        float wy;
-        if (iy0 == gy) wy = 1.f - sm.y_fr[sy];
-        else if (iy0 + 1 == gy) wy = sm.y_fr[sy];
-        else continue;
-        const float* drow = dc + (sy / p.SH) * p.PW;
-        for (int sx = tlo; sx <= thi; ++sx) {
-          const int ix0 = sm.x_i0[sx];
-          float wx;
-          if (ix0 == gx) wx = 1.f - sm.x_fr[sx];
-          else if (ix0 + 1 == gx) wx = sm.x_fr[sx];
-          else continue;
-          sum += drow[sx / p.SW] * (wy * wx);
-        }
+    // footprint of this ROI inside the tile: rows / columns with a non-empty bin range (contiguous)
+    int fr0 = kTH, fr1 = -1, fc0 = kTW, fc1 = -1;
+    for (int r = 0; r < kTH; ++r)
+      if (rlo[r] <= rhi[r]) {
+        fr0 = min(fr0, r);
+        fr1 = r;
       }
-      acc[(c * kTH + r) * kTW + x] += sum;  // one thread per (c, r, x) within a ROI: no conflict
+    for (int x = 0; x < kTW; ++x)
+      if (clo[x] <= chi[x]) {
+        fc0 = min(fc0, x);
+        fc1 = x;
+      }
+    if (fr1 < fr0 || fc1 < fc0) continue;  // CTA-uniform (tables are shared)
+    const int ncol = fc1 - fc0 + 1, nrow = fr1 - fr0 + 1;
+    int wshift = 0;
+    while ((1 << wshift) < ncol) ++wshift;          // lanes: x = lane & (2^wshift - 1), row sub-index = lane >> wshift
+    const int rows_per_it = 32 >> wshift;
+    const int lx = lane & ((1 << wshift) - 1), lr = lane >> wshift;
+    const int x = fc0 + lx;
+    const bool xok = lx < ncol;
+    const int tlo = xok ? clo[x] : 1, thi = xok ? chi[x] : 0;
+    for (int c = warp; c < nc; c += kGatherThreads / 32) {
+      const float* dc = sdout + c * bins;
+      float* ac = acc + c * kTH * kTW;
+      for (int r0 = 0; r0 < nrow; r0 += rows_per_it) {
+        const int r = fr0 + r0 + lr;
+        if (r > fr1 || tlo > thi) continue;
+        const int slo = rlo[r], shi = rhi[r];
+        float sum = 0.f;
+        for (int ph = slo; ph <= shi; ++ph) {
+          const float wyv = wy[r * PH + ph];
+          for (int pw = tlo; pw <= thi; ++pw) sum += dc[ph * PW + pw] * (wyv * wx[x * PW + pw]);
+        }
+        ac[r * kTW + x] += sum;  // one lane per (c, r, x): no conflict
+      }
     }
   }
   __syncthreads();
@@ -595,7 +587,7 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
     if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<false><<<ceil_div(K, 256), 256, 0, st>>>(b));
     BDET_KERNEL("roi_bin_scan_kernel", st, roi_bin_scan_kernel<<<1, 1024, 0, st>>>(b));
     if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<true><<<ceil_div(K, 256), 256, 0, st>>>(b));
-    const size_t smem = ((size_t)kCC * kTH * kTW + (size_t)kCC * PH * PW) * 4;
+    const size_t smem = ((size_t)kCC * kTH * kTW + (size_t)kCC * PH * PW + (size_t)kTH * PH + (size_t)kTW * PW) * 4;
     if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large for the gather kernel");
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chunks = ceil_div(C, kCC);

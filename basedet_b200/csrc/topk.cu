@@ -243,6 +243,12 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
   return s > p.thr;
 }
 
+// Rare path of the filter: exact score, `> thr`, append to the CTA's shared staging buffer.
+__device__ __noinline__ void stage_candidate(const FilterArgs& p, float x, int e, long long coff, uint64_t* skeys, int* scount) {
+  float sc;
+  if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(scount, 1)] = make_key(sc, (uint32_t)e);
+}
+
 constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresholds (FCOS); needs C >= 4096 / 159
 
 // HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
@@ -251,7 +257,7 @@ constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresh
 // fp32 score and the `> thr` test, are staged in shared memory, and the CTA reserves its output range with a single
 // global atomic per tile (a per-candidate atomic on ~40 segment counters serialises in L2).
 template <bool VEC>
-__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p, int total_tiles) {
+__global__ void __launch_bounds__(kFiltThreads, 5) score_filter_kernel(const FilterArgs p, int total_tiles) {
   __shared__ uint64_t skeys[kFiltTile];
   __shared__ float spre[kPosTab];
   __shared__ int scount, sbase;
@@ -307,10 +313,7 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
     __syncthreads();
 
     auto consider = [&](float x, int e, float bound) {
-      if (x > bound) {  // rare
-        float sc;
-        if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(&scount, 1)] = make_key(sc, (uint32_t)e);
-      }
+      if (x > bound) stage_candidate(p, x, e, coff, skeys, &scount);  // rare: kept out of line (register pressure)
     };
     if (VEC) {
 #pragma unroll
@@ -506,7 +509,7 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     }
   }
   if (tiles > 0) {
-    const int grid = min(tiles, sm_count() * 6);  // 6 resident CTAs / SM (33 KB of shared memory each)
+    const int grid = min(tiles, sm_count() * 5);  // 5 resident CTAs / SM (registers; 33 KB of shared memory each)
     if (vec)
       BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
     else
