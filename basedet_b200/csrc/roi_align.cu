@@ -134,93 +134,6 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArg
   }
 }
 
-// Backward.  Shared accumulation buffer covers rows [fy0, fy0+fh) x cols [fx0, fx0+fw) of the level map for a
-// chunk of channels; taps outside the map were zero-padded in the forward pass and receive nothing.
-__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
-  extern __shared__ __align__(16) float sacc[];
-  __shared__ SampleTab ty, tx;
-  __shared__ int sbox[4];
-  const int k = blockIdx.x, t = threadIdx.x;
-  const int PH = p.PH, PW = p.PW, SH = p.SH, SW = p.SW;
-  const RoiGeom g = roi_geom(p, k);
-  if (!g.valid) return;
-  fill_axis(ty, PH, SH, g.start_h, g.bin_h);
-  fill_axis(tx, PW, SW, g.start_w, g.bin_w);
-  __syncthreads();
-  const int H = g.H, W = g.W;
-  if (t == 0) {
-    // sample coordinates are monotone along each axis: first / last sample bound the footprint
-    int y_lo = max(ty.i0[0], 0), y_hi = min(ty.i0[PH * SH - 1] + 1, H - 1);
-    int x_lo = max(tx.i0[0], 0), x_hi = min(tx.i0[PW * SW - 1] + 1, W - 1);
-    sbox[0] = y_lo;
-    sbox[1] = x_lo;
-    sbox[2] = y_hi - y_lo + 1;
-    sbox[3] = x_hi - x_lo + 1;
-  }
-  __syncthreads();
-  const int fy0 = sbox[0], fx0 = sbox[1], fh = sbox[2], fw = sbox[3];
-  if (fh <= 0 || fw <= 0) return;  // ROI entirely outside the map
-  const int bins = PH * PW;
-  const float cnt = (float)(SH * SW);
-  float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
-  const float* dout = p.dout + (long long)k * p.C * bins;
-  const long long area = (long long)fh * fw;
-  const bool use_smem = area <= p.bwd_cap;
-  const int chunk = use_smem ? (int)min((long long)p.C, (long long)p.bwd_cap / area) : p.C;
-
-  for (int c0 = 0; c0 < p.C; c0 += chunk) {
-    const int nc = min(chunk, p.C - c0);
-    if (use_smem) {
-      for (int i = t; i < nc * (int)area; i += kRoiThreads) sacc[i] = 0.f;
-      __syncthreads();
-    }
-    for (int o = t; o < nc * bins; o += kRoiThreads) {
-      const int cl = o / bins, bin = o - cl * bins;
-      const int ph = bin / PW, pw = bin - ph * PW;
-      const float gval = __fdiv_rn(__ldg(dout + (long long)(c0 + cl) * bins + bin), cnt);
-      float* gacc = dfeat + (long long)(c0 + cl) * H * W;
-      float* lacc = sacc + (long long)cl * area;
-      for (int iy = 0; iy < SH; ++iy) {
-        const int sy = ph * SH + iy;
-        const int y0 = ty.i0[sy], y1 = y0 + 1;
-        const float ly = ty.frac[sy];
-        const bool y0ok = y0 >= 0 && y0 < H, y1ok = y1 >= 0 && y1 < H;
-        for (int ix = 0; ix < SW; ++ix) {
-          const int sx = pw * SW + ix;
-          const int x0 = tx.i0[sx], x1 = x0 + 1;
-          const float lx = tx.frac[sx];
-          const bool x0ok = x0 >= 0 && x0 < W, x1ok = x1 >= 0 && x1 < W;
-          const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx;
-          const float w10 = ly * (1.f - lx), w11 = ly * lx;
-          if (use_smem) {
-            if (y0ok && x0ok) atomicAdd(lacc + (y0 - fy0) * fw + (x0 - fx0), gval * w00);
-            if (y0ok && x1ok) atomicAdd(lacc + (y0 - fy0) * fw + (x1 - fx0), gval * w01);
-            if (y1ok && x0ok) atomicAdd(lacc + (y1 - fy0) * fw + (x0 - fx0), gval * w10);
-            if (y1ok && x1ok) atomicAdd(lacc + (y1 - fy0) * fw + (x1 - fx0), gval * w11);
-          } else {
-            if (y0ok && x0ok) atomicAdd(gacc + y0 * W + x0, gval * w00);
-            if (y0ok && x1ok) atomicAdd(gacc + y0 * W + x1, gval * w01);
-            if (y1ok && x0ok) atomicAdd(gacc + y1 * W + x0, gval * w10);
-            if (y1ok && x1ok) atomicAdd(gacc + y1 * W + x1, gval * w11);
-          }
-        }
-      }
-    }
-    if (use_smem) {
-      __syncthreads();
-      for (int i = t; i < nc * (int)area; i += kRoiThreads) {
-        const float v = sacc[i];
-        if (v != 0.f) {
-          const int cl = i / (int)area, rem = i - cl * (int)area;
-          const int yy = rem / fw, xx = rem - yy * fw;
-          atomicAdd(dfeat + ((long long)(c0 + cl) * H + (fy0 + yy)) * W + (fx0 + xx), v);
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Backward, gather form (default).  The feature maps are cut into kTH x kTW pixel tiles; ROIs are binned per tile
 // (count -> scan -> fill); one CTA owns (tile, chunk of kCC channels), accumulates every ROI of its list into a
@@ -445,6 +358,98 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
   }
 }
 
+// Backward, scatter form (no workspace): one CTA per ROI.  The separable bilinear weights of the ROI are tabulated
+// once per footprint chunk -- Wy[row][ph], Wx[col][pw] = summed tap weights of the bin's samples -- and shared by all
+// C channels; a lane then owns one (channel, y, x) of the footprint, sums its few (ph, pw) terms in registers and
+// issues ONE red.global.add.f32 (coalesced along x): footprint x C reds per ROI instead of 16 x P^2 x C, no shared
+// atomics, no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
+constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
+
+__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
+  extern __shared__ __align__(16) float bsm[];
+  const int PH = p.PH, PW = p.PW, bins = PH * PW;
+  float* wy = bsm;                              // kFpChunk * PH
+  float* wx = wy + kFpChunk * PH;               // kFpChunk * PW
+  float* sd = wx + kFpChunk * PW;               // (warps) * bins: dout / S^2 of the warp's current channel
+  __shared__ int rlo[kFpChunk], rhi[kFpChunk], clo[kFpChunk], chi[kFpChunk];
+  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const RoiGeom g = roi_geom(p, k);
+  if (!g.valid) return;
+  int y_lo, y_hi, x_lo, x_hi;
+  if (!roi_footprint(p, g, y_lo, y_hi, x_lo, x_hi)) return;  // ROI entirely outside the map
+  const int H = g.H, W = g.W;
+  const float cnt = (float)(p.SH * p.SW);
+  float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
+  const float* dout = p.dout + (long long)k * p.C * bins;
+  float* sdw = sd + warp * bins;
+  for (int fy = y_lo; fy <= y_hi; fy += kFpChunk) {
+    for (int fx = x_lo; fx <= x_hi; fx += kFpChunk) {
+      const int nr = min(kFpChunk, y_hi - fy + 1), ncol = min(kFpChunk, x_hi - fx + 1);
+      __syncthreads();
+      if (t < nr) {
+        const int y = fy + t;
+        int lo = PH, hi = -1;
+        for (int ph = 0; ph < PH; ++ph) {
+          float w = 0.f;
+          for (int iy = 0; iy < p.SH; ++iy)
+            w += tap_weight(g.start_h + g.bin_h * ((float)ph + __fdiv_rn((float)iy + 0.5f, (float)p.SH)), y);
+          wy[t * PH + ph] = w;
+          if (w != 0.f) {
+            lo = min(lo, ph);
+            hi = ph;
+          }
+        }
+        rlo[t] = lo;
+        rhi[t] = hi;
+      } else if (t >= 128 && t < 128 + ncol) {
+        const int xx = t - 128, x = fx + xx;
+        int lo = PW, hi = -1;
+        for (int pw = 0; pw < PW; ++pw) {
+          float w = 0.f;
+          for (int ix = 0; ix < p.SW; ++ix)
+            w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
+          wx[xx * PW + pw] = w;
+          if (w != 0.f) {
+            lo = min(lo, pw);
+            hi = pw;
+          }
+        }
+        clo[xx] = lo;
+        chi[xx] = hi;
+      }
+      __syncthreads();
+      const int wcols = min(ncol, 32);
+      int wshift = 0;
+      while ((1 << wshift) < wcols) ++wshift;  // lanes: x = lane & (2^wshift - 1), row sub-index = lane >> wshift
+      const int rows_per_it = 32 >> wshift;
+      const int lx = lane & ((1 << wshift) - 1), lr = lane >> wshift;
+      for (int c = warp; c < p.C; c += kRoiThreads / 32) {
+        __syncwarp();
+        for (int i = lane; i < bins; i += 32) sdw[i] = __fdiv_rn(__ldg(dout + (long long)c * bins + i), cnt);
+        __syncwarp();
+        float* gc = dfeat + (long long)c * H * W;
+        for (int x0 = 0; x0 < ncol; x0 += 32) {
+          const int xx = x0 + lx;
+          const bool xok = lx < wcols && xx < ncol;
+          const int tlo = xok ? clo[xx] : 1, thi = xok ? chi[xx] : 0;
+          if (tlo > thi) continue;  // lane idle for this column block (no warp-level sync inside)
+          for (int r0 = 0; r0 < nr; r0 += rows_per_it) {
+            const int r = r0 + lr;
+            if (r >= nr) continue;
+            const int slo = rlo[r], shi = rhi[r];
+            float sum = 0.f;
+            for (int ph = slo; ph <= shi; ++ph) {
+              const float wyv = wy[r * PH + ph];
+              for (int pw = tlo; pw <= thi; ++pw) sum += sdw[ph * PW + pw] * (wyv * wx[xx * PW + pw]);
+            }
+            if (sum != 0.f) atomicAdd(gc + (long long)(fy + r) * W + (fx + xx), sum);
+          }
+        }
+      }
+    }
+  }
+}
+
 static void make_tile_grid(TileGrid* g, int n_levels, const int* hw, int B, int* max_per_image) {
   int base = 0, mx = 1;
   for (int l = 0; l < n_levels; ++l) {
@@ -603,9 +608,10 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
       BDET_CUDA(cudaMemsetAsync(dfeats_host[l], 0, (size_t)B * C * hw_host[2 * l] * hw_host[2 * l + 1] * 4, st));
   }
   if (K == 0) return BDET_OK;
-  const int smem = 64 * 1024;
-  a.bwd_cap = smem / 4;
-  BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const size_t smem = ((size_t)kFpChunk * (PH + PW) + (size_t)(kRoiThreads / 32) * PH * PW) * 4;
+  if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
+  if (smem > 40 * 1024)
+    BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
