@@ -365,24 +365,6 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
 // atomics, no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
 constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
 
-// Four consecutive pixels in one reduction: red.global.add.v4.f32 (sm_90+) when the address is 16-byte aligned,
-// .v2 pairs when 8-byte aligned, scalar otherwise.  Global reds are the bound of this kernel (one per lane-op),
-// so the vector forms cut the bound by up to 4x.
-__device__ __forceinline__ void red_add4(float* ptr, float a, float b, float c, float d, int valid) {
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(ptr);
-  if (valid == 4 && (addr & 15u) == 0) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-  } else if (valid == 4 && (addr & 7u) == 0) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ptr), "f"(a), "f"(b) : "memory");
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ptr + 2), "f"(c), "f"(d) : "memory");
-  } else {
-    if (valid > 0 && a != 0.f) atomicAdd(ptr, a);
-    if (valid > 1 && b != 0.f) atomicAdd(ptr + 1, b);
-    if (valid > 2 && c != 0.f) atomicAdd(ptr + 2, c);
-    if (valid > 3 && d != 0.f) atomicAdd(ptr + 3, d);
-  }
-}
-
 __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
   extern __shared__ __align__(16) float bsm[];
   const int PH = p.PH, PW = p.PW, bins = PH * PW;
@@ -401,8 +383,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   const float* dout = p.dout + (long long)k * p.C * bins;
   float* sdw = sd + warp * bins;
   for (int fy = y_lo; fy <= y_hi; fy += kFpChunk) {
-    for (int fx = x_lo & ~3; fx <= x_hi; fx += kFpChunk) {  // chunk origin on a 4-pixel boundary (vector reds)
-      const int nr = min(kFpChunk, y_hi - fy + 1), ncol = min(kFpChunk, min(x_hi, W - 1) - fx + 1);
+    for (int fx = x_lo; fx <= x_hi; fx += kFpChunk) {
+      const int nr = min(kFpChunk, y_hi - fy + 1), ncol = min(kFpChunk, x_hi - fx + 1);
       __syncthreads();
       if (t < nr) {
         const int y = fy + t;
@@ -419,59 +401,49 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
         }
         rlo[t] = lo;
         rhi[t] = hi;
-      } else if (t >= 128 && t < 128 + kFpChunk) {
+      } else if (t >= 128 && t < 128 + ncol) {
         const int xx = t - 128, x = fx + xx;
         int lo = PW, hi = -1;
         for (int pw = 0; pw < PW; ++pw) {
           float w = 0.f;
-          if (xx < ncol && x >= x_lo)
-            for (int ix = 0; ix < p.SW; ++ix)
-              w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
+          for (int ix = 0; ix < p.SW; ++ix)
+            w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
           wx[xx * PW + pw] = w;
           if (w != 0.f) {
             lo = min(lo, pw);
             hi = pw;
           }
         }
-        clo[xx] = lo;  // empty range (lo > hi) for columns outside the ROI footprint / the map
+        clo[xx] = lo;
         chi[xx] = hi;
       }
       __syncthreads();
-      const int nquad = (ncol + 3) >> 2;           // <= 16
+      const int wcols = min(ncol, 32);
       int wshift = 0;
-      while ((1 << wshift) < nquad) ++wshift;      // lanes: quad = lane & (2^wshift - 1), row sub-index = lane >> wshift
+      while ((1 << wshift) < wcols) ++wshift;  // lanes: x = lane & (2^wshift - 1), row sub-index = lane >> wshift
       const int rows_per_it = 32 >> wshift;
-      const int lq = lane & ((1 << wshift) - 1), lr = lane >> wshift;
-      const int xq = 4 * lq;
-      const bool qok = lq < nquad;
-      int tlo[4], thi[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        tlo[j] = qok ? clo[xq + j] : 1;
-        thi[j] = qok ? chi[xq + j] : 0;
-      }
-      const int valid = qok ? min(4, W - (fx + xq)) : 0;  // pixels of the quad inside the map row
-      const bool any_col = (tlo[0] <= thi[0]) || (tlo[1] <= thi[1]) || (tlo[2] <= thi[2]) || (tlo[3] <= thi[3]);
+      const int lx = lane & ((1 << wshift) - 1), lr = lane >> wshift;
       for (int c = warp; c < p.C; c += kRoiThreads / 32) {
         __syncwarp();
         for (int i = lane; i < bins; i += 32) sdw[i] = __fdiv_rn(__ldg(dout + (long long)c * bins + i), cnt);
         __syncwarp();
-        if (!any_col) continue;
         float* gc = dfeat + (long long)c * H * W;
-        for (int r0 = 0; r0 < nr; r0 += rows_per_it) {
-          const int r = r0 + lr;
-          if (r >= nr) continue;
-          const int slo = rlo[r], shi = rhi[r];
-          if (slo > shi) continue;
-          float sum[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int ph = slo; ph <= shi; ++ph) {
-            const float wyv = wy[r * PH + ph];
-            const float* drow = sdw + ph * PW;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              for (int pw = tlo[j]; pw <= thi[j]; ++pw) sum[j] += drow[pw] * (wyv * wx[(xq + j) * PW + pw]);
+        for (int x0 = 0; x0 < ncol; x0 += 32) {
+          const int xx = x0 + lx;
+          const bool xok = lx < wcols && xx < ncol;
+          const int tlo = xok ? clo[xx] : 1, thi = xok ? chi[xx] : 0;
+          if (tlo > thi) continue;  // lane idle for this column block (no warp-level sync inside)
+          for (int r0 = 0; r0 < nr; r0 += rows_per_it) {
+            const int r = r0 + lr;
+            if (r >= nr) continue;
+            const int slo = rlo[r], shi = rhi[r];
+            float sum = 0.f;
+            for (int ph = slo; ph <= shi; ++ph) {
+              const float wyv = wy[r * PH + ph];
+              for (int pw = tlo; pw <= thi; ++pw) sum += sdw[ph * PW + pw] * (wyv * wx[xx * PW + pw]);
+            }
+            if (sum != 0.f) atomicAdd(gc + (long long)(fy + r) * W + (fx + xx), sum);
           }
-          red_add4(gc + (long long)(fy + r) * W + (fx + xq), sum[0], sum[1], sum[2], sum[3], valid);
         }
       }
     }
