@@ -6,9 +6,9 @@
 // the UNIQUE 64-bit key  (~ord(score) << 32) | index, so "top-k sorted" == "the k smallest keys, ascending";
 // a radix select finds the k-th key, a shared-memory bitonic network sorts the <= k survivors.
 //
-//   stage 1 (score_filter_kernel, HBM-read bound: 4 B/logit, grid-wide): 128-bit logit loads, a raw-logit
+//   stage 1 (score_filter_kernel, HBM-read bound: 4 B/logit, persistent grid): 128-bit logit loads, a raw-logit
 //           pre-filter (monotonicity of sigmoid) rejects ~99 % of the elements with one compare; survivors get the
-//           exact fp32 score, the `> thr` test, and are appended (warp-aggregated atomics) as keys.
+//           exact fp32 score and the `> thr` test, are staged in shared memory and flushed with one atomic per ~1k keys.
 //   stage 2 (select_sort_kernel, one CTA per segment): MSB-first 8-bit radix select over the candidates with
 //           early exit + small-bucket buffering in shared memory, then bitonic sort and write-out.
 #include <limits>
@@ -243,113 +243,150 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
   return s > p.thr;
 }
 
-// Rare path of the filter: exact score, `> thr`, append to the CTA's shared staging buffer.
-__device__ __noinline__ void stage_candidate(const FilterArgs& p, float x, int e, long long coff, uint64_t* skeys, int* scount) {
+constexpr int kStage = 2048;     // candidate keys staged in shared memory per CTA between flushes
+constexpr int kFlushAt = 1024;   // flush once this many are staged (a 4096-element tile rarely adds more than 1024)
+
+// Rare path of the filter: exact score, `> thr`, append to the CTA's shared staging buffer; if the buffer is full
+// (dense candidates) the key goes straight to the segment's global list.
+__device__ __noinline__ void stage_candidate(const FilterArgs& p, float x, int e, const SegDesc& sd, int s, uint64_t* skeys,
+                                             int* scount) {
   float sc;
-  if (exact_score(p, x, coff + e / p.C, sc)) skeys[atomicAdd(scount, 1)] = make_key(sc, (uint32_t)e);
+  if (!exact_score(p, x, sd.ctr_start + e / p.C, sc)) return;
+  const uint64_t key = make_key(sc, (uint32_t)e);
+  const int slot = atomicAdd(scount, 1);
+  if (slot < kStage) skeys[slot] = key;
+  else p.keys[sd.key_off + atomicAdd(p.cand_count + s, 1)] = key;
 }
 
 constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresholds (FCOS); needs C >= 4096 / 159
 
+__device__ __forceinline__ void load_tile(const float* src, int n, int e0, int t, float4 (&v)[kFiltVec]) {
+#pragma unroll
+  for (int j = 0; j < kFiltVec; ++j) {
+    const int e = e0 + (j * kFiltThreads + t) * 4;
+    const float ninf = -CUDART_INF_F;
+    if (e + 3 < n) {
+      v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
+    } else {  // ragged tail of the segment
+      v[j].x = e < n ? __ldg(src + e) : ninf;
+      v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
+      v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
+      v[j].w = ninf;
+    }
+  }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void load_tile_any(const float* src, int n, int e0, int t, float4 (&v)[kFiltVec]) {
+  if (VEC) {
+    load_tile(src, n, e0, t, v);
+  } else {  // unaligned segment start: scalar loads, same element -> register mapping as the vector path
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) {
+      const int e = e0 + (j * kFiltThreads + t) * 4;
+      const float ninf = -CUDART_INF_F;
+      v[j].x = e < n ? __ldcs(src + e) : ninf;
+      v[j].y = e + 1 < n ? __ldcs(src + e + 1) : ninf;
+      v[j].z = e + 2 < n ? __ldcs(src + e + 2) : ninf;
+      v[j].w = e + 3 < n ? __ldcs(src + e + 3) : ninf;
+    }
+  }
+}
+
 // HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
 // (monotonicity of sigmoid; for FCOS the bound is per position: sigmoid(x) * sigmoid(ctr) > thr^2  <=>
 // x > logit(thr^2 / sigmoid(ctr)), computed once per position into shared memory).  The ~1 % survivors get the exact
-// fp32 score and the `> thr` test, are staged in shared memory, and the CTA reserves its output range with a single
-// global atomic per tile (a per-candidate atomic on ~40 segment counters serialises in L2).
+// fp32 score and the `> thr` test and are staged in shared memory; the CTA reserves output ranges with one global
+// atomic per ~1024 candidates (a per-candidate atomic on ~40 segment counters serialises in L2).
+// Persistent CTAs walk the tiles with a grid stride, prefetching the next tile's logits before the single
+// barrier of the current one.
 template <bool VEC>
-__global__ void __launch_bounds__(kFiltThreads, 5) score_filter_kernel(const FilterArgs p, int total_tiles) {
-  __shared__ uint64_t skeys[kFiltTile];
-  __shared__ float spre[kPosTab];
+__global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const FilterArgs p, int total_tiles) {
+  __shared__ uint64_t skeys[kStage];
+  __shared__ float spre[2][kPosTab];
   __shared__ int scount, sbase;
   const int t = threadIdx.x;
-  // Persistent CTAs walk the tiles with a grid stride; the tile -> segment map only moves forward, so the search
-  // is one (cached) descriptor read per tile instead of a dependent binary search per CTA.
-  int s = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
-    const SegDesc sd = p.seg[s];
-    const int n = sd.len;
-    const int e0 = (tile - sd.tile_start) * kFiltTile;
-    const float* src = p.logits + sd.start;
-    const long long coff = sd.ctr_start;
-    // issue this tile's loads first; everything below overlaps with them
-    float4 v[kFiltVec];
-    float sv[VEC ? 1 : kFiltVec * 4];
-    if (VEC) {
-#pragma unroll
-      for (int j = 0; j < kFiltVec; ++j) {
-        const int e = e0 + (j * kFiltThreads + t) * 4;
-        const float ninf = -CUDART_INF_F;
-        if (e + 3 < n) {
-          v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
-        } else {  // ragged tail of the segment
-          v[j].x = e < n ? __ldg(src + e) : ninf;
-          v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
-          v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
-          v[j].w = ninf;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kFiltVec * 4; ++j) {
-        const int e = e0 + j * kFiltThreads + t;
-        sv[j] = (e < n) ? __ldcs(src + e) : -CUDART_INF_F;
-      }
-    }
-    if (t == 0) scount = 0;
-    const int pos0 = e0 / p.C;
-    const bool use_tab = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
-    if (use_tab) {
-      const int npos = min((min(e0 + kFiltTile, n) - 1) / p.C - pos0 + 1, kPosTab);
-      for (int i = t; i < npos; i += kFiltThreads) {
-        const float sc = sigmoid_f(__ldg(p.ctr + coff + pos0 + i));
-        const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
-        float bound = CUDART_INF_F;
-        if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
-        else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
-        spre[i] = bound;
-      }
-    }
-    __syncthreads();
+  if (t == 0) scount = 0;
+  int s = 0;           // segment of the tile being processed (tiles only move forward)
+  int tile = blockIdx.x;
+  if (tile >= total_tiles) return;
+  while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
+  SegDesc sd = p.seg[s];
+  float4 v[kFiltVec];
+  load_tile_any<VEC>(p.logits + sd.start, sd.len, (tile - sd.tile_start) * kFiltTile, t, v);
+  const bool tab_mode = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
+  int buf = 0;
 
-    auto consider = [&](float x, int e, float bound) {
-      if (x > bound) stage_candidate(p, x, e, coff, skeys, &scount);  // rare: kept out of line (register pressure)
-    };
-    if (VEC) {
-#pragma unroll
-      for (int j = 0; j < kFiltVec; ++j) {
-        const int e = e0 + (j * kFiltThreads + t) * 4;
-        float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
-        if (use_tab) {
-          const int q0 = e / p.C - pos0;
-          const int r0 = e - (q0 + pos0) * p.C;
-          b0 = spre[min(q0, kPosTab - 1)];
-          b1 = spre[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
-          b2 = spre[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
-          b3 = spre[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
-        }
-        consider(v[j].x, e, b0);
-        consider(v[j].y, e + 1, b1);
-        consider(v[j].z, e + 2, b2);
-        consider(v[j].w, e + 3, b3);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kFiltVec * 4; ++j) {
-        const int e = e0 + j * kFiltThreads + t;
-        const float bound = use_tab ? spre[min(e / p.C - pos0, kPosTab - 1)] : p.pre;
-        consider(sv[j], e, bound);
-      }
+  auto build_table = [&](const SegDesc& d, int e0, float* tab) {
+    const int pos0 = e0 / p.C;
+    const int npos = min((min(e0 + kFiltTile, d.len) - 1) / p.C - pos0 + 1, kPosTab);
+    for (int i = t; i < npos; i += kFiltThreads) {
+      const float sc = sigmoid_f(__ldg(p.ctr + d.ctr_start + pos0 + i));
+      const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
+      float bound = CUDART_INF_F;
+      if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
+      else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
+      tab[i] = bound;
     }
+  };
+  if (tab_mode) build_table(sd, (tile - sd.tile_start) * kFiltTile, spre[0]);
+  __syncthreads();
+
+  auto flush = [&](const SegDesc& d, int seg) {  // CTA-uniform; leaves scount == 0
+    const int cnt = min(scount, kStage);
     __syncthreads();
-    const int cnt = scount;
-    if (cnt > 0) {  // CTA-uniform
-      if (t == 0) sbase = atomicAdd(p.cand_count + s, cnt);
+    if (cnt > 0) {
+      if (t == 0) {
+        sbase = atomicAdd(p.cand_count + seg, cnt);
+        scount = 0;
+      }
       __syncthreads();
-      uint64_t* keys = p.keys + sd.key_off + sbase;
+      uint64_t* keys = p.keys + d.key_off + sbase;
       for (int i = t; i < cnt; i += kFiltThreads) keys[i] = skeys[i];
+      __syncthreads();
     }
-    __syncthreads();  // skeys / scount are reused by the next tile
+  };
+
+  while (true) {
+    const int e0 = (tile - sd.tile_start) * kFiltTile;
+    const int pos0 = e0 / p.C;
+    const float* tab = spre[buf];
+    // ---- process the tile held in registers
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) {
+      const int e = e0 + (j * kFiltThreads + t) * 4;
+      float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
+      if (tab_mode) {
+        const int q0 = e / p.C - pos0;
+        const int r0 = e - (q0 + pos0) * p.C;
+        b0 = tab[min(q0, kPosTab - 1)];
+        b1 = tab[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
+        b2 = tab[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
+        b3 = tab[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
+      }
+      if (v[j].x > b0) stage_candidate(p, v[j].x, e, sd, s, skeys, &scount);
+      if (v[j].y > b1) stage_candidate(p, v[j].y, e + 1, sd, s, skeys, &scount);
+      if (v[j].z > b2) stage_candidate(p, v[j].z, e + 2, sd, s, skeys, &scount);
+      if (v[j].w > b3) stage_candidate(p, v[j].w, e + 3, sd, s, skeys, &scount);
+    }
+    // ---- prefetch the next tile (and its FCOS table) before the barrier
+    const int next = tile + gridDim.x;
+    const bool more = next < total_tiles;
+    int ns = s;
+    SegDesc nd = sd;
+    if (more) {
+      while (ns + 1 < p.n_seg && p.seg[ns + 1].tile_start <= next) ++ns;
+      if (ns != s) nd = p.seg[ns];
+      load_tile_any<VEC>(p.logits + nd.start, nd.len, (next - nd.tile_start) * kFiltTile, t, v);
+      if (tab_mode) build_table(nd, (next - nd.tile_start) * kFiltTile, spre[buf ^ 1]);
+    }
+    __syncthreads();  // staged keys + next table visible
+    if (!more || ns != s || scount >= kFlushAt) flush(sd, s);  // CTA-uniform conditions
+    if (!more) break;
+    tile = next;
+    s = ns;
+    sd = nd;
+    buf ^= 1;
   }
 }
 
@@ -509,7 +546,7 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     }
   }
   if (tiles > 0) {
-    const int grid = min(tiles, sm_count() * 5);  // 5 resident CTAs / SM (registers; 33 KB of shared memory each)
+    const int grid = min(tiles, sm_count() * 4);  // persistent: 4 resident CTAs / SM
     if (vec)
       BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
     else
