@@ -244,7 +244,8 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
 }
 
 constexpr int kStage = 2048;     // candidate keys staged in shared memory per CTA between flushes
-constexpr int kFlushAt = 1024;   // flush once this many are staged (a 4096-element tile rarely adds more than 1024)
+constexpr int kFlushAt = 1024;
+constexpr int kSurv = 2048;      // pre-filter survivors recorded per tile before the dense exact-scoring pass   // flush once this many are staged (a 4096-element tile rarely adds more than 1024)
 
 // Rare path of the filter: exact score, `> thr`, append to the CTA's shared staging buffer; if the buffer is full
 // (dense candidates) the key goes straight to the segment's global list.
@@ -303,10 +304,15 @@ __device__ __forceinline__ void load_tile_any(const float* src, int n, int e0, i
 template <bool VEC>
 __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const FilterArgs p, int total_tiles) {
   __shared__ uint64_t skeys[kStage];
+  __shared__ float sx[kSurv];
+  __shared__ int se[kSurv];
   __shared__ float spre[2][kPosTab];
-  __shared__ int scount, sbase;
+  __shared__ int scount, sbase, nsurv;
   const int t = threadIdx.x;
-  if (t == 0) scount = 0;
+  if (t == 0) {
+    scount = 0;
+    nsurv = 0;
+  }
   int s = 0;           // segment of the tile being processed (tiles only move forward)
   int tile = blockIdx.x;
   if (tile >= total_tiles) return;
@@ -332,6 +338,15 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
   if (tab_mode) build_table(sd, (tile - sd.tile_start) * kFiltTile, spre[0]);
   __syncthreads();
 
+  auto record = [&](float x, int e) {
+    const int slot = atomicAdd(&nsurv, 1);
+    if (slot < kSurv) {
+      sx[slot] = x;
+      se[slot] = e;
+    } else {
+      stage_candidate(p, x, e, sd, s, skeys, &scount);  // list full (dense candidates): score it right here
+    }
+  };
   auto flush = [&](const SegDesc& d, int seg) {  // CTA-uniform; leaves scount == 0
     const int cnt = min(scount, kStage);
     __syncthreads();
@@ -364,10 +379,13 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
         b2 = tab[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
         b3 = tab[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
       }
-      if (v[j].x > b0) stage_candidate(p, v[j].x, e, sd, s, skeys, &scount);
-      if (v[j].y > b1) stage_candidate(p, v[j].y, e + 1, sd, s, skeys, &scount);
-      if (v[j].z > b2) stage_candidate(p, v[j].z, e + 2, sd, s, skeys, &scount);
-      if (v[j].w > b3) stage_candidate(p, v[j].w, e + 3, sd, s, skeys, &scount);
+      // A rare per-lane event is a frequent per-warp event (P(any of 32 lanes) ~ 20 %): the survivors of the one-compare
+      // pre-filter are only RECORDED here (a few instructions under divergence); the ~150-instruction exact scoring runs
+      // densely over the recorded list after the barrier, with full lanes.
+      if (v[j].x > b0) record(v[j].x, e);
+      if (v[j].y > b1) record(v[j].y, e + 1);
+      if (v[j].z > b2) record(v[j].z, e + 2);
+      if (v[j].w > b3) record(v[j].w, e + 3);
     }
     // ---- prefetch the next tile (and its FCOS table) before the barrier
     const int next = tile + gridDim.x;
@@ -380,7 +398,13 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
       load_tile_any<VEC>(p.logits + nd.start, nd.len, (next - nd.tile_start) * kFiltTile, t, v);
       if (tab_mode) build_table(nd, (next - nd.tile_start) * kFiltTile, spre[buf ^ 1]);
     }
-    __syncthreads();  // staged keys + next table visible
+    __syncthreads();  // survivor list + next table visible
+    {
+      const int nsv = min(nsurv, kSurv);
+      for (int i = t; i < nsv; i += kFiltThreads) stage_candidate(p, sx[i], se[i], sd, s, skeys, &scount);
+    }
+    __syncthreads();  // staged keys complete; survivor list free
+    if (t == 0) nsurv = 0;
     if (!more || ns != s || scount >= kFlushAt) flush(sd, s);  // CTA-uniform conditions
     if (!more) break;
     tile = next;
