@@ -229,7 +229,7 @@ struct FilterArgs {
 
 constexpr int kFiltThreads = 256;
 constexpr int kFiltVec = 4;                               // float4 per thread per tile
-constexpr int kFiltTile = kFiltThreads * kFiltVec * 4;    // 4096 elements
+constexpr int kFiltTile = 32 * kFiltVec * 4;              // 512 elements: one WARP iteration
 
 // Exact fp32 score of one candidate (same expressions as scores_kernel, so a dense bdet_scores tensor is bit-identical).
 __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long long ci, float& s) {
@@ -243,49 +243,35 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
   return s > p.thr;
 }
 
-constexpr int kStage = 2048;     // candidate keys staged in shared memory per CTA between flushes
-constexpr int kFlushAt = 1024;
-constexpr int kSurv = 2048;      // pre-filter survivors recorded per tile before the dense exact-scoring pass   // flush once this many are staged (a 4096-element tile rarely adds more than 1024)
+// ---- stage 1: warp-autonomous streaming filter --------------------------------------------------------------
+// HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
+// (monotonicity of sigmoid; for FCOS the bound is per position: sigmoid(x) * sigmoid(ctr) > thr^2  <=>
+// x > logit(thr^2 / sigmoid(ctr))).  Each WARP walks its own 512-element tiles (grid stride), prefetching the next
+// tile before touching the current one, and keeps two private shared-memory lists: pre-filter survivors (x, index)
+// and finished keys.  A rare per-lane event is a frequent per-warp event, so survivors are only RECORDED under the
+// ballot (no divergent slow path); the ~150-instruction exact scoring runs 32 survivors at a time with full lanes.
+// Keys leave the SM ~100 at a time with one global atomic.  No CTA barrier anywhere.
+constexpr int kWarpsPerCta = kFiltThreads / 32;
+constexpr int kSurv = 64;       // survivor list per warp (drained whenever >= 32)
+constexpr int kKeys = 160;      // key staging per warp (flushed whenever >= 96)
+constexpr int kWTab = 64;       // FCOS per-position bounds of one warp tile (needs kFiltTile / C + 2 <= 64)
 
-// Rare path of the filter: exact score, `> thr`, append to the CTA's shared staging buffer; if the buffer is full
-// (dense candidates) the key goes straight to the segment's global list.
-__device__ __noinline__ void stage_candidate(const FilterArgs& p, float x, int e, const SegDesc& sd, int s, uint64_t* skeys,
-                                             int* scount) {
-  float sc;
-  if (!exact_score(p, x, sd.ctr_start + e / p.C, sc)) return;
-  const uint64_t key = make_key(sc, (uint32_t)e);
-  const int slot = atomicAdd(scount, 1);
-  if (slot < kStage) skeys[slot] = key;
-  else p.keys[sd.key_off + atomicAdd(p.cand_count + s, 1)] = key;
-}
-
-constexpr int kPosTab = 160;  // per-tile table of per-position raw-logit thresholds (FCOS); needs C >= 4096 / 159
-
-__device__ __forceinline__ void load_tile(const float* src, int n, int e0, int t, float4 (&v)[kFiltVec]) {
-#pragma unroll
-  for (int j = 0; j < kFiltVec; ++j) {
-    const int e = e0 + (j * kFiltThreads + t) * 4;
-    const float ninf = -CUDART_INF_F;
-    if (e + 3 < n) {
-      v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
-    } else {  // ragged tail of the segment
-      v[j].x = e < n ? __ldg(src + e) : ninf;
-      v[j].y = e + 1 < n ? __ldg(src + e + 1) : ninf;
-      v[j].z = e + 2 < n ? __ldg(src + e + 2) : ninf;
-      v[j].w = ninf;
-    }
-  }
-}
+struct WarpLists {
+  float sx[kSurv];
+  int se[kSurv];
+  uint64_t keys[kKeys];
+  float tab[kWTab];
+};
 
 template <bool VEC>
-__device__ __forceinline__ void load_tile_any(const float* src, int n, int e0, int t, float4 (&v)[kFiltVec]) {
-  if (VEC) {
-    load_tile(src, n, e0, t, v);
-  } else {  // unaligned segment start: scalar loads, same element -> register mapping as the vector path
+__device__ __forceinline__ void load_tile(const float* src, int n, int e0, int lane, float4 (&v)[kFiltVec]) {
 #pragma unroll
-    for (int j = 0; j < kFiltVec; ++j) {
-      const int e = e0 + (j * kFiltThreads + t) * 4;
-      const float ninf = -CUDART_INF_F;
+  for (int j = 0; j < kFiltVec; ++j) {
+    const int e = e0 + (j * 32 + lane) * 4;
+    const float ninf = -CUDART_INF_F;
+    if (VEC && e + 3 < n) {
+      v[j] = __ldcs(reinterpret_cast<const float4*>(src + e));
+    } else {  // ragged tail / unaligned segment
       v[j].x = e < n ? __ldcs(src + e) : ninf;
       v[j].y = e + 1 < n ? __ldcs(src + e + 1) : ninf;
       v[j].z = e + 2 < n ? __ldcs(src + e + 2) : ninf;
@@ -294,123 +280,128 @@ __device__ __forceinline__ void load_tile_any(const float* src, int n, int e0, i
   }
 }
 
-// HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
-// (monotonicity of sigmoid; for FCOS the bound is per position: sigmoid(x) * sigmoid(ctr) > thr^2  <=>
-// x > logit(thr^2 / sigmoid(ctr)), computed once per position into shared memory).  The ~1 % survivors get the exact
-// fp32 score and the `> thr` test and are staged in shared memory; the CTA reserves output ranges with one global
-// atomic per ~1024 candidates (a per-candidate atomic on ~40 segment counters serialises in L2).
-// Persistent CTAs walk the tiles with a grid stride, prefetching the next tile's logits before the single
-// barrier of the current one.
 template <bool VEC>
-__global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const FilterArgs p, int total_tiles) {
-  __shared__ uint64_t skeys[kStage];
-  __shared__ float sx[kSurv];
-  __shared__ int se[kSurv];
-  __shared__ float spre[2][kPosTab];
-  __shared__ int scount, sbase, nsurv;
-  const int t = threadIdx.x;
-  if (t == 0) {
-    scount = 0;
-    nsurv = 0;
-  }
-  int s = 0;           // segment of the tile being processed (tiles only move forward)
-  int tile = blockIdx.x;
+__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p, int total_tiles) {
+  __shared__ WarpLists lists[kWarpsPerCta];
+  const int lane = threadIdx.x & 31;
+  WarpLists& L = lists[threadIdx.x >> 5];
+  const uint32_t lt = (1u << lane) - 1u;
+  const int nwarps = gridDim.x * kWarpsPerCta;
+  int tile = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (tile >= total_tiles) return;
+  int nsv = 0, nk = 0;  // warp-uniform list lengths
+  int s = 0;
   while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
   SegDesc sd = p.seg[s];
-  float4 v[kFiltVec];
-  load_tile_any<VEC>(p.logits + sd.start, sd.len, (tile - sd.tile_start) * kFiltTile, t, v);
-  const bool tab_mode = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kPosTab;
-  int buf = 0;
+  const bool tab_mode = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kWTab;
 
-  auto build_table = [&](const SegDesc& d, int e0, float* tab) {
-    const int pos0 = e0 / p.C;
-    const int npos = min((min(e0 + kFiltTile, d.len) - 1) / p.C - pos0 + 1, kPosTab);
-    for (int i = t; i < npos; i += kFiltThreads) {
-      const float sc = sigmoid_f(__ldg(p.ctr + d.ctr_start + pos0 + i));
-      const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
-      float bound = CUDART_INF_F;
-      if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
-      else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
-      tab[i] = bound;
-    }
+  auto flush_keys = [&]() {  // warp-uniform
+    if (nk == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.cand_count + s, nk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    uint64_t* dst = p.keys + sd.key_off + base;
+    for (int i = lane; i < nk; i += 32) dst[i] = L.keys[i];
+    __syncwarp();
+    nk = 0;
   };
-  if (tab_mode) build_table(sd, (tile - sd.tile_start) * kFiltTile, spre[0]);
-  __syncthreads();
-
-  auto record = [&](float x, int e) {
-    const int slot = atomicAdd(&nsurv, 1);
-    if (slot < kSurv) {
-      sx[slot] = x;
-      se[slot] = e;
-    } else {
-      stage_candidate(p, x, e, sd, s, skeys, &scount);  // list full (dense candidates): score it right here
-    }
-  };
-  auto flush = [&](const SegDesc& d, int seg) {  // CTA-uniform; leaves scount == 0
-    const int cnt = min(scount, kStage);
-    __syncthreads();
-    if (cnt > 0) {
-      if (t == 0) {
-        sbase = atomicAdd(p.cand_count + seg, cnt);
-        scount = 0;
+  auto drain = [&](int count) {  // exact-score the first `count` survivors (count <= nsv), 32 at a time
+    for (int i0 = 0; i0 < count; i0 += 32) {
+      const int i = i0 + lane;
+      bool ok = false;
+      float sc = 0.f;
+      int e = 0;
+      if (i < count) {
+        e = L.se[i];
+        ok = exact_score(p, L.sx[i], sd.ctr_start + e / p.C, sc);
       }
-      __syncthreads();
-      uint64_t* keys = p.keys + d.key_off + sbase;
-      for (int i = t; i < cnt; i += kFiltThreads) keys[i] = skeys[i];
-      __syncthreads();
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (ok) L.keys[nk + __popc(m & lt)] = make_key(sc, (uint32_t)e);
+      nk += __popc(m);
+      __syncwarp();
+      if (nk >= kKeys - 64) flush_keys();
     }
+    const int rem = nsv - count;  // < 32: move the tail to the front
+    float tx = 0.f;
+    int te = 0;
+    if (lane < rem) {
+      tx = L.sx[count + lane];
+      te = L.se[count + lane];
+    }
+    __syncwarp();
+    if (lane < rem) {
+      L.sx[lane] = tx;
+      L.se[lane] = te;
+    }
+    __syncwarp();
+    nsv = rem;
   };
 
+  float4 v[kFiltVec];
+  load_tile<VEC>(p.logits + sd.start, sd.len, (tile - sd.tile_start) * kFiltTile, lane, v);
   while (true) {
     const int e0 = (tile - sd.tile_start) * kFiltTile;
     const int pos0 = e0 / p.C;
-    const float* tab = spre[buf];
-    // ---- process the tile held in registers
-#pragma unroll
-    for (int j = 0; j < kFiltVec; ++j) {
-      const int e = e0 + (j * kFiltThreads + t) * 4;
-      float b0 = p.pre, b1 = p.pre, b2 = p.pre, b3 = p.pre;
-      if (tab_mode) {
-        const int q0 = e / p.C - pos0;
-        const int r0 = e - (q0 + pos0) * p.C;
-        b0 = tab[min(q0, kPosTab - 1)];
-        b1 = tab[min(q0 + (r0 + 1 >= p.C), kPosTab - 1)];
-        b2 = tab[min(q0 + (r0 + 2 >= p.C), kPosTab - 1)];
-        b3 = tab[min(q0 + (r0 + 3 >= p.C), kPosTab - 1)];
+    if (tab_mode) {
+      const int npos = min((min(e0 + kFiltTile, sd.len) - 1) / p.C - pos0 + 1, kWTab);
+      for (int i = lane; i < npos; i += 32) {
+        const float sc = sigmoid_f(__ldg(p.ctr + sd.ctr_start + pos0 + i));
+        const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
+        float bound = CUDART_INF_F;
+        if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
+        else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
+        L.tab[i] = bound;
       }
-      // A rare per-lane event is a frequent per-warp event (P(any of 32 lanes) ~ 20 %): the survivors of the one-compare
-      // pre-filter are only RECORDED here (a few instructions under divergence); the ~150-instruction exact scoring runs
-      // densely over the recorded list after the barrier, with full lanes.
-      if (v[j].x > b0) record(v[j].x, e);
-      if (v[j].y > b1) record(v[j].y, e + 1);
-      if (v[j].z > b2) record(v[j].z, e + 2);
-      if (v[j].w > b3) record(v[j].w, e + 3);
+      __syncwarp();
     }
-    // ---- prefetch the next tile (and its FCOS table) before the barrier
-    const int next = tile + gridDim.x;
+    // keep the current tile in `cur`, prefetch the next one into `v`
+    float4 cur[kFiltVec];
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) cur[j] = v[j];
+    const int next = tile + nwarps;
     const bool more = next < total_tiles;
     int ns = s;
     SegDesc nd = sd;
     if (more) {
       while (ns + 1 < p.n_seg && p.seg[ns + 1].tile_start <= next) ++ns;
       if (ns != s) nd = p.seg[ns];
-      load_tile_any<VEC>(p.logits + nd.start, nd.len, (next - nd.tile_start) * kFiltTile, t, v);
-      if (tab_mode) build_table(nd, (next - nd.tile_start) * kFiltTile, spre[buf ^ 1]);
+      load_tile<VEC>(p.logits + nd.start, nd.len, (next - nd.tile_start) * kFiltTile, lane, v);
     }
-    __syncthreads();  // survivor list + next table visible
-    {
-      const int nsv = min(nsurv, kSurv);
-      for (int i = t; i < nsv; i += kFiltThreads) stage_candidate(p, sx[i], se[i], sd, s, skeys, &scount);
+#pragma unroll
+    for (int j = 0; j < kFiltVec; ++j) {
+      const int e = e0 + (j * 32 + lane) * 4;
+      const float xs[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+      float bd[4] = {p.pre, p.pre, p.pre, p.pre};
+      if (tab_mode) {
+        const int q0 = e / p.C - pos0;
+        const int r0 = e - (q0 + pos0) * p.C;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bd[q] = L.tab[min(q0 + (r0 + q >= p.C), kWTab - 1)];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool pass = xs[q] > bd[q];
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (m) {  // warp-uniform
+          if (pass) {
+            const int slot = nsv + __popc(m & lt);
+            L.sx[slot] = xs[q];
+            L.se[slot] = e + q;
+          }
+          nsv += __popc(m);
+          __syncwarp();
+          if (nsv >= 32) drain(nsv & ~31);
+        }
+      }
     }
-    __syncthreads();  // staged keys complete; survivor list free
-    if (t == 0) nsurv = 0;
-    if (!more || ns != s || scount >= kFlushAt) flush(sd, s);  // CTA-uniform conditions
+    if (!more || ns != s) {  // leaving this segment: finish its survivors and keys
+      drain(nsv);
+      flush_keys();
+    }
     if (!more) break;
     tile = next;
     s = ns;
     sd = nd;
-    buf ^= 1;
   }
 }
 
@@ -570,7 +561,7 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     }
   }
   if (tiles > 0) {
-    const int grid = min(tiles, sm_count() * 4);  // persistent: 4 resident CTAs / SM
+    const int grid = min(ceil_div(tiles, kFiltThreads / 32), sm_count() * 3);  // persistent warps (3 CTAs / SM at 80 registers)
     if (vec)
       BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
     else
