@@ -246,8 +246,8 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
 // ---- stage 1: warp-autonomous streaming filter --------------------------------------------------------------
 // HBM-read bound: every logit is read once (128-bit loads) and rejected by ONE compare against a raw-logit bound
 // (monotonicity of sigmoid; for FCOS the bound is per position: sigmoid(x) * sigmoid(ctr) > thr^2  <=>
-// x > logit(thr^2 / sigmoid(ctr))).  Each WARP walks its own 512-element tiles (grid stride), prefetching the next
-// tile before touching the current one, and keeps two private shared-memory lists: pre-filter survivors (x, index)
+// x > logit(thr^2 / sigmoid(ctr))).  Each WARP walks its own 512-element tiles (grid stride, 2 KB in flight per warp,
+// 32 warps per SM) and keeps two private shared-memory lists: pre-filter survivors (x, index)
 // and finished keys.  A rare per-lane event is a frequent per-warp event, so survivors are only RECORDED under the
 // ballot (no divergent slow path); the ~150-instruction exact scoring runs 32 survivors at a time with full lanes.
 // Keys leave the SM ~100 at a time with one global atomic.  No CTA barrier anywhere.
@@ -281,7 +281,7 @@ __device__ __forceinline__ void load_tile(const float* src, int n, int e0, int l
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const FilterArgs p, int total_tiles) {
+__global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const FilterArgs p, int total_tiles) {
   __shared__ WarpLists lists[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   WarpLists& L = lists[threadIdx.x >> 5];
@@ -337,11 +337,12 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
     nsv = rem;
   };
 
-  float4 v[kFiltVec];
-  load_tile<VEC>(p.logits + sd.start, sd.len, (tile - sd.tile_start) * kFiltTile, lane, v);
   while (true) {
     const int e0 = (tile - sd.tile_start) * kFiltTile;
     const int pos0 = e0 / p.C;
+    // this tile's loads first (latency is hidden by the other ~32 resident warps, each with 2 KB in flight)
+    float4 cur[kFiltVec];
+    load_tile<VEC>(p.logits + sd.start, sd.len, e0, lane, cur);
     if (tab_mode) {
       const int npos = min((min(e0 + kFiltTile, sd.len) - 1) / p.C - pos0 + 1, kWTab);
       for (int i = lane; i < npos; i += 32) {
@@ -354,19 +355,11 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
       }
       __syncwarp();
     }
-    // keep the current tile in `cur`, prefetch the next one into `v`
-    float4 cur[kFiltVec];
-#pragma unroll
-    for (int j = 0; j < kFiltVec; ++j) cur[j] = v[j];
     const int next = tile + nwarps;
     const bool more = next < total_tiles;
     int ns = s;
-    SegDesc nd = sd;
-    if (more) {
+    if (more)
       while (ns + 1 < p.n_seg && p.seg[ns + 1].tile_start <= next) ++ns;
-      if (ns != s) nd = p.seg[ns];
-      load_tile<VEC>(p.logits + nd.start, nd.len, (next - nd.tile_start) * kFiltTile, lane, v);
-    }
 #pragma unroll
     for (int j = 0; j < kFiltVec; ++j) {
       const int e = e0 + (j * 32 + lane) * 4;
@@ -400,8 +393,10 @@ __global__ void __launch_bounds__(kFiltThreads) score_filter_kernel(const Filter
     }
     if (!more) break;
     tile = next;
-    s = ns;
-    sd = nd;
+    if (ns != s) {
+      s = ns;
+      sd = p.seg[s];
+    }
   }
 }
 
@@ -561,7 +556,7 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
     }
   }
   if (tiles > 0) {
-    const int grid = min(ceil_div(tiles, kFiltThreads / 32), sm_count() * 3);  // persistent warps (3 CTAs / SM at 80 registers)
+    const int grid = min(ceil_div(tiles, kFiltThreads / 32), sm_count() * 4);  // persistent warps, 4 CTAs / SM
     if (vec)
       BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
     else
