@@ -134,103 +134,6 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArg
   }
 }
 
-// Forward, separable form (7x7 bins, 2x2 samples -- every shipped config).  The bilinear value of a sample is
-//   top + (bot - top) * ly,  top = row(y0)[sx],  bot = row(y0 + 1)[sx],  row(y)[sx] = f[y][x0] + (f[y][x0+1] - f[y][x0]) * lx
-// -- exactly the reference's operation order -- and row(y)[sx] is shared by every sample on feature row y.  A warp
-// owns one channel at a time: it first builds row(y)[0..14) for the ROI's footprint rows in its shared-memory slice
-// (2 global loads per entry), then each bin reads 2 x 4 entries.  ~(rows + 14) * 28 loads per (roi, channel) instead
-// of 49 * 16 scattered taps, which is what made the direct kernel L1/LSU bound.
-constexpr int kSepRows = 48;  // footprint rows held per warp (larger ROIs take the direct path)
-
-__global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_sep_kernel(const RoiArgs p) {
-  constexpr int P = 7, S = 2, NS = P * S, BINS = P * P;
-  __shared__ SampleTab ty, tx;
-  __shared__ float srow[kRoiThreads / 32][kSepRows * NS];
-  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const RoiGeom g = roi_geom(p, k);
-  float* out = p.out + (long long)k * p.C * BINS;
-  const int total = p.C * BINS;
-  if (!g.valid) {
-    for (int o = t; o < total; o += kRoiThreads) out[o] = 0.f;
-    return;
-  }
-  fill_axis(ty, P, S, g.start_h, g.bin_h);
-  fill_axis(tx, P, S, g.start_w, g.bin_w);
-  __syncthreads();
-  const int H = g.H, W = g.W;
-  const float* feat = p.lv.feat[g.lvl] + (long long)g.n * p.C * H * W;
-  const int y_first = ty.i0[0];
-  const int nrows = ty.i0[NS - 1] + 2 - y_first;  // rows y_first .. i0[last] + 1 (un-clipped; rows outside the map are 0)
-  if (nrows > kSepRows || nrows <= 0) {
-    // direct path (huge or degenerate footprint): one thread per output, 16 taps each
-    for (int o = t; o < total; o += kRoiThreads) {
-      const int c = o / BINS, bin = o - c * BINS;
-      const int ph = bin / P, pw = bin - ph * P;
-      const float* f = feat + (long long)c * H * W;
-      float acc = 0.f;
-#pragma unroll
-      for (int iy = 0; iy < S; ++iy) {
-        const int sy = ph * S + iy;
-        const int y0 = ty.i0[sy], y1 = y0 + 1;
-        const float ly = ty.frac[sy];
-        const bool y0ok = y0 >= 0 && y0 < H, y1ok = y1 >= 0 && y1 < H;
-#pragma unroll
-        for (int ix = 0; ix < S; ++ix) {
-          const int sx = pw * S + ix;
-          const int x0 = tx.i0[sx], x1 = x0 + 1;
-          const float lx = tx.frac[sx];
-          const bool x0ok = x0 >= 0 && x0 < W, x1ok = x1 >= 0 && x1 < W;
-          const float tl = (y0ok && x0ok) ? __ldg(f + y0 * W + x0) : 0.f;
-          const float tr = (y0ok && x1ok) ? __ldg(f + y0 * W + x1) : 0.f;
-          const float bl = (y1ok && x0ok) ? __ldg(f + y1 * W + x0) : 0.f;
-          const float br = (y1ok && x1ok) ? __ldg(f + y1 * W + x1) : 0.f;
-          const float top = tl + (tr - tl) * lx;
-          const float bot = bl + (br - bl) * lx;
-          acc += top + (bot - top) * ly;
-        }
-      }
-      out[o] = __fdiv_rn(acc, 4.f);
-    }
-    return;
-  }
-  float* rows = srow[warp];
-  const int entries = nrows * NS;
-  for (int c = warp; c < p.C; c += kRoiThreads / 32) {
-    const float* f = feat + (long long)c * H * W;
-    __syncwarp();
-    for (int i = lane; i < entries; i += 32) {
-      const int r = i / NS, sx = i - r * NS;
-      const int y = y_first + r;
-      float v = 0.f;
-      if (y >= 0 && y < H) {
-        const int x0 = tx.i0[sx], x1 = x0 + 1;
-        const float a = (x0 >= 0 && x0 < W) ? __ldg(f + y * W + x0) : 0.f;
-        const float b = (x1 >= 0 && x1 < W) ? __ldg(f + y * W + x1) : 0.f;
-        v = a + (b - a) * tx.frac[sx];
-      }
-      rows[i] = v;
-    }
-    __syncwarp();
-    for (int bin = lane; bin < BINS; bin += 32) {
-      const int ph = bin / P, pw = bin - ph * P;
-      float acc = 0.f;
-#pragma unroll
-      for (int iy = 0; iy < S; ++iy) {
-        const int sy = ph * S + iy;
-        const float* r0 = rows + (ty.i0[sy] - y_first) * NS;
-        const float ly = ty.frac[sy];
-#pragma unroll
-        for (int ix = 0; ix < S; ++ix) {
-          const int sx = pw * S + ix;
-          const float top = r0[sx], bot = r0[NS + sx];
-          acc += top + (bot - top) * ly;
-        }
-      }
-      out[(long long)c * BINS + bin] = __fdiv_rn(acc, 4.f);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Backward, gather form (default).  The feature maps are cut into kTH x kTW pixel tiles; ROIs are binned per tile
 // (count -> scan -> fill); one CTA owns (tile, chunk of kCC channels), accumulates every ROI of its list into a
@@ -640,7 +543,7 @@ extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, 
   a.out = out;
   cudaStream_t st = as_stream(stream);
   if (PH == 7 && PW == 7 && sample_h == 2 && sample_w == 2)
-    BDET_KERNEL("roi_align_fwd_sep_kernel", st, roi_align_fwd_sep_kernel<<<K, kRoiThreads, 0, st>>>(a));
+    BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a));
   else
     BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<0, 0, 0><<<K, kRoiThreads, 0, st>>>(a));
   BDET_LAUNCH_CHECK();

@@ -45,7 +45,7 @@ KERNELS = ["anchors_grid_kernel", "pairwise_kernel", "match_colmax_kernel", "mat
            "box_encode_kernel", "box_decode_kernel", "score_filter_kernel", "select_sort_kernel", "select_decode_kernel",
            "nms_sort_small_kernel", "nms_tile_sort_kernel", "nms_global_step_kernel", "nms_tile_tail_kernel", "nms_gather_kernel",
            "nms_maxcoord_kernel", "nms_fused_kernel", "nms_mask_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
-           "roi_align_fwd_kernel", "roi_align_fwd_sep_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel"]
+           "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel"]
 rng = np.random.default_rng(0)
 
 # ---- config 2: target assignment, batch 16
@@ -110,7 +110,7 @@ rois = T(W.make_rois(rng, 512, B3, 800, 1344, 8, 600))
 dout = torch.randn((K, Cn, 7, 7), device=dev, generator=g)
 pyr = sum(B3 * Cn * h * w * 4 for h, w in fs)
 run("c3_roi_fwd", lambda: pipelines.roi_pool_forward_backward(feats, rois, W.FRCNN_RCNN_STRIDES, (7, 7)),
-    {"roi_align_fwd_kernel": K * Cn * 49 * 4 + pyr, "roi_align_fwd_sep_kernel": K * Cn * 49 * 4 + pyr}, iters=5)
+    {"roi_align_fwd_kernel": K * Cn * 49 * 4 + pyr}, iters=5)
 dfe = [torch.empty_like(f) for f in feats]
 lv = ops.roi_assign_levels(rois, 2, 5)
 wsb = ops._workspace(_lib.load().bdet_roi_align_bwd_workspace(4, _lib.iarr([v for f in feats for v in f.shape[-2:]]), B3, K), dev)
