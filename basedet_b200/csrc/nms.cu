@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs 
       }
       const uint32_t lo = __ballot_sync(0xffffffffu, s0);
       const uint32_t hi = __ballot_sync(0xffffffffu, s1);
+      __syncwarp();  // every lane has consumed remv[w] before lane 0 rewrites it
       if (lane == 0) remv[w] = cur | ((uint64_t)hi << 32) | lo;
     }
   }
