@@ -31,7 +31,7 @@ __device__ __forceinline__ void bitonic_strides(uint64_t* a, int n, long long ba
   const int t = threadIdx.x, nt = blockDim.x;
   for (int stride = first_stride; stride > 0; stride >>= 1) {
     __syncthreads();
-    if (ITERS > 0) {
+    if constexpr (ITERS > 0) {
       // all loads of the thread's (disjoint) pairs first, then the stores: the compiler cannot prove the pairs
       // disjoint, so left to itself it serialises load -> store -> load
       uint64_t x[ITERS], y[ITERS];

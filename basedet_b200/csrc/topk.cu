@@ -9,14 +9,21 @@
 //   stage 1 (score_filter_kernel, HBM-read bound: 4 B/logit, persistent grid): 128-bit logit loads, a raw-logit
 //           pre-filter (monotonicity of sigmoid) rejects ~99 % of the elements with one compare; survivors get the
 //           exact fp32 score and the `> thr` test, are staged in shared memory and flushed with one atomic per ~1k keys.
-//   stage 2 (select_sort_kernel, one CTA per segment): MSB-first 8-bit radix select over the candidates with
-//           early exit + small-bucket buffering in shared memory, then bitonic sort and write-out.
+//   stage 2 (select_sort_kernel, one 8-CTA cluster per segment): MSB-first 8-bit radix select over the candidates,
+//           histograms merged through distributed shared memory, early exit + small-bucket buffering, then the
+//           <= k survivors are gathered into cluster rank 0, bitonic-sorted and written out.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
 #include <limits>
 
 #include "common.cuh"
 #include "sortnet.cuh"
 
 namespace bdet {
+
+namespace cg = cooperative_groups;
 
 constexpr int kSelThreads = 1024;
 constexpr int kBufCap = 4096;  // candidate keys buffered in shared memory once a radix bucket is this small
@@ -31,6 +38,8 @@ struct SegDesc {
   long long ctr_start;  // FCOS: ctrness index of element 0
   int len;
   int tile_start;       // first filter tile of this segment
+  int order;            // select stage: cluster c works on segment seg[c].order (longest segments first)
+  int pad_;
 };
 
 struct RawSrc {
@@ -42,8 +51,17 @@ struct KeySrc {
   __device__ __forceinline__ uint64_t key(int i) const { return k[i]; }
 };
 
+// Every `stride`-th element of another source (threshold estimation).
+template <class Src>
+struct SampleSrc {
+  Src base;
+  int stride;
+  __device__ __forceinline__ uint64_t key(int i) const { return base.key(i * stride); }
+};
+
 // Shared-memory histogram increment.  Score keys are concentrated (few exponents), so most warps hit ONE bin: that
-// case costs one atomic per warp; mixed warps fall back to per-lane shared atomics (__match_any_sync is far slower).
+// case costs one atomic per warp; mixed warps fall back to per-lane shared atomics (__match_any_sync and peeling
+// the distinct bins one by one are both slower on a spread-out digit).
 __device__ __forceinline__ void hist_add(int* hist, int bin, bool active) {
   const uint32_t act = __ballot_sync(0xffffffffu, active);
   if (act == 0u) return;
@@ -67,26 +85,38 @@ __device__ __forceinline__ int append_slot(int* counter, bool active) {
   return active ? base + __popc(act & ((1u << lane) - 1u)) : -1;
 }
 
+// ---- stage 2: cluster radix select ---------------------------------------------------------------------------
+// One thread-block CLUSTER of kCS CTAs per segment (a single CTA is instruction-bound on one SM: ~250 thread
+// instructions per key over the sweeps).  Each CTA owns 1/kCS of the segment's keys and a private 256-bin histogram;
+// after a cluster barrier every CTA sums the kCS histograms through distributed shared memory and redundantly picks
+// the same bucket, so nothing is broadcast.  Histograms are double-buffered: one cluster barrier per digit.
+// The cluster size is a launch attribute (1, 2, 4 or 8): with many segments one CTA each already fills the GPU.
+constexpr int kMaxCS = 8;
+
 struct SelSmem {
-  int hist[256];
+  int hist[2][256];
   int scan[256];
   int nbuf;
   int nsel;
+  int nsurv;
   int bin, below, cnt;
 };
 
-// k-th smallest key (1 <= k <= n), keys unique.
-template <class Src>
-__device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint64_t* buf) {
+// k-th smallest key (1 <= k <= n) of the whole segment; this CTA sweeps elements [lo, hi).  Keys unique.
+// SOLO: the calling CTA works alone on [lo, hi) (no cluster barrier, own histogram only).
+template <bool SOLO, class Src>
+__device__ uint64_t radix_select(cg::cluster_group& cluster, const Src& src, int lo, int hi, int k, SelSmem& sm, uint64_t* buf) {
   const int t = threadIdx.x;
+  const int CS = SOLO ? 1 : (int)cluster.num_blocks();
+  bool buffered = false;
   uint64_t prefix = 0, mask = 0;
   int krem = k;
-  bool buffered = false;
   for (int d = 7; d >= 0; --d) {
     const int shift = 8 * d;
-    if (t < 256) sm.hist[t] = 0;
+    int* hist = sm.hist[d & 1];
+    if (t < 256) hist[t] = 0;
     __syncthreads();
-    const int m = buffered ? sm.nbuf : n;
+    const int m = buffered ? sm.nbuf : hi - lo;
     // kSelUnroll independent loads in flight per thread: a one-load-per-iteration sweep is pure L2 latency
     for (int i0 = 0; i0 < m; i0 += kSelThreads * kSelUnroll) {
       uint64_t key[kSelUnroll];
@@ -95,18 +125,22 @@ __device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint
       for (int u = 0; u < kSelUnroll; ++u) {
         const int i = i0 + u * kSelThreads + t;
         in[u] = i < m;
-        key[u] = in[u] ? (buffered ? buf[i] : src.key(i)) : 0;
+        key[u] = in[u] ? (buffered ? buf[i] : src.key(lo + i)) : 0;
       }
 #pragma unroll
       for (int u = 0; u < kSelUnroll; ++u) {
         const bool act = in[u] && ((key[u] & mask) == prefix);
-        hist_add(sm.hist, (int)((key[u] >> shift) & 255), act);
+        hist_add(hist, (int)((key[u] >> shift) & 255), act);
       }
     }
-    __syncthreads();
-    // inclusive scan of the 256 bins (8 warps)
+    if (SOLO) __syncthreads();
+    else cluster.sync();  // every CTA's histogram of this digit is complete
+    int tot = 0;
     if (t < 256) {
-      int v = sm.hist[t];
+      if (SOLO) tot = hist[t];
+      else
+        for (int r = 0; r < CS; ++r) tot += cluster.map_shared_rank(hist, r)[t];
+      int v = tot;
 #pragma unroll
       for (int s = 1; s < 32; s <<= 1) {
         int o = __shfl_up_sync(0xffffffffu, v, s);
@@ -119,11 +153,11 @@ __device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint
       int add = 0;
       for (int w = 0; w < (t >> 5); ++w) add += sm.scan[w * 32 + 31];
       int incl = sm.scan[t] + add;
-      int excl = incl - sm.hist[t];
+      int excl = incl - tot;
       if (excl < krem && krem <= incl) {
         sm.bin = t;
         sm.below = excl;
-        sm.cnt = sm.hist[t];
+        sm.cnt = tot;
       }
     }
     __syncthreads();
@@ -132,20 +166,20 @@ __device__ uint64_t radix_select(const Src& src, int n, int k, SelSmem& sm, uint
     prefix |= (uint64_t)bin << shift;
     mask |= (uint64_t)255 << shift;
     if (krem == cnt) return prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);  // whole bucket selected
-    if (!buffered && cnt <= kBufCap) {
+    if (!buffered && cnt <= kBufCap) {  // cluster-uniform decision; this CTA keeps ITS keys of the bucket
       if (t == 0) sm.nbuf = 0;
       __syncthreads();
-      for (int i0 = 0; i0 < n; i0 += kSelThreads * kSelUnroll) {
+      for (int i0 = 0; i0 < m; i0 += kSelThreads * kSelUnroll) {
         uint64_t key[kSelUnroll];
 #pragma unroll
         for (int u = 0; u < kSelUnroll; ++u) {
           const int i = i0 + u * kSelThreads + t;
-          key[u] = i < n ? src.key(i) : ~0ull;  // ~0 never matches a (prefix, mask) that selected a real bucket
+          key[u] = i < m ? src.key(lo + i) : ~0ull;
         }
 #pragma unroll
         for (int u = 0; u < kSelUnroll; ++u) {
           const int i = i0 + u * kSelThreads + t;
-          const bool act = i < n && ((key[u] & mask) == prefix);
+          const bool act = i < m && ((key[u] & mask) == prefix);
           const int slot = append_slot(&sm.nbuf, act);
           if (act) buf[slot] = key[u];
         }
@@ -168,41 +202,90 @@ struct SelArgs {
   int k, P;                   // P = pow2 >= k
 };
 
-template <bool RAW>
-__global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs p) {
-  extern __shared__ __align__(16) unsigned char raw[];
-  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(raw);  // P
-  uint64_t* buf = sortbuf + p.P;                          // kBufCap
-  __shared__ SelSmem sm;
-  const int s = blockIdx.x, t = threadIdx.x;
-  const long long off = RAW ? p.seg[s].start : p.seg[s].key_off;
-  const int n = RAW ? p.seg[s].len : p.cand_count[s];
-  const int k = min(p.k, n);
-  if (t == 0) {
-    p.out_count[s] = k;
-    sm.nsel = 0;
-  }
-  if (k == 0) return;
-  RawSrc rs{p.scores + off};
-  KeySrc ks{p.keys + off};
-  uint64_t T = ~0ull;
-  if (n > k) T = RAW ? radix_select(rs, n, k, sm, buf) : radix_select(ks, n, k, sm, buf);
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += kSelThreads * kSelUnroll) {
+// Sampled threshold: for n >> k the exact select over all n keys is replaced by (1) an exact select of rank r in a
+// strided sample of kSample keys (every CTA of the cluster does it redundantly: no barrier), r a few sigma above the
+// expected rank k * kSample / n, giving a bound T0 with k <= #{key <= T0} <= kBufCap with overwhelming probability;
+// (2) ONE sweep, split over the cluster, that appends the keys <= T0 to rank 0's shared memory through DSMEM;
+// (3) the exact select among those in rank 0.  The outcome of (2) is checked, and a miss (adversarial data) falls
+// back to the full cluster select, so the result is exact either way.
+constexpr int kSample = 16384;
+
+// Append the keys <= T of [lo, hi) to a (possibly remote) shared-memory list.
+template <class Src>
+__device__ __forceinline__ void gather_le(const Src& src, int lo, int hi, uint64_t T, int* counter, uint64_t* dst, int cap) {
+  const int t = threadIdx.x;
+  for (int i0 = lo; i0 < hi; i0 += kSelThreads * kSelUnroll) {
     uint64_t key[kSelUnroll];
 #pragma unroll
     for (int u = 0; u < kSelUnroll; ++u) {
       const int i = i0 + u * kSelThreads + t;
-      key[u] = i < n ? (RAW ? rs.key(i) : ks.key(i)) : ~0ull;
+      key[u] = i < hi ? src.key(i) : ~0ull;
     }
 #pragma unroll
     for (int u = 0; u < kSelUnroll; ++u) {
       const int i = i0 + u * kSelThreads + t;
-      const bool act = i < n && key[u] <= T;
-      const int slot = append_slot(&sm.nsel, act);
-      if (act) sortbuf[slot] = key[u];
+      const bool act = i < hi && key[u] <= T;
+      const int slot = append_slot(counter, act);
+      if (act && slot < cap) dst[slot] = key[u];
     }
   }
+}
+
+template <bool RAW, class Src>
+__device__ void select_sort_body(cg::cluster_group& cluster, const SelArgs& p, const Src& src, int s, int n, int k, long long off,
+                                 SelSmem& sm, uint64_t* sortbuf, uint64_t* buf, uint64_t* surv) {
+  const int t = threadIdx.x;
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  bool sampled = false;
+  int r = 0;
+  if (n > k && n >= 2 * kSample) {
+    const float mu = (float)k * (float)kSample / (float)n;
+    r = (int)(mu + 5.f * sqrtf(mu) + 16.f);
+    sampled = r < kSample && 1.1f * (float)r * ((float)n / (float)kSample) <= (float)kBufCap;  // expected survivors + 10 %
+  }
+  // short segments are handled by rank 0 alone; the peers leave before any cluster barrier
+  const bool team = n > k && n >= 2 * kSample && (sampled || CS > 1);
+  if (!team && rank != 0) return;
+  uint64_t T = ~0ull;
+  bool done = false;  // sortbuf of rank 0 holds the k selected keys
+  if (team) {
+    cluster.sync();  // all CTAs of the cluster are resident, rank 0's counters are initialised
+    bool full = !sampled;
+    if (sampled) {
+      const SampleSrc<Src> ss{src, n / kSample};
+      const uint64_t T0 = radix_select<true>(cluster, ss, 0, kSample, r, sm, buf);
+      const int lo = (int)((long long)n * rank / CS), hi = (int)((long long)n * (rank + 1) / CS);
+      int* nsurv0 = cluster.map_shared_rank(&sm.nsurv, 0);
+      gather_le(src, lo, hi, T0, nsurv0, cluster.map_shared_rank(surv, 0), kBufCap);
+      cluster.sync();
+      const int total = *nsurv0;
+      cluster.sync();  // rank 0's counter has been read by every peer
+      if (total >= k && total <= kBufCap) {
+        if (rank != 0) return;
+        const KeySrc sv{surv};
+        T = total == k ? T0 : radix_select<true>(cluster, sv, 0, total, k, sm, buf);
+        __syncthreads();
+        gather_le(sv, 0, total, T, &sm.nsel, sortbuf, p.P);
+        done = true;
+      } else {
+        full = true;
+      }
+    }
+    if (full) {
+      const int lo = (int)((long long)n * rank / CS), hi = (int)((long long)n * (rank + 1) / CS);
+      T = radix_select<false>(cluster, src, lo, hi, k, sm, buf);
+      gather_le(src, lo, hi, T, cluster.map_shared_rank(&sm.nsel, 0), cluster.map_shared_rank(sortbuf, 0), p.P);
+      cluster.sync();  // also keeps every CTA's shared memory alive until no peer reads it any more
+      if (rank != 0) return;
+      done = true;
+    }
+  }
+  if (!done) {  // rank 0 alone
+    if (n > k) T = radix_select<true>(cluster, src, 0, n, k, sm, buf);
+    __syncthreads();
+    gather_le(src, 0, n, T, &sm.nsel, sortbuf, p.P);
+  }
+  __syncthreads();
   for (int i = k + t; i < p.P; i += kSelThreads) sortbuf[i] = ~0ull;
   bitonic_sort_smem(sortbuf, p.P);
   for (int i = t; i < k; i += kSelThreads) {
@@ -211,6 +294,29 @@ __global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs 
     p.out_idx[(long long)s * p.k + i] = (int)idx;
     p.out_vals[(long long)s * p.k + i] = RAW ? __ldg(p.scores + off + idx) : key_score(key);
   }
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(kSelThreads) select_sort_kernel(const SelArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(raw);  // P (used in cluster rank 0, written by all ranks)
+  uint64_t* buf = sortbuf + p.P;                          // kBufCap: small-bucket buffer of the radix select
+  uint64_t* surv = buf + kBufCap;                         // kBufCap: survivors of the sampled threshold (rank 0)
+  __shared__ SelSmem sm;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int s = p.seg[blockIdx.x / cluster.num_blocks()].order, t = threadIdx.x;
+  const long long off = RAW ? p.seg[s].start : p.seg[s].key_off;
+  const int n = RAW ? p.seg[s].len : p.cand_count[s];
+  const int k = min(p.k, n);
+  if (t == 0) {
+    if (cluster.block_rank() == 0) p.out_count[s] = k;
+    sm.nsel = 0;
+    sm.nsurv = 0;
+  }
+  if (k == 0) return;  // cluster-uniform
+  __syncthreads();
+  if (RAW) select_sort_body<RAW>(cluster, p, RawSrc{p.scores + off}, s, n, k, off, sm, sortbuf, buf, surv);
+  else select_sort_body<RAW>(cluster, p, KeySrc{p.keys + off}, s, n, k, off, sm, sortbuf, buf, surv);
 }
 
 // ------------------------------------------------------------------------------------------ stage 1
@@ -456,15 +562,43 @@ static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t
   host[n_seg].start = host[n_seg].key_off = host[n_seg].ctr_start = 0;
   host[n_seg].len = 0;
   host[n_seg].tile_start = tiles;
+  // select stage launch order: longest segments first (they finish last otherwise)
+  int order[kMaxSeg];
+  for (int s = 0; s < n_seg; ++s) order[s] = s;
+  std::stable_sort(order, order + n_seg, [&](int a, int b) { return len[a] > len[b]; });
+  for (int s = 0; s < n_seg; ++s) host[s].order = order[s];
+  host[n_seg].order = 0;
   return total;
 }
 
 template <bool RAW>
 static int launch_select(const SelArgs& a, int n_seg, cudaStream_t st) {
-  size_t smem = (size_t)(a.P + kBufCap) * 8;
+  size_t smem = (size_t)(a.P + 2 * kBufCap) * 8;
   if (smem > 40 * 1024)  // static shared memory (SelSmem) counts against the 48 KB default limit too
     BDET_CUDA(cudaFuncSetAttribute(select_sort_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BDET_KERNEL("select_sort_kernel", st, select_sort_kernel<RAW><<<n_seg, kSelThreads, smem, st>>>(a));
+  // cluster size: the kernel runs one 1024-thread CTA per SM, and a second wave costs more than wider clusters save
+  // (measured: 5-40 segments -> 8, 80 -> 4, 320 -> 1)
+  int cs = kMaxCS;
+  while (cs > 1 && (long long)n_seg * cs * 10 > 22LL * sm_count()) cs >>= 1;
+  if (const char* e = getenv("BDET_SELECT_CLUSTER")) {  // tuning / debugging knob
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) cs = v;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_seg * cs));
+  cfg.blockDim = dim3(kSelThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaSuccess;
+  BDET_KERNEL("select_sort_kernel", st, err = cudaLaunchKernelEx(&cfg, select_sort_kernel<RAW>, a));
+  BDET_CUDA(err);
   return BDET_OK;
 }
 

@@ -52,6 +52,39 @@ def test_topk_ties_and_special_values(cuda):
     assert np.array_equal(idx[0].cpu().numpy(), np.arange(1000))
 
 
+@pytest.mark.parametrize("case", ["random", "ties", "sample_high", "sample_low", "sorted_desc", "sorted_asc", "constant"])
+@pytest.mark.parametrize("n,k", [(32768, 100), (100000, 1000), (201600, 2000), (300001, 2048), (150000, 5000)])
+def test_topk_sampled_threshold_and_fallback(cuda, case, n, k):
+    """Long segments estimate the k-th score from a strided sample (topk.cu, kSample = 16384) and fall back to the full
+    select when the estimate misses; both must give the exact (score desc, index asc) top-k."""
+    rng = np.random.default_rng(n + k)
+    scores = rng.normal(-3, 2, n).astype(np.float32)
+    stride = n // 16384
+    if case == "ties":
+        scores = np.round(scores, 1)
+    elif case == "sample_high":      # every sampled position is large: the estimated threshold is far too strict
+        scores[::stride] += 50.0
+    elif case == "sample_low":       # the sample sees none of the top scores: far too many survivors
+        scores[::stride] -= 50.0
+    elif case == "sorted_desc":
+        scores = -np.sort(-scores)
+    elif case == "sorted_asc":
+        scores = np.sort(scores)
+    elif case == "constant":
+        scores[:] = 1.5
+    for lens in ([n], [n, 777, n]):
+        sc = np.concatenate([scores if m == n else scores[:m] for m in lens])
+        vals, idx, cnt = ops.topk_segments(T(sc, cuda), lens, k)
+        vals, idx, cnt = vals.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+        off = 0
+        for s, m in enumerate(lens):
+            rv, ri = R.topk_desc(sc[off:off + m], k)
+            assert cnt[s] == len(ri)
+            assert np.array_equal(idx[s, :cnt[s]], ri)
+            assert np.array_equal(vals[s, :cnt[s]], rv)
+            off += m
+
+
 # ------------------------------------------------------------------ fused score filter + top-k
 def _check_filter(cuda, logits, lens, thr, k, mode, C, ctr=None):
     dense = ops.scores(T(logits, cuda), mode, None if ctr is None else T(ctr, cuda), C).cpu().numpy()
