@@ -48,12 +48,14 @@ SIGNATURES = {
     "bdet_score_filter_topk": (c_int, [vp, vp, c_int, lp, lp, lp, c_int, c_float, c_int, c_int, vp, vp, vp, vp,
                                        c_size_t, vp]),
     "bdet_select_decode": (c_int, [POINTER(vp), POINTER(vp), ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,
-                                   fp, fp, vp, c_int, vp, vp, vp, vp, vp]),
+                                   fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_finalize_detections": (c_int, [vp, vp, vp, c_int, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp,
                                          vp]),
     "bdet_scores": (c_int, [vp, vp, c_int, c_int64, c_int, vp, vp]),
     "bdet_nms_workspace": (c_size_t, [c_int, c_int]),
     "bdet_nms": (c_int, [vp, vp, vp, c_int, vp, c_int, c_int, c_float, c_int, vp, c_int, vp, vp, c_size_t, vp]),
+    "bdet_nms_runs": (c_int, [vp, vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_float, c_int, vp, c_int, vp, vp,
+                              c_size_t, vp]),
     "bdet_boxes_scale_clip": (c_int, [vp, c_int, c_float, c_float, c_float, c_float, vp]),
     "bdet_boxes_filter_by_size": (c_int, [vp, c_int, c_float, c_float, vp, vp]),
     "bdet_roi_assign_levels": (c_int, [vp, c_int, c_int, c_int, vp, vp]),

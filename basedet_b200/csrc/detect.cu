@@ -27,6 +27,7 @@ struct SelectArgs {
   float* scores;  // (B, L*k)
   void* labels;   // (B, L*k) int32 (label_mode 0) or fp32 level ids (label_mode 1)
   int* count;     // (B)
+  int* run_end;   // (B, L) optional
 };
 
 __device__ __forceinline__ float4 decode_one(const SelectArgs& p, int l, int b, int a) {
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kDetThreads) select_decode_kernel(const Select
       if (t == 0) sbase = base + total;
       __syncthreads();
     }
+    if (t == 0 && p.run_end) p.run_end[seg] = sbase;
   }
   if (t == 0) p.count[b] = sbase;
 }
@@ -169,7 +171,7 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
                                   int B, int k, int div, int coder, int label_mode, const int* topk_idx,
                                   const float* topk_val, const int* topk_cnt, const float* mean_host, const float* std_host,
                                   const float* im_info, int info_ld, float* boxes, float* scores, void* labels, int* count,
-                                  bdet_stream_t stream) {
+                                  int* run_end, bdet_stream_t stream) {
   BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && k >= 0 && div >= 1, "bad sizes");
   BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
   BDET_REQUIRE(label_mode == 0 || label_mode == 1, "label_mode must be 0 (idx % div) or 1 (level id)");
@@ -178,6 +180,7 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
   cudaStream_t st = as_stream(stream);
   if (k == 0) {
     BDET_CUDA(cudaMemsetAsync(count, 0, (size_t)B * 4, st));
+    if (run_end) BDET_CUDA(cudaMemsetAsync(run_end, 0, (size_t)B * L * 4, st));
     return BDET_OK;
   }
   BDET_REQUIRE(anchors_host && deltas_host && n_l_host && topk_idx && topk_val && topk_cnt && boxes && scores && labels,
@@ -211,6 +214,7 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
   a.scores = scores;
   a.labels = labels;
   a.count = count;
+  a.run_end = run_end;
   BDET_KERNEL("select_decode_kernel", st, select_decode_kernel<<<B, kDetThreads, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;

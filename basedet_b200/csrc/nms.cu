@@ -21,12 +21,15 @@ namespace bdet {
 
 constexpr int kSmallSortMax = 16384;
 constexpr int kSortTile = 4096;
+constexpr int kMaxRuns = 32;
 
 struct NmsArgs {
   const float* boxes;   // (B, Nmax, 4)
   const float* scores;  // (B, Nmax)
   const void* idxs;     // (B, Nmax) int32 / fp32 or nullptr
   const int* n_dev;     // (B) or nullptr
+  const int* run_end;   // (B, n_runs) or nullptr: the image's list is n_runs back-to-back runs, each already in
+  int n_runs;           //   (score desc, index asc) order; run r ends (exclusive) at run_end[b][r]
   int idxs_is_float, Nmax, nwords, P;
   float thr;
   int max_out, keep_ld;
@@ -82,6 +85,50 @@ __global__ void __launch_bounds__(1024) nms_sort_small_kernel(const NmsArgs p) {
     if ((t & 31) == 0) atomicMax(&smax, w);
     __syncthreads();
     mc = ord2f(smax);
+  }
+  if (p.run_end) {
+    // Pre-sorted runs (the per-level top-k output): rank every element by counting -- its position in its own run
+    // plus a binary search in each other run -- instead of sorting.  The promise is verified; a violated one takes
+    // the sorting network below.
+    __shared__ int rend[kMaxRuns + 1];
+    if (t <= p.n_runs) rend[t] = t == 0 ? 0 : __ldg(p.run_end + (long long)b * p.n_runs + t - 1);
+    for (int i = t; i < n; i += 1024) keys[i] = make_key(__ldg(p.scores + base + i), (uint32_t)i);
+    __syncthreads();
+    bool bad = false;
+    if (t < p.n_runs) bad = rend[t + 1] < rend[t] || (t == p.n_runs - 1 && rend[t + 1] != n);
+    bad = __syncthreads_or(bad);
+    if (!bad) {
+      for (int i = t; i < n; i += 1024) {
+        int r = 0;
+        while (rend[r + 1] <= i) ++r;
+        if (i > rend[r] && !(keys[i - 1] < keys[i])) bad = true;
+      }
+      bad = __syncthreads_or(bad);
+    }
+    if (!bad) {
+      for (int i = t; i < n; i += 1024) {
+        const uint64_t key = keys[i];
+        int rank = 0;
+        for (int q = 0; q < p.n_runs; ++q) {
+          int lo = rend[q], hi = rend[q + 1];
+          if (i >= lo && i < hi) {
+            rank += i - lo;
+          } else {
+            const int start = lo;
+            while (lo < hi) {  // lower bound: keys are unique
+              const int mid = (lo + hi) >> 1;
+              if (keys[mid] < key) lo = mid + 1;
+              else hi = mid;
+            }
+            rank += lo - start;
+          }
+        }
+        p.order[base + rank] = i;
+        p.sboxes[base + rank] = shifted_box(p, base + i, mc);
+      }
+      return;
+    }
+    __syncthreads();
   }
   int P = 2;
   while (P < n) P <<= 1;
@@ -392,7 +439,15 @@ extern "C" size_t bdet_nms_workspace(int Nmax, int B) {
 extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
                         int Nmax, int B, float iou_thresh, int max_output, int* keep, int keep_ld, int* keep_count,
                         void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  return bdet_nms_runs(boxes, scores, idxs, idxs_is_float, n_dev, nullptr, 0, Nmax, B, iou_thresh, max_output, keep, keep_ld,
+                       keep_count, workspace, workspace_bytes, stream);
+}
+
+extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
+                             const int* run_end, int n_runs, int Nmax, int B, float iou_thresh, int max_output, int* keep,
+                             int keep_ld, int* keep_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(Nmax >= 0 && B >= 0 && keep_ld >= 0, "negative size");
+  BDET_REQUIRE(!run_end || (n_runs >= 1 && n_runs <= kMaxRuns), "n_runs must be in [1, 32]");
   if (B == 0) return BDET_OK;
   BDET_REQUIRE(keep_count, "null keep_count");
   cudaStream_t st = as_stream(stream);
@@ -414,6 +469,8 @@ extern "C" int bdet_nms(const float* boxes, const float* scores, const void* idx
   a.scores = scores;
   a.idxs = idxs;
   a.n_dev = n_dev;
+  a.run_end = run_end;
+  a.n_runs = run_end ? n_runs : 0;
   a.idxs_is_float = idxs_is_float;
   a.Nmax = Nmax;
   a.nwords = (Nmax + 63) / 64;

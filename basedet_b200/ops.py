@@ -465,9 +465,11 @@ def scores(logits, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1):
     return out
 
 
-def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0, 0, 0, 0), std=(1, 1, 1, 1), im_info=None):
+def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0, 0, 0, 0), std=(1, 1, 1, 1), im_info=None,
+                  with_runs=False):
     """anchors: L tensors (n_l, 4|2); deltas: L tensors (B, n_l, 4); topk = (vals, idx, cnt) with segment s = b*L + l.
-    Returns boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k) [int32 or fp32 level ids], count (B,)."""
+    Returns boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k) [int32 or fp32 level ids], count (B,)
+    [, run_end (B, L): end of every level's (already score-sorted) run, for ``nms_batched(runs=...)``]."""
     lib = _lib.load()
     L = len(anchors)
     anc = [_f32c(a) for a in anchors]
@@ -479,6 +481,7 @@ def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0,
     sc = torch.empty((B, L * k), dtype=torch.float32, device=dev)
     labels = torch.empty((B, L * k), dtype=torch.float32 if label_mode == 1 else torch.int32, device=dev)
     count = torch.empty((B,), dtype=torch.int32, device=dev)
+    run_end = torch.empty((B, L), dtype=torch.int32, device=dev) if with_runs else None
     ap = (ctypes.c_void_p * L)(*[a.data_ptr() for a in anc])
     dp_ = (ctypes.c_void_p * L)(*[d.data_ptr() for d in dl])
     info = _f32c(im_info) if im_info is not None else None
@@ -486,7 +489,9 @@ def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0,
         check(lib.bdet_select_decode(ap, dp_, iarr([a.shape[0] for a in anc]), L, B, int(k), int(div), int(coder),
                                      int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
                                      info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels), _p(count),
-                                     _stream(boxes)))
+                                     _p(run_end), _stream(boxes)))
+    if with_runs:
+        return boxes, sc, labels, count, run_end
     return boxes, sc, labels, count
 
 
@@ -505,8 +510,10 @@ def finalize_detections(boxes, scores_, labels, keep, keep_count, max_out, im_in
 
 
 # ----------------------------------------------------------------------------- NMS
-def nms_batched(boxes, scores_, idxs, iou_thresh, max_output=None, num=None, workspace=None):
+def nms_batched(boxes, scores_, idxs, iou_thresh, max_output=None, num=None, workspace=None, runs=None):
     """boxes (B,Nmax,4), scores (B,Nmax), idxs (B,Nmax) int32/fp32 or None, num (B,) int32 or None.
+    runs (B, R) int32, optional: each image's list is R back-to-back runs already in (score desc, index asc) order,
+    ending at runs[b, r] (``select_decode(with_runs=True)``); only a speed hint, the result is the same.
     Returns (keep (B,cap) int32 original indices in score-descending order, keep_count (B,) int32)."""
     lib = _lib.load()
     b = _f32c(boxes, "boxes")
@@ -526,9 +533,12 @@ def nms_batched(boxes, scores_, idxs, iou_thresh, max_output=None, num=None, wor
     nd = _i32c(num) if num is not None else None
     need = lib.bdet_nms_workspace(Nmax, B)
     ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, b.device)
+    rn = _i32c(runs) if runs is not None else None
+    assert rn is None or (rn.ndim == 2 and rn.shape[0] == B)
     with _guard(b):
-        check(lib.bdet_nms(_p(b), _p(s), _p(ix), int(is_float), _p(nd), Nmax, B, float(iou_thresh),
-                           int(max_output) if max_output else 0, _p(keep), cap, _p(cnt), _p(ws), ws.numel(), _stream(b)))
+        check(lib.bdet_nms_runs(_p(b), _p(s), _p(ix), int(is_float), _p(nd), _p(rn), rn.shape[1] if rn is not None else 0,
+                                Nmax, B, float(iou_thresh), int(max_output) if max_output else 0, _p(keep), cap, _p(cnt),
+                                _p(ws), ws.numel(), _stream(b)))
     return keep, cnt
 
 

@@ -44,8 +44,10 @@ def dense_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_thr
     else:
         top = ops.score_filter_topk_raw(base, starts, lens, cls_threshold, topk, _lib.SCORE_SIGMOID, None, None, C)
         coder = 0
-    boxes, scores, labels, count = ops.select_decode(anchors_list, offsets_list, top, topk, C, coder, 0, reg_mean, reg_std)
-    keep, keep_cnt = ops.nms_batched(boxes, scores, labels, iou_threshold, max_detections, num=count)
+    boxes, scores, labels, count, runs = ops.select_decode(anchors_list, offsets_list, top, topk, C, coder, 0, reg_mean,
+                                                           reg_std, with_runs=True)
+    # every level's candidates arrive score-sorted from the top-k: NMS merges the L runs instead of re-sorting
+    keep, keep_cnt = ops.nms_batched(boxes, scores, labels, iou_threshold, max_detections, num=count, runs=runs)
     dets = ops.finalize_detections(boxes, scores, labels, keep, keep_cnt, max_detections, img_info, mode=0)
     return dets, keep_cnt
 
@@ -60,9 +62,9 @@ def rpn_proposals(scores_list, offsets_list, anchors_list, im_info, prev_nms_top
     sc = [t.float().contiguous() for t in scores_list]
     base, starts, lens = ops._segments(_flat_levels(sc))
     top = ops.topk_raw(base, starts, lens, prev_nms_topk)
-    boxes, scores, levels, count = ops.select_decode(anchors_list, offsets_list, top, prev_nms_topk, 1, 0, 1, reg_mean,
-                                                     reg_std, im_info=im_info)
-    keep, keep_cnt = ops.nms_batched(boxes, scores, levels, nms_threshold, post_nms_topk, num=count)
+    boxes, scores, levels, count, runs = ops.select_decode(anchors_list, offsets_list, top, prev_nms_topk, 1, 0, 1, reg_mean,
+                                                           reg_std, im_info=im_info, with_runs=True)
+    keep, keep_cnt = ops.nms_batched(boxes, scores, levels, nms_threshold, post_nms_topk, num=count, runs=runs)
     rois = ops.finalize_detections(boxes, scores, levels, keep, keep_cnt, post_nms_topk, None, mode=1)
     return rois, keep_cnt
 

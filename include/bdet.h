@@ -173,11 +173,13 @@ int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int
  *   im_info != NULL: drop candidates whose box, clipped to im_info[b, :2] = (h, w), has h <= 0 or w <= 0 (rpn.py:168-171)
  * and writes them compacted, levels concatenated in order (post_processing.py:63-67 / rpn.py:163-165):
  *   boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k), count (B).  anchors_host / deltas_host: L device pointers to
- *   (n_l, 4|2) and (B, n_l, 4).  topk_* as written by bdet_topk / bdet_score_filter_topk with segment s = b*L + l. */
+ *   (n_l, 4|2) and (B, n_l, 4).  topk_* as written by bdet_topk / bdet_score_filter_topk with segment s = b*L + l.
+ *   run_end (B, L) optional: exclusive end of level l's candidates in image b's list (input of bdet_nms_runs). */
 int bdet_select_decode(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host, int L,
                        int B, int k, int div, int coder, int label_mode, const int* topk_idx, const float* topk_val,
                        const int* topk_cnt, const float* mean_host, const float* std_host, const float* im_info,
-                       int info_ld, float* boxes, float* scores, void* labels, int* count, bdet_stream_t stream);
+                       int info_ld, float* boxes, float* scores, void* labels, int* count, int* run_end,
+                       bdet_stream_t stream);
 /* mode 0: post_processing.py:96-101 -- out (B, max_out, 6) = [box scaled by (orig/resized) and clipped to the original
  *         image, score, label] for the kept indices (im_info (B, >=4) [h, w, orig_h, orig_w]; NULL = no scale/clip);
  * mode 1: rpn.py:179-183 -- out (B, max_out, 5) = [batch index, x1, y1, x2, y2].  Rows >= keep_count[b] are zero. */
@@ -195,6 +197,13 @@ size_t bdet_nms_workspace(int Nmax, int B);
 int bdet_nms(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
              int Nmax, int B, float iou_thresh, int max_output, int* keep, int keep_ld, int* keep_count,
              void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* Same, for inputs that are already n_runs back-to-back runs per image, each in (score desc, index asc) order -- the
+ * level concat of per-level top-k results (post_processing.py:63-67, rpn.py:163-165).  run_end (B, n_runs) int32:
+ * exclusive end of every run, run_end[b][n_runs-1] == n_dev[b].  The argsort becomes a merge by ranking; the promise
+ * is checked on the device and an unsorted run silently takes the general sort, so results never differ from bdet_nms. */
+int bdet_nms_runs(const float* boxes, const float* scores, const void* idxs, int idxs_is_float, const int* n_dev,
+                  const int* run_end, int n_runs, int Nmax, int B, float iou_thresh, int max_output, int* keep,
+                  int keep_ld, int* keep_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ a12: Boxes.scale / clip / filter_by_size
  * structures/boxes.py:193-212, :152-177, :132-150.  boxes (N,4) in place: x*=sw, y*=sh then clip to

@@ -198,3 +198,53 @@ def test_nms_large_sort_path(cuda):
     keep, cnt = ops.nms_batched(T(boxes, cuda)[None], T(scores, cuda)[None], T(labels, cuda)[None] * 0 + 2, 0.5, 50)
     ref = R.batched_nms(boxes, scores, labels * 0 + 2, 0.5, 50)
     assert np.array_equal(keep[0, : int(cnt[0])].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("run_lens", [[1000, 1000, 1000, 700, 91], [2000, 2000, 2000, 2000, 819], [0, 5, 0, 0, 0], [3000], [7, 0, 0, 4096, 1]])
+def test_nms_presorted_runs_equal_general_sort(cuda, run_lens):
+    """bdet_nms_runs (merge by ranking of the per-level top-k runs) == bdet_nms on the same input: sorted runs with
+    ties across runs, a broken promise (unsorted run -> device-side check falls back), ragged batch."""
+    rng = np.random.default_rng(sum(run_lens))
+    n = sum(run_lens)
+    B = 3
+    boxes = np.zeros((B, n, 4), np.float32)
+    scores = np.zeros((B, n), np.float32)
+    labels = np.zeros((B, n), np.int32)
+    runs = np.zeros((B, len(run_lens)), np.int32)
+    num = np.zeros((B,), np.int32)
+    for b in range(B):
+        bx, sc, lb = _dense_dets(rng, max(n, 1), 4)
+        sc = np.round(sc, 2 if b == 1 else 6).astype(np.float32)        # image 1: many equal scores across runs
+        lens = list(run_lens) if b < 2 else [m // 2 for m in run_lens]   # image 2: shorter (ragged) runs
+        off = 0
+        for r, m in enumerate(lens):
+            seg = sc[off:off + m]
+            order = np.argsort(-seg, kind="stable")
+            sc[off:off + m] = seg[order]
+            bx[off:off + m] = bx[off:off + m][order]
+            lb[off:off + m] = lb[off:off + m][order]
+            off += m
+            runs[b, r] = off
+        num[b] = off
+        boxes[b, :n], scores[b, :n], labels[b, :n] = bx[:n], sc[:n], lb[:n]
+    args = (T(boxes, cuda), T(scores, cuda), T(labels, cuda), 0.5, 300)
+    k0, c0 = ops.nms_batched(*args, num=T(num, cuda))
+    k1, c1 = ops.nms_batched(*args, num=T(num, cuda), runs=T(runs, cuda))
+    assert np.array_equal(c0.cpu().numpy(), c1.cpu().numpy())
+    for b in range(B):
+        m = int(c0[b])
+        assert np.array_equal(k0[b, :m].cpu().numpy(), k1[b, :m].cpu().numpy())
+        ref = R.batched_nms(boxes[b, :num[b]], scores[b, :num[b]], labels[b, :num[b]], 0.5, 300)
+        assert np.array_equal(k1[b, :m].cpu().numpy(), ref)
+    if n > 10:  # broken promise: shuffle the scores inside the runs
+        perm = rng.permutation(n)
+        sh = (T(boxes[:, perm], cuda), T(scores[:, perm], cuda), T(labels[:, perm], cuda), 0.5, 300)
+        k2, c2 = ops.nms_batched(*sh, num=T(num, cuda))
+        k3, c3 = ops.nms_batched(*sh, num=T(num, cuda), runs=T(runs, cuda))
+        assert np.array_equal(c2.cpu().numpy(), c3.cpu().numpy())
+        for b in range(B):
+            assert np.array_equal(k2[b, :int(c2[b])].cpu().numpy(), k3[b, :int(c3[b])].cpu().numpy())
+        bad = runs.copy()
+        bad[:, -1] += 1                      # inconsistent run table -> general sort as well
+        k4, c4 = ops.nms_batched(*args, num=T(num, cuda), runs=T(bad, cuda))
+        assert np.array_equal(c0.cpu().numpy(), c4.cpu().numpy())
