@@ -22,6 +22,7 @@ namespace bdet {
 constexpr int kSmallSortMax = 16384;
 constexpr int kSortTile = 4096;
 constexpr int kMaxRuns = 32;
+constexpr int kChunkBlocks = 16;   // NMS mask/sweep row chunk: 1024 sorted boxes
 
 struct NmsArgs {
   const float* boxes;   // (B, Nmax, 4)
@@ -38,6 +39,7 @@ struct NmsArgs {
   uint32_t* maxc;       // (B) order-encoded max coordinate (large path)
   uint64_t* keys;       // (B, P) (large path)
   uint64_t* mask;       // (B, Nmax, nwords)
+  uint64_t* remv_g;     // (B, nwords) suppression bitmap carried from one row chunk to the next
   int* keep;
   int* keep_count;
 };
@@ -218,11 +220,17 @@ __device__ __forceinline__ bool nms_overlap(float4 a, float sa, float4 b, float 
   return __fdiv_rn(inter, (sa + sb) - inter) > thr;
 }
 
-__global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p) {
-  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+// Row blocks [blk0, blk0 + gridDim.y) against column blocks >= blk0.  Rows the earlier chunks already suppressed, and
+// everything once max_output boxes are kept, are skipped: the sweep never reads those words.
+__global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p, int blk0) {
+  const int cb = blk0 + blockIdx.x, rb = blk0 + blockIdx.y, b = blockIdx.z;
   if (cb < rb) return;
   const int n = nms_n(p, b);
   if (rb * 64 >= n || cb * 64 >= n) return;
+  const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
+  if (p.keep_count[b] >= max_out) return;
+  const uint64_t gone = p.remv_g[(long long)b * p.nwords + rb];
+  if (gone == ~0ull) return;
   __shared__ float4 srow[64];
   __shared__ float sarea[64];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p) {
     const int lr = warp * 8 + r;
     const int i = rb * 64 + lr;
     if (i >= n) break;  // warp-uniform
+    if ((gone >> lr) & 1ull) continue;
     const float4 a = srow[lr];
     const float sa = sarea[lr];
     bool p0 = (c0 < n) && (c0 > i) && nms_overlap(a, sa, b0, a0, p.thr);
@@ -257,7 +266,9 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p) {
 // ---- sweep -----------------------------------------------------------------------------------------------
 constexpr int kSweepThreads = 256;
 
-__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs p) {
+// Blocks [blk0, blk0 + nblk_chunk) of every image; the bitmap and the running count live in global memory between
+// chunks (zeroed by the entry point).
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs p, int blk0, int nblk_chunk) {
   extern __shared__ __align__(16) unsigned char raw[];
   uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // nwords
   __shared__ int skept[64];
@@ -268,9 +279,12 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs 
   const long long base = (long long)b * p.Nmax;
   const uint64_t* mask = p.mask + base * p.nwords;
   const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
-  for (int w = t; w < nblk; w += kSweepThreads) remv[w] = 0ull;
-  int count = 0;
-  for (int blk = 0; blk < nblk && count < max_out; ++blk) {
+  int count = p.keep_count[b];
+  if (count >= max_out || blk0 >= nblk) return;
+  uint64_t* rg = p.remv_g + (long long)b * p.nwords;
+  for (int w = blk0 + t; w < nblk; w += kSweepThreads) remv[w] = rg[w];
+  const int blk_end = min(nblk, blk0 + nblk_chunk);
+  for (int blk = blk0; blk < blk_end && count < max_out; ++blk) {
     __syncthreads();
     if (t < 32) {
       const int r0 = blk * 64 + lane, r1 = r0 + 32;
@@ -303,6 +317,9 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs 
       remv[w] = acc;
     }
   }
+  __syncthreads();
+  if (blk_end < nblk && count < max_out)
+    for (int w = blk_end + t; w < nblk; w += kSweepThreads) rg[w] = remv[w];
   if (t == 0) p.keep_count[b] = count;
 }
 
@@ -407,7 +424,7 @@ __global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs 
 }
 
 struct NmsWs {
-  size_t order, sboxes, maxc, keys, mask, total;
+  size_t order, sboxes, maxc, keys, remv, mask, total;
 };
 static NmsWs nms_ws(int Nmax, int B) {
   NmsWs w;
@@ -421,6 +438,8 @@ static NmsWs nms_ws(int Nmax, int B) {
   o += align_up((size_t)B * 4, 256);
   w.keys = o;
   if (Nmax > kSmallSortMax) o += align_up((size_t)B * next_pow2(Nmax) * 8, 256);
+  w.remv = o;
+  o += align_up((size_t)B * nwords * 8, 256);
   w.mask = o;
   o += (size_t)B * Nmax * nwords * 8;
   w.total = o + 256;
@@ -483,6 +502,7 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
   a.maxc = reinterpret_cast<uint32_t*>(ws + w.maxc);
   a.keys = reinterpret_cast<uint64_t*>(ws + w.keys);
   a.mask = reinterpret_cast<uint64_t*>(ws + w.mask);
+  a.remv_g = reinterpret_cast<uint64_t*>(ws + w.remv);
   a.keep = keep;
   a.keep_count = keep_count;
 
@@ -515,14 +535,22 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
     BDET_LAUNCH_CHECK();
     return BDET_OK;
   }
+  // Row chunks: mask words of kChunkBlocks x 64 sorted boxes against everything behind them, then the sweep over those
+  // blocks.  Rows suppressed by an earlier chunk are never tested and all work stops once max_output boxes are kept,
+  // so the pair tests are ~(boxes still alive) x N instead of N^2 / 2.
   const int nblk = a.nwords;
   if (nblk > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_nms: too many 64-box blocks");
-  BDET_KERNEL("nms_mask_kernel", st, nms_mask_kernel<<<dim3(nblk, nblk, B), 256, 0, st>>>(a));
-  BDET_LAUNCH_CHECK();
+  BDET_CUDA(cudaMemsetAsync(a.remv_g, 0, (size_t)B * a.nwords * 8, st));
+  BDET_CUDA(cudaMemsetAsync(keep_count, 0, (size_t)B * 4, st));
   size_t sweep_smem = (size_t)a.nwords * 8;
   if (sweep_smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
-  BDET_KERNEL("nms_sweep_kernel", st, nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a));
+  const int chunk = nblk <= 512 ? kChunkBlocks : ceil_div(nblk, 32);
+  for (int blk0 = 0; blk0 < nblk; blk0 += chunk) {
+    const int rows = min(chunk, nblk - blk0);
+    BDET_KERNEL("nms_mask_kernel", st, nms_mask_kernel<<<dim3(nblk - blk0, rows, B), 256, 0, st>>>(a, blk0));
+    BDET_KERNEL("nms_sweep_kernel", st, nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a, blk0, rows));
+  }
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
