@@ -71,6 +71,7 @@ SIGNATURES = {
     "bdet_count_labels": (c_int, [vp, c_int, c_int, vp, vp]),
     "bdet_bw_probe": (c_int, [vp, vp, c_size_t, c_int, c_int, vp]),
     "bdet_profile_begin": (c_int, []),
+    "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),
     "bdet_profile_end": (c_int, []),
 }

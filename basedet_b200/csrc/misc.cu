@@ -125,22 +125,47 @@ __global__ void __launch_bounds__(kCtThreads) cond_take_scatter_kernel(const flo
   }
 }
 
+// Few CTAs per image and ONE atomic triple per CTA: thousands of same-address atomics serialise in L2 and used to
+// cost more than reading the labels.
 __global__ void __launch_bounds__(256) count_labels_kernel(const int* __restrict__ labels, int A, int* __restrict__ counts) {
-  const int b = blockIdx.y;
+  __shared__ int sred[3][8];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int* row = labels + (long long)b * A;
   int neg = 0, zero = 0, pos = 0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < A; i += gridDim.x * 256) {
-    int l = __ldg(labels + (long long)b * A + i);
+  auto tally = [&](int l) {
     neg += l < 0;
     zero += l == 0;
     pos += l > 0;
+  };
+  const int head = min(A, (int)((4 - (((uintptr_t)row >> 2) & 3)) & 3));  // elements before the first 16-byte boundary
+  const int nvec = (A - head) >> 2;
+  const int4* v = reinterpret_cast<const int4*>(row + head);
+  for (int i = blockIdx.x * 256 + t; i < nvec; i += gridDim.x * 256) {
+    const int4 q = __ldg(v + i);
+    tally(q.x);
+    tally(q.y);
+    tally(q.z);
+    tally(q.w);
+  }
+  if (blockIdx.x == 0) {
+    if (t < head) tally(__ldg(row + t));
+    const int tail0 = head + nvec * 4;
+    if (tail0 + t < A) tally(__ldg(row + tail0 + t));  // < 4 elements
   }
   neg = __reduce_add_sync(0xffffffffu, neg);
   zero = __reduce_add_sync(0xffffffffu, zero);
   pos = __reduce_add_sync(0xffffffffu, pos);
-  if ((threadIdx.x & 31) == 0) {
-    if (neg) atomicAdd(counts + b * 3 + 0, neg);
-    if (zero) atomicAdd(counts + b * 3 + 1, zero);
-    if (pos) atomicAdd(counts + b * 3 + 2, pos);
+  if ((t & 31) == 0) {
+    sred[0][t >> 5] = neg;
+    sred[1][t >> 5] = zero;
+    sred[2][t >> 5] = pos;
+  }
+  __syncthreads();
+  if (t < 3) {
+    int sum = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sred[t][w];
+    if (sum) atomicAdd(counts + b * 3 + t, sum);
   }
 }
 
@@ -199,7 +224,7 @@ extern "C" int bdet_count_labels(const int* labels, int A, int B, int* counts, b
   BDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * 4, st));
   if (A == 0) return BDET_OK;
   BDET_REQUIRE(labels, "null labels");
-  BDET_KERNEL("count_labels_kernel", st, count_labels_kernel<<<dim3(min(ceil_div(A, 256), 64), B), 256, 0, st>>>(labels, A, counts));
+  BDET_KERNEL("count_labels_kernel", st, count_labels_kernel<<<dim3(min(ceil_div(A, 8192), 16), B), 256, 0, st>>>(labels, A, counts));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

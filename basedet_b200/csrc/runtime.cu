@@ -56,19 +56,43 @@ struct ProfPair {
 };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfPair>* g_prof = nullptr;
+static thread_local std::vector<cudaEvent_t>* g_pool = nullptr;  // events are recycled: creating one costs microseconds
+static thread_local char g_only[64] = "";                        // bracket only this kernel (others are just counted)
+static thread_local int g_untimed = 0;
+static thread_local bool g_open = false;
+
+static bool pool_get(cudaEvent_t* e) {
+  if (!g_pool->empty()) {
+    *e = g_pool->back();
+    g_pool->pop_back();
+    return true;
+  }
+  return cudaEventCreate(e) == cudaSuccess;
+}
 
 void prof_pre(cudaStream_t st, const char* name) {
   if (!g_prof_on) return;
+  g_open = false;
+  if (g_only[0] && strcmp(g_only, name) != 0) {
+    ++g_untimed;
+    return;
+  }
   ProfPair p;
   p.name = name;
-  if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+  if (!pool_get(&p.a)) return;
+  if (!pool_get(&p.b)) {
+    g_pool->push_back(p.a);
+    return;
+  }
   cudaEventRecord(p.a, st);
   g_prof->push_back(p);
+  g_open = true;
 }
 
 void prof_post(cudaStream_t st) {
-  if (!g_prof_on || g_prof->empty()) return;
+  if (!g_prof_on || !g_open) return;
   cudaEventRecord(g_prof->back().b, st);
+  g_open = false;
 }
 
 }  // namespace bdet
@@ -77,8 +101,15 @@ extern "C" {
 
 int bdet_profile_begin(void) {
   if (!bdet::g_prof) bdet::g_prof = new std::vector<bdet::ProfPair>();
+  if (!bdet::g_pool) bdet::g_pool = new std::vector<cudaEvent_t>();
   bdet_profile_end();
   bdet::g_prof_on = true;
+  return BDET_OK;
+}
+
+int bdet_profile_select(const char* name) {
+  if (name && strlen(name) >= sizeof(bdet::g_only)) return bdet::set_error(BDET_EINVAL, "bdet_profile_select: name too long");
+  strcpy(bdet::g_only, name ? name : "");
   return BDET_OK;
 }
 
@@ -95,6 +126,7 @@ int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_h
       ++n;
     }
   }
+  if (!name) n += bdet::g_untimed;  // launches that were counted but not bracketed (bdet_profile_select)
   if (total_ms_host) *total_ms_host = total;
   if (launches_host) *launches_host = n;
   return BDET_OK;
@@ -102,10 +134,12 @@ int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_h
 
 int bdet_profile_end(void) {
   bdet::g_prof_on = false;
+  bdet::g_untimed = 0;
+  bdet::g_open = false;
   if (bdet::g_prof) {
     for (auto& p : *bdet::g_prof) {
-      cudaEventDestroy(p.a);
-      cudaEventDestroy(p.b);
+      bdet::g_pool->push_back(p.a);
+      bdet::g_pool->push_back(p.b);
     }
     bdet::g_prof->clear();
   }

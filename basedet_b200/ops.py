@@ -647,22 +647,27 @@ def cond_take(x, mask=None):
     return vals[:k], idx[:k]
 
 
-def count_labels(labels):
+def count_labels(labels, out=None):
     """labels (B, A) int32 -> (B, 3) int32 counts of (label < 0, label == 0, label > 0)."""
     lib = _lib.load()
     lab = _i32c(labels, "labels")
     if lab.ndim == 1:
         lab = lab.unsqueeze(0)
     B, A = lab.shape
-    out = torch.empty((B, 3), dtype=torch.int32, device=lab.device)
+    if out is None:
+        out = torch.empty((B, 3), dtype=torch.int32, device=lab.device)
+    assert out.shape == (B, 3) and out.dtype == torch.int32 and out.is_contiguous()
     with _guard(lab):
         check(lib.bdet_count_labels(_p(lab), A, B, _p(out), _stream(lab)))
     return out
 
 
 # ----------------------------------------------------------------------------- measurement hooks
-def profile_begin():
-    check(_lib.load().bdet_profile_begin())
+def profile_begin(only=None):
+    """Bracket kernel launches with CUDA events; ``only`` = time just that kernel (the rest are counted)."""
+    lib = _lib.load()
+    check(lib.bdet_profile_select(only.encode() if only else None))
+    check(lib.bdet_profile_begin())
 
 
 def profile_collect(name=None):

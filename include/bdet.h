@@ -256,11 +256,14 @@ int bdet_count_labels(const int* labels, int A, int B, int* counts, bdet_stream_
 /* ------------------------------------------------------------------ measurement hooks (bench.py only)
  * While profiling is on, every named kernel launch inside the library is bracketed by a CUDA event pair on the
  * launching stream.  bdet_profile_collect synchronises those events and returns the summed duration and the
- * number of launches whose kernel name matches `name` (NULL = all).  Off by default; thread-local. */
+ * number of launches whose kernel name matches `name` (NULL = all).  bdet_profile_select(name) restricts the event
+ * pairs to one kernel (the others are still counted) so that the measurement does not stretch the step it measures;
+ * NULL brackets every kernel again.  Off by default; thread-local. */
 /* Streaming probe: mode 0 write-only (st.v4), 1 read-only (ld.v4), 2 copy, 3 cudaMemsetAsync -- the device's
  * write / read / copy HBM ceilings that the kernels' achieved GB/s are put next to (profiles/). */
 int bdet_bw_probe(void* dst, const void* src, size_t bytes, int mode, int ctas_per_sm, bdet_stream_t stream);
 int bdet_profile_begin(void);
+int bdet_profile_select(const char* name);
 int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_host);
 int bdet_profile_end(void);
 

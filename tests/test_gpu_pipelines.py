@@ -189,3 +189,27 @@ def test_stress_nms_100k_properties():
     for r in rng.choice(k, 300, replace=False):                 # no kept box is suppressed by a better kept box
         better = k[scores[k] > scores[r]]
         assert not (R.box_iou(boxes[r:r + 1], boxes[better])[0] > np.float32(0.5)).any()
+
+
+def test_target_assigner_graph_replay_matches_oracle():
+    """pipelines.TargetAssigner (the step captured in a CUDA graph, host-pinned inputs) == eager == oracle, over
+    several replays with different ground truth (ragged num_gt included)."""
+    from basedet_b200.layers import DefaultAnchorGenerator
+    hw, B, G = (256, 320), 3, 24
+    sizes = W.retinanet_level_sizes(*hw)
+    gen = DefaultAnchorGenerator(W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, 0.5)
+    anchors = np.concatenate(R.default_anchors(sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, 0.5))
+    ta = pipelines.TargetAssigner(gen, sizes, B, G)
+    for it in range(3):
+        gt, ng = W.target_assign_batch(B, G, hw[0], hw[1], seed0=500 + 10 * it, ragged=(it > 0))
+        gt_h, ng_h = torch.from_numpy(gt).pin_memory(), torch.from_numpy(ng).pin_memory()
+        lab, idx, off, counts = ta(gt_h, ng_h)
+        torch.cuda.synchronize()
+        rl, ro, ri = R.retinanet_targets(anchors, gt, ng, [0.4, 0.5], [0, -1, 1], True)
+        assert np.array_equal(lab.cpu().numpy(), rl)
+        assert np.array_equal(idx.cpu().numpy(), ri)
+        assert np.max(np.abs(off.cpu().numpy() - ro)) <= 1e-6
+        c = counts.cpu().numpy()
+        assert np.array_equal(c, np.stack([(rl < 0).sum(1), (rl == 0).sum(1), (rl > 0).sum(1)], 1))
+        el, ei, eo = ops.assign_targets(T(anchors), T(gt), T(ng), [0.4, 0.5], [0, -1, 1], True, True)
+        assert torch.equal(el, lab) and torch.equal(ei, idx) and torch.equal(eo, off)

@@ -283,3 +283,14 @@ def test_assign_targets_config2_one_image(cuda):
     anchors = np.concatenate(retina_anchors_np((800, 800))[1])
     gt, ng = W.target_assign_batch(2)
     _check_assign(cuda, anchors, gt, ng, W.RETINANET_MATCHER)
+
+
+@pytest.mark.parametrize("B,A", [(1, 1), (3, 7), (2, 4099), (16, 120087), (5, 8192)])
+def test_count_labels_census(cuda, B, A):
+    """bdet_count_labels: per-image (#<0, #==0, #>0), rows at any alignment (retinanet.py:142-146 num_fg)."""
+    rng = np.random.default_rng(B * A)
+    lab = rng.integers(-1, 81, (B, A)).astype(np.int32)
+    lab[rng.random((B, A)) < 0.7] = 0
+    got = ops.count_labels(torch.from_numpy(lab).to(cuda)).cpu().numpy()
+    ref = np.stack([(lab < 0).sum(1), (lab == 0).sum(1), (lab > 0).sum(1)], 1)
+    assert np.array_equal(got, ref)
