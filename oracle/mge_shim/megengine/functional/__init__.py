@@ -171,8 +171,45 @@ def sort(x, descending=False):
 def topk(x, k, descending=False, kth_only=False, no_sort=False):  # ASSUMED-3, k clamped to n
     a = _a(x)
     key = -a if descending else a
-    order = np.argsort(key, kind="stable")[: builtins_min(int(k), a.shape[-1])].astype(np.int32)
-    return Tensor(a[order]), Tensor(order)
+    order = np.argsort(key, axis=-1, kind="stable")[..., : builtins_min(int(k), a.shape[-1])].astype(np.int32)
+    return Tensor(np.take_along_axis(a, order.astype(np.int64), -1)), Tensor(order)
+
+
+def gather(x, axis, index):
+    return Tensor(np.take_along_axis(_a(x), _a(index).astype(np.int64), axis))
+
+
+def scatter(x, axis, index, source):
+    out = _a(x).copy()
+    np.put_along_axis(out, _a(index).astype(np.int64), _a(source).astype(out.dtype), axis)
+    return Tensor(out)
+
+
+def _seq_sum(a, axis, keepdims):
+    """fp32 sum accumulated sequentially in index order (ASSUMED-8: the order of MegDNN's reduce is not known)."""
+    a = np.asarray(a, np.float32)
+    out = np.cumsum(a, axis=axis, dtype=np.float32).take(-1, axis=axis)
+    return np.expand_dims(out, axis) if keepdims else out
+
+
+def mean(x, axis=None, keepdims=False):  # ASSUMED-8: sequential fp32 sum, then one divide by n
+    a = _a(_t(x))
+    if axis is None:
+        a, axis = a.reshape(-1), 0
+    return Tensor((_seq_sum(a, axis, keepdims) / f32(a.shape[axis])).astype(f32))
+
+
+def var(x, axis=None, keepdims=False):  # population variance: mean((x - mean(x)) ** 2)
+    a = _a(_t(x))
+    if axis is None:
+        a, axis = a.reshape(-1), 0
+    m = (_seq_sum(a, axis, True) / f32(a.shape[axis])).astype(f32)
+    d = (a - m).astype(f32)
+    return Tensor((_seq_sum((d * d).astype(f32), axis, keepdims) / f32(a.shape[axis])).astype(f32))
+
+
+def std(x, axis=None, keepdims=False):
+    return Tensor(np.sqrt(var(x, axis, keepdims)._a).astype(f32))
 
 
 def indexing_one_hot(src, index, axis=1, keepdims=False):

@@ -18,6 +18,11 @@ reference's own tests.
   ASSUMED-6  F.nn.roi_align(aligned=True): offset 0.5, zero padding for taps outside
              the map (no clamping), lerp written as a + (b - a) * t, average = sum / S^2.
   ASSUMED-7  F.arange(start, stop, step) = fp32(start + i * step) evaluated in float64.
+  ASSUMED-8  F.mean / F.std over the 45 ATSS candidates: fp32 sum accumulated sequentially in index
+             order, one divide by n; std = sqrt(mean((x - mean) ** 2)) (population).  MegDNN's reduce
+             order is unknown; any fixed order differs from another by <= a few ulp of the threshold.
+  ASSUMED-9  ``x ** 2`` on a tensor is ``x * x`` (one rounding); F.topk(descending=False) orders by
+             (value asc, index asc); argmin returns the FIRST index among equal minima.
 """
 import math
 
@@ -415,6 +420,116 @@ def retinanet_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_lq,
         lab_l.append(lab)
         idx_l.append(idx)
     return np.stack(lab_l), np.stack(off_l), np.stack(idx_l)
+
+
+def _ctrness(offsets):
+    """fcos.py:276-281 / atss.py:72-77: sqrt(max(min(l,r)/max(l,r), 0) * max(min(t,b)/max(t,b), 0)).
+    F.maximum(x, 0) and F.clip(x, lower=0) are both the elementwise MAX of ASSUMED-1 (NaN -> 0)."""
+    lr, tb = offsets[:, [0, 2]], offsets[:, [1, 3]]
+    with np.errstate(all="ignore"):
+        a = (lr.min(axis=1) / lr.max(axis=1)).astype(f32)
+        b = (tb.min(axis=1) / tb.max(axis=1)).astype(f32)
+        return np.sqrt((emax(a, _ZERO) * emax(b, _ZERO)).astype(f32)).astype(f32)
+
+
+def fcos_targets(points_list, gt_boxes, num_gt, strides, sizes_of_interest, center_sampling_radius):
+    """FCOS.get_ground_truth, basedet/models/det/fcos.py:222-293.
+
+    points_list: L arrays (n_l, 2); gt_boxes (B, Gmax, 5); num_gt (B,).  Returns labels (B, A) int32 (class of the
+    smallest-area GT that contains the point [inside its centre box when radius > 0] and cares about the level,
+    0 = background), offsets (B, A, 4) = PointCoder.encode(point, matched GT) (GT 0 for background, as the
+    reference's argmin over an all-inf column gives index 0), ctrness (B, A), match_indices (B, A)."""
+    points = np.concatenate([np.asarray(p, f32) for p in points_list], axis=0)
+    lo = np.concatenate([np.full(len(p), f32(s[0]), f32) for p, s in zip(points_list, sizes_of_interest)])  # :236-243
+    hi = np.concatenate([np.full(len(p), f32(s[1]), f32) for p, s in zip(points_list, sizes_of_interest)])
+    lab_l, off_l, ctr_l, idx_l = [], [], [], []
+    for g5, n in zip(gt_boxes, num_gt):
+        g5 = np.asarray(g5, f32)[: int(n)]
+        gt = g5[:, :4]
+        offsets = pointcoder_encode(points, gt[:, None, :])                      # :231 (G, A, 4)
+        max_off = offsets.max(axis=2)                                           # :245
+        cared = (max_off >= lo[None, :]) & (max_off <= hi[None, :])             # :246-249
+        if center_sampling_radius > 0:                                          # :251-264
+            ctr = box_center(gt)
+            parts = []
+            for stride, pts in zip(strides, points_list):
+                radius = stride * center_sampling_radius                        # python float, cast to fp32 per op
+                cb = np.concatenate([emax((ctr - f32(radius)).astype(f32), gt[:, :2]),
+                                     emin((ctr + f32(radius)).astype(f32), gt[:, 2:4])], axis=1)
+                co = pointcoder_encode(np.asarray(pts, f32), cb[:, None, :])
+                parts.append(co.min(axis=2) > 0)
+            in_boxes = np.concatenate(parts, axis=1)
+        else:
+            in_boxes = offsets.min(axis=2) > 0                                  # :266
+        area = ((gt[:, 2] - gt[:, 0]).astype(f32) * (gt[:, 3] - gt[:, 1]).astype(f32)).astype(f32)  # boxes.py:36-42
+        areas = np.broadcast_to(area[:, None], max_off.shape).copy()            # :268
+        areas[~cared] = np.inf                                                  # :269-270
+        areas[~in_boxes] = np.inf
+        idx = np.argmin(areas, axis=0).astype(np.int32)                         # :272 (first index, ASSUMED-9)
+        matched = g5[idx]
+        min_area = areas[idx, np.arange(areas.shape[1])]                        # :274
+        labels = matched[:, 4].astype(np.int32)                                 # :276
+        labels[min_area == np.inf] = 0                                          # :277
+        off = pointcoder_encode(points, matched[:, :4])                         # :278
+        lab_l.append(labels)
+        off_l.append(off)
+        ctr_l.append(_ctrness(off))
+        idx_l.append(idx)
+    return np.stack(lab_l), np.stack(off_l), np.stack(ctr_l), np.stack(idx_l)
+
+
+def seq_sum_f32(x, axis):
+    """ASSUMED-8: fp32 sum accumulated sequentially in index order."""
+    return np.cumsum(np.asarray(x, f32), axis=axis, dtype=f32).take(-1, axis=axis)
+
+
+def atss_targets(points_list, gt_boxes, num_gt, strides, anchor_scale, topk):
+    """ATSS.get_ground_truth, basedet/models/det/atss.py:17-86.  Same returns as fcos_targets."""
+    points = np.concatenate([np.asarray(p, f32) for p in points_list], axis=0)
+    lab_l, off_l, ctr_l, idx_l = [], [], [], []
+    for g5, n in zip(gt_boxes, num_gt):
+        g5 = np.asarray(g5, f32)[: int(n)]
+        gt = g5[:, :4]
+        ious, cands, base = [], [], 0
+        ctr = box_center(gt)                                                    # :39
+        for stride, pts in zip(strides, points_list):
+            pts = np.asarray(pts, f32)
+            half = f32(stride * anchor_scale / 2)                               # :33-34 python float -> fp32 scalar
+            boxes = np.concatenate([(pts - half).astype(f32), (pts + half).astype(f32)], axis=1)
+            ious.append(box_iou(gt, boxes))                                     # :31-37 gt_boxes.iou(anchor boxes)
+            d = (ctr[:, None, :] - pts[None, :, :]).astype(f32)
+            d2 = (d * d).astype(f32)                                            # ** 2 (ASSUMED-9)
+            dist = np.sqrt((d2[..., 0] + d2[..., 1]).astype(f32)).astype(f32)   # :40-42
+            k = min(int(topk), dist.shape[1])
+            order = np.argsort(dist, axis=1, kind="stable")[:, :k]              # :43 topk ascending (ASSUMED-9)
+            cands.append(base + order)
+            base += len(pts)
+        ious = np.concatenate(ious, axis=1)                                     # :46
+        cands = np.concatenate(cands, axis=1)                                   # :47
+        cand_iou = np.take_along_axis(ious, cands, axis=1)                      # :49
+        ncand = f32(cand_iou.shape[1])
+        mean = (seq_sum_f32(cand_iou, 1) / ncand).astype(f32)                   # :50 (ASSUMED-8)
+        dev = (cand_iou - mean[:, None]).astype(f32)
+        std = np.sqrt((seq_sum_f32((dev * dev).astype(f32), 1) / ncand).astype(f32)).astype(f32)  # :51
+        thr = (mean + std).astype(f32)
+        is_cand = np.zeros(ious.shape, bool)
+        np.put_along_axis(is_cand, cands, True, axis=1)                         # :52-54
+        fg = is_cand & (ious >= thr[:, None])
+        in_boxes = pointcoder_encode(points, gt[:, None, :]).min(axis=2) > 0    # :56-58
+        ious = ious.copy()
+        ious[~fg] = -1                                                          # :60-61
+        ious[~in_boxes] = -1
+        idx = np.argmax(ious, axis=0).astype(np.int32)                          # :63 (ASSUMED-2)
+        matched = g5[idx]
+        max_iou = ious[idx, np.arange(ious.shape[1])]                           # :65
+        labels = matched[:, 4].astype(np.int32)                                 # :67
+        labels[max_iou == -1] = 0                                               # :68
+        off = pointcoder_encode(points, matched[:, :4])                         # :69
+        lab_l.append(labels)
+        off_l.append(off)
+        ctr_l.append(_ctrness(off))
+        idx_l.append(idx)
+    return np.stack(lab_l), np.stack(off_l), np.stack(ctr_l), np.stack(idx_l)
 
 
 # --------------------------------------------------------------------------- score filter + top-k

@@ -64,3 +64,31 @@ def load():
         return ns
     finally:
         sys.path.remove(_SHIM)
+
+
+def load_method(rel_path, class_name, method_name, extra_globals=None):
+    """AST-extract ONE method of a reference class (e.g. models/det/fcos.py: FCOS.get_ground_truth) and compile it
+    against the shim -- the model modules themselves cannot be imported (basecore, backbones ...).  The returned
+    function takes ``self`` explicitly; tests pass a SimpleNamespace carrying the few attributes the method reads."""
+    import ast
+
+    import numpy as np
+
+    ref = load()
+    path = os.path.join(REFERENCE, "basedet", rel_path)
+    tree = ast.parse(open(path).read(), path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == method_name:
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    sys.path.insert(0, _SHIM)
+                    try:
+                        import megengine as mge
+                    finally:
+                        sys.path.remove(_SHIM)
+                    glb = {"F": ref.F, "mge": mge, "np": np, "Boxes": ref.boxes.Boxes, "layers": None}
+                    glb.update(extra_globals or {})
+                    exec(compile(mod, path, "exec"), glb)
+                    return glb[method_name]
+    raise KeyError("%s.%s not found in %s" % (class_name, method_name, path))

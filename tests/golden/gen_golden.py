@@ -188,6 +188,35 @@ def build():
     g["roi_out"] = ref.roi_pool.roi_pool([T(f.copy()) for f in rfeats], T(rois.copy()), [4, 8, 16, 32], (7, 7), "roi_align").numpy()
     rr, lv = ref.roi_pool.assign_rois(T(rois.copy()), [4, 8, 16, 32])
     g["roi_levels"] = lv.numpy()[: rois.shape[0]]
+
+    # ---- FCOS.get_ground_truth (models/det/fcos.py:222-293) and ATSS.get_ground_truth (models/det/atss.py:17-86):
+    # the methods themselves, AST-extracted from the reference files and run with a stand-in `self` that carries only
+    # the attributes they read (cfg values from configs/det_model/{fcos,atss}_cfg.py)
+    import types
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    dsizes = W.retinanet_level_sizes(160, 224)
+    g["dense_sizes"] = np.array(dsizes)
+    dfeats = [T(np.zeros((1, 1, h, w), np.float32)) for h, w in dsizes]
+    dpts = ref.anchor_generator.AnchorPointGenerator(1, tuple(W.RETINANET_STRIDES), 0.5)(dfeats)
+    for i, a in enumerate(dpts):
+        g["dense_points_%d" % i] = a.numpy()
+    dgt, dng = W.target_assign_batch(3, num_gt=14, img_h=160, img_w=224, seed0=900, ragged=True)
+    g["dense_gt"], g["dense_num"] = dgt, dng
+    soi = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, float("inf")]]
+    fcos_gt = ref_runner.load_method("models/det/fcos.py", "FCOS", "get_ground_truth")
+    atss_gt = ref_runner.load_method("models/det/atss.py", "ATSS", "get_ground_truth")
+    head = types.SimpleNamespace(strides=list(W.RETINANET_STRIDES))
+    for tag, radius in (("fcos_r15", 1.5), ("fcos_r0", 0)):
+        me = types.SimpleNamespace(cfg=Cfg(MODEL=Cfg(HEAD=Cfg(CENTER_SAMPLING_RADIUS=radius, OBJECT_SIZES_OF_INTEREST=soi))),
+                                   head=head, box_coder=ref.boxcoder.PointCoder())
+        lab, off, ctr = fcos_gt(me, [T(p.numpy().copy()) for p in dpts], T(dgt.copy()), [int(n) for n in dng])
+        g[tag + "_labels"], g[tag + "_offsets"], g[tag + "_ctrness"] = lab.numpy(), off.numpy(), ctr.numpy()
+    me = types.SimpleNamespace(cfg=Cfg(MODEL=Cfg(ANCHOR=Cfg(SCALE=8, TOPK=9))), head=head, box_coder=ref.boxcoder.PointCoder())
+    lab, off, ctr = atss_gt(me, [T(p.numpy().copy()) for p in dpts], T(dgt.copy()), [int(n) for n in dng])
+    g["atss_labels"], g["atss_offsets"], g["atss_ctrness"] = lab.numpy(), off.numpy(), ctr.numpy()
     return g
 
 

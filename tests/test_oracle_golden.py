@@ -96,6 +96,32 @@ def test_retinanet_get_ground_truth():
     same(off, GOLD["gt_offsets"])
 
 
+def _dense_points():
+    return [GOLD["dense_points_%d" % i] for i in range(5)]
+
+
+SOI = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, float("inf")]]
+
+
+@pytest.mark.parametrize("tag,radius", [("fcos_r15", 1.5), ("fcos_r0", 0)])
+def test_fcos_get_ground_truth(tag, radius):
+    """FCOS.get_ground_truth itself (fcos.py:222-293, run from the reference file) == oracle restatement."""
+    lab, off, ctr, _ = R.fcos_targets(_dense_points(), GOLD["dense_gt"], GOLD["dense_num"], W.RETINANET_STRIDES, SOI, radius)
+    same(lab, GOLD[tag + "_labels"])
+    same(off, GOLD[tag + "_offsets"])
+    same(ctr, GOLD[tag + "_ctrness"])
+    assert (lab > 0).sum() > 20
+
+
+def test_atss_get_ground_truth():
+    """ATSS.get_ground_truth itself (atss.py:17-86) == oracle restatement."""
+    lab, off, ctr, _ = R.atss_targets(_dense_points(), GOLD["dense_gt"], GOLD["dense_num"], W.RETINANET_STRIDES, 8, 9)
+    same(lab, GOLD["atss_labels"])
+    same(off, GOLD["atss_offsets"])
+    same(ctr, GOLD["atss_ctrness"])
+    assert (lab > 0).sum() > 20
+
+
 def test_nms_and_post_processing():
     b, s, l = GOLD["nms_boxes"], GOLD["nms_scores"], GOLD["nms_labels"]
     same(R.batched_nms(b, s, l, 0.5), GOLD["nms_keep_05"])
