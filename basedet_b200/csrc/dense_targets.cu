@@ -1,0 +1,319 @@
+// target assignment of the anchor-free dense heads, fused (no (G, A) tensor is materialised).
+// Reference: basedet/models/det/fcos.py:222-293 (FCOS.get_ground_truth: level range of max(l,t,r,b), centre sampling,
+//            smallest-area GT, PointCoder.encode, centerness)
+//            basedet/models/det/atss.py:17-86   (ATSS.get_ground_truth: per-level top-k nearest points, mean+std IoU
+//            threshold, in-box test, argmax IoU, PointCoder.encode, centerness).
+// The reference builds (G, A, 4) offsets, (G, A) masks / areas / IoUs per image and reduces over G; here one thread owns
+// one point (FCOS) or one CTA owns one GT (ATSS candidate search) and the reductions run in registers / shared memory.
+// Arithmetic follows the reference op order (one fp32 rounding per op, -fmad=false), elementwise max/min are MegDNN's
+// x>y?x:y / x<y?x:y (oracle ASSUMED-1), argmin / argmax keep the FIRST index (ASSUMED-2/9), the ATSS threshold sums its
+// candidates sequentially in index order (ASSUMED-8).
+#include <limits>
+
+#include "common.cuh"
+
+namespace bdet {
+
+__device__ __forceinline__ float emaxf(float x, float y) { return x > y ? x : y; }  // MegDNN Elemwise MAX
+__device__ __forceinline__ float eminf(float x, float y) { return x < y ? x : y; }  // MegDNN Elemwise MIN
+
+struct DenseArgs {
+  const float* points;  // (A, 2)
+  const float* gt;      // (B, Gmax, 5)
+  const int* num_gt;    // (B)
+  int A, Gmax, B, L;
+  int lvl_start[BDET_MAX_LEVELS + 1];
+  float lo[BDET_MAX_LEVELS], hi[BDET_MAX_LEVELS];  // FCOS object sizes of interest
+  float radius[BDET_MAX_LEVELS];                    // FCOS stride * center_sampling_radius; ATSS stride * scale / 2
+  int use_center;                                   // FCOS: centre sampling on
+  int topk;                                         // ATSS
+  int* labels;                                      // (B, A)
+  float* offsets;                                   // (B, A, 4)
+  float* ctrness;                                   // (B, A)
+  int* match_idx;                                   // (B, A) optional
+  unsigned long long* best;                         // ATSS (B, A): (IoU bits << 32) | ~g of the best proposal, 0 = none
+};
+
+__device__ __forceinline__ int level_of(const DenseArgs& p, int a) {
+  int l = 0;
+  while (l + 1 < p.L && a >= p.lvl_start[l + 1]) ++l;
+  return l;
+}
+
+// labels / PointCoder.encode / centerness of one point against its matched GT (fcos.py:276-287, atss.py:67-77)
+__device__ __forceinline__ void write_point(const DenseArgs& p, int b, int a, float px, float py, const float* gtb, int G,
+                                            int bi, bool fg) {
+  const long long o = (long long)b * p.A + a;
+  int label = 0;
+  float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ctr = 0.f;
+  if (G > 0) {
+    const float* r = gtb + (long long)bi * 5;
+    const float x1 = __ldg(r), y1 = __ldg(r + 1), x2 = __ldg(r + 2), y2 = __ldg(r + 3);
+    if (fg) label = (int)__ldg(r + 4);  // gt_boxes_matched[:, 4].astype("int32"); background rows are set to 0
+    off = make_float4(px - x1, py - y1, x2 - px, y2 - py);  // boxcoder.py:132-133
+    const float qa = __fdiv_rn(fminf(off.x, off.z), fmaxf(off.x, off.z));
+    const float qb = __fdiv_rn(fminf(off.y, off.w), fmaxf(off.y, off.w));
+    ctr = sqrtf(emaxf(qa, 0.f) * emaxf(qb, 0.f));
+  }
+  p.labels[o] = label;
+  reinterpret_cast<float4*>(p.offsets)[o] = off;
+  p.ctrness[o] = ctr;
+  if (p.match_idx) p.match_idx[o] = bi;
+}
+
+// ------------------------------------------------------------------------------------------------ FCOS
+constexpr int kDenseThreads = 256;
+
+__global__ void __launch_bounds__(kDenseThreads) fcos_targets_kernel(const DenseArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  float4* sbox = reinterpret_cast<float4*>(raw);              // Gmax
+  float2* sctr = reinterpret_cast<float2*>(sbox + p.Gmax);    // Gmax: box centres, op_patch.py:100-113
+  float* sarea = reinterpret_cast<float*>(sctr + p.Gmax);     // Gmax: Boxes.area, boxes.py:36-42
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int G = min(p.num_gt[b], p.Gmax);
+  const float* gtb = p.gt + (long long)b * p.Gmax * 5;
+  for (int g = t; g < G; g += kDenseThreads) {
+    const float* r = gtb + g * 5;
+    const float4 bx = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+    sbox[g] = bx;
+    sctr[g] = make_float2(__fdiv_rn(bx.x + bx.z, 2.f), __fdiv_rn(bx.y + bx.w, 2.f));
+    sarea[g] = (bx.z - bx.x) * (bx.w - bx.y);
+  }
+  __syncthreads();
+  const int a = blockIdx.x * kDenseThreads + t;
+  if (a >= p.A) return;
+  const float2 pt = __ldg(reinterpret_cast<const float2*>(p.points) + a);
+  const int lv = level_of(p, a);
+  const float lo = p.lo[lv], hi = p.hi[lv], rad = p.radius[lv];
+  const float inf = CUDART_INF_F;
+  float best = inf;
+  int bi = 0;
+  for (int g = 0; g < G; ++g) {
+    const float4 bx = sbox[g];
+    const float l = pt.x - bx.x, tt = pt.y - bx.y, r = bx.z - pt.x, bb = bx.w - pt.y;  // fcos.py:231
+    const float mx = fmaxf(fmaxf(l, tt), fmaxf(r, bb));                                // :245
+    bool ok = (mx >= lo) && (mx <= hi);                                                // :246-249
+    if (p.use_center) {                                                                // :251-264
+      const float2 c = sctr[g];
+      const float cx1 = emaxf(c.x - rad, bx.x), cy1 = emaxf(c.y - rad, bx.y);
+      const float cx2 = eminf(c.x + rad, bx.z), cy2 = eminf(c.y + rad, bx.w);
+      const float mn = fminf(fminf(pt.x - cx1, pt.y - cy1), fminf(cx2 - pt.x, cy2 - pt.y));
+      ok = ok && (mn > 0.f);
+    } else {
+      ok = ok && (fminf(fminf(l, tt), fminf(r, bb)) > 0.f);                            // :266
+    }
+    const float ar = ok ? sarea[g] : inf;                                              // :268-270
+    if (ar < best) {                                                                   // :272 argmin, first index
+      best = ar;
+      bi = g;
+    }
+  }
+  write_point(p, b, a, pt.x, pt.y, gtb, G, bi, best != inf);                           // :274-287
+}
+
+// ------------------------------------------------------------------------------------------------ ATSS
+constexpr int kAtssWarps = 8;
+constexpr int kAtssThreads = kAtssWarps * 32;
+constexpr int kMaxTopk = 16;
+constexpr int kMaxCand = BDET_MAX_LEVELS * kMaxTopk;
+
+// Sorted insertion into a register-resident ascending list (the compiler keeps kk[] in registers: every index is static).
+__device__ __forceinline__ void topk_insert(unsigned long long (&kk)[kMaxTopk], unsigned long long key) {
+#pragma unroll
+  for (int j = kMaxTopk - 1; j >= 0; --j) {
+    const unsigned long long prev = j > 0 ? kk[j - 1] : 0ull;
+    if (key < kk[j]) kk[j] = (j > 0 && key < prev) ? prev : key;
+  }
+}
+
+// One CTA per (image, GT): warp w scans the points of levels w, w + 8, ... for the `topk` nearest to the GT centre
+// (atss.py:39-44), then warp 0 evaluates the candidates' IoUs, the mean + std threshold (:49-51), and proposes
+// (IoU, g) to every candidate point that passes the threshold and lies inside the GT (:52-61) with one 64-bit atomicMax.
+__global__ void __launch_bounds__(kAtssThreads) atss_candidates_kernel(const DenseArgs p) {
+  __shared__ unsigned long long slist[kAtssWarps][32][kMaxTopk];  // per-lane sorted lists of the warp's current level
+  __shared__ int scand[kMaxCand];
+  __shared__ float siou[kMaxCand];
+  __shared__ int sslot[BDET_MAX_LEVELS + 1];
+  const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int G = min(p.num_gt[b], p.Gmax);
+  if (g >= G) return;
+  const float* r = p.gt + ((long long)b * p.Gmax + g) * 5;
+  const float4 bx = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+  const float cx = __fdiv_rn(bx.x + bx.z, 2.f), cy = __fdiv_rn(bx.y + bx.w, 2.f);
+  if (t == 0) {
+    int s = 0;
+    for (int l = 0; l < p.L; ++l) {
+      sslot[l] = s;
+      s += min(p.topk, p.lvl_start[l + 1] - p.lvl_start[l]);
+    }
+    sslot[p.L] = s;
+  }
+  __syncthreads();
+  const float2* pts = reinterpret_cast<const float2*>(p.points);
+  for (int l = warp; l < p.L; l += kAtssWarps) {
+    const int s = p.lvl_start[l], e = p.lvl_start[l + 1];
+    const int k = min(p.topk, e - s);
+    unsigned long long kk[kMaxTopk];
+#pragma unroll
+    for (int j = 0; j < kMaxTopk; ++j) kk[j] = ~0ull;
+    for (int i = s + lane; i < e; i += 32) {
+      const float2 q = __ldg(pts + i);
+      const float dx = cx - q.x, dy = cy - q.y;
+      const float d = sqrtf(dx * dx + dy * dy);  // :40-42
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(i - s);
+      if (key < kk[kMaxTopk - 1]) topk_insert(kk, key);
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxTopk; ++j) slist[warp][lane][j] = kk[j];
+    __syncwarp();
+    // k-way merge of the 32 sorted lists: (distance asc, index asc), F.topk(descending=False) (ASSUMED-9)
+    int head = 0;
+    for (int round = 0; round < k; ++round) {
+      const unsigned long long mine = head < kMaxTopk ? slist[warp][lane][head] : ~0ull;
+      const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32));
+      const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32) == hi ? (unsigned)mine : 0xffffffffu);
+      if ((unsigned)(mine >> 32) == hi && (unsigned)mine == lo) {
+        ++head;
+        scand[sslot[l] + round] = s + (int)lo;  // :44 base + topk_idxs
+      }
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  const int nc = sslot[p.L];
+  const float garea = box_area(bx);
+  for (int j = lane; j < nc; j += 32) {
+    const int a = scand[j];
+    const int l = level_of(p, a);
+    const float2 q = __ldg(pts + a);
+    const float h = p.radius[l];
+    const float4 ab = make_float4(q.x - h, q.y - h, q.x + h, q.y + h);  // :31-37
+    siou[j] = iou_pair(bx, garea, ab, box_area(ab));
+  }
+  __syncwarp();
+  float thr = 0.f;
+  if (lane == 0) {  // :50-51, sequential fp32 accumulation (ASSUMED-8)
+    float sum = 0.f;
+    for (int j = 0; j < nc; ++j) sum += siou[j];
+    const float mean = __fdiv_rn(sum, (float)nc);
+    float sq = 0.f;
+    for (int j = 0; j < nc; ++j) {
+      const float d = siou[j] - mean;
+      sq += d * d;
+    }
+    thr = mean + sqrtf(__fdiv_rn(sq, (float)nc));
+  }
+  thr = __shfl_sync(0xffffffffu, thr, 0);
+  for (int j = lane; j < nc; j += 32) {
+    const float v = siou[j];
+    if (!(v >= thr)) continue;  // :52-54
+    const int a = scand[j];
+    const float2 q = __ldg(pts + a);
+    const float mn = fminf(fminf(q.x - bx.x, q.y - bx.y), fminf(bx.z - q.x, bx.w - q.y));
+    if (!(mn > 0.f)) continue;  // :56-58
+    const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned)g);
+    atomicMax(p.best + (long long)b * p.A + a, key);  // :63 argmax over G: highest IoU, lowest g among equals
+  }
+}
+
+__global__ void __launch_bounds__(kDenseThreads) atss_finish_kernel(const DenseArgs p) {
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * kDenseThreads + threadIdx.x;
+  if (a >= p.A) return;
+  const int G = min(p.num_gt[b], p.Gmax);
+  const unsigned long long key = p.best[(long long)b * p.A + a];
+  const bool fg = key != 0ull;  // anchor_max_iou == -1 -> background, match index 0 (atss.py:63-68)
+  const int bi = fg ? (int)(0xffffffffu - (unsigned)key) : 0;
+  const float2 pt = __ldg(reinterpret_cast<const float2*>(p.points) + a);
+  write_point(p, b, a, pt.x, pt.y, p.gt + (long long)b * p.Gmax * 5, G, bi, fg);
+}
+
+static int fill_common(DenseArgs& a, const char* who, const float* points, int A, const int* level_start_host, int L,
+                       const float* gt, int Gmax, const int* num_gt_dev, int B, int* labels, float* offsets, float* ctrness,
+                       int* match_idx) {
+  if (A < 0 || Gmax < 0 || B < 0 || L < 1 || L > BDET_MAX_LEVELS) return set_error(BDET_EINVAL, "%s: bad sizes", who);
+  if (!level_start_host || level_start_host[0] != 0 || level_start_host[L] != A)
+    return set_error(BDET_EINVAL, "%s: level_start must run from 0 to A", who);
+  for (int l = 0; l < L; ++l)
+    if (level_start_host[l + 1] < level_start_host[l]) return set_error(BDET_EINVAL, "%s: level_start must be non-decreasing", who);
+  if (A == 0 || B == 0) return BDET_OK;
+  if (!points || !num_gt_dev || !labels || !offsets || !ctrness || (Gmax > 0 && !gt))
+    return set_error(BDET_EINVAL, "%s: null argument", who);
+  if (!aligned16(offsets) || (reinterpret_cast<uintptr_t>(points) & 7u))
+    return set_error(BDET_EINVAL, "%s: offsets must be 16-byte and points 8-byte aligned", who);
+  if (B > 65535 || Gmax > 65535) return set_error(BDET_EINVAL, "%s: B / Gmax > 65535", who);
+  a.points = points;
+  a.gt = gt;
+  a.num_gt = num_gt_dev;
+  a.A = A;
+  a.Gmax = Gmax;
+  a.B = B;
+  a.L = L;
+  for (int l = 0; l <= L; ++l) a.lvl_start[l] = level_start_host[l];
+  a.labels = labels;
+  a.offsets = offsets;
+  a.ctrness = ctrness;
+  a.match_idx = match_idx;
+  a.best = nullptr;
+  a.use_center = 0;
+  a.topk = 0;
+  return BDET_OK;
+}
+
+}  // namespace bdet
+
+using namespace bdet;
+
+extern "C" int bdet_fcos_targets(const float* points, int A, const int* level_start_host, int L, const float* radius_host,
+                                 const float* size_lo_host, const float* size_hi_host, const float* gt, int Gmax,
+                                 const int* num_gt_dev, int B, int* labels, float* offsets, float* ctrness, int* match_idx,
+                                 bdet_stream_t stream) {
+  DenseArgs a;
+  int rc = fill_common(a, "bdet_fcos_targets", points, A, level_start_host, L, gt, Gmax, num_gt_dev, B, labels, offsets, ctrness,
+                       match_idx);
+  if (rc || A == 0 || B == 0) return rc;
+  BDET_REQUIRE(size_lo_host && size_hi_host, "null size ranges");
+  for (int l = 0; l < L; ++l) {
+    a.lo[l] = size_lo_host[l];
+    a.hi[l] = size_hi_host[l];
+    a.radius[l] = radius_host ? radius_host[l] : 0.f;
+    if (radius_host && radius_host[l] > 0.f) a.use_center = 1;
+  }
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = (size_t)Gmax * (16 + 8 + 4);
+  if (smem > 40 * 1024)
+    BDET_CUDA(cudaFuncSetAttribute(fcos_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BDET_KERNEL("fcos_targets_kernel", st, fcos_targets_kernel<<<dim3(ceil_div(A, kDenseThreads), B), kDenseThreads, smem, st>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" size_t bdet_atss_targets_workspace(int A, int B) {
+  if (A <= 0 || B <= 0) return 16;
+  return (size_t)A * B * 8 + 256;
+}
+
+extern "C" int bdet_atss_targets(const float* points, int A, const int* level_start_host, int L, const float* half_size_host,
+                                 int topk, const float* gt, int Gmax, const int* num_gt_dev, int B, int* labels,
+                                 float* offsets, float* ctrness, int* match_idx, void* workspace, size_t workspace_bytes,
+                                 bdet_stream_t stream) {
+  DenseArgs a;
+  int rc = fill_common(a, "bdet_atss_targets", points, A, level_start_host, L, gt, Gmax, num_gt_dev, B, labels, offsets, ctrness,
+                       match_idx);
+  if (rc || A == 0 || B == 0) return rc;
+  BDET_REQUIRE(half_size_host, "null half sizes");
+  BDET_REQUIRE(topk >= 1 && topk <= kMaxTopk, "topk must be in [1, 16]");
+  const size_t need = bdet_atss_targets_workspace(A, B);
+  if (!workspace || workspace_bytes < need) return set_error(BDET_EWORKSPACE, "bdet_atss_targets: workspace needs %zu bytes", need);
+  BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
+  for (int l = 0; l < L; ++l) a.radius[l] = half_size_host[l];
+  a.topk = topk;
+  a.best = reinterpret_cast<unsigned long long*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  BDET_CUDA(cudaMemsetAsync(a.best, 0, (size_t)A * B * 8, st));
+  if (Gmax > 0) BDET_KERNEL("atss_candidates_kernel", st, atss_candidates_kernel<<<dim3(Gmax, B), kAtssThreads, 0, st>>>(a));
+  BDET_KERNEL("atss_finish_kernel", st, atss_finish_kernel<<<dim3(ceil_div(A, kDenseThreads), B), kDenseThreads, 0, st>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}

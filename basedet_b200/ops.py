@@ -375,6 +375,69 @@ def assign_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_low_qual
     return plan.labels, plan.idx, plan.offsets
 
 
+class DensePlan:
+    """Pre-allocated outputs (+ ATSS workspace) of the anchor-free target assignment, reused across steps."""
+
+    def __init__(self, A, B, device, atss=False):
+        lib = _lib.load()
+        self.A, self.B = A, B
+        self.labels = torch.empty((B, A), dtype=torch.int32, device=device)
+        self.offsets = torch.empty((B, A, 4), dtype=torch.float32, device=device)
+        self.ctrness = torch.empty((B, A), dtype=torch.float32, device=device)
+        self.idx = torch.empty((B, A), dtype=torch.int32, device=device)
+        self.ws = _workspace(lib.bdet_atss_targets_workspace(A, B), device) if atss else None
+
+
+def _dense_inputs(points_list, gt_boxes, num_gt):
+    pts = [_f32c(p, "points") for p in points_list]
+    assert all(p.ndim == 2 and p.shape[1] == 2 for p in pts), "points must be (n_l, 2)"
+    starts = [0]
+    for p in pts:
+        starts.append(starts[-1] + p.shape[0])
+    flat = pts[0] if len(pts) == 1 else torch.cat(pts, dim=0)
+    gt = _f32c(gt_boxes, "gt_boxes")
+    assert gt.ndim == 3 and gt.shape[2] == 5, "gt_boxes must be (B, Gmax, 5)"
+    return flat, starts, gt, _i32c(num_gt, "num_gt")
+
+
+def fcos_targets(points_list, gt_boxes, num_gt, strides, sizes_of_interest, center_sampling_radius, plan=None):
+    """FCOS.get_ground_truth (models/det/fcos.py:222-293) for the whole batch, fused.
+    points_list: L tensors (n_l, 2); gt_boxes (B, Gmax, 5); num_gt (B,).
+    -> labels (B, A) int32, offsets (B, A, 4), ctrness (B, A), match_idx (B, A)."""
+    lib = _lib.load()
+    flat, starts, gt, ng = _dense_inputs(points_list, gt_boxes, num_gt)
+    A, (B, Gmax, _) = flat.shape[0], gt.shape
+    L = len(points_list)
+    assert len(strides) == L and len(sizes_of_interest) == L
+    if plan is None:
+        plan = DensePlan(A, B, flat.device)
+    assert (plan.A, plan.B) == (A, B)
+    radius = [float(s * center_sampling_radius) for s in strides] if center_sampling_radius > 0 else [0.0] * L
+    with _guard(flat):
+        check(lib.bdet_fcos_targets(_p(flat), A, iarr(starts), L, farr(radius), farr([s[0] for s in sizes_of_interest]),
+                                    farr([s[1] for s in sizes_of_interest]), _p(gt), Gmax, _p(ng), B, _p(plan.labels),
+                                    _p(plan.offsets), _p(plan.ctrness), _p(plan.idx), _stream(flat)))
+    return plan.labels, plan.offsets, plan.ctrness, plan.idx
+
+
+def atss_targets(points_list, gt_boxes, num_gt, strides, anchor_scale=8, topk=9, plan=None):
+    """ATSS.get_ground_truth (models/det/atss.py:17-86) for the whole batch, fused.  Same returns as fcos_targets."""
+    lib = _lib.load()
+    flat, starts, gt, ng = _dense_inputs(points_list, gt_boxes, num_gt)
+    A, (B, Gmax, _) = flat.shape[0], gt.shape
+    L = len(points_list)
+    assert len(strides) == L
+    if plan is None:
+        plan = DensePlan(A, B, flat.device, atss=True)
+    assert (plan.A, plan.B) == (A, B) and plan.ws is not None
+    half = [float(s * anchor_scale / 2) for s in strides]  # atss.py:33-34, evaluated in Python floats
+    with _guard(flat):
+        check(lib.bdet_atss_targets(_p(flat), A, iarr(starts), L, farr(half), int(topk), _p(gt), Gmax, _p(ng), B,
+                                    _p(plan.labels), _p(plan.offsets), _p(plan.ctrness), _p(plan.idx), _p(plan.ws),
+                                    plan.ws.numel(), _stream(flat)))
+    return plan.labels, plan.offsets, plan.ctrness, plan.idx
+
+
 # ----------------------------------------------------------------------------- score filter + top-k
 def _segments(tensors, per_image_len=None):
     """Describe (image, level) segments that live in several tensors as element offsets from one base pointer.

@@ -69,6 +69,23 @@ def rpn_proposals(scores_list, offsets_list, anchors_list, im_info, prev_nms_top
     return rois, keep_cnt
 
 
+def fcos_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128),
+                 sizes_of_interest=((-1, 64), (64, 128), (128, 256), (256, 512), (512, float("inf"))),
+                 center_sampling_radius=1.5, plan=None):
+    """FCOS.get_ground_truth, models/det/fcos.py:222-293 (defaults: configs/det_model/fcos_cfg.py:41-47).
+    -> labels (B, A) int32, offsets (B, A, 4), ctrness (B, A)."""
+    lab, off, ctr, _ = ops.fcos_targets(points_list, gt_boxes, num_gt, list(strides), [tuple(s) for s in sizes_of_interest],
+                                        center_sampling_radius, plan=plan)
+    return lab, off, ctr
+
+
+def atss_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128), anchor_scale=8, topk=9, plan=None):
+    """ATSS.get_ground_truth, models/det/atss.py:17-86 (defaults: configs/det_model/atss_cfg.py:8-11).
+    -> labels (B, A) int32, offsets (B, A, 4), ctrness (B, A)."""
+    lab, off, ctr, _ = ops.atss_targets(points_list, gt_boxes, num_gt, list(strides), anchor_scale, topk, plan=plan)
+    return lab, off, ctr
+
+
 class TargetAssigner:
     """The whole `get_ground_truth` step of a dense head (anchors -> IoU -> Matcher -> labels -> BoxCoder.encode ->
     label census) for a FIXED batch shape, captured once into a CUDA graph and replayed every iteration.

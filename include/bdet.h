@@ -140,6 +140,29 @@ int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, 
                         const float* std_host, int* labels, int* match_idx, float* offsets,
                         void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
+/* ------------------------------------------------------------------ 8(f)-1: anchor-free dense-head target assignment
+ * points (A,2) = all levels concatenated (level l owns [level_start[l], level_start[l+1])), gt (B,Gmax,5) rows
+ * [x1,y1,x2,y2,class], num_gt (B).  Outputs for all B images: labels (B,A) int32 (0 = background), offsets (B,A,4) =
+ * PointCoder.encode(point, matched GT) (GT 0 for background points, as the reference's argmin/argmax of an empty
+ * selection gives index 0), ctrness (B,A), match_idx (B,A) optional.  No (G,A) tensor is materialised.
+ * FCOS.get_ground_truth  models/det/fcos.py:222-293: a GT owns a point when max(l,t,r,b) lies in
+ *   [size_lo[l], size_hi[l]] of the point's level (:245-249) and the point is inside the GT's centre box
+ *   [max(c - radius[l], tl), min(c + radius[l], br)] (:251-264; all radius 0 / NULL: inside the GT itself, :266);
+ *   among owners the smallest area wins, first index on ties (:268-272).  radius[l] = stride_l * CENTER_SAMPLING_RADIUS.
+ * ATSS.get_ground_truth  models/det/atss.py:17-86: per GT and level the topk points nearest to the GT centre (:39-44),
+ *   IoU of the GT with their square anchors point +- half_size[l] (= stride_l * SCALE / 2, :31-37), threshold =
+ *   mean + std of those IoUs (:50-51, sequential fp32 sums), positives = candidates with IoU >= threshold that lie inside
+ *   the GT (:52-61); a point takes the GT of highest IoU, first index on ties (:63).
+ * Images with num_gt == 0 (the reference raises there): labels 0, offsets 0, ctrness 0. */
+int bdet_fcos_targets(const float* points, int A, const int* level_start_host, int L, const float* radius_host,
+                      const float* size_lo_host, const float* size_hi_host, const float* gt, int Gmax,
+                      const int* num_gt_dev, int B, int* labels, float* offsets, float* ctrness, int* match_idx,
+                      bdet_stream_t stream);
+size_t bdet_atss_targets_workspace(int A, int B);
+int bdet_atss_targets(const float* points, int A, const int* level_start_host, int L, const float* half_size_host,
+                      int topk, const float* gt, int Gmax, const int* num_gt_dev, int B, int* labels, float* offsets,
+                      float* ctrness, int* match_idx, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
  * Segmented: segment s covers scores[seg_start[s] .. seg_start[s] + seg_len[s]) (element offsets from `scores`;
