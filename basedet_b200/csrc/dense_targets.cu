@@ -82,33 +82,58 @@ __global__ void __launch_bounds__(kDenseThreads) fcos_targets_kernel(const Dense
   }
   __syncthreads();
   const int a = blockIdx.x * kDenseThreads + t;
-  if (a >= p.A) return;
-  const float2 pt = __ldg(reinterpret_cast<const float2*>(p.points) + a);
-  const int lv = level_of(p, a);
+  const bool valid = a < p.A;
+  const int lane = t & 31;
+  const float2 pt = valid ? __ldg(reinterpret_cast<const float2*>(p.points) + a) : make_float2(0.f, 0.f);
+  const int lv = level_of(p, valid ? a : p.A - 1);
   const float lo = p.lo[lv], hi = p.hi[lv], rad = p.radius[lv];
   const float inf = CUDART_INF_F;
+  // Warp pruning: a GT can only own a point that lies strictly inside its (centre) box, so a GT whose box misses the
+  // bounding box of the warp's 32 points is skipped for the whole warp.  Visiting the survivors in ascending g keeps
+  // the first-index argmin.  The warp's largest radius makes the test conservative across a level boundary.
+  const float bx0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(valid ? pt.x : inf)));
+  const float by0 = ord2f(__reduce_min_sync(0xffffffffu, f2ord(valid ? pt.y : inf)));
+  const float bx1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? pt.x : -inf)));
+  const float by1 = ord2f(__reduce_max_sync(0xffffffffu, f2ord(valid ? pt.y : -inf)));
+  const float wrad = ord2f(__reduce_max_sync(0xffffffffu, f2ord(rad)));
   float best = inf;
   int bi = 0;
-  for (int g = 0; g < G; ++g) {
-    const float4 bx = sbox[g];
-    const float l = pt.x - bx.x, tt = pt.y - bx.y, r = bx.z - pt.x, bb = bx.w - pt.y;  // fcos.py:231
-    const float mx = fmaxf(fmaxf(l, tt), fmaxf(r, bb));                                // :245
-    bool ok = (mx >= lo) && (mx <= hi);                                                // :246-249
-    if (p.use_center) {                                                                // :251-264
-      const float2 c = sctr[g];
-      const float cx1 = emaxf(c.x - rad, bx.x), cy1 = emaxf(c.y - rad, bx.y);
-      const float cx2 = eminf(c.x + rad, bx.z), cy2 = eminf(c.y + rad, bx.w);
-      const float mn = fminf(fminf(pt.x - cx1, pt.y - cy1), fminf(cx2 - pt.x, cy2 - pt.y));
-      ok = ok && (mn > 0.f);
-    } else {
-      ok = ok && (fminf(fminf(l, tt), fminf(r, bb)) > 0.f);                            // :266
+  for (int g0 = 0; g0 < G; g0 += 32) {
+    const int gl = g0 + lane;
+    bool live = false;
+    if (gl < G) {
+      float4 q = sbox[gl];
+      if (p.use_center) {
+        const float2 c = sctr[gl];
+        q = make_float4(emaxf(c.x - wrad, q.x), emaxf(c.y - wrad, q.y), eminf(c.x + wrad, q.z), eminf(c.y + wrad, q.w));
+      }
+      live = !(q.z <= bx0 || q.x >= bx1 || q.w <= by0 || q.y >= by1);  // NaN -> live (evaluated exactly below)
     }
-    const float ar = ok ? sarea[g] : inf;                                              // :268-270
-    if (ar < best) {                                                                   // :272 argmin, first index
-      best = ar;
-      bi = g;
+    uint32_t m = __ballot_sync(0xffffffffu, live);
+    while (m) {
+      const int g = g0 + __ffs(m) - 1;
+      m &= m - 1;
+      const float4 bx = sbox[g];
+      const float l = pt.x - bx.x, tt = pt.y - bx.y, r = bx.z - pt.x, bb = bx.w - pt.y;  // fcos.py:231
+      const float mx = fmaxf(fmaxf(l, tt), fmaxf(r, bb));                                // :245
+      bool ok = (mx >= lo) && (mx <= hi);                                                // :246-249
+      if (p.use_center) {                                                                // :251-264
+        const float2 c = sctr[g];
+        const float cx1 = emaxf(c.x - rad, bx.x), cy1 = emaxf(c.y - rad, bx.y);
+        const float cx2 = eminf(c.x + rad, bx.z), cy2 = eminf(c.y + rad, bx.w);
+        const float mn = fminf(fminf(pt.x - cx1, pt.y - cy1), fminf(cx2 - pt.x, cy2 - pt.y));
+        ok = ok && (mn > 0.f);
+      } else {
+        ok = ok && (fminf(fminf(l, tt), fminf(r, bb)) > 0.f);                            // :266
+      }
+      const float ar = ok ? sarea[g] : inf;                                              // :268-270
+      if (ar < best) {                                                                   // :272 argmin, first index
+        best = ar;
+        bi = g;
+      }
     }
   }
+  if (!valid) return;
   write_point(p, b, a, pt.x, pt.y, gtb, G, bi, best != inf);                           // :274-287
 }
 
@@ -117,6 +142,7 @@ constexpr int kAtssWarps = 8;
 constexpr int kAtssThreads = kAtssWarps * 32;
 constexpr int kMaxTopk = 16;
 constexpr int kMaxCand = BDET_MAX_LEVELS * kMaxTopk;
+constexpr int kNear = 128;  // points collected inside the distance bound (typically 10-30)
 
 // Sorted insertion into a register-resident ascending list (the compiler keeps kk[] in registers: every index is static).
 __device__ __forceinline__ void topk_insert(unsigned long long (&kk)[kMaxTopk], unsigned long long key) {
@@ -127,20 +153,37 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&kk)[kMaxTopk], 
   }
 }
 
-// One CTA per (image, GT): warp w scans the points of levels w, w + 8, ... for the `topk` nearest to the GT centre
-// (atss.py:39-44), then warp 0 evaluates the candidates' IoUs, the mean + std threshold (:49-51), and proposes
-// (IoU, g) to every candidate point that passes the threshold and lies inside the GT (:52-61) with one 64-bit atomicMax.
+// One CTA per (image, group of kGPC GTs): every loaded point is tested against the group's centres, which divides
+// the L2 -> SM point traffic (the bound of a one-GT-per-CTA version) by kGPC.  Level by level the CTA finds, per GT,
+// the `topk` points nearest to its centre (atss.py:39-44): a first sweep bounds the k-th distance, a second collects
+// the handful of points inside the bound, rank counting orders them.  Then warp q evaluates GT q's candidates: IoUs,
+// the mean + std threshold (:49-51), and proposes (IoU, g) to every candidate point that passes the threshold and lies
+// inside the GT (:52-61) with one 64-bit atomicMax.
+constexpr int kGPC = 4;
+constexpr int kGroups = kAtssThreads / 4;  // four-lane groups
+
 __global__ void __launch_bounds__(kAtssThreads) atss_candidates_kernel(const DenseArgs p) {
-  __shared__ unsigned long long slist[kAtssWarps][32][kMaxTopk];  // per-lane sorted lists of the warp's current level
-  __shared__ int scand[kMaxCand];
-  __shared__ float siou[kMaxCand];
+  __shared__ unsigned long long slist[kAtssWarps][32][kMaxTopk];  // overflow path only
+  __shared__ unsigned long long swbest[kAtssWarps][kMaxTopk];
+  __shared__ unsigned long long skeys[kGPC][kNear];
+  __shared__ float sgmin[kGPC][kGroups];
+  __shared__ float sU[kGPC];
+  __shared__ int sn[kGPC];
+  __shared__ int scand[kGPC][kMaxCand];
+  __shared__ float siou[kGPC][kMaxCand];
   __shared__ int sslot[BDET_MAX_LEVELS + 1];
-  const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int G = min(p.num_gt[b], p.Gmax);
-  if (g >= G) return;
-  const float* r = p.gt + ((long long)b * p.Gmax + g) * 5;
-  const float4 bx = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-  const float cx = __fdiv_rn(bx.x + bx.z, 2.f), cy = __fdiv_rn(bx.y + bx.w, 2.f);
+  const int g0 = blockIdx.x * kGPC;
+  if (g0 >= G) return;
+  const int ng = min(kGPC, G - g0);
+  float cx[kGPC], cy[kGPC];
+#pragma unroll
+  for (int q = 0; q < kGPC; ++q) {  // slots past the last GT repeat it; their results are never used
+    const float* r = p.gt + ((long long)b * p.Gmax + g0 + min(q, ng - 1)) * 5;
+    cx[q] = __fdiv_rn(__ldg(r) + __ldg(r + 2), 2.f);      // gt_boxes.centers, op_patch.py:100-113
+    cy[q] = __fdiv_rn(__ldg(r + 1) + __ldg(r + 3), 2.f);
+  }
   if (t == 0) {
     int s = 0;
     for (int l = 0; l < p.L; ++l) {
@@ -151,66 +194,161 @@ __global__ void __launch_bounds__(kAtssThreads) atss_candidates_kernel(const Den
   }
   __syncthreads();
   const float2* pts = reinterpret_cast<const float2*>(p.points);
-  for (int l = warp; l < p.L; l += kAtssWarps) {
+  for (int l = 0; l < p.L; ++l) {
     const int s = p.lvl_start[l], e = p.lvl_start[l + 1];
     const int k = min(p.topk, e - s);
-    unsigned long long kk[kMaxTopk];
+    if (k == 0) continue;  // CTA-uniform
+    // pass 1: squared distances (atss.py:40-42 without the monotone sqrt); every thread the minimum over its strided
+    // slice; the k-th smallest of the 64 four-lane group minima bounds the k-th nearest squared distance
+    float mn[kGPC];
 #pragma unroll
-    for (int j = 0; j < kMaxTopk; ++j) kk[j] = ~0ull;
-    for (int i = s + lane; i < e; i += 32) {
-      const float2 q = __ldg(pts + i);
-      const float dx = cx - q.x, dy = cy - q.y;
-      const float d = sqrtf(dx * dx + dy * dy);  // :40-42
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(i - s);
-      if (key < kk[kMaxTopk - 1]) topk_insert(kk, key);
-    }
+    for (int q = 0; q < kGPC; ++q) mn[q] = CUDART_INF_F;
+    for (int i = s + t; i < e; i += kAtssThreads) {
+      const float2 pt = __ldg(pts + i);
 #pragma unroll
-    for (int j = 0; j < kMaxTopk; ++j) slist[warp][lane][j] = kk[j];
-    __syncwarp();
-    // k-way merge of the 32 sorted lists: (distance asc, index asc), F.topk(descending=False) (ASSUMED-9)
-    int head = 0;
-    for (int round = 0; round < k; ++round) {
-      const unsigned long long mine = head < kMaxTopk ? slist[warp][lane][head] : ~0ull;
-      const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32));
-      const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32) == hi ? (unsigned)mine : 0xffffffffu);
-      if ((unsigned)(mine >> 32) == hi && (unsigned)mine == lo) {
-        ++head;
-        scand[sslot[l] + round] = s + (int)lo;  // :44 base + topk_idxs
+      for (int q = 0; q < kGPC; ++q) {
+        const float dx = cx[q] - pt.x, dy = cy[q] - pt.y;
+        mn[q] = fminf(mn[q], dx * dx + dy * dy);
       }
     }
+#pragma unroll
+    for (int q = 0; q < kGPC; ++q) {
+      float v = mn[q];
+      v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+      v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+      if ((lane & 3) == 0) sgmin[q][t >> 2] = v;
+    }
+    if (t < kGPC) sn[t] = 0;
+    __syncthreads();
+    {
+      const int q = t / kGroups, j0 = t % kGroups;  // kGPC * kGroups == kAtssThreads
+      const float v = sgmin[q][j0];
+      int rank = 0;
+      for (int j = 0; j < kGroups; ++j) {
+        const float o = sgmin[q][j];
+        rank += (o < v) || (o == v && j < j0);
+      }
+      if (rank == k - 1) sU[q] = v;  // +inf when fewer than k groups saw a point: everything is collected
+    }
+    __syncthreads();
+    // sqrt is monotone, so U = sqrt(bound) bounds the k-th distance; a point can round to d <= U only if
+    // d2 <= bound * (1 + 2^-21), the cheap pre-filter in front of the exact test
+    float U2[kGPC], U[kGPC];
+#pragma unroll
+    for (int q = 0; q < kGPC; ++q) {
+      U2[q] = sU[q] * 1.000001f;
+      U[q] = sqrtf(sU[q]);
+    }
+    // pass 2: the few points within U, then their exact order (distance asc, index asc) by rank counting
+    for (int i = s + t; i < e; i += kAtssThreads) {
+      const float2 pt = __ldg(pts + i);
+#pragma unroll
+      for (int q = 0; q < kGPC; ++q) {
+        const float dx = cx[q] - pt.x, dy = cy[q] - pt.y;
+        const float d2 = dx * dx + dy * dy;
+        if (d2 > U2[q]) continue;
+        const float d = sqrtf(d2);
+        if (!(d > U[q])) {
+          const int slot = atomicAdd(&sn[q], 1);
+          if (slot < kNear) skeys[q][slot] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(i - s);
+        }
+      }
+    }
+    __syncthreads();
+    for (int q = 0; q < ng; ++q) {
+      const int m = sn[q];
+      if (m <= kNear) {
+        if (t < m) {
+          const unsigned long long key = skeys[q][t];
+          int rank = 0;
+          for (int j = 0; j < m; ++j) rank += skeys[q][j] < key;
+          if (rank < k) scand[q][sslot[l] + rank] = s + (int)(unsigned)key;  // :43-44 base + topk_idxs (ASSUMED-9)
+        }
+        continue;
+      }
+      // more than kNear points inside U (masses of equidistant / duplicate points): per-lane sorted lists, 32 lane
+      // lists -> the warp's k best, 8 warp lists -> the level's k candidates
+      unsigned long long kk[kMaxTopk];
+#pragma unroll
+      for (int j = 0; j < kMaxTopk; ++j) kk[j] = ~0ull;
+      float ccx = cx[0], ccy = cy[0];
+#pragma unroll
+      for (int qq = 1; qq < kGPC; ++qq)
+        if (qq == q) {
+          ccx = cx[qq];
+          ccy = cy[qq];
+        }
+      for (int i = s + t; i < e; i += kAtssThreads) {
+        const float2 pt = __ldg(pts + i);
+        const float dx = ccx - pt.x, dy = ccy - pt.y;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(sqrtf(dx * dx + dy * dy)) << 32) | (unsigned)(i - s);
+        if (key < kk[kMaxTopk - 1]) topk_insert(kk, key);
+      }
+#pragma unroll
+      for (int j = 0; j < kMaxTopk; ++j) slist[warp][lane][j] = kk[j];
+      __syncwarp();
+      int head = 0;
+      for (int round = 0; round < k; ++round) {
+        const unsigned long long mine = head < kMaxTopk ? slist[warp][lane][head] : ~0ull;
+        const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32));
+        const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32) == hi ? (unsigned)mine : 0xffffffffu);
+        if ((unsigned)(mine >> 32) == hi && (unsigned)mine == lo) {
+          ++head;
+          swbest[warp][round] = mine;
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int wh = 0;
+        for (int round = 0; round < k; ++round) {
+          const unsigned long long mine = (lane < kAtssWarps && wh < k) ? swbest[lane][wh] : ~0ull;
+          const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32));
+          const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(mine >> 32) == hi ? (unsigned)mine : 0xffffffffu);
+          if ((unsigned)(mine >> 32) == hi && (unsigned)mine == lo) {
+            ++wh;
+            scand[q][sslot[l] + round] = s + (int)lo;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (warp != 0) return;
+  if (warp >= ng) return;
+  // ---- warp q: candidates of GT g0 + q
+  const int q = warp, g = g0 + q;
+  const float* r = p.gt + ((long long)b * p.Gmax + g) * 5;
+  const float4 bx = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
   const int nc = sslot[p.L];
   const float garea = box_area(bx);
   for (int j = lane; j < nc; j += 32) {
-    const int a = scand[j];
+    const int a = scand[q][j];
     const int l = level_of(p, a);
-    const float2 q = __ldg(pts + a);
+    const float2 pt = __ldg(pts + a);
     const float h = p.radius[l];
-    const float4 ab = make_float4(q.x - h, q.y - h, q.x + h, q.y + h);  // :31-37
-    siou[j] = iou_pair(bx, garea, ab, box_area(ab));
+    const float4 ab = make_float4(pt.x - h, pt.y - h, pt.x + h, pt.y + h);  // :31-37
+    siou[q][j] = iou_pair(bx, garea, ab, box_area(ab));
   }
   __syncwarp();
   float thr = 0.f;
   if (lane == 0) {  // :50-51, sequential fp32 accumulation (ASSUMED-8)
     float sum = 0.f;
-    for (int j = 0; j < nc; ++j) sum += siou[j];
+    for (int j = 0; j < nc; ++j) sum += siou[q][j];
     const float mean = __fdiv_rn(sum, (float)nc);
     float sq = 0.f;
     for (int j = 0; j < nc; ++j) {
-      const float d = siou[j] - mean;
+      const float d = siou[q][j] - mean;
       sq += d * d;
     }
     thr = mean + sqrtf(__fdiv_rn(sq, (float)nc));
   }
   thr = __shfl_sync(0xffffffffu, thr, 0);
   for (int j = lane; j < nc; j += 32) {
-    const float v = siou[j];
+    const float v = siou[q][j];
     if (!(v >= thr)) continue;  // :52-54
-    const int a = scand[j];
-    const float2 q = __ldg(pts + a);
-    const float mn = fminf(fminf(q.x - bx.x, q.y - bx.y), fminf(bx.z - q.x, bx.w - q.y));
+    const int a = scand[q][j];
+    const float2 pt = __ldg(pts + a);
+    const float mn = fminf(fminf(pt.x - bx.x, pt.y - bx.y), fminf(bx.z - pt.x, bx.w - pt.y));
     if (!(mn > 0.f)) continue;  // :56-58
     const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - (unsigned)g);
     atomicMax(p.best + (long long)b * p.A + a, key);  // :63 argmax over G: highest IoU, lowest g among equals
@@ -312,7 +450,7 @@ extern "C" int bdet_atss_targets(const float* points, int A, const int* level_st
   a.best = reinterpret_cast<unsigned long long*>(workspace);
   cudaStream_t st = as_stream(stream);
   BDET_CUDA(cudaMemsetAsync(a.best, 0, (size_t)A * B * 8, st));
-  if (Gmax > 0) BDET_KERNEL("atss_candidates_kernel", st, atss_candidates_kernel<<<dim3(Gmax, B), kAtssThreads, 0, st>>>(a));
+  if (Gmax > 0) BDET_KERNEL("atss_candidates_kernel", st, atss_candidates_kernel<<<dim3(ceil_div(Gmax, kGPC), B), kAtssThreads, 0, st>>>(a));
   BDET_KERNEL("atss_finish_kernel", st, atss_finish_kernel<<<dim3(ceil_div(A, kDenseThreads), B), kDenseThreads, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;

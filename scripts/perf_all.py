@@ -45,7 +45,8 @@ KERNELS = ["anchors_grid_kernel", "pairwise_kernel", "match_colmax_kernel", "mat
            "box_encode_kernel", "box_decode_kernel", "score_filter_kernel", "select_sort_kernel", "select_decode_kernel",
            "nms_sort_small_kernel", "nms_tile_sort_kernel", "nms_global_step_kernel", "nms_tile_tail_kernel", "nms_gather_kernel",
            "nms_maxcoord_kernel", "nms_fused_kernel", "nms_mask_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
-           "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel"]
+           "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel",
+           "fcos_targets_kernel", "atss_candidates_kernel", "atss_finish_kernel", "count_labels_kernel"]
 rng = np.random.default_rng(0)
 
 # ---- config 2: target assignment, batch 16
@@ -91,6 +92,17 @@ info4 = T(np.array([[800, 1344, 800, 1333, 0.0]] * B4, np.float32))
 run("c4_fcos_b64", lambda: pipelines.dense_postprocess(lg4, lt4, pts, info4, 0.05, 0.6, 100, 1000, ctrness_list=ct4),
     {"score_filter_kernel": B4 * 22400 * 80 * 4 + B4 * 22400 * 4})
 del lg4, ct4, lt4
+# config-4 shape, training side: FCOS / ATSS target assignment, 64 images x 22 400 points x 100 GT
+gt4, ng4 = W.target_assign_batch(B4, 100, 800, 1344, seed0=4000)
+gt4_d, ng4_d = T(gt4), T(ng4)
+A4 = sum(h * w for h, w in sz4)
+SOI = [(-1, 64), (64, 128), (128, 256), (256, 512), (512, float("inf"))]
+dplan = ops.DensePlan(A4, B4, dev, atss=True)
+dense_bytes = B4 * (A4 * (4 + 16 + 4 + 4) + 100 * 20) + A4 * 8   # labels + offsets + ctrness + match_idx written, gt + points read
+run("c4_fcos_targets_b64", lambda: ops.fcos_targets(pts, gt4_d, ng4_d, W.RETINANET_STRIDES, SOI, 1.5, plan=dplan),
+    {"fcos_targets_kernel": dense_bytes})
+run("c4_atss_targets_b64", lambda: ops.atss_targets(pts, gt4_d, ng4_d, W.RETINANET_STRIDES, 8, 9, plan=dplan),
+    {"atss_finish_kernel": dense_bytes + B4 * A4 * 8})
 
 # ---- config 3: RPN proposals + ROIAlign fwd/bwd, batch 16 @ 800x1344
 B3 = 16

@@ -128,3 +128,28 @@ def test_dense_targets_config4_full_size_properties():
         dec = np.stack([px[..., 0] - off[..., 0], px[..., 1] - off[..., 1], px[..., 0] + off[..., 2], px[..., 1] + off[..., 3]], -1)
         assert np.max(np.abs(dec[fg] - m[fg][:, :4])) <= 1e-3
         assert np.all((ctr[fg] > 0) & (ctr[fg] <= 1))
+
+
+def test_atss_equidistant_points_take_the_index_order_fallback():
+    """Hundreds of points at the same distance from a GT centre (duplicates, rings): F.topk ascending keeps the lowest
+    indices (ASSUMED-9); exercises the path for > 256 points inside the distance bound."""
+    rng = np.random.default_rng(77)
+    ring = np.stack([200 + 64 * np.cos(np.linspace(0, 2 * np.pi, 600, endpoint=False)),
+                     160 + 64 * np.sin(np.linspace(0, 2 * np.pi, 600, endpoint=False))], 1)
+    pts = [np.concatenate([np.full((700, 2), 100.0), rng.uniform(0, 400, (300, 2))]).astype(np.float32),
+           np.round(ring).astype(np.float32),
+           rng.uniform(0, 400, (50, 2)).astype(np.float32)]
+    gt = np.zeros((2, 3, 5), np.float32)
+    gt[0, 0] = [60, 60, 140, 140, 3]      # centre exactly on the 700 duplicates
+    gt[0, 1] = [136, 96, 264, 224, 5]     # centre (200, 160): the rounded ring is full of equal distances
+    gt[0, 2] = [10, 10, 390, 390, 7]
+    gt[1, 0] = [90, 90, 110, 110, 2]
+    ng = np.array([3, 1], np.int32)
+    strides = [8, 16, 32]
+    for topk in (9, 16):
+        lab, off, ctr, idx = ops.atss_targets([T(p) for p in pts], T(gt), T(ng), strides, 8, topk)
+        rl, ro, rc, ri = R.atss_targets(pts, gt, ng, strides, 8, topk)
+        same(idx, ri)
+        same(lab, rl)
+        same(off, ro)
+        same(ctr, rc)
