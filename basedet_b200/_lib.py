@@ -73,6 +73,7 @@ SIGNATURES = {
     "bdet_fcos_targets": (c_int, [vp, c_int, ip, c_int, fp, fp, fp, vp, c_int, vp, c_int, vp, vp, vp, vp, vp]),
     "bdet_atss_targets_workspace": (c_size_t, [c_int, c_int]),
     "bdet_atss_targets": (c_int, [vp, c_int, ip, c_int, fp, c_int, vp, c_int, vp, c_int, vp, vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_sample_labels": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),

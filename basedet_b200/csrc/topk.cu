@@ -602,9 +602,90 @@ static int launch_select(const SelArgs& a, int n_seg, cudaStream_t st) {
   return BDET_OK;
 }
 
+// ---- sample_labels ----------------------------------------------------------------------------
+// basedet/layers/common/sampling.py:7-30 with the random draw made explicit (one uniform variate per element, the
+// reference's uniform(size=num_valid) being the variates of the selected positions): keep `num_samples` of the
+// elements equal to `value`, set the ones with the LARGEST variates to `ignore`.  F.topk(random_tensor, k < 0) there
+// selects the |k| largest of a tensor that is 0 outside the mask, ordered (value desc, index asc) -- exactly the
+// |k| smallest keys of this file, so the same cluster radix select finds the cut.
+struct SampleArgs {
+  int* labels;          // (B, A), in place
+  const float* noise;   // (B, A)
+  const int* ns_dev;    // (B) per-image num_samples or nullptr
+  int A, value, ignore, ns_const;
+};
+
+struct NoiseSrc {
+  const int* lab;
+  const float* noise;
+  int value;
+  __device__ __forceinline__ uint64_t key(int i) const {
+    return make_key(__ldg(lab + i) == value ? __ldg(noise + i) : 0.f, (uint32_t)i);  // sampling.py:24-25
+  }
+};
+
+__global__ void __launch_bounds__(kSelThreads) sample_labels_kernel(const SampleArgs p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  uint64_t* buf = reinterpret_cast<uint64_t*>(raw);  // kBufCap
+  __shared__ SelSmem sm;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int b = blockIdx.x / CS, t = threadIdx.x;
+  int* lab = p.labels + (long long)b * p.A;
+  const NoiseSrc src{lab, p.noise + (long long)b * p.A, p.value};
+  const int lo = (int)((long long)p.A * rank / CS), hi = (int)((long long)p.A * (rank + 1) / CS);
+  if (t == 0) sm.nsel = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = lo + t; i < hi; i += kSelThreads) mine += lab[i] == p.value;  // sampling.py:19-20
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((t & 31) == 0 && mine) atomicAdd(&sm.nsel, mine);
+  cluster.sync();
+  int num_valid = 0;
+  for (int r = 0; r < CS; ++r) num_valid += *cluster.map_shared_rank(&sm.nsel, r);
+  cluster.sync();  // every peer has read this CTA's count
+  const int ns = max(p.ns_dev ? p.ns_dev[b] : p.ns_const, 0);
+  if (num_valid <= ns) return;  // :21-22, cluster-uniform
+  const int k = num_valid - ns;  // :27
+  const uint64_t T = radix_select<false>(cluster, src, lo, hi, k, sm, buf);
+  // :29 -- a CTA rewrites only the range it alone reads, so a faster peer cannot disturb a slower one's keys
+  for (int i = lo + t; i < hi; i += kSelThreads)
+    if (src.key(i) <= T) lab[i] = p.ignore;
+}
+
 }  // namespace bdet
 
 using namespace bdet;
+
+extern "C" int bdet_sample_labels(int* labels, const float* noise, int A, int B, int label_value, int ignore_label,
+                                  int num_samples, const int* num_samples_dev, bdet_stream_t stream) {
+  BDET_REQUIRE(A >= 0 && B >= 0, "negative size");
+  if (A == 0 || B == 0) return BDET_OK;
+  BDET_REQUIRE(labels && noise, "null argument");
+  BDET_REQUIRE(num_samples_dev || num_samples >= 0, "negative num_samples");
+  SampleArgs a{labels, noise, num_samples_dev, A, label_value, ignore_label, num_samples};
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = (size_t)kBufCap * 8;
+  int cs = kMaxCS;
+  while (cs > 1 && ((long long)B * cs * 10 > 22LL * sm_count() || A < cs * 4096)) cs >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cs));
+  cfg.blockDim = dim3(kSelThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaSuccess;
+  BDET_KERNEL("sample_labels_kernel", st, err = cudaLaunchKernelEx(&cfg, sample_labels_kernel, a));
+  BDET_CUDA(err);
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
 
 extern "C" size_t bdet_topk_workspace(int64_t total, int n_seg, int k) {
   (void)k;

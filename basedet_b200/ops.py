@@ -725,6 +725,25 @@ def count_labels(labels, out=None):
     return out
 
 
+def sample_labels(labels, noise, num_samples, label_value, ignore_label=-1):
+    """sample_labels (layers/common/sampling.py:7-30) for a batch, IN PLACE on ``labels`` (B, A) int32.
+    noise (B, A) fp32: one uniform variate per element (the explicit RNG contract, see include/bdet.h);
+    num_samples: int, or a (B,) int32 device tensor (per-image budget).  Returns ``labels``."""
+    lib = _lib.load()
+    lab = _dev(as_tensor(labels), "labels")
+    assert lab.dtype == torch.int32 and lab.is_contiguous(), "labels must be a contiguous int32 tensor (modified in place)"
+    if lab.ndim == 1:
+        lab = lab.unsqueeze(0)
+    nz = _f32c(noise, "noise").reshape(lab.shape)
+    B, A = lab.shape
+    ns_dev = _i32c(num_samples, "num_samples") if torch.is_tensor(num_samples) else None
+    assert ns_dev is None or ns_dev.numel() == B
+    with _guard(lab):
+        check(lib.bdet_sample_labels(_p(lab), _p(nz), A, B, int(label_value), int(ignore_label),
+                                     0 if ns_dev is not None else int(num_samples), _p(ns_dev), _stream(lab)))
+    return labels
+
+
 # ----------------------------------------------------------------------------- measurement hooks
 def profile_begin(only=None):
     """Bracket kernel launches with CUDA events; ``only`` = time just that kernel (the rest are counted)."""

@@ -69,6 +69,21 @@ def rpn_proposals(scores_list, offsets_list, anchors_list, im_info, prev_nms_top
     return rois, keep_cnt
 
 
+def rpn_targets(anchors, gt_boxes, num_gt, noise_pos, noise_neg, thresholds=(0.3, 0.7), labels=(0, -1, 1),
+                allow_low_quality=True, num_sample_anchors=256, positive_anchor_ratio=0.5, reg_mean=(0, 0, 0, 0),
+                reg_std=(1, 1, 1, 1), plan=None):
+    """RPN.get_ground_truth, models/det/rpn.py:215-240 (defaults configs/det_model/faster_rcnn_cfg.py:23-24,60-64):
+    fused IoU -> Matcher -> encode, then sample_labels for positives and negatives with caller-supplied uniform
+    variates noise_pos / noise_neg (B, A) (RNG contract in include/bdet.h).  -> labels (B, A) in {-1, 0, 1}, offsets."""
+    lab, idx, off = ops.assign_targets(anchors, gt_boxes, num_gt, list(thresholds), list(labels), allow_low_quality,
+                                       False, reg_mean, reg_std, plan=plan)
+    num_pos = int(positive_anchor_ratio * num_sample_anchors)                  # rpn.py:29
+    ops.sample_labels(lab, noise_pos, num_pos, 1, -1)                          # :229
+    num_neg = num_sample_anchors - ops.count_labels(lab)[:, 2]                 # :231 (labels == 1).sum(), stays on device
+    ops.sample_labels(lab, noise_neg, num_neg.to(torch.int32), 0, -1)          # :232
+    return lab, off
+
+
 def fcos_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128),
                  sizes_of_interest=((-1, 64), (64, 128), (128, 256), (256, 512), (512, float("inf"))),
                  center_sampling_radius=1.5, plan=None):

@@ -163,6 +163,17 @@ int bdet_atss_targets(const float* points, int A, const int* level_start_host, i
                       int topk, const float* gt, int Gmax, const int* num_gt_dev, int B, int* labels, float* offsets,
                       float* ctrness, int* match_idx, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
+/* ------------------------------------------------------------------ 8(f)-2: fg / bg subsampling
+ * sample_labels  layers/common/sampling.py:7-30 (used by models/det/rpn.py:228-232 and layers/head/rcnn.py:124-127).
+ * labels (B,A) int32 IN PLACE, per image: if more than num_samples elements equal label_value, the surplus -- those
+ * with the LARGEST variates -- is set to ignore_label.  RNG contract: noise (B,A) holds one uniform [0,1) variate per
+ * element, drawn by the caller's framework; the reference's uniform(size=num_valid) is the variates of the selected
+ * positions in index order, so feeding it those reproduces the reference decision for decision (ties: lower index
+ * goes first).  num_samples_dev (B) optional device array overrides num_samples per image (rpn.py:231: the number of
+ * negatives depends on the positives that survived). */
+int bdet_sample_labels(int* labels, const float* noise, int A, int B, int label_value, int ignore_label,
+                       int num_samples, const int* num_samples_dev, bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
  * Segmented: segment s covers scores[seg_start[s] .. seg_start[s] + seg_len[s]) (element offsets from `scores`;

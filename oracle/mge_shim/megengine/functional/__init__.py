@@ -170,6 +170,8 @@ def sort(x, descending=False):
 
 def topk(x, k, descending=False, kth_only=False, no_sort=False):  # ASSUMED-3, k clamped to n
     a = _a(x)
+    if int(k) < 0:  # ASSUMED-10: MegDNN TopK takes a signed k, negative = the |k| LARGEST (sampling.py:27 relies on it)
+        k, descending = -int(k), not descending
     key = -a if descending else a
     order = np.argsort(key, axis=-1, kind="stable")[..., : builtins_min(int(k), a.shape[-1])].astype(np.int32)
     return Tensor(np.take_along_axis(a, order.astype(np.int64), -1)), Tensor(order)

@@ -21,6 +21,8 @@ reference's own tests.
   ASSUMED-8  F.mean / F.std over the 45 ATSS candidates: fp32 sum accumulated sequentially in index
              order, one divide by n; std = sqrt(mean((x - mean) ** 2)) (population).  MegDNN's reduce
              order is unknown; any fixed order differs from another by <= a few ulp of the threshold.
+  ASSUMED-10 F.topk takes a signed k (MegDNN TopK): a negative k selects the |k| LARGEST elements, ordered
+             (value desc, index asc).  ``sample_labels`` (sampling.py:27) relies on it.
   ASSUMED-9  ``x ** 2`` on a tensor is ``x * x`` (one rounding); F.topk(descending=False) orders by
              (value asc, index asc); argmin returns the FIRST index among equal minima.
 """
@@ -420,6 +422,45 @@ def retinanet_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_lq,
         lab_l.append(lab)
         idx_l.append(idx)
     return np.stack(lab_l), np.stack(off_l), np.stack(idx_l)
+
+
+def sample_labels(labels, num_samples, label_value, ignore_label, noise):
+    """sample_labels, basedet/layers/common/sampling.py:7-30, with the random draw made explicit.
+
+    RNG contract: ``noise`` has one uniform variate PER ELEMENT of ``labels``; the reference's
+    ``uniform(size=num_valid)`` (:24) is ``noise[mask]`` (the variates of the selected positions, in index order).
+    Keeps ``num_samples`` elements equal to ``label_value`` and sets the others to ``ignore_label``: the ones with
+    the LARGEST variates go (topk with negative k, ASSUMED-10; ties (value desc, index asc), ASSUMED-3).  Returns a
+    new array (the reference mutates in place and also returns it)."""
+    labels = np.array(labels, copy=True)
+    mask = labels == label_value                                                # :19
+    num_valid = int(mask.sum())                                                 # :20
+    if num_valid <= num_samples:                                                # :21-22
+        return labels
+    random_tensor = np.zeros(labels.shape, f32)                                 # :24
+    random_tensor[mask] = np.asarray(noise, f32)[mask]                          # :25
+    k = num_valid - num_samples                                                 # :27 (passed as a negative k)
+    invalid = np.argsort(-random_tensor, kind="stable")[:k]
+    labels[invalid] = ignore_label                                              # :29
+    return labels
+
+
+def rpn_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_lq, num_sample_anchors, num_pos_anchor,
+                noise_pos, noise_neg, mean=(0, 0, 0, 0), std=(1, 1, 1, 1)):
+    """RPN.get_ground_truth, basedet/models/det/rpn.py:215-240: IoU -> Matcher -> encode -> sample positives ->
+    sample negatives.  noise_pos / noise_neg (B, A): the variates of the two sample_labels calls (see sample_labels).
+    Returns labels (B, A) int32 in {-1, 0, 1} and offsets (B, A, 4)."""
+    lab_l, off_l = [], []
+    for b, (g, n) in enumerate(zip(gt_boxes, num_gt)):
+        g = np.asarray(g, dtype=f32)[: int(n)]
+        overlaps = box_iou(g[:, :4], anchors)                                   # :223
+        idx, lab = matcher(overlaps, thresholds, labels, allow_lq)              # :224
+        off_l.append(boxcoder_encode(anchors, g[idx][:, :4], mean, std))        # :226
+        lab = sample_labels(lab, num_pos_anchor, 1, -1, noise_pos[b])           # :229
+        num_negative = num_sample_anchors - int((lab == 1).sum())               # :231
+        lab = sample_labels(lab, num_negative, 0, -1, noise_neg[b])             # :232
+        lab_l.append(lab)
+    return np.stack(lab_l), np.stack(off_l)
 
 
 def _ctrness(offsets):

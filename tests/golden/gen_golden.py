@@ -217,6 +217,43 @@ def build():
     me = types.SimpleNamespace(cfg=Cfg(MODEL=Cfg(ANCHOR=Cfg(SCALE=8, TOPK=9))), head=head, box_coder=ref.boxcoder.PointCoder())
     lab, off, ctr = atss_gt(me, [T(p.numpy().copy()) for p in dpts], T(dgt.copy()), [int(n) for n in dng])
     g["atss_labels"], g["atss_offsets"], g["atss_ctrness"] = lab.numpy(), off.numpy(), ctr.numpy()
+
+    # ---- RPN.get_ground_truth (models/det/rpn.py:215-240) with the reference's own sample_labels
+    # (layers/common/sampling.py).  The variates are explicit: noise_* (B, A) hold one uniform value per anchor and the
+    # shim's megengine.random.uniform is fed noise[mask] in the order the reference draws (oracle RNG contract).
+    import importlib
+
+    import megengine.random as mrand
+
+    from oracle import ref_ops as R
+
+    sampling = importlib.import_module("basedet.layers.common.sampling")
+    rpn_gt = ref_runner.load_method("models/det/rpn.py", "RPN", "get_ground_truth", {"sample_labels": sampling.sample_labels})
+    ssizes = W.frcnn_level_sizes(128, 160)
+    g["samp_sizes"] = np.array(ssizes)
+    sgen = ref.anchor_generator.DefaultAnchorGenerator(W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5)
+    sanchors = [a.numpy() for a in sgen([T(np.zeros((1, 1, h, w), np.float32)) for h, w in ssizes])]
+    sall = np.concatenate(sanchors)
+    sgt, sng = W.target_assign_batch(3, num_gt=8, img_h=128, img_w=160, seed0=1300, ragged=True)
+    srng = np.random.default_rng(1301)
+    noise_p = srng.uniform(0, 1, (3, len(sall))).astype(np.float32)
+    noise_n = (np.floor(srng.uniform(0, 1, (3, len(sall))) * 512) / 512).astype(np.float32)   # ties among the variates
+    g["samp_gt"], g["samp_num"], g["samp_noise_pos"], g["samp_noise_neg"] = sgt, sng, noise_p, noise_n
+    npos_cfg, ntot = 6, 48
+    for b in range(3):  # which variates the reference will draw, image by image (the oracle is only the bookkeeper here)
+        gb = sgt[b, : sng[b]]
+        _, lab0 = R.matcher(R.box_iou(gb[:, :4], sall), [0.3, 0.7], [0, -1, 1], True)
+        if (lab0 == 1).sum() > npos_cfg:
+            mrand.feed(noise_p[b][lab0 == 1])
+        lab1 = R.sample_labels(lab0, npos_cfg, 1, -1, noise_p[b])
+        if (lab1 == 0).sum() > ntot - (lab1 == 1).sum():
+            mrand.feed(noise_n[b][lab1 == 0])
+    me = types.SimpleNamespace(matcher=ref.matcher.Matcher([0.3, 0.7], [0, -1, 1], True),
+                               box_coder=ref.boxcoder.BoxCoder((0., 0., 0., 0.), (1., 1., 1., 1.)),
+                               num_pos_anchor=npos_cfg, num_sample_anchors=ntot)
+    rl, ro = rpn_gt(me, [T(a.copy()) for a in sanchors], T(sgt.copy()), [int(n) for n in sng])
+    assert not mrand._queue, "the reference drew fewer variates than were fed"
+    g["samp_labels"], g["samp_offsets"] = rl.numpy().reshape(3, -1), ro.numpy().reshape(3, -1, 4)
     return g
 
 

@@ -179,3 +179,17 @@ def test_roi_pool(cuda):
     out = roi_pool(feats, rois, [4, 8, 16, 32], (7, 7), "roi_align")
     close(out, GOLD["roi_out"], tol=1e-5)
     same(out, GOLD["roi_out"])  # same op order, no FMA contraction: bit-exact in practice
+
+
+def test_rpn_get_ground_truth_with_sampling_golden(cuda):
+    """RPN.get_ground_truth + sample_labels (rpn.py:215-240, sampling.py:7-30) vs the vectors the reference source
+    produced with the same explicit variates."""
+    from basedet_b200 import pipelines
+    sizes = [tuple(int(v) for v in x) for x in GOLD["samp_sizes"]]
+    gen = DefaultAnchorGenerator(W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5)
+    anchors = gen.generate_all_level_anchors(sizes, cuda)
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda)  # noqa: E731
+    lab, off = pipelines.rpn_targets(anchors, Tc(GOLD["samp_gt"]), Tc(GOLD["samp_num"]), Tc(GOLD["samp_noise_pos"]),
+                                     Tc(GOLD["samp_noise_neg"]), (0.3, 0.7), (0, -1, 1), True, 48, 6 / 48)
+    assert np.array_equal(lab.cpu().numpy(), GOLD["samp_labels"])
+    assert np.max(np.abs(off.cpu().numpy() - GOLD["samp_offsets"])) <= 1e-6

@@ -294,3 +294,46 @@ def test_count_labels_census(cuda, B, A):
     got = ops.count_labels(torch.from_numpy(lab).to(cuda)).cpu().numpy()
     ref = np.stack([(lab < 0).sum(1), (lab == 0).sum(1), (lab > 0).sum(1)], 1)
     assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ sample_labels / RPN.get_ground_truth
+@pytest.mark.parametrize("A,B,ns,quant", [(50, 2, 8, 0), (5000, 3, 128, 0), (5000, 3, 128, 16), (268569, 2, 256, 0),
+                                           (268569, 2, 256, 64), (4096, 4, 0, 0), (300, 2, 1000, 0)])
+def test_sample_labels_bit_exact(cuda, A, B, ns, quant):
+    """layers/common/sampling.py:7-30 with explicit variates: the kept / ignored sets are exactly the oracle's,
+    including ties between equal variates (lower index is ignored first) and budgets above the population."""
+    from basedet_b200 import workloads as W  # noqa: F401
+    rng = np.random.default_rng(A + ns + quant)
+    lab = rng.choice(np.array([-1, 0, 1], np.int32), size=(B, A), p=[0.1, 0.8, 0.1]).astype(np.int32)
+    noise = rng.uniform(0, 1, (B, A)).astype(np.float32)
+    if quant:
+        noise = (np.floor(noise * quant) / quant).astype(np.float32)   # many equal variates, some exactly 0
+    for value, ignore in ((0, -1), (1, -1), (1, 0)):
+        ref = np.stack([R.sample_labels(lab[b], ns, value, ignore, noise[b]) for b in range(B)])
+        got = ops.sample_labels(torch.from_numpy(lab.copy()).to(cuda), torch.from_numpy(noise).to(cuda), ns, value, ignore)
+        assert np.array_equal(got.cpu().numpy(), ref)
+    budgets = rng.integers(0, 400, B).astype(np.int32)               # per-image budgets from a device tensor
+    ref = np.stack([R.sample_labels(lab[b], int(budgets[b]), 0, -1, noise[b]) for b in range(B)])
+    got = ops.sample_labels(torch.from_numpy(lab.copy()).to(cuda), torch.from_numpy(noise).to(cuda),
+                            torch.from_numpy(budgets).to(cuda), 0, -1)
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("hw,B,G", [((96, 128), 2, 6), ((320, 480), 3, 25), ((800, 1344), 2, 60)])
+def test_rpn_get_ground_truth_with_sampling(cuda, hw, B, G):
+    """RPN.get_ground_truth (rpn.py:215-240): fused match/encode + two sample_labels calls == oracle."""
+    from basedet_b200 import pipelines
+    from basedet_b200 import workloads as W
+    sizes = W.frcnn_level_sizes(*hw)
+    anchors = np.concatenate(R.default_anchors(sizes, W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5))
+    gt, ng = W.target_assign_batch(B, G, hw[0], hw[1], seed0=hw[0], ragged=True)
+    rng = np.random.default_rng(hw[1])
+    A = anchors.shape[0]
+    npz, nnz = rng.uniform(0, 1, (B, A)).astype(np.float32), rng.uniform(0, 1, (B, A)).astype(np.float32)
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda)  # noqa: E731
+    for total, ratio in ((256, 0.5), (64, 0.25)):
+        lab, off = pipelines.rpn_targets(Tc(anchors), Tc(gt), Tc(ng), Tc(npz), Tc(nnz), (0.3, 0.7), (0, -1, 1), True, total, ratio)
+        rl, ro = R.rpn_targets(anchors, gt, ng, [0.3, 0.7], [0, -1, 1], True, total, int(ratio * total), npz, nnz)
+        assert np.array_equal(lab.cpu().numpy(), rl)
+        assert np.max(np.abs(off.cpu().numpy() - ro)) <= 1e-6
+        assert np.all((rl == 1).sum(1) <= int(ratio * total)) and np.all((rl >= 0).sum(1) <= total)

@@ -122,6 +122,17 @@ def test_atss_get_ground_truth():
     assert (lab > 0).sum() > 20
 
 
+def test_rpn_get_ground_truth_with_sample_labels():
+    """RPN.get_ground_truth + sample_labels run from the reference files (variates fed explicitly) == oracle."""
+    sizes = [tuple(x) for x in GOLD["samp_sizes"]]
+    anchors = np.concatenate(R.default_anchors(sizes, W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5))
+    lab, off = R.rpn_targets(anchors, GOLD["samp_gt"], GOLD["samp_num"], [0.3, 0.7], [0, -1, 1], True, 48, 6,
+                             GOLD["samp_noise_pos"], GOLD["samp_noise_neg"])
+    same(lab, GOLD["samp_labels"])
+    same(off, GOLD["samp_offsets"])
+    assert np.all((lab == 1).sum(1) <= 6) and np.all((lab >= 0).sum(1) == 48)
+
+
 def test_nms_and_post_processing():
     b, s, l = GOLD["nms_boxes"], GOLD["nms_scores"], GOLD["nms_labels"]
     same(R.batched_nms(b, s, l, 0.5), GOLD["nms_keep_05"])
