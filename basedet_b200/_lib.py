@@ -74,6 +74,8 @@ SIGNATURES = {
     "bdet_atss_targets_workspace": (c_size_t, [c_int, c_int]),
     "bdet_atss_targets": (c_int, [vp, c_int, ip, c_int, fp, c_int, vp, c_int, vp, c_int, vp, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_sample_labels": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
+    "bdet_rcnn_match": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_float, c_float, c_float, vp, vp, vp, vp, vp, vp, vp]),
+    "bdet_rcnn_collect": (c_int, [vp, vp, vp, vp, vp, vp, c_int, vp, c_int, c_int, fp, fp, c_int, vp, vp, vp, vp, vp]),
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),

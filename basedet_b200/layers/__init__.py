@@ -6,10 +6,11 @@ from .function import is_empty_tensor, meshgrid, non_zeros, permute_to_N_Any_K, 
 from .matcher import Matcher
 from .post_processing import batched_nms, post_process_with_empty_input, post_processing, py_cpu_nms
 from .roi_pool import assign_rois, roi_pool
+from .sampling import sample_labels
 
 __all__ = [
     "AnchorPointGenerator", "BaseAnchorGenerator", "DefaultAnchorGenerator", "FastPointGenerator",
     "create_anchor_grid", "is_empty_tensor", "meshgrid", "non_zeros", "permute_to_N_Any_K", "safelog",
     "Matcher", "batched_nms", "post_process_with_empty_input", "post_processing", "py_cpu_nms",
-    "assign_rois", "roi_pool",
+    "assign_rois", "roi_pool", "sample_labels",
 ]

@@ -744,6 +744,45 @@ def sample_labels(labels, noise, num_samples, label_value, ignore_label=-1):
     return labels
 
 
+def rcnn_match(rois, n_rois, gt_boxes, num_gt, fg_thresh=0.5, bg_thresh_low=0.0, bg_thresh_high=0.5):
+    """First step of RCNN.get_ground_truth (layers/head/rcnn.py:105-123) for the batch.  rois (B, Rmax, 5) padded,
+    n_rois (B,).  -> dict(all_rois (B,N,5), n_all (B,), assign (B,N), cls (B,N) fp32, fg (B,N) int32, bg (B,N) int32)."""
+    lib = _lib.load()
+    r = _f32c(rois, "rois")
+    gt = _f32c(gt_boxes, "gt_boxes")
+    assert r.ndim == 3 and r.shape[2] == 5 and gt.ndim == 3 and gt.shape[2] == 5 and r.shape[0] == gt.shape[0]
+    B, Rmax, Gmax = r.shape[0], r.shape[1], gt.shape[1]
+    N, dev = Rmax + Gmax, r.device
+    out = dict(all_rois=torch.empty((B, N, 5), dtype=torch.float32, device=dev),
+               n_all=torch.empty((B,), dtype=torch.int32, device=dev),
+               assign=torch.empty((B, N), dtype=torch.int32, device=dev),
+               cls=torch.empty((B, N), dtype=torch.float32, device=dev),
+               fg=torch.empty((B, N), dtype=torch.int32, device=dev), bg=torch.empty((B, N), dtype=torch.int32, device=dev))
+    with _guard(r):
+        check(lib.bdet_rcnn_match(_p(r), _p(_i32c(n_rois, "n_rois")), Rmax, _p(gt), _p(_i32c(num_gt, "num_gt")), Gmax, B,
+                                  float(fg_thresh), float(bg_thresh_low), float(bg_thresh_high), _p(out["all_rois"]),
+                                  _p(out["n_all"]), _p(out["assign"]), _p(out["cls"]), _p(out["fg"]), _p(out["bg"]), _stream(r)))
+    return out
+
+
+def rcnn_collect(m, gt_boxes, num_out, mean=(0, 0, 0, 0), std=(0.1, 0.1, 0.2, 0.2)):
+    """Last step of RCNN.get_ground_truth (rcnn.py:130-137) from the (sampled) masks of ``rcnn_match``.
+    -> rois (B, num_out, 5), labels (B, num_out) int32, bbox_targets (B, num_out, 4), count (B,)."""
+    lib = _lib.load()
+    gt = _f32c(gt_boxes, "gt_boxes")
+    B, N = m["fg"].shape
+    dev = gt.device
+    rois = torch.empty((B, num_out, 5), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, num_out), dtype=torch.int32, device=dev)
+    targets = torch.empty((B, num_out, 4), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    with _guard(gt):
+        check(lib.bdet_rcnn_collect(_p(m["all_rois"]), _p(m["n_all"]), _p(m["assign"]), _p(m["cls"]), _p(m["fg"]), _p(m["bg"]), N,
+                                    _p(gt), gt.shape[1], B, farr(mean), farr(std), int(num_out), _p(rois), _p(labels),
+                                    _p(targets), _p(count), _stream(gt)))
+    return rois, labels, targets, count
+
+
 # ----------------------------------------------------------------------------- measurement hooks
 def profile_begin(only=None):
     """Bracket kernel launches with CUDA events; ``only`` = time just that kernel (the rest are counted)."""

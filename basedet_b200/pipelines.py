@@ -84,6 +84,20 @@ def rpn_targets(anchors, gt_boxes, num_gt, noise_pos, noise_neg, thresholds=(0.3
     return lab, off
 
 
+def rcnn_targets(rois, n_rois, gt_boxes, num_gt, noise_fg, noise_bg, num_rois=512, fg_ratio=0.5, fg_thresh=0.5,
+                 bg_thresh_high=0.5, bg_thresh_low=0.0, reg_mean=(0, 0, 0, 0), reg_std=(0.1, 0.1, 0.2, 0.2)):
+    """RCNN.get_ground_truth (training), layers/head/rcnn.py:95-147 (defaults configs/det_model/faster_rcnn_cfg.py:37-41,
+    56-59), for the whole batch.  rois (B, Rmax, 5) padded as ``rpn_proposals`` returns them with counts n_rois (B,);
+    noise_fg / noise_bg (B, Rmax + Gmax): uniform variates of the two sample_labels calls (RNG contract in
+    include/bdet.h).  -> rois (B, num_rois, 5), labels (B, num_rois) int32, bbox_targets (B, num_rois, 4), count (B,);
+    the reference returns the per-image results concatenated: ``x[b, :count[b]]``."""
+    m = ops.rcnn_match(rois, n_rois, gt_boxes, num_gt, fg_thresh, bg_thresh_low, bg_thresh_high)
+    ops.sample_labels(m["fg"], noise_fg, int(num_rois * fg_ratio), 1, 0)        # rcnn.py:125-126
+    num_bg = num_rois - ops.count_labels(m["fg"])[:, 2]                         # :127 fg_inds_mask.sum(), on the device
+    ops.sample_labels(m["bg"], noise_bg, num_bg.to(torch.int32), 1, 0)          # :128
+    return ops.rcnn_collect(m, gt_boxes, num_rois, reg_mean, reg_std)
+
+
 def fcos_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128),
                  sizes_of_interest=((-1, 64), (64, 128), (128, 256), (256, 512), (512, float("inf"))),
                  center_sampling_radius=1.5, plan=None):

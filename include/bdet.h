@@ -173,6 +173,23 @@ int bdet_atss_targets(const float* points, int A, const int* level_start_host, i
  * negatives depends on the positives that survived). */
 int bdet_sample_labels(int* labels, const float* noise, int A, int B, int label_value, int ignore_label,
                        int num_samples, const int* num_samples_dev, bdet_stream_t stream);
+/* RCNN.get_ground_truth (training)  layers/head/rcnn.py:95-147, in three steps that never build the (R,G) matrix:
+ * bdet_rcnn_match: rois (B,Rmax,5) rows [batch,x1,y1,x2,y2] (image b's first n_rois[b] rows; what
+ *   rpn_rois[rpn_rois[:,0]==b] selects) + gt (B,Gmax,5) -> all_rois (B,N,5) = proposals then [b, gt box] rows (:108-112),
+ *   N = Rmax+Gmax, n_all (B), assign (B,N) = argmax IoU over the image's GT (first index), matched_class (B,N) fp32,
+ *   fg_mask / bg_mask (B,N) int32 0/1: (max >= fg_thresh) & (class >= 0), bg_low <= max < bg_high (:114-123).
+ * then bdet_sample_labels(fg_mask, noise_fg, N, B, 1, 0, int(num_rois*fg_ratio)) and, with the per-image budget
+ *   num_rois - sum(fg_mask) in a device array, bdet_sample_labels(bg_mask, ...) (:125-128);
+ * bdet_rcnn_collect: kept rows (fg|bg) in order -> out_rois (B,num_out,5), out_labels (B,num_out) (class, 0 for bg),
+ *   out_targets (B,num_out,4) = BoxCoder.encode(roi, matched GT) with the RCNN mean/std, out_count (B); rows past the
+ *   count are zero (:130-137).  The reference concatenates the per-image results; slice with out_count to do the same. */
+int bdet_rcnn_match(const float* rois, const int* n_rois_dev, int Rmax, const float* gt, const int* num_gt_dev,
+                    int Gmax, int B, float fg_thresh, float bg_thresh_low, float bg_thresh_high, float* all_rois,
+                    int* n_all, int* assign, float* matched_class, int* fg_mask, int* bg_mask, bdet_stream_t stream);
+int bdet_rcnn_collect(const float* all_rois, const int* n_all, const int* assign, const float* matched_class,
+                      const int* fg_mask, const int* bg_mask, int N, const float* gt, int Gmax, int B,
+                      const float* mean_host, const float* std_host, int num_out, float* out_rois, int* out_labels,
+                      float* out_targets, int* out_count, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.

@@ -463,6 +463,37 @@ def rpn_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_lq, num_sam
     return np.stack(lab_l), np.stack(off_l)
 
 
+def rcnn_targets(rois_list, gt_boxes, num_gt, noise_fg, noise_bg, num_rois=512, fg_ratio=0.5, fg_thresh=0.5,
+                 bg_thresh_high=0.5, bg_thresh_low=0.0, mean=(0, 0, 0, 0), std=(0.1, 0.1, 0.2, 0.2)):
+    """RCNN.get_ground_truth (training branch), basedet/layers/head/rcnn.py:95-147.
+
+    rois_list[b]: (R_b, 5) rows [batch, x1, y1, x2, y2] of image b (what ``rpn_rois[rpn_rois[:, 0] == bid]`` selects);
+    noise_fg / noise_bg [b]: one uniform variate per row of all_rois (R_b + G_b), see sample_labels.
+    Returns per image (rois (n, 5), labels (n,) int32, bbox_targets (n, 4)); the reference concatenates them."""
+    out = []
+    for bid, (rois, g5, n) in enumerate(zip(rois_list, gt_boxes, num_gt)):
+        g5 = np.asarray(g5, f32)[: int(n)]                                      # :106-107
+        gt_rois = np.concatenate([np.full((len(g5), 1), f32(bid), f32), g5[:, :4]], axis=1)   # :108-109
+        all_rois = np.concatenate([np.asarray(rois, f32), gt_rois], axis=0)     # :112
+        overlaps = box_iou(all_rois[:, 1:], g5[:, :4])                          # :114 (R, G)
+        max_ov = overlaps.max(axis=1)                                           # :115
+        assign = np.argmax(overlaps, axis=1).astype(np.int32)                   # :116 (ASSUMED-2)
+        labels = g5[assign, 4].copy()                                           # :117 (fp32)
+        fg = (max_ov >= f32(fg_thresh)) & (labels >= 0)                         # :119
+        bg = (max_ov >= f32(bg_thresh_low)) & (max_ov < f32(bg_thresh_high))    # :120-123
+        num_fg = int(num_rois * fg_ratio)                                       # :125
+        fg_s = sample_labels(fg, num_fg, True, False, noise_fg[bid])            # :126
+        num_bg = int(num_rois - fg_s.sum())                                     # :127
+        bg_s = sample_labels(bg, num_bg, True, False, noise_bg[bid])            # :128
+        labels[bg_s] = 0                                                        # :130
+        keep = fg_s | bg_s                                                      # :132
+        lab = labels[keep].astype(np.int32)                                     # :133
+        kept = all_rois[keep]                                                   # :134
+        targets = boxcoder_encode(kept[:, 1:], g5[assign[keep], :4], mean, std).reshape(-1, 4)   # :135-137
+        out.append((kept, lab, targets))
+    return out
+
+
 def _ctrness(offsets):
     """fcos.py:276-281 / atss.py:72-77: sqrt(max(min(l,r)/max(l,r), 0) * max(min(t,b)/max(t,b), 0)).
     F.maximum(x, 0) and F.clip(x, lower=0) are both the elementwise MAX of ASSUMED-1 (NaN -> 0)."""

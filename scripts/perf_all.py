@@ -46,7 +46,8 @@ KERNELS = ["anchors_grid_kernel", "pairwise_kernel", "match_colmax_kernel", "mat
            "nms_sort_small_kernel", "nms_tile_sort_kernel", "nms_global_step_kernel", "nms_tile_tail_kernel", "nms_gather_kernel",
            "nms_maxcoord_kernel", "nms_fused_kernel", "nms_mask_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
            "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel",
-           "fcos_targets_kernel", "atss_candidates_kernel", "atss_finish_kernel", "count_labels_kernel"]
+           "fcos_targets_kernel", "atss_candidates_kernel", "atss_finish_kernel", "count_labels_kernel", "sample_labels_kernel",
+           "rcnn_match_kernel", "rcnn_collect_kernel"]
 rng = np.random.default_rng(0)
 
 # ---- config 2: target assignment, batch 16
@@ -113,6 +114,18 @@ g = torch.Generator(device=dev); g.manual_seed(3)
 sc3 = [torch.randn((B3, a.shape[0]), device=dev, generator=g) * 2 - 3 for a in anc3]
 dl3 = [torch.randn((B3, a.shape[0], 4), device=dev, generator=g) * 0.2 for a in anc3]
 info3 = T(np.array([[800, 1344, 800, 1333, 0.0]] * B3, np.float32))
+# training-side glue of config 3: RPN targets with sampling, RCNN label assignment
+gt3, ng3 = W.target_assign_batch(B3, 100, 800, 1344, seed0=3000)
+gt3_d, ng3_d = T(gt3), T(ng3)
+anc3_all = torch.cat(anc3)
+A3 = anc3_all.shape[0]
+nz1, nz2 = torch.rand((B3, A3), device=dev, generator=g), torch.rand((B3, A3), device=dev, generator=g)
+plan3 = ops.AssignPlan(A3, 100, B3, dev)
+run("c3_rpn_targets_b16", lambda: pipelines.rpn_targets(anc3_all, gt3_d, ng3_d, nz1, nz2, plan=plan3))
+rois3 = T(np.stack([W.make_rois(np.random.default_rng(80 + b), 2000, 1, 800, 1344, 8, 600) for b in range(B3)]))
+nr3 = torch.full((B3,), 2000, dtype=torch.int32, device=dev)
+nz3, nz4 = torch.rand((B3, 2100), device=dev, generator=g), torch.rand((B3, 2100), device=dev, generator=g)
+run("c3_rcnn_targets_b16", lambda: pipelines.rcnn_targets(rois3, nr3, gt3_d, ng3_d, nz3, nz4))
 run("c3_rpn_train_b16", lambda: pipelines.rpn_proposals(sc3, dl3, anc3, info3, 2000, 1000, 0.7))
 run("c3_rpn_test_b16", lambda: pipelines.rpn_proposals(sc3, dl3, anc3, info3, 1000, 1000, 0.7))
 Cn, K = 256, 512 * B3

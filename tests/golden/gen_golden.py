@@ -254,6 +254,46 @@ def build():
     rl, ro = rpn_gt(me, [T(a.copy()) for a in sanchors], T(sgt.copy()), [int(n) for n in sng])
     assert not mrand._queue, "the reference drew fewer variates than were fed"
     g["samp_labels"], g["samp_offsets"] = rl.numpy().reshape(3, -1), ro.numpy().reshape(3, -1, 4)
+
+    # ---- RCNN.get_ground_truth, training branch (layers/head/rcnn.py:95-147), same explicit-variate replay
+    rcnn_gt = ref_runner.load_method("layers/head/rcnn.py", "RCNN", "get_ground_truth", {"sample_labels": sampling.sample_labels})
+    rrng = np.random.default_rng(1400)
+    RB, RG, Rmax = 3, 7, 90
+    rgt, rng_ = W.target_assign_batch(RB, num_gt=RG, img_h=200, img_w=300, seed0=1401, ragged=True)
+    rois_pad = np.zeros((RB, Rmax, 5), np.float32)
+    rcount = np.array([60, 90, 75], np.int32)
+    for b in range(RB):
+        r = W.make_rois(rrng, int(rcount[b]), 1, 200, 300, 8, 150)
+        r[:, 0] = b
+        j = rrng.integers(0, rng_[b], 25)
+        r[:25, 1:] = rgt[b, j, :4] + rrng.normal(0, 4, (25, 4)).astype(np.float32)   # near-GT proposals -> foreground exists
+        rois_pad[b, : rcount[b]] = r
+    N = Rmax + RG
+    nfg = rrng.uniform(0, 1, (RB, N)).astype(np.float32)
+    nbg = (np.floor(rrng.uniform(0, 1, (RB, N)) * 64) / 64).astype(np.float32)       # ties among the variates
+    g["rcnn_rois"], g["rcnn_nrois"], g["rcnn_gt"], g["rcnn_num"] = rois_pad, rcount, rgt, rng_
+    g["rcnn_noise_fg"], g["rcnn_noise_bg"] = nfg, nbg
+    NUM, RATIO = 32, 0.25
+    for b in range(RB):  # feed the variates in the reference's draw order
+        g5 = rgt[b, : rng_[b]]
+        allr = np.concatenate([rois_pad[b, : rcount[b]], np.concatenate([np.full((rng_[b], 1), b, np.float32), g5[:, :4]], 1)])
+        ov = R.box_iou(allr[:, 1:], g5[:, :4])
+        mx, lab = ov.max(1), g5[ov.argmax(1), 4]
+        fg, bg = (mx >= 0.5) & (lab >= 0), (mx >= 0.0) & (mx < 0.5)
+        n_b = len(allr)
+        if fg.sum() > int(NUM * RATIO):
+            mrand.feed(nfg[b, :n_b][fg])
+        fgs = R.sample_labels(fg, int(NUM * RATIO), True, False, nfg[b, :n_b])
+        if bg.sum() > NUM - fgs.sum():
+            mrand.feed(nbg[b, :n_b][bg])
+    im_info = np.zeros((RB, 5), np.float32)
+    im_info[:, 4] = rng_
+    me = types.SimpleNamespace(training=True, num_rois=NUM, fg_ratio=RATIO, fg_thresh=0.5, bg_thresh_high=0.5, bg_thresh_low=0.0,
+                               box_coder=ref.boxcoder.BoxCoder([0., 0., 0., 0.], [0.1, 0.1, 0.2, 0.2]))
+    flat = np.concatenate([rois_pad[b, : rcount[b]] for b in range(RB)])
+    rr, rl, rt = rcnn_gt(me, T(flat.copy()), T(im_info), T(rgt.copy()))
+    assert not mrand._queue, "the reference drew fewer variates than were fed"
+    g["rcnn_out_rois"], g["rcnn_out_labels"], g["rcnn_out_targets"] = rr.numpy(), rl.numpy(), rt.numpy()
     return g
 
 

@@ -229,3 +229,26 @@ def test_cpu_tensors_are_rejected():
 
     with pytest.raises(RuntimeError):
         ops.pairwise(torch.zeros(2, 4), torch.zeros(3, 4))
+
+
+def test_sample_labels_dropin(cuda):
+    """layers.sample_labels keeps the reference call (sampling.py:7): in-place int labels, bool masks, budget respected,
+    nothing touched when the population fits, explicit variates reproduce the oracle."""
+    from basedet_b200.layers import sample_labels
+    from oracle import ref_ops as R
+    rng = np.random.default_rng(3)
+    lab = rng.choice(np.array([-1, 0, 1], np.int32), size=4000, p=[0.2, 0.7, 0.1]).astype(np.int32)
+    noise = rng.uniform(0, 1, 4000).astype(np.float32)
+    t = torch.from_numpy(lab.copy()).to(cuda)
+    out = sample_labels(t, 64, 1, -1, noise=torch.from_numpy(noise).to(cuda))
+    assert out is t and np.array_equal(t.cpu().numpy(), R.sample_labels(lab, 64, 1, -1, noise))
+    t2 = torch.from_numpy(lab.copy()).to(cuda)
+    sample_labels(t2, 100, 0)                                  # variates from torch's generator
+    got = t2.cpu().numpy()
+    assert (got == 0).sum() == 100 and np.array_equal(got[lab != 0], lab[lab != 0]) and set(got[lab == 0]) <= {0, -1}
+    m = torch.from_numpy(lab == 1).to(cuda)
+    ms = sample_labels(m, 10, True, False)
+    assert ms.dtype == torch.bool and int(ms.sum()) == 10 and bool((ms & ~m).sum() == 0)
+    t3 = torch.from_numpy(lab.copy()).to(cuda)
+    sample_labels(t3, 10 ** 6, 0)
+    assert np.array_equal(t3.cpu().numpy(), lab)

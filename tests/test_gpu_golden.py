@@ -193,3 +193,19 @@ def test_rpn_get_ground_truth_with_sampling_golden(cuda):
                                      Tc(GOLD["samp_noise_neg"]), (0.3, 0.7), (0, -1, 1), True, 48, 6 / 48)
     assert np.array_equal(lab.cpu().numpy(), GOLD["samp_labels"])
     assert np.max(np.abs(off.cpu().numpy() - GOLD["samp_offsets"])) <= 1e-6
+
+
+def test_rcnn_get_ground_truth_golden(cuda):
+    """RCNN.get_ground_truth (layers/head/rcnn.py:95-147) vs the vectors produced by the reference method itself."""
+    from basedet_b200 import pipelines
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda)  # noqa: E731
+    rois, labels, targets, count = pipelines.rcnn_targets(Tc(GOLD["rcnn_rois"]), Tc(GOLD["rcnn_nrois"]), Tc(GOLD["rcnn_gt"]),
+                                                          Tc(GOLD["rcnn_num"]), Tc(GOLD["rcnn_noise_fg"]), Tc(GOLD["rcnn_noise_bg"]),
+                                                          32, 0.25, 0.5, 0.5, 0.0)
+    count = count.cpu().numpy()
+    cat = lambda x: np.concatenate([x[b, : count[b]].cpu().numpy() for b in range(len(count))])  # noqa: E731
+    assert np.array_equal(cat(rois), GOLD["rcnn_out_rois"])
+    assert np.array_equal(cat(labels), GOLD["rcnn_out_labels"])
+    assert np.max(np.abs(cat(targets) - GOLD["rcnn_out_targets"])) <= 1e-5   # logf / divide by std 0.1, 0.2
+    for b in range(len(count)):
+        assert float(rois[b, count[b]:].abs().sum()) == 0.0

@@ -133,6 +133,19 @@ def test_rpn_get_ground_truth_with_sample_labels():
     assert np.all((lab == 1).sum(1) <= 6) and np.all((lab >= 0).sum(1) == 48)
 
 
+def test_rcnn_get_ground_truth():
+    """RCNN.get_ground_truth (rcnn.py:95-147) run from the reference file == oracle restatement."""
+    rois, cnt, N = GOLD["rcnn_rois"], GOLD["rcnn_nrois"], GOLD["rcnn_noise_fg"].shape[1]
+    rois_list = [rois[b, : cnt[b]] for b in range(len(cnt))]
+    n_all = [int(cnt[b] + GOLD["rcnn_num"][b]) for b in range(len(cnt))]
+    out = R.rcnn_targets(rois_list, GOLD["rcnn_gt"], GOLD["rcnn_num"], [GOLD["rcnn_noise_fg"][b, :n] for b, n in enumerate(n_all)],
+                         [GOLD["rcnn_noise_bg"][b, :n] for b, n in enumerate(n_all)], 32, 0.25, 0.5, 0.5, 0.0)
+    same(np.concatenate([o[0] for o in out]), GOLD["rcnn_out_rois"])
+    same(np.concatenate([o[1] for o in out]), GOLD["rcnn_out_labels"])
+    same(np.concatenate([o[2] for o in out]), GOLD["rcnn_out_targets"])
+    assert (GOLD["rcnn_out_labels"] > 0).sum() >= 8 and N == rois.shape[1] + GOLD["rcnn_gt"].shape[1]
+
+
 def test_nms_and_post_processing():
     b, s, l = GOLD["nms_boxes"], GOLD["nms_scores"], GOLD["nms_labels"]
     same(R.batched_nms(b, s, l, 0.5), GOLD["nms_keep_05"])
