@@ -3,16 +3,22 @@
 // (MegEngine NMSKeep: argsort by score, 64-bit overlap masks, serial sweep; oracle ASSUMED-3/5).
 //
 // Per image (all B images in the same launches):
-//   1. sort  : (score desc, index asc) via unique 64-bit keys; one CTA + shared-memory bitonic network for
-//              N <= 16384, tiled global bitonic network above that.  The same pass applies the reference's
-//              fp32 class offset  boxes + idxs * (max(boxes) + 1)  and gathers the boxes in sorted order.
-//   2. mask  : 64x64 tiles of the upper triangle; a warp takes a row box, its lanes two column boxes each,
-//              two __ballot_sync build the 64-bit suppression word (IoU > thr, IEEE division as the reference).
+//   1. sort  : (score desc, index asc) via unique 64-bit keys.  N <= 16384: one CTA; if the caller marks the input as
+//              back-to-back runs that are already sorted (the per-level top-k output, bdet_nms_runs) the order comes
+//              from a merge by ranking (own position + binary searches in the other runs, promise verified on the
+//              device), otherwise from a shared-memory bitonic network; tiled global bitonic network above 16384.
+//              The same pass applies the reference's fp32 class offset  boxes + idxs * (max(boxes) + 1)  and gathers
+//              the boxes in sorted order.
+//   2+3 fused (nms_fused_kernel) when max_output x N is small (every detector head): one CTA per image walks the
+//              sorted boxes 64 at a time, the ballot words are built only for kept rows and never leave the SM.
+//   otherwise, in row chunks of 1024 sorted boxes:
+//   2. mask  : 64x64 tiles of the chunk's rows against every later column; a warp takes a row box, its lanes two
+//              column boxes each, two __ballot_sync build the 64-bit suppression word (IoU > thr, IEEE division as
+//              the reference).  Rows an earlier chunk suppressed are skipped, and everything once max_output is
+//              reached: the sweep never reads those words.
 //   3. sweep : per image, warp 0 resolves one 64-box block at a time from the diagonal words held in registers
-//              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' masks into the
-//              shared-memory `removed` bitmap; stops at max_output.
-//   2+3 fused (nms_fused_kernel) when max_output x N is small (every detector config): the ballot words are built
-//              only for kept rows, block by block, and never leave the SM.
+//              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' masks into the `removed`
+//              bitmap (shared memory inside a chunk, global memory between chunks); stops at max_output.
 // Rated in pair tests/s (issue bound), not HBM GB/s.
 #include "common.cuh"
 #include "sortnet.cuh"

@@ -7,10 +7,11 @@
 //           into shared memory; threads then walk the (channel, bin) outputs in memory order, so the 49-float
 //           output rows are written fully coalesced and the 16 taps of a bin hit L1/L2 (the ROI footprint is a
 //           few KB per channel).  All levels in one launch; output directly in the original ROI order.
-// backward: (default, with workspace) atomics-free tile gather -- ROIs are binned per feature-map tile, one CTA
-//           accumulates its tile x channel chunk in shared memory and writes every dfeat element exactly once;
-//           (no workspace) scatter form: one CTA per ROI accumulates the ROI footprint in shared memory and
-//           flushes each touched pixel once with red.global.add.f32.
+// backward: (no workspace; the faster one, ~L2 atomic throughput) scatter form: per ROI and channel the separable
+//           Wy / Wx weight tables give every footprint pixel its total weight, accumulated in registers and flushed
+//           with ONE red.global.add.f32 per touched pixel;
+//           (workspace given) atomics-free tile gather -- ROIs are binned per feature-map tile, one CTA accumulates its
+//           tile x channel chunk in shared memory and writes every dfeat element exactly once: bit-deterministic.
 #include "common.cuh"
 
 namespace bdet {
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward, gather form (default).  The feature maps are cut into kTH x kTW pixel tiles; ROIs are binned per tile
+// Backward, gather form (chosen by passing a workspace).  The feature maps are cut into kTH x kTW pixel tiles; ROIs are binned per tile
 // (count -> scan -> fill); one CTA owns (tile, chunk of kCC channels), accumulates every ROI of its list into a
 // shared-memory tile and writes each dfeat element exactly once: no global atomics, no memset, deterministic.
 // Per pixel the contributing samples form a contiguous range along each axis (sample coordinates are monotone), so
