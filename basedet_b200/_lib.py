@@ -76,6 +76,10 @@ SIGNATURES = {
     "bdet_sample_labels": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
     "bdet_rcnn_match": (c_int, [vp, vp, c_int, vp, vp, c_int, c_int, c_float, c_float, c_float, vp, vp, vp, vp, vp, vp, vp]),
     "bdet_rcnn_collect": (c_int, [vp, vp, vp, vp, vp, vp, c_int, vp, c_int, c_int, fp, fp, c_int, vp, vp, vp, vp, vp]),
+    "bdet_score_filter_topk_nchw": (c_int, [vp, vp, c_int, c_int, lp, ip, lp, c_int, c_float, c_int, c_int, vp, vp, vp, vp,
+                                            c_size_t, vp]),
+    "bdet_select_decode_nchw": (c_int, [POINTER(vp), POINTER(vp), ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,
+                                        fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),

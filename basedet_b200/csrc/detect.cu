@@ -16,6 +16,7 @@ struct SelectArgs {
   const float* anchors[BDET_MAX_LEVELS];  // (n_l, 4) boxes or (n_l, 2) points
   const float* deltas[BDET_MAX_LEVELS];   // (B, n_l, 4)
   int n_l[BDET_MAX_LEVELS];
+  int hw[BDET_MAX_LEVELS];                // > 0: deltas of this level are the head output (B, A*4, H, W), hw = H*W
   int L, B, k, div, coder, label_mode, filter;
   const int* topk_idx;     // (B, L, k) flat index within the (image, level) segment
   const float* topk_val;   // (B, L, k)
@@ -31,7 +32,15 @@ struct SelectArgs {
 };
 
 __device__ __forceinline__ float4 decode_one(const SelectArgs& p, int l, int b, int a) {
-  const float4 d = ldg4(p.deltas[l] + ((long long)b * p.n_l[l] + a) * 4);
+  float4 d;
+  if (p.hw[l] > 0) {  // NCHW head output: box a = pos * A + anchor, component c lives at ((anchor*4 + c) * HW + pos)
+    const int hw = p.hw[l], na = p.n_l[l] / hw;
+    const int pos = a / na, an = a - pos * na;
+    const float* q = p.deltas[l] + ((long long)b * na * 4 + an * 4) * hw + pos;
+    d = make_float4(__ldg(q), __ldg(q + hw), __ldg(q + 2 * hw), __ldg(q + 3 * hw));
+  } else {
+    d = ldg4(p.deltas[l] + ((long long)b * p.n_l[l] + a) * 4);
+  }
   if (p.coder == 1) {  // PointCoder.decode, structures/boxcoder.py:135-141
     const float2 pt = __ldg(reinterpret_cast<const float2*>(p.anchors[l]) + a);
     return make_float4(pt.x - d.x, pt.y - d.y, pt.x + d.z, pt.y + d.w);
@@ -172,6 +181,16 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
                                   const float* topk_val, const int* topk_cnt, const float* mean_host, const float* std_host,
                                   const float* im_info, int info_ld, float* boxes, float* scores, void* labels, int* count,
                                   int* run_end, bdet_stream_t stream) {
+  return bdet_select_decode_nchw(anchors_host, deltas_host, n_l_host, nullptr, L, B, k, div, coder, label_mode, topk_idx, topk_val,
+                                 topk_cnt, mean_host, std_host, im_info, info_ld, boxes, scores, labels, count, run_end, stream);
+}
+
+extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
+                                       const int* hw_host, int L, int B, int k, int div, int coder, int label_mode,
+                                       const int* topk_idx, const float* topk_val, const int* topk_cnt,
+                                       const float* mean_host, const float* std_host, const float* im_info, int info_ld,
+                                       float* boxes, float* scores, void* labels, int* count, int* run_end,
+                                       bdet_stream_t stream) {
   BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && k >= 0 && div >= 1, "bad sizes");
   BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
   BDET_REQUIRE(label_mode == 0 || label_mode == 1, "label_mode must be 0 (idx % div) or 1 (level id)");
@@ -189,10 +208,13 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
   BDET_REQUIRE(!im_info || info_ld >= 2, "im_info rows need at least [h, w]");
   SelectArgs a;
   for (int l = 0; l < L; ++l) {
-    BDET_REQUIRE(anchors_host[l] && deltas_host[l] && aligned16(deltas_host[l]), "null / unaligned level pointer");
+    const int hw = hw_host ? hw_host[l] : 0;
+    BDET_REQUIRE(anchors_host[l] && deltas_host[l] && (hw > 0 || aligned16(deltas_host[l])), "null / unaligned level pointer");
+    BDET_REQUIRE(hw >= 0 && (hw == 0 || n_l_host[l] % hw == 0), "NCHW level: n_l must be H*W*A");
     a.anchors[l] = anchors_host[l];
     a.deltas[l] = deltas_host[l];
     a.n_l[l] = n_l_host[l];
+    a.hw[l] = hw;
   }
   a.L = L;
   a.B = B;

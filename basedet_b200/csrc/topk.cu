@@ -39,7 +39,7 @@ struct SegDesc {
   int len;
   int tile_start;       // first filter tile of this segment
   int order;            // select stage: cluster c works on segment seg[c].order (longest segments first)
-  int pad_;
+  int hw;               // > 0: the segment is a head output in NCHW order, (A*C, H, W) with hw = H*W (see key_index)
 };
 
 struct RawSrc {
@@ -330,8 +330,25 @@ struct FilterArgs {
   int* cand_count;
   float* scores_out;          // optional dense score output (bdet_scores)
   int n_seg, C, mode;
+  int na;                     // anchors per position (NCHW segments only)
   float thr, pre;             // pre: raw-logit pre-filter (sigmoid mode)
 };
+
+// Candidate index reported for element e of a segment, and the index of its centerness value.
+// Plain segments are already in the reference's flattened (h, w, anchor, class) order (permute_to_N_Any_K,
+// layers/common/function.py:26-32).  NCHW segments are the head tensor as the network wrote it, (A*C, H, W): the sweep
+// stays linear in memory and only the rare survivors are re-indexed, which removes the transpose pass altogether.
+__device__ __forceinline__ void key_index(const FilterArgs& p, const SegDesc& sd, int e, int& idx, long long& ci) {
+  if (sd.hw > 0) {
+    const int ch = e / sd.hw, pos = e - ch * sd.hw;
+    const int a = ch / p.C, c = ch - a * p.C;
+    idx = (pos * p.na + a) * p.C + c;
+    ci = sd.ctr_start + (long long)a * sd.hw + pos;  // centerness (A, H, W)
+  } else {
+    idx = e;
+    ci = sd.ctr_start + e / p.C;
+  }
+}
 
 constexpr int kFiltThreads = 256;
 constexpr int kFiltVec = 4;                               // float4 per thread per tile
@@ -399,7 +416,7 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
   int s = 0;
   while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
   SegDesc sd = p.seg[s];
-  const bool tab_mode = p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kWTab;
+  const bool tab_mode = p.mode == BDET_SCORE_FCOS && p.na == 0 && (kFiltTile / p.C + 2) <= kWTab;
 
   auto flush_keys = [&]() {  // warp-uniform
     if (nk == 0) return;
@@ -418,8 +435,9 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
       float sc = 0.f;
       int e = 0;
       if (i < count) {
-        e = L.se[i];
-        ok = exact_score(p, L.sx[i], sd.ctr_start + e / p.C, sc);
+        long long ci;
+        key_index(p, sd, L.se[i], e, ci);
+        ok = exact_score(p, L.sx[i], ci, sc);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
       if (ok) L.keys[nk + __popc(m & lt)] = make_key(sc, (uint32_t)e);
@@ -542,7 +560,7 @@ constexpr int kMaxSeg = 4096;
 
 // Host-side descriptor table; returns total length (or -1 after set_error).
 static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t* len, const int64_t* ctr_start, int C,
-                              int n_seg, bool* vec_ok, const char* who) {
+                              int n_seg, bool* vec_ok, const char* who, const int* hw = nullptr) {
   int64_t total = 0;
   int tiles = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -554,6 +572,7 @@ static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t
     host[s].key_off = total;
     host[s].ctr_start = ctr_start ? ctr_start[s] : start[s] / C;
     host[s].len = (int)len[s];
+    host[s].hw = hw ? hw[s] : 0;
     host[s].tile_start = tiles;
     if (start[s] % 4 != 0) *vec_ok = false;
     total += len[s];
@@ -561,6 +580,7 @@ static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t
   }
   host[n_seg].start = host[n_seg].key_off = host[n_seg].ctr_start = 0;
   host[n_seg].len = 0;
+  host[n_seg].hw = 0;
   host[n_seg].tile_start = tiles;
   // select stage launch order: longest segments first (they finish last otherwise)
   int order[kMaxSeg];
@@ -723,10 +743,10 @@ extern "C" int bdet_topk(const float* scores, const int64_t* seg_start_host, con
   return BDET_OK;
 }
 
-extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_start_host,
-                                      const int64_t* seg_len_host, const int64_t* ctr_start_host, int n_seg, float threshold,
-                                      int k, int mode, float* out_scores, int* out_idx, int* out_count, void* workspace,
-                                      size_t workspace_bytes, bdet_stream_t stream) {
+static int score_filter_topk_impl(const float* logits, const float* ctrness, int C, const int64_t* seg_start_host,
+                                  const int64_t* seg_len_host, const int64_t* ctr_start_host, const int* seg_hw_host, int na,
+                                  int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
+                                  int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(n_seg >= 0 && k >= 0 && C >= 1, "bad size");
   BDET_REQUIRE(mode >= BDET_SCORE_RAW && mode <= BDET_SCORE_FCOS, "unknown mode");
   BDET_REQUIRE(mode != BDET_SCORE_FCOS || ctrness, "FCOS mode needs ctrness");
@@ -737,9 +757,14 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
   if (n_seg > kMaxSeg) return set_error(BDET_EUNSUPPORTED, "bdet_score_filter_topk: more than %d segments", kMaxSeg);
   static thread_local SegDesc host[kMaxSeg + 1];
   bool vec = aligned16(logits);
-  const int64_t total = build_segments(host, seg_start_host, seg_len_host, ctr_start_host, C, n_seg, &vec, "bdet_score_filter_topk");
+  const int64_t total = build_segments(host, seg_start_host, seg_len_host, ctr_start_host, C, n_seg, &vec, "bdet_score_filter_topk",
+                                       seg_hw_host);
   if (total < 0) return BDET_EINVAL;
   BDET_REQUIRE(total == 0 || logits, "null logits");
+  if (seg_hw_host)
+    for (int s = 0; s < n_seg; ++s)
+      BDET_REQUIRE(seg_hw_host[s] >= 0 && seg_len_host[s] == (int64_t)seg_hw_host[s] * na * C && ctr_start_host,
+                   "NCHW segment: len must be H*W*A*C and ctr_start given");
   TopkWs w = carve_ws(workspace, total, n_seg, true);
   if (!workspace || workspace_bytes < w.bytes)
     return set_error(BDET_EWORKSPACE, "bdet_score_filter_topk: workspace needs %zu bytes", w.bytes);
@@ -758,6 +783,7 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
   f.n_seg = n_seg;
   f.C = C;
   f.mode = mode;
+  f.na = seg_hw_host ? na : 0;
   f.thr = threshold;
   // raw-logit pre-filter: sigmoid(x) > q  needs  x > logit(q); keep a safety margin for fp32 rounding.
   f.pre = -std::numeric_limits<float>::infinity();
@@ -782,6 +808,31 @@ extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness,
   if (rc) return rc;
   BDET_LAUNCH_CHECK();
   return BDET_OK;
+}
+
+extern "C" int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, const int64_t* seg_start_host,
+                                      const int64_t* seg_len_host, const int64_t* ctr_start_host, int n_seg, float threshold,
+                                      int k, int mode, float* out_scores, int* out_idx, int* out_count, void* workspace,
+                                      size_t workspace_bytes, bdet_stream_t stream) {
+  return score_filter_topk_impl(logits, ctrness, C, seg_start_host, seg_len_host, ctr_start_host, nullptr, 0, n_seg, threshold, k,
+                                mode, out_scores, out_idx, out_count, workspace, workspace_bytes, stream);
+}
+
+extern "C" int bdet_score_filter_topk_nchw(const float* logits, const float* ctrness, int C, int num_anchors,
+                                           const int64_t* seg_start_host, const int* seg_hw_host,
+                                           const int64_t* ctr_start_host, int n_seg, float threshold, int k, int mode,
+                                           float* out_scores, int* out_idx, int* out_count, void* workspace,
+                                           size_t workspace_bytes, bdet_stream_t stream) {
+  BDET_REQUIRE(num_anchors >= 1 && C >= 1 && n_seg >= 0 && n_seg <= kMaxSeg, "bad size");
+  BDET_REQUIRE(n_seg == 0 || (seg_hw_host && seg_start_host), "null argument");
+  static thread_local int64_t len[kMaxSeg], cst[kMaxSeg];
+  for (int s = 0; s < n_seg; ++s) {
+    BDET_REQUIRE(seg_hw_host[s] >= 0, "negative H*W");
+    len[s] = (int64_t)seg_hw_host[s] * num_anchors * C;
+    cst[s] = ctr_start_host ? ctr_start_host[s] : 0;
+  }
+  return score_filter_topk_impl(logits, ctrness, C, seg_start_host, len, cst, seg_hw_host, num_anchors, n_seg, threshold, k, mode,
+                                out_scores, out_idx, out_count, workspace, workspace_bytes, stream);
 }
 
 extern "C" int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int mode, float* out,

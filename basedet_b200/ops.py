@@ -518,6 +518,37 @@ def score_filter_topk_raw(base, starts, lens, threshold, k, mode, ctr_base=None,
     return vals, idx, cnt
 
 
+def score_filter_topk_nchw(head_list, threshold, k, num_classes, mode=_lib.SCORE_SIGMOID, ctr_list=None, workspace=None):
+    """Score filter + per-level top-k straight from the head outputs: head_list[l] (B, A*C, H, W) as the network
+    writes them (ctr_list[l] (B, A, H, W) for FCOS).  Segment s = b*L + l; indices are those of the reference's
+    permuted layout (function.py:26-32), so the result equals score_filter_topk on the permuted tensors."""
+    lib = _lib.load()
+    hs = [_f32c(h, "logits") for h in head_list]
+    C = int(num_classes)
+    A = hs[0].shape[1] // C
+    assert all(h.ndim == 4 and h.shape[1] == A * C for h in hs)
+    base, starts, lens = _segments([h.reshape(h.shape[0], -1) for h in hs])
+    hw = []
+    for b in range(hs[0].shape[0]):
+        hw += [h.shape[2] * h.shape[3] for h in hs]
+    cbase, cstarts = None, None
+    if ctr_list is not None:
+        cs = [_f32c(c, "ctrness") for c in ctr_list]
+        assert all(c.shape[1] == A for c in cs)
+        cbase, cstarts, _ = _segments([c.reshape(c.shape[0], -1) for c in cs])
+    S, dev = len(lens), base.device
+    vals = torch.empty((S, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((S, k), dtype=torch.int32, device=dev)
+    cnt = torch.empty((S,), dtype=torch.int32, device=dev)
+    need = lib.bdet_score_filter_topk_workspace(sum(int(n) for n in lens), S, k)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+    with _guard(base):
+        check(lib.bdet_score_filter_topk_nchw(_p(base), _p(cbase), C, A, larr(starts), iarr(hw),
+                                              larr(cstarts) if cstarts is not None else None, S, float(threshold), int(k),
+                                              int(mode), _p(vals), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream(base)))
+    return vals, idx, cnt
+
+
 def scores(logits, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1):
     lib = _lib.load()
     lg = _f32c(logits, "logits")
@@ -529,8 +560,9 @@ def scores(logits, mode=_lib.SCORE_SIGMOID, ctrness=None, num_classes=1):
 
 
 def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0, 0, 0, 0), std=(1, 1, 1, 1), im_info=None,
-                  with_runs=False):
-    """anchors: L tensors (n_l, 4|2); deltas: L tensors (B, n_l, 4); topk = (vals, idx, cnt) with segment s = b*L + l.
+                  with_runs=False, nchw=False):
+    """anchors: L tensors (n_l, 4|2); deltas: L tensors (B, n_l, 4) -- or, with nchw=True, the head outputs
+    (B, A*4, H, W); topk = (vals, idx, cnt) with segment s = b*L + l.
     Returns boxes (B, L*k, 4), scores (B, L*k), labels (B, L*k) [int32 or fp32 level ids], count (B,)
     [, run_end (B, L): end of every level's (already score-sorted) run, for ``nms_batched(runs=...)``]."""
     lib = _lib.load()
@@ -548,11 +580,15 @@ def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0,
     ap = (ctypes.c_void_p * L)(*[a.data_ptr() for a in anc])
     dp_ = (ctypes.c_void_p * L)(*[d.data_ptr() for d in dl])
     info = _f32c(im_info) if im_info is not None else None
+    hw = None
+    if nchw:
+        assert all(d.ndim == 4 and d.shape[1] * d.shape[2] * d.shape[3] == 4 * a.shape[0] for d, a in zip(dl, anc))
+        hw = iarr([d.shape[2] * d.shape[3] for d in dl])
     with _guard(boxes):
-        check(lib.bdet_select_decode(ap, dp_, iarr([a.shape[0] for a in anc]), L, B, int(k), int(div), int(coder),
-                                     int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
-                                     info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels), _p(count),
-                                     _p(run_end), _stream(boxes)))
+        check(lib.bdet_select_decode_nchw(ap, dp_, iarr([a.shape[0] for a in anc]), hw, L, B, int(k), int(div), int(coder),
+                                          int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
+                                          info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels),
+                                          _p(count), _p(run_end), _stream(boxes)))
     if with_runs:
         return boxes, sc, labels, count, run_end
     return boxes, sc, labels, count

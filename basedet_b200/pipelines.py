@@ -52,6 +52,23 @@ def dense_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_thr
     return dets, keep_cnt
 
 
+def dense_postprocess_nchw(head_logits, head_offsets, anchors_list, img_info, num_classes, cls_threshold=0.05,
+                           iou_threshold=0.5, max_detections=100, topk=1000, head_ctrness=None, reg_mean=(0, 0, 0, 0),
+                           reg_std=(1, 1, 1, 1)):
+    """``dense_postprocess`` fed with the head outputs as the network writes them -- head_logits[l] (B, A*C, H, W),
+    head_offsets[l] (B, A*4, H, W), head_ctrness[l] (B, A, H, W) -- i.e. without the reference's
+    ``permute_to_N_Any_K`` passes (layers/common/function.py:26-32, models/det/retinanet.py:119-124).  The filter sweeps
+    the NCHW memory linearly and re-indexes only the survivors; results are identical to permuting first."""
+    mode = _lib.SCORE_FCOS if head_ctrness is not None else _lib.SCORE_SIGMOID
+    top = ops.score_filter_topk_nchw(head_logits, cls_threshold, topk, num_classes, mode, head_ctrness)
+    boxes, scores, labels, count, runs = ops.select_decode(anchors_list, head_offsets, top, topk, num_classes,
+                                                           1 if head_ctrness is not None else 0, 0, reg_mean, reg_std,
+                                                           with_runs=True, nchw=True)
+    keep, keep_cnt = ops.nms_batched(boxes, scores, labels, iou_threshold, max_detections, num=count, runs=runs)
+    dets = ops.finalize_detections(boxes, scores, labels, keep, keep_cnt, max_detections, img_info, mode=0)
+    return dets, keep_cnt
+
+
 def rpn_proposals(scores_list, offsets_list, anchors_list, im_info, prev_nms_topk=2000, post_nms_topk=1000,
                   nms_threshold=0.7, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1)):
     """RPN.find_top_rpn_proposals, models/det/rpn.py:134-186, for a whole batch.

@@ -213,6 +213,15 @@ int bdet_score_filter_topk(const float* logits, const float* ctrness, int C, con
                            const int64_t* seg_len_host, const int64_t* ctr_start_host, int n_seg, float threshold,
                            int k, int mode, float* out_scores, int* out_idx, int* out_count, void* workspace,
                            size_t workspace_bytes, bdet_stream_t stream);
+/* Same, reading the head outputs as the network writes them: segment s is a (num_anchors*C, H, W)
+ * block starting at logits + seg_start[s] with seg_hw[s] = H*W; centerness (FCOS) a (num_anchors, H, W) block at
+ * ctrness + ctr_start[s].  The reported indices are those of the reference's permuted layout
+ * (permute_to_N_Any_K, layers/common/function.py:26-32: idx = ((h*W + w)*A + a)*C + c), so results are identical to
+ * permuting first -- without the transpose pass. */
+int bdet_score_filter_topk_nchw(const float* logits, const float* ctrness, int C, int num_anchors,
+                                const int64_t* seg_start_host, const int* seg_hw_host, const int64_t* ctr_start_host,
+                                int n_seg, float threshold, int k, int mode, float* out_scores, int* out_idx,
+                                int* out_count, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 /* F.sigmoid / fcos score as a plain elementwise op (so tests can feed bit-identical scores to the oracle). */
 int bdet_scores(const float* logits, const float* ctrness, int C, int64_t n, int mode, float* out,
                 bdet_stream_t stream);
@@ -231,6 +240,12 @@ int bdet_select_decode(const float* const* anchors_host, const float* const* del
                        const int* topk_cnt, const float* mean_host, const float* std_host, const float* im_info,
                        int info_ld, float* boxes, float* scores, void* labels, int* count, int* run_end,
                        bdet_stream_t stream);
+/* hw_host[l] > 0: deltas of level l are the head output (B, A*4, H, W) with H*W = hw_host[l] (n_l = H*W*A). */
+int bdet_select_decode_nchw(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
+                            const int* hw_host, int L, int B, int k, int div, int coder, int label_mode,
+                            const int* topk_idx, const float* topk_val, const int* topk_cnt, const float* mean_host,
+                            const float* std_host, const float* im_info, int info_ld, float* boxes, float* scores,
+                            void* labels, int* count, int* run_end, bdet_stream_t stream);
 /* mode 0: post_processing.py:96-101 -- out (B, max_out, 6) = [box scaled by (orig/resized) and clipped to the original
  *         image, score, label] for the kept indices (im_info (B, >=4) [h, w, orig_h, orig_w]; NULL = no scale/clip);
  * mode 1: rpn.py:179-183 -- out (B, max_out, 5) = [batch index, x1, y1, x2, y2].  Rows >= keep_count[b] are zero. */

@@ -213,3 +213,31 @@ def test_target_assigner_graph_replay_matches_oracle():
         assert np.array_equal(c, np.stack([(rl < 0).sum(1), (rl == 0).sum(1), (rl > 0).sum(1)], 1))
         el, ei, eo = ops.assign_targets(T(anchors), T(gt), T(ng), [0.4, 0.5], [0, -1, 1], True, True)
         assert torch.equal(el, lab) and torch.equal(ei, idx) and torch.equal(eo, off)
+
+
+@pytest.mark.parametrize("fcos", [False, True])
+def test_dense_postprocess_from_nchw_head_outputs(fcos):
+    """reading (B, A*C, H, W) head outputs directly == permute_to_N_Any_K (function.py:26-32) first."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    B, C, hw = 3, 80, (320, 416)
+    sizes = W.retinanet_level_sizes(*hw)
+    A = 1 if fcos else 9
+    if fcos:
+        anchors = [T(p) for p in R.anchor_points(sizes, 1, W.RETINANET_STRIDES, 0.5)]
+    else:
+        anchors = [T(a) for a in R.default_anchors(sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, 0.5)]
+    logits = [torch.randn((B, A * C, h, w), device="cuda", generator=g) * 1.25 - (4.0 if fcos else 6.0) for h, w in sizes]
+    offsets = [torch.randn((B, A * 4, h, w), device="cuda", generator=g).abs() * (8 if fcos else 0.15) for h, w in sizes]
+    ctr = [torch.randn((B, A, h, w), device="cuda", generator=g) for h, w in sizes] if fcos else None
+    info = T(np.array([[hw[0], hw[1], 400.0, 520.0, 0.0]] * B, np.float32))
+
+    def perm(t, k):  # permute_to_N_Any_K
+        n, _, h, w = t.shape
+        return t.reshape(n, -1, k, h, w).permute(0, 3, 4, 1, 2).reshape(n, -1, k).contiguous()
+
+    d0, c0 = pipelines.dense_postprocess([perm(x, C) for x in logits], [perm(x, 4) for x in offsets], anchors, info, 0.05, 0.6, 100, 1000,
+                                         ctrness_list=[perm(x, 1) for x in ctr] if fcos else None)
+    d1, c1 = pipelines.dense_postprocess_nchw(logits, offsets, anchors, info, C, 0.05, 0.6, 100, 1000, head_ctrness=ctr)
+    assert torch.equal(c0, c1) and int(c0.sum()) > 50
+    assert torch.equal(d0, d1)
