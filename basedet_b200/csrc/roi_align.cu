@@ -361,17 +361,18 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
 
 // Backward, scatter form (no workspace): one CTA per ROI.  The separable bilinear weights of the ROI are tabulated
 // once per footprint chunk -- Wy[row][ph], Wx[col][pw] = summed tap weights of the bin's samples -- and shared by all
-// C channels; a lane then owns one (channel, y, x) of the footprint, sums its few (ph, pw) terms in registers and
-// issues ONE red.global.add.f32 (coalesced along x): footprint x C reds per ROI instead of 16 x P^2 x C, no shared
-// atomics, no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
+// C channels; a warp takes a channel, a lane one footprint column, and every (channel, y, x) of the footprint gets
+// ONE red.global.add.f32 (coalesced along x): footprint x C reds per ROI instead of 16 x P^2 x C, no shared atomics,
+// no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
 constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
 
 __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
   extern __shared__ __align__(16) float bsm[];
-  const int PH = p.PH, PW = p.PW, bins = PH * PW;
-  float* wy = bsm;                              // kFpChunk * PH
-  float* wx = wy + kFpChunk * PH;               // kFpChunk * PW
-  float* sd = wx + kFpChunk * PW;               // (warps) * bins: dout / S^2 of the warp's current channel
+  const int PH = p.PH, PW = p.PW;
+  const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;  // table rows padded to 16 bytes (128-bit shared loads)
+  float* wy = bsm;                              // kFpChunk * PHs
+  float* wx = wy + kFpChunk * PHs;              // kFpChunk * PWs
+  float* sd = wx + kFpChunk * PWs;              // (warps) * PH * PWs: dout / S^2 of the warp's current channel
   __shared__ int rlo[kFpChunk], rhi[kFpChunk], clo[kFpChunk], chi[kFpChunk];
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
@@ -381,8 +382,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   const int H = g.H, W = g.W;
   const float cnt = (float)(p.SH * p.SW);
   float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
-  const float* dout = p.dout + (long long)k * p.C * bins;
-  float* sdw = sd + warp * bins;
+  const float* dout = p.dout + (long long)k * p.C * PH * PW;
+  float* sdw = sd + warp * PH * PWs;
   for (int fy = y_lo; fy <= y_hi; fy += kFpChunk) {
     for (int fx = x_lo; fx <= x_hi; fx += kFpChunk) {
       const int nr = min(kFpChunk, y_hi - fy + 1), ncol = min(kFpChunk, x_hi - fx + 1);
@@ -390,11 +391,12 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
       if (t < nr) {
         const int y = fy + t;
         int lo = PH, hi = -1;
-        for (int ph = 0; ph < PH; ++ph) {
+        for (int ph = 0; ph < PHs; ++ph) {
           float w = 0.f;
-          for (int iy = 0; iy < p.SH; ++iy)
-            w += tap_weight(g.start_h + g.bin_h * ((float)ph + __fdiv_rn((float)iy + 0.5f, (float)p.SH)), y);
-          wy[t * PH + ph] = w;
+          if (ph < PH)
+            for (int iy = 0; iy < p.SH; ++iy)
+              w += tap_weight(g.start_h + g.bin_h * ((float)ph + __fdiv_rn((float)iy + 0.5f, (float)p.SH)), y);
+          wy[t * PHs + ph] = w;
           if (w != 0.f) {
             lo = min(lo, ph);
             hi = ph;
@@ -405,11 +407,12 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
       } else if (t >= 128 && t < 128 + ncol) {
         const int xx = t - 128, x = fx + xx;
         int lo = PW, hi = -1;
-        for (int pw = 0; pw < PW; ++pw) {
+        for (int pw = 0; pw < PWs; ++pw) {
           float w = 0.f;
-          for (int ix = 0; ix < p.SW; ++ix)
-            w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
-          wx[xx * PW + pw] = w;
+          if (pw < PW)
+            for (int ix = 0; ix < p.SW; ++ix)
+              w += tap_weight(g.start_w + g.bin_w * ((float)pw + __fdiv_rn((float)ix + 0.5f, (float)p.SW)), x);
+          wx[xx * PWs + pw] = w;
           if (w != 0.f) {
             lo = min(lo, pw);
             hi = pw;
@@ -419,6 +422,70 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
         chi[xx] = hi;
       }
       __syncthreads();
+      if (PH == 7 && PW == 7) {
+        // 7 x 7 bins (every shipped config): two separable passes per channel, all in registers.  A lane owns one
+        // footprint column: T[ph] = sum_pw Wx[x][pw] * dout[ph][pw], then per footprint row (warp-uniform weights,
+        // broadcast loads) sum_ph Wy[y][ph] * T[ph] and one coalesced red.  Dense 7-term sums: weights outside a
+        // bin's range are zero, so there is no data-dependent branch.
+        for (int x0 = 0; x0 < ncol; x0 += 32) {
+          const int xx = x0 + lane;
+          const bool xok = xx < ncol;
+          float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+          if (xok) {
+            wa = *reinterpret_cast<const float4*>(wx + xx * 8);
+            wb = *reinterpret_cast<const float4*>(wx + xx * 8 + 4);
+          }
+          // dout of the next channel is fetched while the current one is processed (the load is the only long
+          // latency of the loop)
+          const int i1 = lane + 32;
+          const int s0 = (lane / 7) * 8 + (lane % 7), s1 = (i1 / 7) * 8 + (i1 % 7);
+          float d0 = 0.f, d1 = 0.f;
+          if (warp < p.C) {
+            d0 = __ldg(dout + (long long)warp * 49 + lane);
+            if (i1 < 49) d1 = __ldg(dout + (long long)warp * 49 + i1);
+          }
+          for (int c = warp; c < p.C; c += kRoiThreads / 32) {
+            __syncwarp();
+            sdw[s0] = __fdiv_rn(d0, cnt);
+            if (i1 < 49) sdw[s1] = __fdiv_rn(d1, cnt);
+            __syncwarp();
+            const int cn = c + kRoiThreads / 32;
+            if (cn < p.C) {
+              d0 = __ldg(dout + (long long)cn * 49 + lane);
+              if (i1 < 49) d1 = __ldg(dout + (long long)cn * 49 + i1);
+            }
+            float T[7];
+#pragma unroll
+            for (int ph = 0; ph < 7; ++ph) {
+              const float4 a = *reinterpret_cast<const float4*>(sdw + ph * 8);
+              const float4 b = *reinterpret_cast<const float4*>(sdw + ph * 8 + 4);
+              float v = wa.x * a.x;
+              v = __fmaf_rn(wa.y, a.y, v);
+              v = __fmaf_rn(wa.z, a.z, v);
+              v = __fmaf_rn(wa.w, a.w, v);
+              v = __fmaf_rn(wb.x, b.x, v);
+              v = __fmaf_rn(wb.y, b.y, v);
+              v = __fmaf_rn(wb.z, b.z, v);
+              T[ph] = v;
+            }
+            float* gp = dfeat + (long long)c * H * W + (long long)fy * W + (fx + xx);
+#pragma unroll 4
+            for (int r = 0; r < nr; ++r, gp += W) {
+              const float4 u = *reinterpret_cast<const float4*>(wy + r * 8);
+              const float4 w2 = *reinterpret_cast<const float4*>(wy + r * 8 + 4);
+              float sum = u.x * T[0];
+              sum = __fmaf_rn(u.y, T[1], sum);
+              sum = __fmaf_rn(u.z, T[2], sum);
+              sum = __fmaf_rn(u.w, T[3], sum);
+              sum = __fmaf_rn(w2.x, T[4], sum);
+              sum = __fmaf_rn(w2.y, T[5], sum);
+              sum = __fmaf_rn(w2.z, T[6], sum);
+              if (xok && sum != 0.f) atomicAdd(gp, sum);
+            }
+          }
+        }
+        continue;
+      }
       const int wcols = min(ncol, 32);
       int wshift = 0;
       while ((1 << wshift) < wcols) ++wshift;  // lanes: x = lane & (2^wshift - 1), row sub-index = lane >> wshift
@@ -426,7 +493,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
       const int lx = lane & ((1 << wshift) - 1), lr = lane >> wshift;
       for (int c = warp; c < p.C; c += kRoiThreads / 32) {
         __syncwarp();
-        for (int i = lane; i < bins; i += 32) sdw[i] = __fdiv_rn(__ldg(dout + (long long)c * bins + i), cnt);
+        for (int i = lane; i < PH * PW; i += 32)
+          sdw[(i / PW) * PWs + (i % PW)] = __fdiv_rn(__ldg(dout + (long long)c * PH * PW + i), cnt);
         __syncwarp();
         float* gc = dfeat + (long long)c * H * W;
         for (int x0 = 0; x0 < ncol; x0 += 32) {
@@ -440,8 +508,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
             const int slo = rlo[r], shi = rhi[r];
             float sum = 0.f;
             for (int ph = slo; ph <= shi; ++ph) {
-              const float wyv = wy[r * PH + ph];
-              for (int pw = tlo; pw <= thi; ++pw) sum += sdw[ph * PW + pw] * (wyv * wx[xx * PW + pw]);
+              const float wyv = wy[r * PHs + ph];
+              for (int pw = tlo; pw <= thi; ++pw) sum += sdw[ph * PWs + pw] * (wyv * wx[xx * PWs + pw]);
             }
             if (sum != 0.f) atomicAdd(gc + (long long)(fy + r) * W + (fx + xx), sum);
           }
@@ -609,7 +677,8 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
       BDET_CUDA(cudaMemsetAsync(dfeats_host[l], 0, (size_t)B * C * hw_host[2 * l] * hw_host[2 * l + 1] * 4, st));
   }
   if (K == 0) return BDET_OK;
-  const size_t smem = ((size_t)kFpChunk * (PH + PW) + (size_t)(kRoiThreads / 32) * PH * PW) * 4;
+  const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;
+  const size_t smem = ((size_t)kFpChunk * (PHs + PWs) + (size_t)(kRoiThreads / 32) * PH * PWs) * 4;
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
