@@ -671,6 +671,7 @@ __global__ void __launch_bounds__(kSelThreads) sample_labels_kernel(const Sample
   // :29 -- a CTA rewrites only the range it alone reads, so a faster peer cannot disturb a slower one's keys
   for (int i = lo + t; i < hi; i += kSelThreads)
     if (src.key(i) <= T) lab[i] = p.ignore;
+  cluster.sync();  // a peer may still be summing this CTA's last histogram: shared memory must outlive that read
 }
 
 }  // namespace bdet
