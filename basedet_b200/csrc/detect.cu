@@ -117,6 +117,35 @@ __global__ void __launch_bounds__(kDetThreads) select_decode_kernel(const Select
   if (t == 0) p.count[b] = sbase;
 }
 
+// No size filter (dense heads): the output slot of candidate j of level l is known from the per-level counts alone,
+// so every (image, level, 256 candidates) block works independently -- no per-image serial compaction.
+__global__ void __launch_bounds__(256) select_decode_flat_kernel(const SelectArgs p) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const int seg = b * p.L + l;
+  int before = 0, total = 0;
+  for (int q = 0; q < p.L; ++q) {
+    const int c = min(p.topk_cnt[b * p.L + q], p.k);
+    if (q < l) before += c;
+    total += c;
+  }
+  const int cnt = min(p.topk_cnt[seg], p.k);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.run_end) p.run_end[seg] = before + cnt;
+    if (l == 0) p.count[b] = total;
+  }
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= cnt) return;
+  const long long cap = (long long)p.L * p.k;
+  const long long o = b * cap + before + j;
+  const int idx = __ldg(p.topk_idx + (long long)seg * p.k + j);
+  reinterpret_cast<float4*>(p.boxes)[o] = decode_one(p, l, b, idx / p.div);
+  p.scores[o] = __ldg(p.topk_val + (long long)seg * p.k + j);
+  if (p.label_mode == 0)
+    reinterpret_cast<int*>(p.labels)[o] = idx % p.div;   // retinanet.py:194
+  else
+    reinterpret_cast<float*>(p.labels)[o] = (float)l;    // rpn.py:160
+}
+
 struct FinalArgs {
   const float* boxes;   // (B, N, 4)
   const float* scores;  // (B, N)
@@ -191,7 +220,7 @@ extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const f
                                        const float* mean_host, const float* std_host, const float* im_info, int info_ld,
                                        float* boxes, float* scores, void* labels, int* count, int* run_end,
                                        bdet_stream_t stream) {
-  BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && k >= 0 && div >= 1, "bad sizes");
+  BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && B <= 65535 && k >= 0 && div >= 1, "bad sizes");
   BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
   BDET_REQUIRE(label_mode == 0 || label_mode == 1, "label_mode must be 0 (idx % div) or 1 (level id)");
   if (B == 0) return BDET_OK;
@@ -237,7 +266,10 @@ extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const f
   a.labels = labels;
   a.count = count;
   a.run_end = run_end;
-  BDET_KERNEL("select_decode_kernel", st, select_decode_kernel<<<B, kDetThreads, 0, st>>>(a));
+  if (a.filter)
+    BDET_KERNEL("select_decode_kernel", st, select_decode_kernel<<<B, kDetThreads, 0, st>>>(a));
+  else
+    BDET_KERNEL("select_decode_kernel", st, select_decode_flat_kernel<<<dim3(ceil_div(k, 256), L, B), 256, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
