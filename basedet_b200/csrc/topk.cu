@@ -338,8 +338,9 @@ struct FilterArgs {
 // Plain segments are already in the reference's flattened (h, w, anchor, class) order (permute_to_N_Any_K,
 // layers/common/function.py:26-32).  NCHW segments are the head tensor as the network wrote it, (A*C, H, W): the sweep
 // stays linear in memory and only the rare survivors are re-indexed, which removes the transpose pass altogether.
+template <bool NCHW>
 __device__ __forceinline__ void key_index(const FilterArgs& p, const SegDesc& sd, int e, int& idx, long long& ci) {
-  if (sd.hw > 0) {
+  if (NCHW) {
     const int ch = e / sd.hw, pos = e - ch * sd.hw;
     const int a = ch / p.C, c = ch - a * p.C;
     idx = (pos * p.na + a) * p.C + c;
@@ -403,7 +404,7 @@ __device__ __forceinline__ void load_tile(const float* src, int n, int e0, int l
   }
 }
 
-template <bool VEC>
+template <bool VEC, bool NCHW>
 __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const FilterArgs p, int total_tiles) {
   __shared__ WarpLists lists[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
   int s = 0;
   while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
   SegDesc sd = p.seg[s];
-  const bool tab_mode = p.mode == BDET_SCORE_FCOS && p.na == 0 && (kFiltTile / p.C + 2) <= kWTab;
+  const bool tab_mode = !NCHW && p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kWTab;
 
   auto flush_keys = [&]() {  // warp-uniform
     if (nk == 0) return;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
       int e = 0;
       if (i < count) {
         long long ci;
-        key_index(p, sd, L.se[i], e, ci);
+        key_index<NCHW>(p, sd, L.se[i], e, ci);
         ok = exact_score(p, L.sx[i], ci, sc);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
@@ -799,10 +800,16 @@ static int score_filter_topk_impl(const float* logits, const float* ctrness, int
   }
   if (tiles > 0) {
     const int grid = min(ceil_div(tiles, kFiltThreads / 32), sm_count() * 4);  // persistent warps, 4 CTAs / SM
-    if (vec)
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
-    else
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+    if (f.na > 0) {  // NCHW head outputs: survivors are re-indexed (two integer divisions each)
+      if (vec)
+        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+      else
+        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+    } else if (vec) {
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+    } else {
+      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+    }
   }
   SelArgs a{nullptr, w.keys, w.cand_count, w.seg, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
   int rc = launch_select<false>(a, n_seg, st);
