@@ -10,7 +10,7 @@
 //              The same pass applies the reference's fp32 class offset  boxes + idxs * (max(boxes) + 1)  and gathers
 //              the boxes in sorted order.
 //   2+3 fused (nms_fused_kernel) when max_output x N is small (every detector head): one CTA per image walks the
-//              sorted boxes 64 at a time, the ballot words are built only for kept rows and never leave the SM.
+//              sorted boxes 64 at a time and tests them against the list of boxes kept so far (shared memory).
 //   otherwise, in row chunks of 1024 sorted boxes:
 //   2. mask  : 64x64 tiles of the chunk's rows against every later column; a warp takes a row box, its lanes two
 //              column boxes each, two __ballot_sync build the 64-bit suppression word (IoU > thr, IEEE division as
@@ -329,46 +329,61 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs 
   if (t == 0) p.keep_count[b] = count;
 }
 
-// ---- keep-driven path: mask words only for KEPT rows, nothing in HBM ---------------------------------------
-// One CTA per image walks the sorted boxes 64 at a time:
+// ---- keep-driven path: nothing in HBM ---------------------------------------------------------------------
+// One CTA per image walks the sorted boxes 64 at a time and keeps the boxes kept so far (<= max_output) in shared memory:
+//   (a) pull: the block's 64 boxes are tested against the kept list (thread = column x 1/16 of the list) -> removed word;
 //   (c) the 64x64 diagonal words of the still-alive rows are built with ballots (2 rows per warp);
 //   (d) warp 0 resolves the block from those words (visiting only un-suppressed boxes), stopping at max_output;
-//   (f) every warp takes later 64-column words: its lanes hold two column boxes each, the kept rows' boxes are
-//       broadcast from shared memory, two ballots per kept row are ORed into the shared `removed` bitmap.
-// Pair tests: kept x N instead of N^2/2, and no N x N/64 mask in HBM.  Decisions are the same overlap predicate as
-// the mask kernel, so the keep list is identical.
+//   (e) the newly kept boxes are appended to the list.
+// Pair tests: (boxes examined) x (boxes kept so far) -- a block that is never reached because max_output boxes are
+// already kept costs nothing, unlike a push form that suppresses all N columns for every kept row.  Decisions are the
+// same overlap predicate as the mask kernel, so the keep list is identical.
 constexpr int kFusedThreads = 1024;
 
 __global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs p) {
   extern __shared__ __align__(16) unsigned char raw[];
-  uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // nwords
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int max_out = min(p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld, p.Nmax);  // == host-side kmax
+  float4* kbox = reinterpret_cast<float4*>(raw);             // max_out: boxes kept so far
+  float* karea = reinterpret_cast<float*>(kbox + max_out);   // max_out
   __shared__ float4 srow[64];
   __shared__ float sarea[64];
   __shared__ uint64_t sdiag[64];
   __shared__ int skept[64];
   __shared__ int snk;
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ uint32_t srem[2];
   const int n = nms_n(p, b);
   const int nblk = (n + 63) >> 6;
   const long long base = (long long)b * p.Nmax;
   const float4* sb = p.sboxes + base;
-  const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
-  for (int w = t; w < nblk; w += kFusedThreads) remv[w] = 0ull;
   int count = 0;
   for (int blk = 0; blk < nblk && count < max_out; ++blk) {
-    __syncthreads();  // remv complete for this block; previous block's shared rows free
+    __syncthreads();  // previous block's shared rows / kept list updates are complete
     const int r0 = blk * 64;
     const int nv = min(64, n - r0);
     const uint64_t valid = nv >= 64 ? ~0ull : ((1ull << nv) - 1ull);
-    const uint64_t alive = ~remv[blk] & valid;
-    if (alive == 0ull) continue;  // CTA-uniform
     if (t < 64) {
       const float4 bx = t < nv ? sb[r0 + t] : make_float4(0.f, 0.f, 0.f, 0.f);
       srow[t] = bx;
       sarea[t] = box_area(bx);
       sdiag[t] = 0ull;
     }
+    if (t < 2) srem[t] = 0u;
     __syncthreads();
+    {  // (a) pull: which of the block's 64 boxes does a box kept earlier suppress?  thread = (column, 1/16 of the kept list)
+      const int col = ((warp & 1) << 5) | lane, slice = warp >> 1;
+      bool sup = false;
+      if (col < nv) {
+        const float4 c = srow[col];
+        const float ca = sarea[col];
+        for (int q = slice; q < count && !sup; q += kFusedThreads / 64) sup = nms_overlap(kbox[q], karea[q], c, ca, p.thr);
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && m) atomicOr(&srem[warp & 1], m);
+    }
+    __syncthreads();
+    const uint64_t alive = ~(((uint64_t)srem[1] << 32) | srem[0]) & valid;
+    if (alive == 0ull) continue;  // CTA-uniform
     {  // (c) diagonal words: warp w -> rows w and w + 32
       const float4 c0 = srow[lane], c1 = srow[lane + 32];
       const float a0 = sarea[lane], a1 = sarea[lane + 32];
@@ -400,31 +415,13 @@ __global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs 
     }
     __syncthreads();
     const int nk = snk;
-    if (t < nk) p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + r0 + skept[t]];
-    count += nk;
-    if (count >= max_out || nk == 0) continue;
-    // (f) OR the kept rows' masks into the later words
-    for (int w = blk + 1 + warp; w < nblk; w += kFusedThreads / 32) {
-      const uint64_t cur = remv[w];
-      if (cur == ~0ull) continue;
-      const int c0 = w * 64 + lane, c1 = c0 + 32;
-      const bool live0 = c0 < n && !((cur >> lane) & 1ull), live1 = c1 < n && !((cur >> (lane + 32)) & 1ull);
-      const float4 b0 = live0 ? sb[c0] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 b1 = live1 ? sb[c1] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float a0 = box_area(b0), a1 = box_area(b1);
-      bool s0 = false, s1 = false;
-      for (int q = 0; q < nk; ++q) {
-        const int i = skept[q];
-        const float4 a = srow[i];
-        const float sa = sarea[i];
-        s0 = s0 || (live0 && nms_overlap(a, sa, b0, a0, p.thr));
-        s1 = s1 || (live1 && nms_overlap(a, sa, b1, a1, p.thr));
-      }
-      const uint32_t lo = __ballot_sync(0xffffffffu, s0);
-      const uint32_t hi = __ballot_sync(0xffffffffu, s1);
-      __syncwarp();  // every lane has consumed remv[w] before lane 0 rewrites it
-      if (lane == 0) remv[w] = cur | ((uint64_t)hi << 32) | lo;
+    if (t < nk) {
+      const int i = skept[t];
+      p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + r0 + i];
+      kbox[count + t] = srow[i];  // (e) the kept boxes join the list the later blocks are tested against
+      karea[count + t] = sarea[i];
     }
+    count += nk;
   }
   if (t == 0) p.keep_count[b] = count;
 }
@@ -534,7 +531,8 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
   // keep-driven single-CTA path when (boxes that can be kept) x N stays small; otherwise the full bitmask + sweep
   const long long cap = max_output > 0 ? (long long)min(max_output, Nmax) : (long long)Nmax;
   if (cap * (long long)Nmax <= (2ll << 20)) {  // e.g. 100 detections out of 5 000; RPN (1 000 of ~9 000) takes the mask path
-    const size_t fsmem = (size_t)a.nwords * 8;
+    const int kmax = min(max_output > 0 ? min(max_output, keep_ld) : keep_ld, Nmax);
+    const size_t fsmem = (size_t)kmax * 20 + 16;
     if (fsmem > 40 * 1024)
       BDET_CUDA(cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     BDET_KERNEL("nms_fused_kernel", st, nms_fused_kernel<<<B, kFusedThreads, fsmem, st>>>(a));
