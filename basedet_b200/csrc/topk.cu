@@ -208,7 +208,8 @@ struct SelArgs {
 // (2) ONE sweep, split over the cluster, that appends the keys <= T0 to rank 0's shared memory through DSMEM;
 // (3) the exact select among those in rank 0.  The outcome of (2) is checked, and a miss (adversarial data) falls
 // back to the full cluster select, so the result is exact either way.
-constexpr int kSample = 16384;
+constexpr int kSample = 16384;      // largest sample; the smallest of {kSample/4, kSample} whose bound fits is used
+constexpr int kSampleMinN = 32768;  // shorter segments are selected directly
 
 // Append the keys <= T of [lo, hi) to a (possibly remote) shared-memory list.
 template <class Src>
@@ -238,13 +239,18 @@ __device__ void select_sort_body(cg::cluster_group& cluster, const SelArgs& p, c
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   bool sampled = false;
   int r = 0;
-  if (n > k && n >= 2 * kSample) {
-    const float mu = (float)k * (float)kSample / (float)n;
-    r = (int)(mu + 5.f * sqrtf(mu) + 16.f);
-    sampled = r < kSample && 1.1f * (float)r * ((float)n / (float)kSample) <= (float)kBufCap;  // expected survivors + 10 %
+  int msamp = kSample;
+  if (n > k && n >= kSampleMinN) {
+#pragma unroll
+    for (int m = kSample / 4; m <= kSample && !sampled; m *= 4) {
+      const float mu = (float)k * (float)m / (float)n;
+      r = (int)(mu + 5.f * sqrtf(mu) + 16.f);
+      sampled = r < m && 1.1f * (float)r * ((float)n / (float)m) <= (float)kBufCap;  // expected survivors + 10 %
+      msamp = m;
+    }
   }
   // short segments are handled by rank 0 alone; the peers leave before any cluster barrier
-  const bool team = n > k && n >= 2 * kSample && (sampled || CS > 1);
+  const bool team = n > k && n >= kSampleMinN && (sampled || CS > 1);
   if (!team && rank != 0) return;
   uint64_t T = ~0ull;
   bool done = false;  // sortbuf of rank 0 holds the k selected keys
@@ -252,8 +258,8 @@ __device__ void select_sort_body(cg::cluster_group& cluster, const SelArgs& p, c
     cluster.sync();  // all CTAs of the cluster are resident, rank 0's counters are initialised
     bool full = !sampled;
     if (sampled) {
-      const SampleSrc<Src> ss{src, n / kSample};
-      const uint64_t T0 = radix_select<true>(cluster, ss, 0, kSample, r, sm, buf);
+      const SampleSrc<Src> ss{src, n / msamp};
+      const uint64_t T0 = radix_select<true>(cluster, ss, 0, msamp, r, sm, buf);
       const int lo = (int)((long long)n * rank / CS), hi = (int)((long long)n * (rank + 1) / CS);
       int* nsurv0 = cluster.map_shared_rank(&sm.nsurv, 0);
       gather_le(src, lo, hi, T0, nsurv0, cluster.map_shared_rank(surv, 0), kBufCap);

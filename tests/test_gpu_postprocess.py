@@ -59,13 +59,15 @@ def test_topk_sampled_threshold_and_fallback(cuda, case, n, k):
     select when the estimate misses; both must give the exact (score desc, index asc) top-k."""
     rng = np.random.default_rng(n + k)
     scores = rng.normal(-3, 2, n).astype(np.float32)
-    stride = n // 16384
+    sampled = np.zeros(n, bool)      # positions either sample size (4096 / 16384 keys) would read
+    for m in (4096, 16384):
+        sampled[(np.arange(m) * (n // m))] = True
     if case == "ties":
         scores = np.round(scores, 1)
     elif case == "sample_high":      # every sampled position is large: the estimated threshold is far too strict
-        scores[::stride] += 50.0
+        scores[sampled] += 50.0
     elif case == "sample_low":       # the sample sees none of the top scores: far too many survivors
-        scores[::stride] -= 50.0
+        scores[sampled] -= 50.0
     elif case == "sorted_desc":
         scores = -np.sort(-scores)
     elif case == "sorted_asc":
