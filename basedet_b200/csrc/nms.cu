@@ -11,14 +11,14 @@
 //              the boxes in sorted order.
 //   2+3 fused (nms_fused_kernel) when max_output x N is small (every detector head): one CTA per image walks the
 //              sorted boxes 64 at a time and tests them against the list of boxes kept so far (shared memory).
-//   otherwise, in row chunks of 1024 sorted boxes:
-//   2. mask  : 64x64 tiles of the chunk's rows against every later column; a warp takes a row box, its lanes two
-//              column boxes each, two __ballot_sync build the 64-bit suppression word (IoU > thr, IEEE division as
-//              the reference).  Rows an earlier chunk suppressed are skipped, and everything once max_output is
-//              reached: the sweep never reads those words.
+//   otherwise, in row chunks of 1024 sorted boxes (nms_chunk_kernel + nms_sweep_kernel per chunk):
+//   2. pull  : the chunk's columns are tested against the boxes KEPT by the earlier chunks (a list in global
+//              memory) -> removed bits of the chunk; mask: 64x64 tiles of the chunk's own upper triangle; a warp
+//              takes a row box, its lanes two column boxes each, two __ballot_sync build the 64-bit suppression
+//              word (IoU > thr, IEEE division as the reference).  Nothing runs once max_output boxes are kept.
 //   3. sweep : per image, warp 0 resolves one 64-box block at a time from the diagonal words held in registers
-//              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' masks into the `removed`
-//              bitmap (shared memory inside a chunk, global memory between chunks); stops at max_output.
+//              (only un-suppressed boxes are visited), then the CTA ORs the kept rows' chunk-local words into the
+//              `removed` bitmap of the chunk and appends the kept boxes to the list; stops at max_output.
 // Rated in pair tests/s (issue bound), not HBM GB/s.
 #include "common.cuh"
 #include "sortnet.cuh"
@@ -45,7 +45,9 @@ struct NmsArgs {
   uint32_t* maxc;       // (B) order-encoded max coordinate (large path)
   uint64_t* keys;       // (B, P) (large path)
   uint64_t* mask;       // (B, Nmax, nwords)
-  uint64_t* remv_g;     // (B, nwords) suppression bitmap carried from one row chunk to the next
+  uint64_t* remv_g;     // (B, nwords) columns suppressed by boxes kept in earlier chunks (pull CTAs)
+  float4* kbox;         // (B, kcap) boxes kept so far, in keep order
+  int kcap, pull_slices, mwords;  // mask rows hold only the chunk-local words: (B, Nmax, mwords)
   int* keep;
   int* keep_count;
 };
@@ -226,21 +228,54 @@ __device__ __forceinline__ bool nms_overlap(float4 a, float sa, float4 b, float 
   return __fdiv_rn(inter, (sa + sb) - inter) > thr;
 }
 
-// Row blocks [blk0, blk0 + gridDim.y) against column blocks >= blk0.  Rows the earlier chunks already suppressed, and
-// everything once max_output boxes are kept, are skipped: the sweep never reads those words.
-__global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p, int blk0) {
-  const int cb = blk0 + blockIdx.x, rb = blk0 + blockIdx.y, b = blockIdx.z;
-  if (cb < rb) return;
+// One launch per row chunk [blk0, blk0 + cb_n) x 64 sorted boxes, two kinds of CTAs (blockIdx.y):
+//   y <  cb_n : PULL  -- column block blk0 + x of the chunk against a slice of the boxes kept by the EARLIER chunks
+//               (kept list in global memory); suppressed columns are ORed into remv_g.  A kept box that is never
+//               followed by a live column costs nothing, and nothing is computed once max_output boxes are kept.
+//   y >= cb_n : MASK  -- 64 x 64 tile (rb = blk0 + y - cb_n, cb = blk0 + x >= rb) of the chunk's own upper triangle.
+// Pair tests per image: N x (kept so far) / 1 + chunk^2 / 2 per chunk, instead of (alive rows) x N.
+constexpr int kPullSlice = 4096;  // kept boxes per pull CTA
+
+__global__ void __launch_bounds__(256) nms_chunk_kernel(const NmsArgs p, int blk0, int cb_n) {
+  const int b = blockIdx.z, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = nms_n(p, b);
-  if (rb * 64 >= n || cb * 64 >= n) return;
+  const int cb = blk0 + blockIdx.x;
+  if (cb * 64 >= n) return;
   const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
-  if (p.keep_count[b] >= max_out) return;
-  const uint64_t gone = p.remv_g[(long long)b * p.nwords + rb];
-  if (gone == ~0ull) return;
+  const int count = p.keep_count[b];
+  if (count >= max_out) return;
+  const float4* sb = p.sboxes + (long long)b * p.Nmax;
+  if ((int)blockIdx.y < p.pull_slices) {  // ---- pull
+    const int q0 = blockIdx.y * kPullSlice, q1 = min(count, q0 + kPullSlice);
+    if (q0 >= q1) return;
+    __shared__ uint32_t srem[2];
+    if (t < 2) srem[t] = 0u;
+    __syncthreads();
+    const int col = cb * 64 + (((warp & 1) << 5) | lane), sub = warp >> 1;  // 4 sub-slices of the kept range
+    bool sup = false;
+    if (col < n) {
+      const float4 c = sb[col];
+      const float ca = box_area(c);
+      const float4* kb = p.kbox + (long long)b * p.kcap;
+      for (int q = q0 + sub; q < q1 && !sup; q += 4) {
+        const float4 k = kb[q];
+        sup = nms_overlap(k, box_area(k), c, ca, p.thr);
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, sup);
+    if (lane == 0 && m) atomicOr(&srem[warp & 1], m);
+    __syncthreads();
+    if (t == 0) {
+      const uint64_t w = ((uint64_t)srem[1] << 32) | srem[0];
+      if (w) atomicOr(reinterpret_cast<unsigned long long*>(p.remv_g + (long long)b * p.nwords + cb), (unsigned long long)w);
+    }
+    return;
+  }
+  // ---- mask tile inside the chunk
+  const int rb = blk0 + (int)blockIdx.y - p.pull_slices;
+  if (cb < rb || rb * 64 >= n) return;
   __shared__ float4 srow[64];
   __shared__ float sarea[64];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const float4* sb = p.sboxes + (long long)b * p.Nmax;
   if (t < 64) {
     int i = rb * 64 + t;
     float4 bx = i < n ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -252,80 +287,102 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(const NmsArgs p, int blk0
   const float4 b1 = c1 < n ? sb[c1] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float a0 = box_area(b0), a1 = box_area(b1);
   __syncthreads();
-  uint64_t* mrow = p.mask + ((long long)b * p.Nmax + rb * 64) * p.nwords + cb;
+  uint64_t* mrow = p.mask + ((long long)b * p.Nmax + rb * 64) * p.mwords + (cb - blk0);
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int lr = warp * 8 + r;
     const int i = rb * 64 + lr;
     if (i >= n) break;  // warp-uniform
-    if ((gone >> lr) & 1ull) continue;
     const float4 a = srow[lr];
     const float sa = sarea[lr];
     bool p0 = (c0 < n) && (c0 > i) && nms_overlap(a, sa, b0, a0, p.thr);
     bool p1 = (c1 < n) && (c1 > i) && nms_overlap(a, sa, b1, a1, p.thr);
     uint32_t lo = __ballot_sync(0xffffffffu, p0);
     uint32_t hi = __ballot_sync(0xffffffffu, p1);
-    if (lane == 0) mrow[(long long)lr * p.nwords] = ((uint64_t)hi << 32) | lo;
+    if (lane == 0) mrow[(long long)lr * p.mwords] = ((uint64_t)hi << 32) | lo;
   }
 }
 
 // ---- sweep -----------------------------------------------------------------------------------------------
 constexpr int kSweepThreads = 256;
 
-// Blocks [blk0, blk0 + nblk_chunk) of every image; the bitmap and the running count live in global memory between
-// chunks (zeroed by the entry point).
-__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs p, int blk0, int nblk_chunk) {
+// Blocks [blk0, blk0 + cb_n) of every image: the chunk's removed words come from the pull CTAs, suppression inside
+// the chunk from the chunk-local mask words; kept boxes are appended to the global kept list for the later chunks.
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const NmsArgs p, int blk0, int cb_n, int staged) {
   extern __shared__ __align__(16) unsigned char raw[];
-  uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // nwords
+  uint64_t* remv = reinterpret_cast<uint64_t*>(raw);  // cb_n words of this chunk (+ the staged mask)
   __shared__ int skept[64];
   __shared__ int snk;
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
   const int n = nms_n(p, b);
   const int nblk = (n + 63) >> 6;
   const long long base = (long long)b * p.Nmax;
-  const uint64_t* mask = p.mask + base * p.nwords;
+  const uint64_t* mask = p.mask + base * p.mwords;
   const int max_out = p.max_out > 0 ? min(p.max_out, p.keep_ld) : p.keep_ld;
   int count = p.keep_count[b];
   if (count >= max_out || blk0 >= nblk) return;
-  uint64_t* rg = p.remv_g + (long long)b * p.nwords;
-  for (int w = blk0 + t; w < nblk; w += kSweepThreads) remv[w] = rg[w];
-  const int blk_end = min(nblk, blk0 + nblk_chunk);
+  const int blk_end = min(nblk, blk0 + cb_n);
+  for (int w = t; w < blk_end - blk0; w += kSweepThreads) remv[w] = p.remv_g[(long long)b * p.nwords + blk0 + w];
+  if (staged) {
+    // the chunk-local mask (<= 1024 rows x 16 words = 128 KB) is pulled into shared memory once: the block-by-block
+    // loop below is a serial chain, and every global access in it would cost an L2 round trip
+    uint64_t* sm = remv + cb_n;
+    const int rows = min(n, blk_end * 64) - blk0 * 64;
+    const uint64_t* src = mask + (long long)blk0 * 64 * p.mwords;
+    for (int i = t; i < rows * p.mwords; i += kSweepThreads) sm[i] = src[i];
+    mask = sm - (long long)blk0 * 64 * p.mwords;  // same indexing as the global array
+  }
   for (int blk = blk0; blk < blk_end && count < max_out; ++blk) {
     __syncthreads();
+    const int wl = blk - blk0;
     if (t < 32) {
       const int r0 = blk * 64 + lane, r1 = r0 + 32;
-      const uint64_t d0 = r0 < n ? mask[(long long)r0 * p.nwords + blk] : 0ull;
-      const uint64_t d1 = r1 < n ? mask[(long long)r1 * p.nwords + blk] : 0ull;
+      const uint64_t d0 = r0 < n ? mask[(long long)r0 * p.mwords + wl] : 0ull;
+      const uint64_t d1 = r1 < n ? mask[(long long)r1 * p.mwords + wl] : 0ull;
       const int nv = min(64, n - blk * 64);
       const uint64_t valid = nv >= 64 ? ~0ull : ((1ull << nv) - 1ull);
-      uint64_t cand = ~remv[blk] & valid;
+      uint64_t cand = ~remv[wl] & valid;
       int nk = 0;
-      while (cand != 0ull && count + nk < max_out) {
-        const int i = __ffsll((long long)cand) - 1;
-        if (lane == 0) skept[nk] = i;
-        ++nk;
-        const uint64_t mine = (i < 32) ? d0 : d1;
-        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)mine, i & 31);
-        const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(mine >> 32), i & 31);
-        cand &= ~(((uint64_t)hi << 32) | lo);
-        cand &= ~(1ull << i);
+      const bool hit0 = ((cand >> lane) & 1ull) && (d0 & cand), hit1 = ((cand >> (lane + 32)) & 1ull) && (d1 & cand);
+      if (!__any_sync(0xffffffffu, hit0 || hit1)) {
+        // no live box of the block suppresses another live one: all of them are kept, in order, without the serial walk
+        const int room = max_out - count;
+        nk = min(__popcll(cand), room);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = lane + 32 * h;
+          const int rank = __popcll(cand & ((1ull << i) - 1ull));
+          if (((cand >> i) & 1ull) && rank < room) skept[rank] = i;
+        }
+      } else {
+        while (cand != 0ull && count + nk < max_out) {
+          const int i = __ffsll((long long)cand) - 1;
+          if (lane == 0) skept[nk] = i;
+          ++nk;
+          const uint64_t mine = (i < 32) ? d0 : d1;
+          const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)mine, i & 31);
+          const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(mine >> 32), i & 31);
+          cand &= ~(((uint64_t)hi << 32) | lo);
+          cand &= ~(1ull << i);
+        }
       }
       if (lane == 0) snk = nk;
     }
     __syncthreads();
     const int nk = snk;
-    if (t < nk) p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + blk * 64 + skept[t]];
+    if (t < nk) {
+      const int row = blk * 64 + skept[t];
+      p.keep[(long long)b * p.keep_ld + count + t] = p.order[base + row];
+      p.kbox[(long long)b * p.kcap + count + t] = p.sboxes[base + row];
+    }
     count += nk;
     if (count >= max_out || nk == 0) continue;
-    for (int w = blk + 1 + t; w < nblk; w += kSweepThreads) {
+    for (int w = wl + 1 + t; w < blk_end - blk0; w += kSweepThreads) {
       uint64_t acc = remv[w];
-      for (int q = 0; q < nk; ++q) acc |= mask[(long long)(blk * 64 + skept[q]) * p.nwords + w];
+      for (int q = 0; q < nk; ++q) acc |= mask[(long long)(blk * 64 + skept[q]) * p.mwords + w];
       remv[w] = acc;
     }
   }
-  __syncthreads();
-  if (blk_end < nblk && count < max_out)
-    for (int w = blk_end + t; w < nblk; w += kSweepThreads) rg[w] = remv[w];
   if (t == 0) p.keep_count[b] = count;
 }
 
@@ -426,8 +483,11 @@ __global__ void __launch_bounds__(kFusedThreads) nms_fused_kernel(const NmsArgs 
   if (t == 0) p.keep_count[b] = count;
 }
 
+// 64-box blocks per row chunk of the mask / sweep path
+static int chunk_blocks(int nblk) { return nblk <= 512 ? kChunkBlocks : ceil_div(nblk, 32); }
+
 struct NmsWs {
-  size_t order, sboxes, maxc, keys, remv, mask, total;
+  size_t order, sboxes, maxc, keys, remv, kbox, mask, total;
 };
 static NmsWs nms_ws(int Nmax, int B) {
   NmsWs w;
@@ -443,8 +503,10 @@ static NmsWs nms_ws(int Nmax, int B) {
   if (Nmax > kSmallSortMax) o += align_up((size_t)B * next_pow2(Nmax) * 8, 256);
   w.remv = o;
   o += align_up((size_t)B * nwords * 8, 256);
+  w.kbox = o;
+  o += align_up((size_t)B * Nmax * 16, 256);
   w.mask = o;
-  o += (size_t)B * Nmax * nwords * 8;
+  o += (size_t)B * Nmax * chunk_blocks((int)nwords) * 8;  // only the chunk-local words of a row are ever stored
   w.total = o + 256;
   return w;
 }
@@ -506,6 +568,10 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
   a.keys = reinterpret_cast<uint64_t*>(ws + w.keys);
   a.mask = reinterpret_cast<uint64_t*>(ws + w.mask);
   a.remv_g = reinterpret_cast<uint64_t*>(ws + w.remv);
+  a.kbox = reinterpret_cast<float4*>(ws + w.kbox);
+  a.kcap = Nmax;
+  a.mwords = chunk_blocks(a.nwords);
+  a.pull_slices = 1;
   a.keep = keep;
   a.keep_count = keep_count;
 
@@ -539,21 +605,24 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
     BDET_LAUNCH_CHECK();
     return BDET_OK;
   }
-  // Row chunks: mask words of kChunkBlocks x 64 sorted boxes against everything behind them, then the sweep over those
-  // blocks.  Rows suppressed by an earlier chunk are never tested and all work stops once max_output boxes are kept,
-  // so the pair tests are ~(boxes still alive) x N instead of N^2 / 2.
+  // Row chunks of kChunkBlocks x 64 sorted boxes.  Per chunk one launch tests the chunk's columns against the boxes
+  // kept by the earlier chunks (pull) and builds the chunk's own triangular mask; the sweep then resolves the chunk
+  // and appends its kept boxes to the list.  Everything stops once max_output boxes are kept.
   const int nblk = a.nwords;
   if (nblk > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_nms: too many 64-box blocks");
   BDET_CUDA(cudaMemsetAsync(a.remv_g, 0, (size_t)B * a.nwords * 8, st));
   BDET_CUDA(cudaMemsetAsync(keep_count, 0, (size_t)B * 4, st));
-  size_t sweep_smem = (size_t)a.nwords * 8;
+  const int chunk = a.mwords;
+  const int kmax = min(max_output > 0 ? min(max_output, keep_ld) : keep_ld, Nmax);
+  a.pull_slices = max(1, ceil_div(kmax, kPullSlice));
+  const int staged = chunk <= kChunkBlocks;  // chunk-local mask fits shared memory
+  size_t sweep_smem = (size_t)chunk * 8 + (staged ? (size_t)chunk * 64 * chunk * 8 : 0);
   if (sweep_smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
-  const int chunk = nblk <= 512 ? kChunkBlocks : ceil_div(nblk, 32);
   for (int blk0 = 0; blk0 < nblk; blk0 += chunk) {
     const int rows = min(chunk, nblk - blk0);
-    BDET_KERNEL("nms_mask_kernel", st, nms_mask_kernel<<<dim3(nblk - blk0, rows, B), 256, 0, st>>>(a, blk0));
-    BDET_KERNEL("nms_sweep_kernel", st, nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a, blk0, rows));
+    BDET_KERNEL("nms_chunk_kernel", st, nms_chunk_kernel<<<dim3(rows, a.pull_slices + rows, B), 256, 0, st>>>(a, blk0, rows));
+    BDET_KERNEL("nms_sweep_kernel", st, nms_sweep_kernel<<<B, kSweepThreads, sweep_smem, st>>>(a, blk0, rows, staged));
   }
   BDET_LAUNCH_CHECK();
   return BDET_OK;

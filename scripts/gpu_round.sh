@@ -12,5 +12,5 @@ timeout 600 python scripts/perf_all.py > gpurun_out/perf_all.log 2>&1; tail -3 g
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_fused.csv python bench.py --steps 5 --warmup 3 > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench_materialised.csv python bench.py --steps 3 --warmup 3 --path materialised > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'assign_main|assign_lq|pairwise_kernel|match_colmax|match_lq' -s 8 -c 8 -o gpurun_out/prof_targets -f python scripts/profile_targets.py > gpurun_out/ncu_targets.log 2>&1; tail -1 gpurun_out/ncu_targets.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_sort|nms_sort_small|select_decode|nms_fused|roi_align|score_filter|nms_mask|nms_sweep" -s 28 -c 28 -o gpurun_out/prof_post -f python scripts/profile_post.py > gpurun_out/ncu_post.log 2>&1; tail -1 gpurun_out/ncu_post.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_sort|nms_sort_small|select_decode|nms_fused|roi_align|score_filter|nms_chunk|nms_sweep" -s 28 -c 28 -o gpurun_out/prof_post -f python scripts/profile_post.py > gpurun_out/ncu_post.log 2>&1; tail -1 gpurun_out/ncu_post.log
 ls -la gpurun_out | tail -20

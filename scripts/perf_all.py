@@ -44,7 +44,7 @@ def run(name, fn, bytes_by_kernel=None, iters=10):
 KERNELS = ["anchors_grid_kernel", "pairwise_kernel", "match_colmax_kernel", "match_lq_kernel", "assign_main_kernel", "assign_lq_kernel",
            "box_encode_kernel", "box_decode_kernel", "score_filter_kernel", "select_sort_kernel", "select_decode_kernel",
            "nms_sort_small_kernel", "nms_tile_sort_kernel", "nms_global_step_kernel", "nms_tile_tail_kernel", "nms_gather_kernel",
-           "nms_maxcoord_kernel", "nms_fused_kernel", "nms_mask_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
+           "nms_maxcoord_kernel", "nms_fused_kernel", "nms_chunk_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
            "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel",
            "fcos_targets_kernel", "atss_candidates_kernel", "atss_finish_kernel", "count_labels_kernel", "sample_labels_kernel",
            "rcnn_match_kernel", "rcnn_collect_kernel"]
