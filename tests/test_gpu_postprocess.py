@@ -250,3 +250,23 @@ def test_nms_presorted_runs_equal_general_sort(cuda, run_lens):
         bad[:, -1] += 1                      # inconsistent run table -> general sort as well
         k4, c4 = ops.nms_batched(*args, num=T(num, cuda), runs=T(bad, cuda))
         assert np.array_equal(c0.cpu().numpy(), c4.cpu().numpy())
+
+
+def test_nms_chunked_path_edge_cases(cuda):
+    """Mask/sweep path (max_output x N above the fused limit): max_output reached inside the first chunk, exactly at a
+    chunk border, N not a multiple of 64, ragged batch with an empty image, all boxes identical (one survivor)."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    boxes, scores, _ = _dense_dets(rng, n, 1)
+    for max_out in (1000, 1024, 1025, None):
+        keep, cnt = ops.nms_batched(T(boxes, cuda)[None], T(scores, cuda)[None], None, 0.7, max_out)
+        ref = R.nms(boxes, scores, 0.7, max_out)
+        assert int(cnt[0]) == len(ref) and np.array_equal(keep[0, : int(cnt[0])].cpu().numpy(), ref)
+    b2 = np.stack([boxes, boxes[::-1].copy(), np.tile(boxes[:1], (n, 1))])
+    s2 = np.stack([scores, scores[::-1].copy(), scores])
+    num = np.array([2999, 0, n], np.int32)
+    keep, cnt = ops.nms_batched(T(b2, cuda), T(s2, cuda), None, 0.5, 2000, num=T(num, cuda))
+    for b in range(3):
+        ref = R.nms(b2[b, : num[b]], s2[b, : num[b]], 0.5, 2000)
+        assert int(cnt[b]) == len(ref) and np.array_equal(keep[b, : int(cnt[b])].cpu().numpy(), ref)
+    assert int(cnt[2]) == 1

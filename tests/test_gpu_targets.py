@@ -372,3 +372,31 @@ def test_rcnn_get_ground_truth_vs_oracle(cuda, B, Rmax, G, num, ratio):
         # proposals (non-positive width after the jitter) give inf / NaN targets in both
         assert np.allclose(otgt[b, : ocnt[b]].cpu().numpy(), rt, rtol=2e-6, atol=1e-5, equal_nan=True)
         assert (rl > 0).sum() <= int(num * ratio) and len(rl) <= num
+
+
+def test_new_target_entry_points_degenerate_inputs(cuda):
+    """Empty / degenerate shapes of the 8(f) entry points: no GT, no proposals, zero budgets, one element."""
+    from basedet_b200 import pipelines
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda)  # noqa: E731
+    # sample_labels: nothing to do / everything ignored
+    lab = np.array([[1, 0, 1, -1, 0]], np.int32)
+    nz = np.array([[0.5, 0.1, 0.9, 0.3, 0.2]], np.float32)
+    assert np.array_equal(ops.sample_labels(Tc(lab.copy()), Tc(nz), 5, 1, -1).cpu().numpy(), lab)
+    assert np.array_equal(ops.sample_labels(Tc(lab.copy()), Tc(nz), 0, 1, -1).cpu().numpy(), R.sample_labels(lab[0], 0, 1, -1, nz[0])[None])
+    assert np.array_equal(ops.sample_labels(Tc(lab.copy()), Tc(nz), 1, 0, 7).cpu().numpy(), R.sample_labels(lab[0], 1, 0, 7, nz[0])[None])
+    # RCNN glue: an image without GT contributes nothing, an image without proposals still keeps its GT rows
+    gt = np.zeros((2, 3, 5), np.float32)
+    gt[1, 0] = [10, 10, 60, 70, 4]
+    gt[1, 1] = [100, 20, 180, 90, 9]
+    ng = np.array([0, 2], np.int32)
+    rois = np.zeros((2, 6, 5), np.float32)
+    rois[0, :, 1:] = [5, 5, 50, 50]
+    nr = np.array([6, 0], np.int32)
+    nz2 = np.random.default_rng(0).uniform(0, 1, (2, 9)).astype(np.float32)
+    orois, olab, otgt, cnt = pipelines.rcnn_targets(Tc(rois), Tc(nr), Tc(gt), Tc(ng), Tc(nz2), Tc(nz2), 8, 0.5)
+    cnt = cnt.cpu().numpy()
+    assert cnt[0] == 0
+    ref = R.rcnn_targets([rois[1, :0]], gt[1:], ng[1:], [nz2[1, :2]], [nz2[1, :2]], 8, 0.5)[0]
+    assert cnt[1] == len(ref[1]) == 2
+    assert np.array_equal(orois[1, :2].cpu().numpy()[:, 1:], ref[0][:, 1:]) and np.array_equal(olab[1, :2].cpu().numpy(), ref[1])
+    assert np.allclose(otgt[1, :2].cpu().numpy(), ref[2], atol=1e-6)
