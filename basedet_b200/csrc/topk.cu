@@ -100,6 +100,7 @@ struct SelSmem {
   int nsel;
   int nsurv;
   int bin, below, cnt;
+  uint64_t thr;
 };
 
 // k-th smallest key (1 <= k <= n) of the whole segment; this CTA sweeps elements [lo, hi).  Keys unique.
@@ -651,29 +652,122 @@ struct NoiseSrc {
   }
 };
 
+// Reversed keys of the elements that can be removed without touching the zero-valued remainder of random_tensor:
+// ascending order = (variate asc, index desc), everything else is +inf.
+struct KeepSrc {
+  const int* lab;
+  const float* noise;
+  int value;
+  __device__ __forceinline__ uint64_t key(int i) const {
+    const float v = __ldg(noise + i);
+    return (__ldg(lab + i) == value && v > 0.f) ? ~make_key(v, (uint32_t)i) : ~0ull;
+  }
+};
+
+// k-th smallest key of a segment whose `n_finite` keys below ~0ull are known, delivered to EVERY CTA of the cluster.
+// Few finite keys: they are gathered into rank 0 and selected there; many: sampled threshold as in select_sort_body
+// (checked, falls back); otherwise the full cluster select.  All CTAs must call it (cluster-uniform arguments).
+template <class Src>
+__device__ uint64_t cluster_select_kth(cg::cluster_group& cluster, const Src& src, int n, int n_finite, int k, SelSmem& sm,
+                                       uint64_t* buf, uint64_t* surv) {
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int lo = (int)((long long)n * rank / CS), hi = (int)((long long)n * (rank + 1) / CS);
+  bool gather = n_finite <= kBufCap;
+  uint64_t T0 = ~0ull - 1ull;  // every finite key
+  if (!gather && n >= kSampleMinN) {
+    bool sampled = false;
+    int r = 0, msamp = kSample;
+#pragma unroll
+    for (int m = kSample / 4; m <= kSample && !sampled; m *= 4) {
+      const float mu = (float)k * (float)m / (float)n;
+      r = (int)(mu + 5.f * sqrtf(mu) + 16.f);
+      sampled = r < m && 1.1f * (float)r * ((float)n / (float)m) <= (float)kBufCap;
+      msamp = m;
+    }
+    if (sampled) {
+      const SampleSrc<Src> ss{src, n / msamp};
+      T0 = radix_select<true>(cluster, ss, 0, msamp, r, sm, buf);
+      gather = T0 != ~0ull;  // the sample ran out of finite keys: no usable bound
+    }
+  }
+  if (gather) {
+    if (threadIdx.x == 0) sm.nsurv = 0;
+    cluster.sync();
+    int* nsurv0 = cluster.map_shared_rank(&sm.nsurv, 0);
+    gather_le(src, lo, hi, T0, nsurv0, cluster.map_shared_rank(surv, 0), kBufCap);
+    cluster.sync();
+    const int total = *nsurv0;
+    if (total >= k && total <= kBufCap) {
+      if (rank == 0) {
+        const KeySrc sv{surv};
+        const uint64_t T = total == k ? T0 : radix_select<true>(cluster, sv, 0, total, k, sm, buf);
+        if (threadIdx.x == 0) sm.thr = T;
+      }
+      cluster.sync();
+      const uint64_t T = *cluster.map_shared_rank(&sm.thr, 0);
+      cluster.sync();  // rank 0's shared memory has been read by every peer
+      return T;
+    }
+    cluster.sync();  // peers have read the counter before anything reuses it
+  }
+  const uint64_t T = radix_select<false>(cluster, src, lo, hi, k, sm, buf);
+  cluster.sync();  // a peer may still be summing this CTA's last histogram
+  return T;
+}
+
 __global__ void __launch_bounds__(kSelThreads) sample_labels_kernel(const SampleArgs p) {
   extern __shared__ __align__(16) unsigned char raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(raw);  // kBufCap
+  uint64_t* surv = buf + kBufCap;                     // kBufCap
   __shared__ SelSmem sm;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   const int b = blockIdx.x / CS, t = threadIdx.x;
   int* lab = p.labels + (long long)b * p.A;
-  const NoiseSrc src{lab, p.noise + (long long)b * p.A, p.value};
+  const float* nz = p.noise + (long long)b * p.A;
   const int lo = (int)((long long)p.A * rank / CS), hi = (int)((long long)p.A * (rank + 1) / CS);
-  if (t == 0) sm.nsel = 0;
+  if (t == 0) {
+    sm.nsel = 0;
+    sm.nbuf = 0;
+  }
   __syncthreads();
-  int mine = 0;
-  for (int i = lo + t; i < hi; i += kSelThreads) mine += lab[i] == p.value;  // sampling.py:19-20
+  int mine = 0, pos = 0;
+  for (int i = lo + t; i < hi; i += kSelThreads) {
+    const bool m = lab[i] == p.value;  // sampling.py:19-20
+    mine += m;
+    pos += m && nz[i] > 0.f;
+  }
   mine = __reduce_add_sync(0xffffffffu, mine);
-  if ((t & 31) == 0 && mine) atomicAdd(&sm.nsel, mine);
+  pos = __reduce_add_sync(0xffffffffu, pos);
+  if ((t & 31) == 0 && mine) {
+    atomicAdd(&sm.nsel, mine);
+    atomicAdd(&sm.nbuf, pos);
+  }
   cluster.sync();
-  int num_valid = 0;
-  for (int r = 0; r < CS; ++r) num_valid += *cluster.map_shared_rank(&sm.nsel, r);
-  cluster.sync();  // every peer has read this CTA's count
+  int num_valid = 0, P = 0;
+  for (int r = 0; r < CS; ++r) {
+    num_valid += *cluster.map_shared_rank(&sm.nsel, r);
+    P += *cluster.map_shared_rank(&sm.nbuf, r);
+  }
+  cluster.sync();  // every peer has read this CTA's counts
   const int ns = max(p.ns_dev ? p.ns_dev[b] : p.ns_const, 0);
   if (num_valid <= ns) return;  // :21-22, cluster-uniform
-  const int k = num_valid - ns;  // :27
+  const int k = num_valid - ns;  // :27: the k LARGEST entries of random_tensor are dropped
+  if (k <= P) {
+    // all k of them are selected elements with a positive variate, so the zero-valued rest of random_tensor never
+    // enters the order: keep the P - k SMALLEST positive variates instead -- a short select however many are dropped
+    const int keep = P - k;
+    const KeepSrc ksrc{lab, nz, p.value};
+    uint64_t T = 0ull;  // keep == 0: nothing below it
+    if (keep > 0) T = cluster_select_kth(cluster, ksrc, p.A, P, keep, sm, buf, surv);
+    for (int i = lo + t; i < hi; i += kSelThreads) {
+      const uint64_t key = ksrc.key(i);
+      if (key != ~0ull && (keep == 0 || key > T)) lab[i] = p.ignore;  // :29
+    }
+    return;
+  }
+  // more entries to drop than positive variates (zero / negative variates in play): the literal top-k of random_tensor
+  const NoiseSrc src{lab, nz, p.value};
   const uint64_t T = radix_select<false>(cluster, src, lo, hi, k, sm, buf);
   // :29 -- a CTA rewrites only the range it alone reads, so a faster peer cannot disturb a slower one's keys
   for (int i = lo + t; i < hi; i += kSelThreads)
@@ -693,21 +787,31 @@ extern "C" int bdet_sample_labels(int* labels, const float* noise, int A, int B,
   BDET_REQUIRE(num_samples_dev || num_samples >= 0, "negative num_samples");
   SampleArgs a{labels, noise, num_samples_dev, A, label_value, ignore_label, num_samples};
   cudaStream_t st = as_stream(stream);
-  const size_t smem = (size_t)kBufCap * 8;
-  int cs = kMaxCS;
-  while (cs > 1 && ((long long)B * cs * 10 > 22LL * sm_count() || A < cs * 4096)) cs >>= 1;
+  const size_t smem = (size_t)2 * kBufCap * 8;
+  BDET_CUDA(cudaFuncSetAttribute(sample_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(B * cs));
   cfg.blockDim = dim3(kSelThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // widest cluster that still runs all B images in ONE wave (a 1024-thread CTA owns an SM, and only ~15 clusters of 8
+  // fit the GPCs: a 16th image would wait for a second wave and double the kernel time)
+  int cs = kMaxCS;
+  for (; cs > 1; cs >>= 1) {
+    if (A < cs * 4096) continue;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    cfg.gridDim = dim3((unsigned)(B * cs));
+    int active = 0;
+    if (cudaOccupancyMaxActiveClusters(&active, sample_labels_kernel, &cfg) == cudaSuccess && active >= B) break;
+  }
+  cudaGetLastError();
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  cfg.gridDim = dim3((unsigned)(B * cs));
   cudaError_t err = cudaSuccess;
   BDET_KERNEL("sample_labels_kernel", st, err = cudaLaunchKernelEx(&cfg, sample_labels_kernel, a));
   BDET_CUDA(err);
