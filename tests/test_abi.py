@@ -70,7 +70,7 @@ def test_host_argument_errors_without_gpu():
     rc = lib.bdet_match(None, 8, 0, None, 1, 8, 1, thr, labs, 3, 0, None, None, None, 0, None)
     assert rc == -1 and b"sorted" in lib.bdet_last_error()  # matcher.py:23
     assert lib.bdet_match_workspace(100, 120087, 16) > 0
-    assert lib.bdet_nms_workspace(5000, 1) > 5000 * 79 * 8
+    assert lib.bdet_nms_workspace(5000, 1) > 5000 * 16 * 8  # sorted boxes + kept list + chunk-local mask words
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
