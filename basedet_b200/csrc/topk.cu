@@ -599,6 +599,28 @@ static int64_t build_segments(SegDesc* host, const int64_t* start, const int64_t
   return total;
 }
 
+// The descriptor table travels to the device as KERNEL PARAMETERS (<= 96 descriptors = 3.8 KB per launch) instead of a
+// cudaMemcpyAsync from pageable host memory: no staging copy, no hidden host synchronisation, and the whole call can be
+// captured into a CUDA graph.
+constexpr int kSegPerUpload = 96;
+struct SegBatch {
+  SegDesc d[kSegPerUpload];
+};
+__global__ void seg_upload_kernel(SegDesc* dst, const SegBatch b, int n) {
+  const int i = threadIdx.x;
+  if (i < n) dst[i] = b.d[i];
+}
+static int upload_segments(SegDesc* dev, const SegDesc* host, int count, cudaStream_t st) {
+  for (int o = 0; o < count; o += kSegPerUpload) {
+    SegBatch b;
+    const int n = std::min(kSegPerUpload, count - o);
+    for (int i = 0; i < n; ++i) b.d[i] = host[o + i];
+    seg_upload_kernel<<<1, kSegPerUpload, 0, st>>>(dev + o, b, n);
+  }
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
 template <bool RAW>
 static int launch_select(const SelArgs& a, int n_seg, cudaStream_t st) {
   size_t smem = (size_t)(a.P + 2 * kBufCap) * 8;
@@ -847,7 +869,7 @@ extern "C" int bdet_topk(const float* scores, const int64_t* seg_start_host, con
   if (!workspace || workspace_bytes < w.bytes) return set_error(BDET_EWORKSPACE, "bdet_topk: workspace needs %zu bytes", w.bytes);
   BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
   cudaStream_t st = as_stream(stream);
-  BDET_CUDA(cudaMemcpyAsync(w.seg, host, (size_t)(n_seg + 1) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+  if (int rc = upload_segments(w.seg, host, n_seg + 1, st)) return rc;
   SelArgs a{scores, nullptr, nullptr, w.seg, out_vals, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
   int rc = launch_select<true>(a, n_seg, st);
   if (rc) return rc;
@@ -883,7 +905,7 @@ static int score_filter_topk_impl(const float* logits, const float* ctrness, int
   BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "workspace must be 8-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int tiles = host[n_seg].tile_start;
-  BDET_CUDA(cudaMemcpyAsync(w.seg, host, (size_t)(n_seg + 1) * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+  if (int rc = upload_segments(w.seg, host, n_seg + 1, st)) return rc;
   BDET_CUDA(cudaMemsetAsync(w.cand_count, 0, (size_t)n_seg * 4, st));
   FilterArgs f;
   f.logits = logits;

@@ -178,6 +178,42 @@ class TargetAssigner:
         return self.plan.labels, self.plan.idx, self.plan.offsets, self.counts
 
 
+class GraphedPipeline:
+    """Capture one of the pipelines above on FIXED input tensors into a CUDA graph and replay it every iteration.
+
+    The post-processing / proposal pipelines are chains of ~6-30 short launches (filter, cluster select, decode, NMS
+    chunks, finalize); replayed as one graph they cost the kernels only -- no per-launch host work, no allocator
+    traffic.  ``fn(*args, **kwargs)`` is run twice for warm-up and once under capture; the tensors among the arguments
+    must keep their addresses (write the next batch INTO them: ``t.copy_(new)``), the returned tensors are the same
+    objects after every ``replay()``.  Example::
+
+        post = GraphedPipeline(dense_postprocess_nchw, head_logits, head_offsets, anchors, img_info, 80)
+        for batch in loader:
+            run_network_into(head_logits, head_offsets)     # or copy_ into them
+            dets, counts = post.replay()
+    """
+
+    def __init__(self, fn, *args, **kwargs):
+        tensors = [a for a in args if torch.is_tensor(a)] + [t for a in args if isinstance(a, (list, tuple)) for t in a
+                                                             if torch.is_tensor(t)]
+        assert tensors and tensors[0].is_cuda, "GraphedPipeline needs CUDA tensor arguments"
+        self.device = tensors[0].device
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn(*args, **kwargs)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.outputs = fn(*args, **kwargs)
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+
 def roi_pool_forward_backward(features, rois, strides, pool_shape=(7, 7), dout=None):
     """RCNN.forward's roi_pool (layers/head/rcnn.py:56 -> layers/common/roi_pool.py:35-78) and, if ``dout`` is
     given, the gradient w.r.t. the features that MegEngine's autodiff would produce."""

@@ -241,3 +241,37 @@ def test_dense_postprocess_from_nchw_head_outputs(fcos):
     d1, c1 = pipelines.dense_postprocess_nchw(logits, offsets, anchors, info, C, 0.05, 0.6, 100, 1000, head_ctrness=ctr)
     assert torch.equal(c0, c1) and int(c0.sum()) > 50
     assert torch.equal(d0, d1)
+
+
+def test_graphed_pipelines_replay_equals_eager():
+    """pipelines.GraphedPipeline: dense post-processing and RPN proposals captured once, replayed on new inputs written
+    into the same tensors == eager results (segment tables travel as kernel parameters, so the capture is legal)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    B, C, hw = 2, 80, (256, 320)
+    sizes = W.retinanet_level_sizes(*hw)
+    anchors = [T(a) for a in R.default_anchors(sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, 0.5)]
+    logits = [torch.randn((B, h * w * 9, C), device="cuda", generator=g) * 1.25 - 6.0 for h, w in sizes]
+    offsets = [torch.randn((B, h * w * 9, 4), device="cuda", generator=g) * 0.15 for h, w in sizes]
+    info = T(np.array([[hw[0], hw[1], 300.0, 380.0, 0.0]] * B, np.float32))
+    post = pipelines.GraphedPipeline(pipelines.dense_postprocess, logits, offsets, anchors, info, 0.05, 0.5, 100, 1000)
+    for it in range(3):
+        for t in logits:
+            t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 1.25 - 6.0)
+        for t in offsets:
+            t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 0.15)
+        dets, cnt = post.replay()
+        ed, ec = pipelines.dense_postprocess(logits, offsets, anchors, info, 0.05, 0.5, 100, 1000)
+        assert torch.equal(cnt, ec) and torch.equal(dets, ed) and int(cnt.sum()) > 0
+    fs = W.frcnn_level_sizes(256, 320)
+    ranchors = [T(a) for a in R.default_anchors(fs, W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5)]
+    sc = [torch.randn((B, a.shape[0]), device="cuda", generator=g) * 2 - 3 for a in ranchors]
+    dl = [torch.randn((B, a.shape[0], 4), device="cuda", generator=g) * 0.2 for a in ranchors]
+    rinfo = T(np.array([[256, 320, 256, 320, 0.0]] * B, np.float32))
+    rpn = pipelines.GraphedPipeline(pipelines.rpn_proposals, sc, dl, ranchors, rinfo, 2000, 1000, 0.7)
+    for it in range(2):
+        for t in sc:
+            t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 2 - 3)
+        rois, cnt = rpn.replay()
+        er, ec = pipelines.rpn_proposals(sc, dl, ranchors, rinfo, 2000, 1000, 0.7)
+        assert torch.equal(cnt, ec) and torch.equal(rois, er)
