@@ -20,3 +20,16 @@ class Matcher:
         assert len(matrix.shape) == 2
         assert matrix.shape[0] > 0, "Matcher needs at least one row (the reference's max over an empty axis raises)"
         return ops.match(matrix, self.thresholds[1:-1], self.labels, self.allow_low_quality_matches)
+
+
+class OTATopkMatcher:
+    """Drop-in for ``basedet.layers.OTATopkMatcher`` (layers/common/matcher.py:129-161): dynamic-k matching."""
+
+    def __init__(self, candidate_k=10):
+        self.candidate_k = candidate_k
+
+    def __call__(self, cost, ious):
+        """cost: (#boxes, #anchors) cost matrix; ious: pairwise IoU of gt boxes and anchors, same shape.
+        Returns the matched gt index per anchor, ``#boxes`` for unmatched anchors."""
+        from .. import ops
+        return ops.ota_topk_match(cost, ious, self.candidate_k)

@@ -819,6 +819,21 @@ def rcnn_collect(m, gt_boxes, num_out, mean=(0, 0, 0, 0), std=(0.1, 0.1, 0.2, 0.
     return rois, labels, targets, count
 
 
+def ota_topk_match(cost, ious, candidate_k=10):
+    """OTATopkMatcher (layers/common/matcher.py:134-161): cost, ious (G, A) fp32 -> matched GT per anchor (A,) int32,
+    G = background."""
+    lib = _lib.load()
+    c = _f32c(cost, "cost")
+    u = _f32c(ious, "ious")
+    assert c.ndim == 2 and c.shape == u.shape
+    G, A = c.shape
+    out = torch.empty((A,), dtype=torch.int32, device=c.device)
+    ws = _workspace(lib.bdet_ota_topk_match_workspace(A), c.device)
+    with _guard(c):
+        check(lib.bdet_ota_topk_match(_p(c), A, _p(u), A, G, A, int(candidate_k), _p(out), _p(ws), ws.numel(), _stream(c)))
+    return out
+
+
 # ----------------------------------------------------------------------------- measurement hooks
 def profile_begin(only=None):
     """Bracket kernel launches with CUDA events; ``only`` = time just that kernel (the rest are counted)."""

@@ -191,6 +191,15 @@ int bdet_rcnn_collect(const float* all_rois, const int* n_all, const int* assign
                       const float* mean_host, const float* std_host, int num_out, float* out_rois, int* out_labels,
                       float* out_targets, int* out_count, bdet_stream_t stream);
 
+/* ------------------------------------------------------------------ 8(f)-3: dynamic-k matching (OTA / YOLOX)
+ * OTATopkMatcher.__call__  layers/common/matcher.py:134-161.  cost, ious: (G,A) fp32 with row strides ldc / ldi (the
+ * matrices models/det/ota.py:76-180 builds from its losses).  Per GT: k = clip(int32(sum of its candidate_k largest
+ * IoUs), 1) anchors of smallest cost are matched; an anchor matched by several GTs goes to the GT of smallest cost
+ * over all GTs; matched_gt (A) int32 = GT index, G for background.  candidate_k <= 16. */
+size_t bdet_ota_topk_match_workspace(int A);
+int bdet_ota_topk_match(const float* cost, int ldc, const float* ious, int ldi, int G, int A, int candidate_k,
+                        int* matched_gt, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
  * Segmented: segment s covers scores[seg_start[s] .. seg_start[s] + seg_len[s]) (element offsets from `scores`;

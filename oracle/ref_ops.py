@@ -494,6 +494,31 @@ def rcnn_targets(rois_list, gt_boxes, num_gt, noise_fg, noise_bg, num_rois=512, 
     return out
 
 
+def ota_topk_match(cost, ious, candidate_k=10):
+    """OTATopkMatcher.__call__, basedet/layers/common/matcher.py:134-161 (dynamic-k matching of OTA / YOLOX).
+
+    cost, ious: (G, A) fp32.  Returns matched GT index per anchor (A,) int32, G = background.
+    The sum of the top-k IoUs (:146) is accumulated sequentially in descending order (ASSUMED-8); its int32 cast
+    truncates."""
+    cost = np.asarray(cost, f32)
+    ious = np.asarray(ious, f32)
+    G, A = cost.shape
+    matching = np.zeros((G, A), f32)                                            # :143
+    k = min(int(candidate_k), A)
+    topk_ious = -np.sort(-ious, axis=1, kind="stable")[:, :k]                   # :145 values, descending
+    dynamic_ks = np.maximum(seq_sum_f32(topk_ious, 1).astype(np.int32), 1)      # :146
+    for g in range(G):                                                          # :147-149
+        idx = np.argsort(cost[g], kind="stable")[: dynamic_ks[g]]              # topk ascending (ASSUMED-9)
+        matching[g, idx] = 1.0
+    multi = matching.sum(0) > 1                                                 # :154
+    if multi.sum() > 0:                                                         # :155-158
+        cost_argmin = np.argmin(cost[:, multi], axis=0)
+        matching[:, multi] = 0.0
+        matching[cost_argmin, multi] = 1.0
+    full = np.concatenate([matching * 2, np.ones((1, A), f32)], axis=0)         # :160-161
+    return np.argmax(full, axis=0).astype(np.int32)                             # first index (ASSUMED-2)
+
+
 def _ctrness(offsets):
     """fcos.py:276-281 / atss.py:72-77: sqrt(max(min(l,r)/max(l,r), 0) * max(min(t,b)/max(t,b), 0)).
     F.maximum(x, 0) and F.clip(x, lower=0) are both the elementwise MAX of ASSUMED-1 (NaN -> 0)."""

@@ -294,6 +294,17 @@ def build():
     rr, rl, rt = rcnn_gt(me, T(flat.copy()), T(im_info), T(rgt.copy()))
     assert not mrand._queue, "the reference drew fewer variates than were fed"
     g["rcnn_out_rois"], g["rcnn_out_labels"], g["rcnn_out_targets"] = rr.numpy(), rl.numpy(), rt.numpy()
+
+    # ---- OTATopkMatcher (layers/common/matcher.py:129-161): the reference class itself
+    orng = np.random.default_rng(1500)
+    for tag, (G, A, q) in (("ota_a", (9, 700, 0)), ("ota_b", (17, 3000, 32))):
+        ious = (orng.uniform(0, 1, (G, A)) ** 3).astype(np.float32)
+        cost = orng.uniform(0, 5, (G, A)).astype(np.float32)
+        if q:  # quantised: equal costs / IoUs everywhere, anchors claimed by several GTs
+            ious, cost = (np.floor(ious * q) / q).astype(np.float32), (np.floor(cost * q) / q).astype(np.float32)
+        cost[:, ::7] += 1e6
+        g[tag + "_cost"], g[tag + "_ious"] = cost, ious
+        g[tag + "_match"] = ref.matcher.OTATopkMatcher(10)(T(cost.copy()), T(ious.copy())).numpy()
     return g
 
 

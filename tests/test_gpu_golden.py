@@ -209,3 +209,12 @@ def test_rcnn_get_ground_truth_golden(cuda):
     assert np.max(np.abs(cat(targets) - GOLD["rcnn_out_targets"])) <= 1e-5   # logf / divide by std 0.1, 0.2
     for b in range(len(count)):
         assert float(rois[b, count[b]:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("tag", ["ota_a", "ota_b"])
+def test_ota_topk_matcher_golden(cuda, tag):
+    """layers.OTATopkMatcher (matcher.py:129-161) vs the vectors produced by the reference class."""
+    from basedet_b200.layers import OTATopkMatcher
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(cuda)  # noqa: E731
+    out = OTATopkMatcher(10)(Tc(GOLD[tag + "_cost"]), Tc(GOLD[tag + "_ious"]))
+    assert out.dtype == torch.int32 and np.array_equal(out.cpu().numpy(), GOLD[tag + "_match"])

@@ -400,3 +400,25 @@ def test_new_target_entry_points_degenerate_inputs(cuda):
     assert cnt[1] == len(ref[1]) == 2
     assert np.array_equal(orois[1, :2].cpu().numpy()[:, 1:], ref[0][:, 1:]) and np.array_equal(olab[1, :2].cpu().numpy(), ref[1])
     assert np.allclose(otgt[1, :2].cpu().numpy(), ref[2], atol=1e-6)
+
+
+@pytest.mark.parametrize("G,A,q,kc", [(1, 40, 0, 10), (12, 9, 0, 10), (50, 22400, 0, 10), (50, 22400, 16, 10), (100, 8400, 0, 16),
+                                      (30, 5000, 0, 1), (8, 3000, -1, 10)])
+def test_ota_topk_match_vs_oracle(cuda, G, A, q, kc):
+    """Dynamic-k matching (matcher.py:134-161) at OTA / YOLOX sizes: ties from quantised inputs, anchors claimed by
+    several GTs, rows shorter than candidate_k, and (q = -1) a cost row whose small values all sit in one thread's
+    strided slice (the > 256-keys-inside-the-bound path)."""
+    rng = np.random.default_rng(G * A + kc)
+    ious = (rng.uniform(0, 1, (G, A)) ** 3).astype(np.float32)
+    cost = rng.uniform(0, 5, (G, A)).astype(np.float32)
+    if q > 0:
+        ious, cost = (np.floor(ious * q) / q).astype(np.float32), (np.floor(cost * q) / q).astype(np.float32)
+    if q < 0:
+        cost[:, 5::256] = rng.uniform(-9, -8, cost[:, 5::256].shape).astype(np.float32)   # slice of thread 5 only... 
+        cost[:, 261::256] -= 3.0
+        ious[:, 7::256] = 0.99
+    cost[:, ::7] += 1e6
+    got = ops.ota_topk_match(torch.from_numpy(cost).to(cuda), torch.from_numpy(ious).to(cuda), kc).cpu().numpy()
+    ref = R.ota_topk_match(cost, ious, kc)
+    assert np.array_equal(got, ref)
+    assert (ref < G).sum() >= 1

@@ -146,6 +146,13 @@ def test_rcnn_get_ground_truth():
     assert (GOLD["rcnn_out_labels"] > 0).sum() >= 8 and N == rois.shape[1] + GOLD["rcnn_gt"].shape[1]
 
 
+@pytest.mark.parametrize("tag", ["ota_a", "ota_b"])
+def test_ota_topk_matcher(tag):
+    """OTATopkMatcher (matcher.py:129-161) run from the reference file == oracle restatement."""
+    same(R.ota_topk_match(GOLD[tag + "_cost"], GOLD[tag + "_ious"], 10), GOLD[tag + "_match"])
+    assert (GOLD[tag + "_match"] < GOLD[tag + "_cost"].shape[0]).sum() > 20
+
+
 def test_nms_and_post_processing():
     b, s, l = GOLD["nms_boxes"], GOLD["nms_scores"], GOLD["nms_labels"]
     same(R.batched_nms(b, s, l, 0.5), GOLD["nms_keep_05"])
