@@ -47,7 +47,7 @@ KERNELS = ["anchors_grid_kernel", "pairwise_kernel", "match_colmax_kernel", "mat
            "nms_maxcoord_kernel", "nms_fused_kernel", "nms_chunk_kernel", "nms_sweep_kernel", "finalize_kernel", "roi_assign_levels_kernel",
            "roi_align_fwd_kernel", "roi_align_bwd_kernel", "roi_align_bwd_gather_kernel", "roi_bin_kernel", "roi_bin_scan_kernel",
            "fcos_targets_kernel", "atss_candidates_kernel", "atss_finish_kernel", "count_labels_kernel", "sample_labels_kernel",
-           "rcnn_match_kernel", "rcnn_collect_kernel"]
+           "rcnn_match_kernel", "rcnn_collect_kernel", "ota_rows_kernel", "ota_resolve_kernel"]
 rng = np.random.default_rng(0)
 
 # ---- config 2: target assignment, batch 16
@@ -104,6 +104,11 @@ run("c4_fcos_targets_b64", lambda: ops.fcos_targets(pts, gt4_d, ng4_d, W.RETINAN
     {"fcos_targets_kernel": dense_bytes})
 run("c4_atss_targets_b64", lambda: ops.atss_targets(pts, gt4_d, ng4_d, W.RETINANET_STRIDES, 8, 9, plan=dplan),
     {"atss_finish_kernel": dense_bytes + B4 * A4 * 8})
+
+# OTA dynamic-k matching: one image, 100 GT x 22 400 points, cost / IoU matrices given
+cost4 = torch.rand((100, A4), device=dev, generator=g) * 5
+iou4 = torch.rand((100, A4), device=dev, generator=g) ** 3
+run("c4_ota_match_1img", lambda: ops.ota_topk_match(cost4, iou4, 10), {"ota_rows_kernel": 3 * 100 * A4 * 4 + 100 * A4 * 4})
 
 # ---- config 3: RPN proposals + ROIAlign fwd/bwd, batch 16 @ 800x1344
 B3 = 16
