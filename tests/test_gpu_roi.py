@@ -132,3 +132,17 @@ def test_roi_align_backward_large_footprint_fallback(cuda):
     for gather in (False, True):
         got = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [1.0], (7, 7), gather=gather)[0].cpu().numpy()
         assert np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
+
+
+@pytest.mark.parametrize("pool,samples", [((3, 5), (1, 3)), ((4, 4), (2, 2)), ((14, 14), (2, 2)), ((7, 7), (3, 3))])
+def test_roi_align_backward_scatter_generic_shapes(cuda, pool, samples):
+    """The scatter kernel's generic path (anything but 7 x 7 bins takes the table loops, padded table rows) and 7 x 7 bins
+    with another sample count (separable register path) against the oracle."""
+    rng = np.random.default_rng(pool[0] * 10 + samples[1])
+    C, feat_shape = 5, (2, 5, 40, 56)
+    rois = W.make_rois(rng, 17, 2, 160, 224, 6, 200)
+    rois[0, 1:] = [-20, -10, 60, 50]
+    dout = rng.normal(0, 1, (rois.shape[0], C, pool[0], pool[1])).astype(np.float32)
+    got = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], pool, samples, gather=False)[0].cpu().numpy()
+    ref = R.roi_align_backward(dout, feat_shape, rois, pool, 0.25, samples)
+    assert np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
