@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(1024) nms_sort_small_kernel(const NmsArgs p) {
       bad = __syncthreads_or(bad);
     }
     if (!bad) {
-      for (int i = t; i < n; i += 1024) {
+      // gridDim.y CTAs share an image: each holds all keys (cheap to rebuild) and ranks / gathers its slice of the
+      // elements, so the binary searches of one image run on several SMs instead of one
+      for (int i = blockIdx.y * 1024 + t; i < n; i += 1024 * gridDim.y) {
         const uint64_t key = keys[i];
         int rank = 0;
         for (int q = 0; q < p.n_runs; ++q) {
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(1024) nms_sort_small_kernel(const NmsArgs p) {
     }
     __syncthreads();
   }
+  if (blockIdx.y != 0) return;  // the sorting network is a one-CTA job (every slice CTA reached the same verdict)
   int P = 2;
   while (P < n) P <<= 1;
   for (int i = t; i < P; i += 1024) keys[i] = i < n ? make_key(__ldg(p.scores + base + i), (uint32_t)i) : ~0ull;
@@ -579,7 +582,8 @@ extern "C" int bdet_nms_runs(const float* boxes, const float* scores, const void
     size_t smem = (size_t)a.P * 8;
     if (smem > 40 * 1024)
       BDET_CUDA(cudaFuncSetAttribute(nms_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BDET_KERNEL("nms_sort_small_kernel", st, nms_sort_small_kernel<<<B, 1024, smem, st>>>(a));
+    const int slices = (a.run_end && Nmax >= 2048) ? 8 : 1;
+    BDET_KERNEL("nms_sort_small_kernel", st, nms_sort_small_kernel<<<dim3(B, slices), 1024, smem, st>>>(a));
   } else {
     if (a.P < kSortTile) a.P = kSortTile;
     BDET_CUDA(cudaMemsetAsync(a.maxc, 0, (size_t)B * 4, st));
