@@ -5,8 +5,8 @@
 //   rcnn_match_kernel   : one thread per row of all_rois: IoU against the image's GT held in shared memory, running
 //                         (max, first argmax), class of the matched GT, fg / bg flags (rcnn.py:108-123); no (R, G) matrix.
 //   bdet_sample_labels  : (topk.cu) the two subsampling steps on the flag arrays, budgets on the device (:125-128).
-//   rcnn_collect_kernel : one CTA per image: ordered compaction of the kept rows, labels[bg] = 0, BoxCoder.encode
-//                         against the matched GT (:130-137).
+//   rcnn_collect_kernel : ordered compaction of the kept rows (every 256-row CTA counts the kept rows before it),
+//                         labels[bg] = 0, BoxCoder.encode against the matched GT (:130-137).
 #include "common.cuh"
 
 namespace bdet {
@@ -98,50 +98,52 @@ __global__ void __launch_bounds__(kRcnnThreads) rcnn_match_kernel(const RcnnArgs
 
 constexpr int kCollectThreads = 256;
 
+// grid (ceil(N / 256), B): a CTA owns 256 consecutive rows of all_rois; the output slot of its first row is the number
+// of kept rows before it, which every CTA counts for itself from the flag arrays (<= a few thousand flags) -- no
+// per-image serial compaction.
 __global__ void __launch_bounds__(kCollectThreads) rcnn_collect_kernel(const RcnnArgs p) {
   __shared__ int warp_cnt[kCollectThreads / 32];
-  __shared__ int sbase;
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ int sred[kCollectThreads / 32];
+  const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = min(p.n_all[b], p.N);
-  const float* gtb = p.gt + (long long)b * p.Gmax * 5;
-  if (t == 0) sbase = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += kCollectThreads) {
-    const int i = i0 + t;
-    const long long o = (long long)b * p.N + i;
-    int fg = 0, bg = 0;
-    if (i < n) {
-      fg = p.fg[o];
-      bg = p.bg[o];
-    }
-    const bool keep = (fg | bg) != 0;                             // :132
-    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kCollectThreads / 32; ++w) {
-      const int cnt = warp_cnt[w];
-      if (w < warp) before += cnt;
-      total += cnt;
-    }
-    const int base = sbase;
-    const int pos = base + before + __popc(bal & ((1u << lane) - 1u));
-    if (keep && pos < p.num_out) {
-      const long long d = (long long)b * p.num_out + pos;
-      const float* r = p.all_rois + o * 5;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) p.out_rois[d * 5 + j] = r[j];    // :134
-      p.out_labels[d] = bg ? 0 : (int)p.cls[o];                    // :130, :133
-      const float* gr = gtb + (long long)p.assign[o] * 5;          // :135
-      const float4 tg = encode_box<false>(make_float4(r[1], r[2], r[3], r[4]),
-                                          make_float4(__ldg(gr), __ldg(gr + 1), __ldg(gr + 2), __ldg(gr + 3)), p.mean, p.stdv);
-      reinterpret_cast<float4*>(p.out_targets)[d] = tg;            // :136-137
-    }
-    __syncthreads();
-    if (t == 0) sbase = base + total;
-    __syncthreads();
+  const int i0 = blockIdx.x * kCollectThreads;
+  const long long rowb = (long long)b * p.N;
+  // kept rows before this CTA's first row (and, in the last CTA of the image, the image's total)
+  int before = 0;
+  for (int i = t; i < min(i0, n); i += kCollectThreads) before += (p.fg[rowb + i] | p.bg[rowb + i]) != 0;
+  before = __reduce_add_sync(0xffffffffu, before);
+  if (lane == 0) sred[warp] = before;
+  const int i = i0 + t;
+  const long long o = rowb + i;
+  int fg = 0, bg = 0;
+  if (i < n) {
+    fg = p.fg[o];
+    bg = p.bg[o];
   }
-  if (t == 0) p.out_count[b] = min(sbase, p.num_out);
+  const bool keep = (fg | bg) != 0;                             // rcnn.py:132
+  const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, inblock = 0, mine = 0;
+  for (int w = 0; w < kCollectThreads / 32; ++w) {
+    base += sred[w];
+    if (w < warp) mine += warp_cnt[w];
+    inblock += warp_cnt[w];
+  }
+  if (t == 0 && i0 < n && i0 + kCollectThreads >= n) p.out_count[b] = min(base + inblock, p.num_out);
+  if (t == 0 && n == 0 && blockIdx.x == 0) p.out_count[b] = 0;
+  const int pos = base + mine + __popc(bal & ((1u << lane) - 1u));
+  if (!keep || pos >= p.num_out) return;
+  const float* gtb = p.gt + (long long)b * p.Gmax * 5;
+  const long long d = (long long)b * p.num_out + pos;
+  const float* r = p.all_rois + o * 5;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) p.out_rois[d * 5 + j] = r[j];      // :134
+  p.out_labels[d] = bg ? 0 : (int)p.cls[o];                      // :130, :133
+  const float* gr = gtb + (long long)p.assign[o] * 5;            // :135
+  const float4 tg = encode_box<false>(make_float4(r[1], r[2], r[3], r[4]),
+                                      make_float4(__ldg(gr), __ldg(gr + 1), __ldg(gr + 2), __ldg(gr + 3)), p.mean, p.stdv);
+  reinterpret_cast<float4*>(p.out_targets)[d] = tg;              // :136-137
 }
 
 }  // namespace bdet
@@ -226,7 +228,8 @@ extern "C" int bdet_rcnn_collect(const float* all_rois, const int* n_all, const 
   BDET_CUDA(cudaMemsetAsync(out_rois, 0, (size_t)B * num_out * 5 * 4, st));
   BDET_CUDA(cudaMemsetAsync(out_labels, 0, (size_t)B * num_out * 4, st));
   BDET_CUDA(cudaMemsetAsync(out_targets, 0, (size_t)B * num_out * 16, st));
-  BDET_KERNEL("rcnn_collect_kernel", st, rcnn_collect_kernel<<<B, kCollectThreads, 0, st>>>(a));
+  BDET_REQUIRE(B <= 65535, "B > 65535");
+  BDET_KERNEL("rcnn_collect_kernel", st, rcnn_collect_kernel<<<dim3(ceil_div(N, kCollectThreads), B), kCollectThreads, 0, st>>>(a));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
