@@ -68,7 +68,21 @@ def _stream(t=None):
     return _VP(torch.cuda.current_stream(dev).cuda_stream)
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
 def _guard(t):
+    """Make t's device current for the call; a no-op (no cudaSetDevice round trip) when it already is."""
+    if t.device.index == torch.cuda.current_device():
+        return _NO_GUARD
     return torch.cuda.device(t.device)
 
 
