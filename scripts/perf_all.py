@@ -5,7 +5,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from basedet_b200 import ops, pipelines, _lib, workloads as W
 from basedet_b200.layers import DefaultAnchorGenerator
-from oracle import ref_ops as R
 
 NCU = "--ncu" in sys.argv
 ONLY = [a for a in sys.argv[1:] if not a.startswith("--")]
@@ -28,7 +27,7 @@ def run(name, fn, bytes_by_kernel=None, iters=10):
         s.record(); fn(); e.record(); torch.cuda.synchronize(); tot.append(s.elapsed_time(e))
     out = {"total_ms_median": float(np.median(tot)), "kernels": {}}
     names = set()
-    import ctypes
+
     for k in KERNELS:
         ms, n = ops.profile_collect(k)
         if n:

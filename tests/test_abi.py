@@ -58,7 +58,6 @@ def test_signatures_are_plain_c():
 
 def test_host_argument_errors_without_gpu():
     """Argument validation mirrors the reference's Python asserts and happens before any launch."""
-    import ctypes
 
     from basedet_b200 import _lib
 

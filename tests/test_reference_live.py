@@ -1,6 +1,5 @@
 """CPU, build container only: the committed golden vectors are what the reference's own source produces NOW, and the
 oracle agrees with the live reference code on additional seeds.  Skipped where /root/reference is absent (GPU box)."""
-import os
 
 import numpy as np
 import pytest
