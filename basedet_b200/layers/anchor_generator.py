@@ -62,14 +62,14 @@ class DefaultAnchorGenerator(BaseAnchorGenerator):
                 for s, r in zip(scales, ratios)]
 
     def generate_base_anchors(self, scales, ratios):
-        base_anchors = []
-        areas = [s ** 2.0 for s in scales]
-        for area in areas:
-            for ratio in ratios:
-                w = math.sqrt(area / ratio)
-                h = ratio * w
-                base_anchors.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
-        return base_anchors
+        """Cell anchors centred on the origin, scales outer / ratios inner, in float64 like the reference
+        (anchor_generator.py:99-109): width = sqrt(scale^2 / ratio), height = ratio * width."""
+        def centred(scale, ratio):
+            width = math.sqrt(scale ** 2.0 / ratio)
+            height = ratio * width
+            return [-width / 2.0, -height / 2.0, width / 2.0, height / 2.0]
+
+        return [centred(scale, ratio) for scale in scales for ratio in ratios]
 
     def _plan(self, sizes):
         key = tuple(tuple(int(v) for v in s) for s in sizes)

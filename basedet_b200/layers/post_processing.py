@@ -53,24 +53,22 @@ def post_processing(boxes_container, img_info, iou_threshold, process_method="nm
 
 
 def py_cpu_nms(dets: np.ndarray, thresh: float):
-    """The reference's own numpy helper (post_processing.py:106-132), kept verbatim in behaviour.  Host utility,
-    not used by any path of this package."""
-    x1 = np.ascontiguousarray(dets[:, 0])
-    y1 = np.ascontiguousarray(dets[:, 1])
-    x2 = np.ascontiguousarray(dets[:, 2])
-    y2 = np.ascontiguousarray(dets[:, 3])
-    areas = (x2 - x1) * (y2 - y1)
-    order = dets[:, 4].argsort()[::-1]
-    keep = list()
-    while order.size > 0:
-        pick_idx = order[0]
-        keep.append(pick_idx)
-        order = order[1:]
-        xx1 = np.maximum(x1[pick_idx], x1[order])
-        yy1 = np.maximum(y1[pick_idx], y1[order])
-        xx2 = np.minimum(x2[pick_idx], x2[order])
-        yy2 = np.minimum(y2[pick_idx], y2[order])
-        inter = np.maximum(xx2 - xx1, 0) * np.maximum(yy2 - yy1, 0)
-        iou = inter / np.maximum(areas[pick_idx] + areas[order] - inter, 1e-5)
-        order = order[iou <= thresh]
+    """Host-side greedy NMS on ``dets`` rows [x1, y1, x2, y2, score] (the reference ships the same utility,
+    post_processing.py:106-132): highest score first, a box is dropped when its IoU with a kept box exceeds ``thresh``
+    (union clamped at 1e-5).  Returns the kept row indices in score order.  Not used by any GPU path of this package."""
+    dets = np.asarray(dets)
+    corners, scores = dets[:, :4], dets[:, 4]
+    area = (corners[:, 2] - corners[:, 0]) * (corners[:, 3] - corners[:, 1])
+    order = scores.argsort()[::-1]
+    alive = np.ones(order.shape[0], dtype=bool)
+    keep = []
+    for pos, i in enumerate(order):
+        if not alive[pos]:
+            continue
+        keep.append(i)
+        rest = order[pos + 1:]
+        wh = np.maximum(np.minimum(corners[i, 2:], corners[rest, 2:]) - np.maximum(corners[i, :2], corners[rest, :2]), 0)
+        inter = wh[:, 0] * wh[:, 1]
+        iou = inter / np.maximum(area[i] + area[rest] - inter, 1e-5)
+        alive[pos + 1:] &= iou <= thresh
     return keep

@@ -2,27 +2,25 @@
 
 
 class Container(dict):
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
-        self.__dict__.update(kwargs)
+    """Fields are reachable as attributes and as keys; ``c[idx]`` with a non-string index slices every field."""
 
-    def __setattr__(self, key, value):
-        super().__setattr__(key, value)
-        dict.__setitem__(self, key, value)
+    def __init__(self, **fields):
+        super().__init__()
+        for name, value in fields.items():
+            self[name] = value
 
-    def __setitem__(self, key, value):
-        dict.__setitem__(self, key, value)
-        super().__setattr__(key, value)
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def __setitem__(self, name, value):
+        dict.__setitem__(self, name, value)
+        object.__setattr__(self, name, value)
 
     def __getitem__(self, idx):
         if isinstance(idx, str):
             return dict.__getitem__(self, idx)
-        values = {}
-        for k, v in vars(self).items():
-            values[k] = v[idx]
-        return Container(**values)
+        return type(self)(**{name: value[idx] for name, value in self.items()})
 
     def __str__(self):
-        s = self.__class__.__name__ + "("
-        s += "data=[{}])".format(", ".join((f"{k}: {v}" for k, v in vars(self).items())))
-        return s
+        body = ", ".join("{}: {}".format(name, value) for name, value in self.items())
+        return "{}(data=[{}])".format(type(self).__name__, body)
