@@ -286,7 +286,7 @@ def run_b200(args):
             except Exception:
                 pass
         out["cpu_baseline"] = cpu_baseline(gt_np, ng_np, sizes)
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -345,7 +345,7 @@ def run_reference(args):
     A = sum(h * w * 9 for h, w in sizes)
     sample = ("1 image per step; C restatement (oracle/c/oracle.c) of the reference's MegEngine op sequence on %d "
               "pthreads; the reference is pure Python over MegEngine, not installable offline" % arm.cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -357,7 +357,21 @@ def run_reference(args):
     }))
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; see main()."""
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
+
+
 def main():
+    # Libraries (NCCL prints its version banner, torch warnings ...) write to fd 1 at will; the contract is one JSON
+    # line on stdout, so everything else is routed to stderr and the result is written to the saved descriptor.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
