@@ -132,50 +132,76 @@ def atss_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128), an
     return lab, off, ctr
 
 
+class _AssignSlot:
+    """One set of static input / output buffers of TargetAssigner with its captured graph."""
+
+    def __init__(self, owner, batch, max_gt):
+        dev = owner.device
+        self.gt = torch.zeros((batch, max_gt, 5), dtype=torch.float32, device=dev)
+        self.num_gt = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self.counts = torch.zeros((batch, 3), dtype=torch.int32, device=dev)
+        self.plan = ops.AssignPlan(owner.num_anchors, max_gt, batch, dev)
+        self.loaded = torch.cuda.Event()   # inputs of this slot are on the device
+        self.done = torch.cuda.Event()     # the step that used this slot has finished
+        self.graph = None
+
+    def step(self, owner):
+        thr, lab, lq, cls, mean, std = owner.cfg
+        anchors = owner.gen.generate_all_level_anchors(owner.sizes, owner.device)
+        ops.assign_targets(anchors, self.gt, self.num_gt, thr, lab, lq, cls, mean, std, plan=self.plan)
+        ops.count_labels(self.plan.labels, out=self.counts)
+
+
 class TargetAssigner:
     """The whole `get_ground_truth` step of a dense head (anchors -> IoU -> Matcher -> labels -> BoxCoder.encode ->
     label census) for a FIXED batch shape, captured once into a CUDA graph and replayed every iteration.
 
     models/det/retinanet.py:116 (anchors regenerated per forward), :211-232 (targets), :142-146 (num_fg).  The step
     is three short kernels plus the census; replaying them as one graph removes the per-launch host work that bounds
-    the eager path when the inputs arrive from the host every iteration.  Inputs are copied into static device
-    buffers (host tensors should be pinned), outputs are the same tensors every call:
-      labels (B, A) int32, match_idx (B, A) int32, offsets (B, A, 4) fp32, counts (B, 3) int32 (<0, ==0, >0)."""
+    the eager path when the inputs arrive from the host every iteration.  There are ``depth`` (default 2) sets of
+    static buffers used in turn: the host-to-device copies of step i+1 run on a copy stream while step i computes,
+    so a loop fed from (pinned) host memory runs at the speed of the kernels.  Returns
+      labels (B, A) int32, match_idx (B, A) int32, offsets (B, A, 4) fp32, counts (B, 3) int32 (<0, ==0, >0),
+    valid until the ``depth``-th following call reuses their slot."""
 
     def __init__(self, anchor_generator, feature_sizes, batch, max_gt, thresholds=(0.4, 0.5), labels=(0, -1, 1),
-                 allow_low_quality=True, apply_class=True, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1), device=None):
+                 allow_low_quality=True, apply_class=True, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1), device=None,
+                 depth=2):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.gen, self.sizes = anchor_generator, [tuple(s) for s in feature_sizes]
         self.cfg = (list(thresholds), list(labels), bool(allow_low_quality), bool(apply_class), tuple(reg_mean), tuple(reg_std))
-        self.gt = torch.zeros((batch, max_gt, 5), dtype=torch.float32, device=self.device)
-        self.num_gt = torch.zeros((batch,), dtype=torch.int32, device=self.device)
-        self.counts = torch.zeros((batch, 3), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            anchors = self.gen.generate_all_level_anchors(self.sizes, self.device)
-            self.plan = ops.AssignPlan(anchors.shape[0], max_gt, batch, self.device)
+            self.num_anchors = self.gen.generate_all_level_anchors(self.sizes, self.device).shape[0]
+            self.slots = [_AssignSlot(self, batch, max_gt) for _ in range(max(1, int(depth)))]
+            self.copy_stream = torch.cuda.Stream(self.device)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up outside the capture (lazy module loading, allocator)
-                    self._step()
+                    self.slots[0].step(self)
             torch.cuda.current_stream(self.device).wait_stream(side)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._step()
+            for slot in self.slots:
+                slot.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(slot.graph):
+                    slot.step(self)
+                slot.done.record()
+        self.turn = 0
         self.kernels_per_replay = 4  # anchors_grid, assign_main, assign_lq, count_labels
-
-    def _step(self):
-        thr, lab, lq, cls, mean, std = self.cfg
-        self.anchors = self.gen.generate_all_level_anchors(self.sizes, self.device)
-        ops.assign_targets(self.anchors, self.gt, self.num_gt, thr, lab, lq, cls, mean, std, plan=self.plan)
-        ops.count_labels(self.plan.labels, out=self.counts)
 
     def __call__(self, gt_boxes, num_gt):
         """gt_boxes (B, max_gt, 5) fp32 and num_gt (B,) int32, host (pinned) or device."""
-        self.gt.copy_(gt_boxes, non_blocking=True)
-        self.num_gt.copy_(num_gt, non_blocking=True)
-        self.graph.replay()
-        return self.plan.labels, self.plan.idx, self.plan.offsets, self.counts
+        slot = self.slots[self.turn]
+        self.turn = (self.turn + 1) % len(self.slots)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.done)  # the step that last read these input buffers is over
+            slot.gt.copy_(gt_boxes, non_blocking=True)
+            slot.num_gt.copy_(num_gt, non_blocking=True)
+            slot.loaded.record()
+        main.wait_event(slot.loaded)
+        slot.graph.replay()
+        slot.done.record(main)
+        return slot.plan.labels, slot.plan.idx, slot.plan.offsets, slot.counts
 
 
 class GraphedPipeline:
