@@ -263,7 +263,8 @@ def run_b200(args):
                     "note": "pinned host gt -> H2D -> step -> per-image label census (num_fg normaliser) -> D2H; "
                             "wall clock between device syncs; labels/offsets stay on the GPU as in the reference's loss; "
                             + ("the step is pipelines.TargetAssigner: the same 3 kernels + census replayed as one CUDA graph "
-                               "(%d kernel nodes per step), no L2 flush between steps" % e2e_launches if e2e_launches else
+                               "(%d kernel nodes per step), two buffer sets so that the copies of step i+1 overlap step i, "
+                               "no L2 flush between steps" % e2e_launches if e2e_launches else
                                "eager launches"),
                     "num_fg_last_step": num_fg},
             "gpu_launches": int(launches),
