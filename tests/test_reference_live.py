@@ -54,3 +54,44 @@ def test_reference_py_cpu_nms_agrees_with_oracle_nms():
     scores = W.distinct_scores(rng, n)
     keep = ref.post_processing.py_cpu_nms(np.concatenate([boxes, scores[:, None]], 1), 0.5)
     assert [int(k) for k in keep] == R.nms(boxes, scores, 0.5).tolist()
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_dense_head_targets_oracle_matches_live_reference_methods(seed):
+    """FCOS / ATSS get_ground_truth and OTATopkMatcher, run from the reference files on fresh seeds (beyond the committed
+    golden vectors), against the oracle restatements."""
+    import types
+
+    ref = ref_runner.load()
+    T = ref.Tensor
+    strides = [8, 16, 32, 64, 128]
+    soi = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, float("inf")]]
+    hw = (128 + 32 * (seed % 3), 192)
+    sizes = W.retinanet_level_sizes(*hw)
+    pts = R.anchor_points(sizes, 1, strides, 0.5)
+    gt, ng = W.target_assign_batch(2, 10, hw[0], hw[1], seed0=seed * 10, ragged=True)
+    fcos = ref_runner.load_method("models/det/fcos.py", "FCOS", "get_ground_truth")
+    atss = ref_runner.load_method("models/det/atss.py", "ATSS", "get_ground_truth")
+    head = types.SimpleNamespace(strides=strides)
+    for radius in (1.5, 0):
+        me = types.SimpleNamespace(cfg=_Cfg(MODEL=_Cfg(HEAD=_Cfg(CENTER_SAMPLING_RADIUS=radius, OBJECT_SIZES_OF_INTEREST=soi))),
+                                   head=head, box_coder=ref.boxcoder.PointCoder())
+        out = [o.numpy() for o in fcos(me, [T(p) for p in pts], T(gt), [int(n) for n in ng])]
+        mine = R.fcos_targets(pts, gt, ng, strides, soi, radius)
+        for a, b in zip(out, mine[:3]):
+            assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    me = types.SimpleNamespace(cfg=_Cfg(MODEL=_Cfg(ANCHOR=_Cfg(SCALE=8, TOPK=9))), head=head, box_coder=ref.boxcoder.PointCoder())
+    out = [o.numpy() for o in atss(me, [T(p) for p in pts], T(gt), [int(n) for n in ng])]
+    mine = R.atss_targets(pts, gt, ng, strides, 8, 9)
+    for a, b in zip(out, mine[:3]):
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    rng = np.random.default_rng(seed)
+    G, A = 6 + seed % 5, 900
+    ious = (rng.uniform(0, 1, (G, A)) ** 3).astype(np.float32)
+    cost = (np.floor(rng.uniform(0, 5, (G, A)) * 64) / 64).astype(np.float32)
+    got = ref.matcher.OTATopkMatcher(10)(T(cost.copy()), T(ious.copy())).numpy()
+    assert np.array_equal(got, R.ota_topk_match(cost, ious, 10))
