@@ -4,7 +4,8 @@
 //            basedet/models/det/atss.py:17-86   (ATSS.get_ground_truth: per-level top-k nearest points, mean+std IoU
 //            threshold, in-box test, argmax IoU, PointCoder.encode, centerness).
 // The reference builds (G, A, 4) offsets, (G, A) masks / areas / IoUs per image and reduces over G; here one thread owns
-// one point (FCOS) or one CTA owns one GT (ATSS candidate search) and the reductions run in registers / shared memory.
+// one point (FCOS) or one CTA owns a group of four GTs (ATSS candidate search) and the reductions run in registers /
+// shared memory.
 // Arithmetic follows the reference op order (one fp32 rounding per op, -fmad=false), elementwise max/min are MegDNN's
 // x>y?x:y / x<y?x:y (oracle ASSUMED-1), argmin / argmax keep the FIRST index (ASSUMED-2/9), the ATSS threshold sums its
 // candidates sequentially in index order (ASSUMED-8).
