@@ -82,6 +82,9 @@ SIGNATURES = {
                                         fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_ota_topk_match_workspace": (c_size_t, [c_int]),
     "bdet_ota_topk_match": (c_int, [vp, c_int, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
+    "bdet_select_decode_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "bdet_select_decode_ws": (c_int, [POINTER(vp), POINTER(vp), ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,
+                                      fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),

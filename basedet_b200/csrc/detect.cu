@@ -29,6 +29,8 @@ struct SelectArgs {
   void* labels;   // (B, L*k) int32 (label_mode 0) or fp32 level ids (label_mode 1)
   int* count;     // (B)
   int* run_end;   // (B, L) optional
+  uint32_t* flagw;  // workspace: (B, L, nblk, 8) keep ballots of the 256-candidate blocks (filter path)
+  int* blkcnt;      // workspace: (B, L, nblk) kept candidates per block
 };
 
 __device__ __forceinline__ float4 decode_one(const SelectArgs& p, int l, int b, int a) {
@@ -146,6 +148,91 @@ __global__ void __launch_bounds__(256) select_decode_flat_kernel(const SelectArg
     reinterpret_cast<float*>(p.labels)[o] = (float)l;    // rpn.py:160
 }
 
+// Size filter with a workspace: two fully parallel launches over (256 candidates, level, image) blocks instead of one
+// serial CTA per image.  Pass 1 decodes, tests and stores the keep ballots and block counts; pass 2 sums the counts of
+// the blocks in front (<= L * nblk values), decodes again (cheaper than parking 16 B per candidate) and writes.
+__device__ __forceinline__ bool rpn_keep(const SelectArgs& p, int b, int l, int j, int cnt, float4& bx, int& idx) {
+  bool keep = j < cnt;
+  bx = make_float4(0.f, 0.f, 0.f, 0.f);
+  idx = 0;
+  if (keep) {
+    idx = __ldg(p.topk_idx + (long long)(b * p.L + l) * p.k + j);
+    bx = decode_one(p, l, b, idx / p.div);
+    const float ih = __ldg(p.im_info + (long long)b * p.info_ld), iw = __ldg(p.im_info + (long long)b * p.info_ld + 1);
+    const float x1 = fminf(fmaxf(bx.x, 0.f), iw), y1 = fminf(fmaxf(bx.y, 0.f), ih);  // rpn.py:168-169, see above
+    const float x2 = fminf(fmaxf(bx.z, 0.f), iw), y2 = fminf(fmaxf(bx.w, 0.f), ih);
+    keep = (y2 - y1 > 0.f) && (x2 - x1 > 0.f);
+  }
+  return keep;
+}
+
+__global__ void __launch_bounds__(256) select_flags_kernel(const SelectArgs p) {
+  __shared__ int wc[8];
+  const int b = blockIdx.z, l = blockIdx.y, blk = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nblk = gridDim.x;
+  const int cnt = min(p.topk_cnt[b * p.L + l], p.k);
+  float4 bx;
+  int idx;
+  const uint32_t bal = __ballot_sync(0xffffffffu, rpn_keep(p, b, l, blk * 256 + t, cnt, bx, idx));
+  const long long e = ((long long)b * p.L + l) * nblk + blk;
+  if (lane == 0) {
+    p.flagw[e * 8 + warp] = bal;
+    wc[warp] = __popc(bal);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += wc[w];
+    p.blkcnt[e] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) select_write_kernel(const SelectArgs p) {
+  __shared__ int sred[8];
+  const int b = blockIdx.z, l = blockIdx.y, blk = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nblk = gridDim.x;
+  const int mine = l * nblk + blk, total = p.L * nblk;
+  const int* bc = p.blkcnt + (long long)b * total;
+  int before = 0, all = 0;
+  for (int i = t; i < total; i += 256) {
+    const int c = bc[i];
+    if (i < mine) before += c;
+    all += c;
+  }
+  before = __reduce_add_sync(0xffffffffu, before);
+  all = __reduce_add_sync(0xffffffffu, all);
+  if (lane == 0) sred[warp] = before;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < 8; ++w) base += sred[w];
+  __syncthreads();
+  if (lane == 0) sred[warp] = all;
+  __syncthreads();
+  if (mine == 0 && t == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += sred[w];
+    p.count[b] = s;
+  }
+  if (p.run_end && blk == nblk - 1 && t == 0) p.run_end[b * p.L + l] = base + bc[mine];
+  const uint32_t* fw = p.flagw + ((long long)b * total + mine) * 8;
+  const uint32_t bal = fw[warp];
+  if (!((bal >> lane) & 1u)) return;
+  int pos = base + __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) pos += __popc(fw[w]);
+  const int cnt = min(p.topk_cnt[b * p.L + l], p.k);
+  const int j = blk * 256 + t;
+  float4 bx;
+  int idx;
+  rpn_keep(p, b, l, j, cnt, bx, idx);
+  const long long cap = (long long)p.L * p.k, o = b * cap + pos;
+  reinterpret_cast<float4*>(p.boxes)[o] = bx;
+  p.scores[o] = __ldg(p.topk_val + (long long)(b * p.L + l) * p.k + j);
+  if (p.label_mode == 0)
+    reinterpret_cast<int*>(p.labels)[o] = idx % p.div;   // retinanet.py:194
+  else
+    reinterpret_cast<float*>(p.labels)[o] = (float)l;    // rpn.py:160
+}
+
 struct FinalArgs {
   const float* boxes;   // (B, N, 4)
   const float* scores;  // (B, N)
@@ -210,8 +297,14 @@ extern "C" int bdet_select_decode(const float* const* anchors_host, const float*
                                   const float* topk_val, const int* topk_cnt, const float* mean_host, const float* std_host,
                                   const float* im_info, int info_ld, float* boxes, float* scores, void* labels, int* count,
                                   int* run_end, bdet_stream_t stream) {
-  return bdet_select_decode_nchw(anchors_host, deltas_host, n_l_host, nullptr, L, B, k, div, coder, label_mode, topk_idx, topk_val,
-                                 topk_cnt, mean_host, std_host, im_info, info_ld, boxes, scores, labels, count, run_end, stream);
+  return bdet_select_decode_ws(anchors_host, deltas_host, n_l_host, nullptr, L, B, k, div, coder, label_mode, topk_idx, topk_val,
+                               topk_cnt, mean_host, std_host, im_info, info_ld, boxes, scores, labels, count, run_end, nullptr, 0,
+                               stream);
+}
+
+extern "C" size_t bdet_select_decode_workspace(int L, int B, int k) {
+  if (L <= 0 || B <= 0 || k <= 0) return 16;
+  return (size_t)B * L * ceil_div(k, 256) * (8 + 1) * 4 + 256;
 }
 
 extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
@@ -220,6 +313,17 @@ extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const f
                                        const float* mean_host, const float* std_host, const float* im_info, int info_ld,
                                        float* boxes, float* scores, void* labels, int* count, int* run_end,
                                        bdet_stream_t stream) {
+  return bdet_select_decode_ws(anchors_host, deltas_host, n_l_host, hw_host, L, B, k, div, coder, label_mode, topk_idx, topk_val,
+                               topk_cnt, mean_host, std_host, im_info, info_ld, boxes, scores, labels, count, run_end, nullptr, 0,
+                               stream);
+}
+
+extern "C" int bdet_select_decode_ws(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
+                                     const int* hw_host, int L, int B, int k, int div, int coder, int label_mode,
+                                     const int* topk_idx, const float* topk_val, const int* topk_cnt,
+                                     const float* mean_host, const float* std_host, const float* im_info, int info_ld,
+                                     float* boxes, float* scores, void* labels, int* count, int* run_end, void* workspace,
+                                     size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && B <= 65535 && k >= 0 && div >= 1, "bad sizes");
   BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
   BDET_REQUIRE(label_mode == 0 || label_mode == 1, "label_mode must be 0 (idx % div) or 1 (level id)");
@@ -266,7 +370,19 @@ extern "C" int bdet_select_decode_nchw(const float* const* anchors_host, const f
   a.labels = labels;
   a.count = count;
   a.run_end = run_end;
-  if (a.filter)
+  a.flagw = nullptr;
+  a.blkcnt = nullptr;
+  if (a.filter && workspace) {
+    const size_t need = bdet_select_decode_workspace(L, B, k);
+    if (workspace_bytes < need) return set_error(BDET_EWORKSPACE, "bdet_select_decode_ws: workspace needs %zu bytes", need);
+    BDET_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 3u) == 0, "workspace must be 4-byte aligned");
+    const int nblk = ceil_div(k, 256);
+    a.flagw = reinterpret_cast<uint32_t*>(workspace);
+    a.blkcnt = reinterpret_cast<int*>(a.flagw + (size_t)B * L * nblk * 8);
+    const dim3 grid(nblk, L, B);
+    BDET_KERNEL("select_decode_kernel", st, select_flags_kernel<<<grid, 256, 0, st>>>(a));
+    BDET_KERNEL("select_decode_kernel", st, select_write_kernel<<<grid, 256, 0, st>>>(a));
+  } else if (a.filter)
     BDET_KERNEL("select_decode_kernel", st, select_decode_kernel<<<B, kDetThreads, 0, st>>>(a));
   else
     BDET_KERNEL("select_decode_kernel", st, select_decode_flat_kernel<<<dim3(ceil_div(k, 256), L, B), 256, 0, st>>>(a));

@@ -598,11 +598,13 @@ def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0,
     if nchw:
         assert all(d.ndim == 4 and d.shape[1] * d.shape[2] * d.shape[3] == 4 * a.shape[0] for d, a in zip(dl, anc))
         hw = iarr([d.shape[2] * d.shape[3] for d in dl])
+    ws = _workspace(lib.bdet_select_decode_workspace(L, B, int(k)), dev) if info is not None else None
     with _guard(boxes):
-        check(lib.bdet_select_decode_nchw(ap, dp_, iarr([a.shape[0] for a in anc]), hw, L, B, int(k), int(div), int(coder),
-                                          int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
-                                          info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels),
-                                          _p(count), _p(run_end), _stream(boxes)))
+        check(lib.bdet_select_decode_ws(ap, dp_, iarr([a.shape[0] for a in anc]), hw, L, B, int(k), int(div), int(coder),
+                                        int(label_mode), _p(idx), _p(vals), _p(cnt), farr(mean), farr(std), _p(info),
+                                        info.shape[1] if info is not None else 0, _p(boxes), _p(sc), _p(labels),
+                                        _p(count), _p(run_end), _p(ws), ws.numel() if ws is not None else 0,
+                                        _stream(boxes)))
     if with_runs:
         return boxes, sc, labels, count, run_end
     return boxes, sc, labels, count

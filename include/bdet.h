@@ -255,6 +255,15 @@ int bdet_select_decode_nchw(const float* const* anchors_host, const float* const
                             const int* topk_idx, const float* topk_val, const int* topk_cnt, const float* mean_host,
                             const float* std_host, const float* im_info, int info_ld, float* boxes, float* scores,
                             void* labels, int* count, int* run_end, bdet_stream_t stream);
+/* Same with a scratch buffer: with the size filter (im_info != NULL) the ordered compaction then runs as two fully
+ * parallel launches instead of one CTA per image.  workspace NULL = bdet_select_decode_nchw. */
+size_t bdet_select_decode_workspace(int L, int B, int k);
+int bdet_select_decode_ws(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
+                          const int* hw_host, int L, int B, int k, int div, int coder, int label_mode,
+                          const int* topk_idx, const float* topk_val, const int* topk_cnt, const float* mean_host,
+                          const float* std_host, const float* im_info, int info_ld, float* boxes, float* scores,
+                          void* labels, int* count, int* run_end, void* workspace, size_t workspace_bytes,
+                          bdet_stream_t stream);
 /* mode 0: post_processing.py:96-101 -- out (B, max_out, 6) = [box scaled by (orig/resized) and clipped to the original
  *         image, score, label] for the kept indices (im_info (B, >=4) [h, w, orig_h, orig_w]; NULL = no scale/clip);
  * mode 1: rpn.py:179-183 -- out (B, max_out, 5) = [batch index, x1, y1, x2, y2].  Rows >= keep_count[b] are zero. */
