@@ -278,8 +278,14 @@ def run_b200(args):
         }
         if args.path == "fused":
             out["roofline"]["note"] = ("assign_main_kernel never materialises the (G, A) matrix: it is issue-bound on fp32 pair "
-                                       "tests (ncu: ~84 % issue-active, profiles/), so its HBM fraction is low by construction; "
+                                       "tests (ncu: ~76-84 % issue-active, profiles/), so its HBM fraction is low by construction; "
                                        "the HBM-bound kernels of the drop-in path are listed in roofline_memory_bound_kernels")
+            # the fused path is rated in pair evaluations per second, not in HBM %
+            pairs = float(IMAGES_PER_GPU) * G * A
+            out["roofline"]["pair_evaluations_per_s"] = pairs / (dom_ms / max(dom_n, 1) * 1e-3) if dom_ms else None
+            out["roofline"]["materialised_equivalent_GBps"] = (
+                algorithmic_bytes(A, B, G, "materialised") + B * (4 * G * A + 8 * A)) / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 \
+                if dom_ms else None
         traffic = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic):
             try:
