@@ -89,3 +89,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_segment_descriptors_from_views_of_one_allocation():
+    """ops._segments (host logic of the batched top-k / filter calls): (image, level) segments that live in several
+    tensors are described as element offsets from the lowest base pointer, image-major."""
+    import torch
+
+    from basedet_b200 import ops
+
+    store = torch.zeros(2 * (6 + 10), dtype=torch.float32)
+    lvl0 = store[:12].view(2, 6)           # level 0: 2 images x 6
+    lvl1 = store[12:].view(2, 10)          # level 1: 2 images x 10
+    base, starts, lens = ops._segments([lvl1, lvl0])   # order of the list = level order, not address order
+    assert base.data_ptr() == store.data_ptr()
+    assert lens == [10, 6, 10, 6]
+    assert starts == [12, 0, 22, 6]
