@@ -88,6 +88,7 @@ SIGNATURES = {
     "bdet_profile_begin": (c_int, []),
     "bdet_profile_select": (c_int, [c_char_p]),
     "bdet_profile_collect": (c_int, [c_char_p, fp, ip]),
+    "bdet_profile_report": (c_int, [c_char_p, c_size_t]),
     "bdet_profile_end": (c_int, []),
 }
 

@@ -132,6 +132,29 @@ int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_h
   return BDET_OK;
 }
 
+int bdet_profile_report(char* buf_host, size_t buf_bytes) {
+  if (!buf_host || buf_bytes < 2) return bdet::set_error(BDET_EINVAL, "bdet_profile_report: buffer too small");
+  buf_host[0] = 0;
+  if (!bdet::g_prof) return BDET_OK;
+  std::vector<const char*> names;
+  for (auto& p : *bdet::g_prof) {
+    bool seen = false;
+    for (auto n : names) seen = seen || strcmp(n, p.name) == 0;
+    if (!seen) names.push_back(p.name);
+  }
+  size_t used = 0;
+  for (auto n : names) {
+    float ms = 0.f;
+    int cnt = 0;
+    int rc = bdet_profile_collect(n, &ms, &cnt);
+    if (rc) return rc;
+    int w = snprintf(buf_host + used, buf_bytes - used, "%s %.6f %d\n", n, ms, cnt);
+    if (w < 0 || (size_t)w >= buf_bytes - used) return bdet::set_error(BDET_EINVAL, "bdet_profile_report: buffer too small");
+    used += (size_t)w;
+  }
+  return BDET_OK;
+}
+
 int bdet_profile_end(void) {
   bdet::g_prof_on = false;
   bdet::g_untimed = 0;

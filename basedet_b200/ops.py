@@ -162,19 +162,21 @@ def pairwise(boxes1, boxes2, mode=_lib.PAIR_IOU):
 
 
 def pairwise_batched(gt, num_gt, anchors, mode=_lib.PAIR_IOU, out=None):
-    """gt (B, Gmax, >=4) contiguous, num_gt (B,) int32 or None, anchors (A, 4) shared -> (B, Gmax, A).
-    Rows >= num_gt[b] are left untouched.  ``out`` may be a view made by ``_padded_rows``."""
+    """gt (B, Gmax, >=4) contiguous, num_gt (B,) int32 or None, anchors (A, 4) shared by the batch or (B, A, 4) per
+    image -> (B, Gmax, A).  Rows >= num_gt[b] are left untouched.  ``out`` may be a view made by ``_padded_rows``."""
     lib = _lib.load()
     gt = _f32c(gt, "gt")
     anchors = _f32c(anchors, "anchors")
     B, Gmax, ld = gt.shape
-    A = anchors.shape[0]
+    A = anchors.shape[-2]
+    assert anchors.shape[-1] == 4 and (anchors.ndim == 2 or anchors.shape[0] == B)
+    bs2 = A * 4 if anchors.ndim == 3 else 0
     if out is None:
         out, _ = _padded_rows((B, Gmax), A, gt.device)
     assert out.shape == (B, Gmax, A) and out.stride(2) == 1 and out.stride(0) == Gmax * out.stride(1)
     n1 = _i32c(num_gt, "num_gt") if num_gt is not None else None
     with _guard(out):
-        check(lib.bdet_pairwise_batched(_p(gt), ld, Gmax * ld, _p(n1), Gmax, _p(anchors), 4, 0, A, _p(out),
+        check(lib.bdet_pairwise_batched(_p(gt), ld, Gmax * ld, _p(n1), Gmax, _p(anchors), 4, bs2, A, _p(out),
                                         out.stride(1), out.stride(0), B, mode, _stream(out)))
     return out
 
@@ -863,6 +865,17 @@ def profile_collect(name=None):
     ms, n = ctypes.c_float(0), ctypes.c_int(0)
     check(_lib.load().bdet_profile_collect(name.encode() if name else None, ctypes.byref(ms), ctypes.byref(n)))
     return ms.value, n.value
+
+
+def profile_report():
+    """{kernel name: (total_ms, launches)} of every bracketed kernel since profile_begin()."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(_lib.load().bdet_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(n))
+    return out
 
 
 def profile_end():

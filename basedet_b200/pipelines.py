@@ -252,3 +252,54 @@ def roi_pool_forward_backward(features, rois, strides, pool_shape=(7, 7), dout=N
         return out
     grads = ops.roi_align_bwd(dout, [tuple(f.shape) for f in features], rois, levels, scales, pool_shape)
     return out, grads
+
+
+def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets, features, gt_boxes, num_gt, im_info,
+                        noise_rpn, noise_rcnn, dout=None, rpn_strides=(4, 8, 16, 32, 64), rcnn_strides=(4, 8, 16, 32), prev_nms_topk=2000,
+                        post_nms_topk=1000, nms_threshold=0.7, num_rois=512, pool_shape=(7, 7), plan=None, dfeats=None):
+    """Every box op of one Faster R-CNN FPN training step, for the whole batch (BASELINE configs[2]):
+
+      FasterRCNN.get_losses, models/det/faster_rcnn.py:73-94
+        RPN.forward, models/det/rpn.py:91-132: anchors (per forward, :109) -> find_top_rpn_proposals (:134-186:
+          top-k per level, BoxCoder.decode, clip / filter_by_size, batched_nms 0.7, <= post_nms_topk rois)
+          + get_ground_truth (:215-240: IoU, Matcher(.3/.7, low-quality), BoxCoder.encode, sample_labels x 2)
+        RCNN.get_ground_truth, layers/head/rcnn.py:95-147 (rois + gt -> IoU, argmax, fg / bg sampling, targets)
+        roi_pool, layers/common/roi_pool.py:35-78 (assign_rois + ROIAlign 7x7 on the 512 sampled rois per image)
+        ... and, with ``dout`` (the gradient of the box head w.r.t. the pooled features), the ROIAlign backward
+        that MegEngine's autodiff runs for the same step.
+
+    feature_sizes[l] = (H_l, W_l) of the RPN levels (``features[l].shape[-2:]`` in rpn.py:109), rpn_scores[l] (B, n_l)
+    objectness logits in (h, w, anchor) order, rpn_offsets[l] (B, n_l, 4), features[l]
+    (B, C, H_l, W_l) for the RCNN levels, gt_boxes (B, Gmax, 5), num_gt (B,), im_info (B, >= 2), noise_rpn (B, 2, A)
+    and noise_rcnn (B, 2, post_nms_topk + Gmax): the uniform variates of the four sample_labels calls.
+    Returns a dict of device tensors; nothing is copied to the host."""
+    dev = gt_boxes.device
+    B = gt_boxes.shape[0]
+    # anchors: one launch for all levels; the per-level tensors are views of the flat buffer
+    n_l = [int(s.shape[1]) for s in rpn_scores]
+    anchors_all = anchor_generator.generate_all_level_anchors(feature_sizes, dev)
+    offs = [0]
+    for n in n_l:
+        offs.append(offs[-1] + n)
+    anchors_list = [anchors_all[offs[i]:offs[i + 1]] for i in range(len(n_l))]
+    # RPN proposals (no gradient flows through them, rpn.py:186)
+    rois, n_rois = rpn_proposals(rpn_scores, rpn_offsets, anchors_list, im_info, prev_nms_topk, post_nms_topk, nms_threshold)
+    # RPN targets
+    rpn_labels, rpn_targets_ = rpn_targets(anchors_all, gt_boxes, num_gt, noise_rpn[:, 0], noise_rpn[:, 1], plan=plan)
+    # RCNN targets on the proposals
+    s_rois, s_labels, s_targets, s_count = rcnn_targets(rois, n_rois, gt_boxes, num_gt, noise_rcnn[:, 0], noise_rcnn[:, 1],
+                                                        num_rois=num_rois)
+    # ROIAlign on the sampled rois.  The reference concatenates the per-image lists (rcnn.py:139-146); rows beyond
+    # count[b] are zero rois of image b here (fixed shapes), which pool to whatever a zero box pools to and carry no
+    # gradient because their dout rows are zero in a real step.
+    flat_rois = s_rois.reshape(B * num_rois, 5)
+    levels = ops.roi_assign_levels(flat_rois, int(math.log2(rcnn_strides[0])), int(math.log2(rcnn_strides[-1])))
+    scales = [1.0 / s for s in rcnn_strides]
+    pooled = ops.roi_align_fwd(features, flat_rois, levels, scales, pool_shape)
+    out = dict(rois=rois, n_rois=n_rois, rpn_labels=rpn_labels, rpn_targets=rpn_targets_, rcnn_rois=s_rois,
+               rcnn_labels=s_labels, rcnn_targets=s_targets, rcnn_count=s_count, pooled=pooled, levels=levels)
+    if dout is not None:
+        out["dfeats"] = ops.roi_align_bwd(dout, [tuple(f.shape) for f in features], flat_rois, levels, scales, pool_shape,
+                                          dfeats=dfeats)
+    return out
+

@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 box-op hot path (contract in the task statement).
+"""bench.py -- benchmark of the B200 box-op hot path (contract in the task statement).
 
-    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU restatement of the reference path
+    python bench.py --gpus N --steps K --warmup W                    # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference path
 
-Workload (BASELINE.json configs[1]): RetinaNet training target assignment, batch 16 per GPU, 800x800 input ->
-A = 120 087 anchors, G = 100 GT boxes per image.  One "step" = anchor generation + pairwise IoU + max-IoU Matcher
-(thresholds .4/.5, low-quality matches) + class labels + BoxCoder.encode for the 16 images of one GPU.
-Images are sharded across ranks (weak scaling, no collective on the data path).
-Prints ONE JSON line on rank 0.
+Headline (`value`, `e2e`, `roofline`): BASELINE.json configs[2] -- every box op of one Faster R-CNN R50-FPN training
+step (anchors, RPN top-k + decode + NMS 0.7 -> proposals, RPN targets, RCNN targets, ROIAlign 7x7 forward + backward),
+16 images -- the one config that contains IoU, matching, NMS and ROIAlign, which is what the metric names.  The `configs`
+object of the same JSON line carries configs[0..4] (c1..c5), each with images/s, its dominant kernel's roofline (or
+pair-test rate) and its own end-to-end figure.
+
+Scaling: images are sharded across ranks with no collective on the data path.  Default `--scaling strong`:
+the config's batch (16 / 16 / 64 / 8 images; config 1 is a single image and runs as one replica per rank) is split over
+the N ranks, so per-GPU work shrinks with N; `--scaling weak` gives every rank the full batch.  At N > 1 the strong run
+also reports the headline at the weak size (`weak_scaling`).  One "step" = one pass of the pipeline over the rank's
+images, replayed as ONE CUDA graph; timing = per-step CUDA events on the launching stream, max over ranks, L2 flushed
+between steps (outside the event pairs).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -25,11 +32,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "box-op images/sec (IoU+match+NMS+ROIAlign) @1/2/4/8 B200; % of HBM roofline"
 UNIT = "images/s"
-IMAGES_PER_GPU = 16
-NUM_GT = 100
-IMG_HW = (800, 800)
-THRESHOLDS, LABELS, ALLOW_LQ = [0.4, 0.5], [0, -1, 1], True
 FALLBACK_HBM_GBS = 6650.0
+HEADLINE = "c3"
 
 
 def measured_peak():
@@ -39,6 +43,15 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic():
+    """ncu dram bytes per launch per kernel, committed under profiles/ (NOT measured in this run)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -64,12 +77,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: list of (t0, t1) perf_counter intervals that were under load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
         self.proc.terminate()
-        rows = [s for (t, s) in self.samples if t0 <= t <= t1] or [s for (_, s) in self.samples]
+        rows = [s for (t, s) in self.samples if any(a <= t <= b for a, b in windows)] or [s for (_, s) in self.samples]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -86,23 +100,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------- workload
-def make_inputs(rank):
-    from basedet_b200 import workloads as W
-    gt, ng = W.target_assign_batch(IMAGES_PER_GPU, NUM_GT, IMG_HW[0], IMG_HW[1], seed0=100 + rank * IMAGES_PER_GPU)
-    sizes = W.retinanet_level_sizes(*IMG_HW)
-    return gt, ng, sizes
-
-
-def algorithmic_bytes(A, B, G, path):
-    """Per-step HBM bytes of the dominant kernel (DESIGN.md 'Roofline accounting')."""
-    if path == "fused":
-        # assign_main_kernel: anchors read once (16 B), labels + idx + offsets written per image (24 B), GT rows
-        return A * 16 + B * (A * 24 + G * 20)
-    # pairwise_kernel: the (G, A) fp32 matrix written once per image + box reads
-    return B * (4 * G * A + 16 * G) + 16 * A
-
-
+# ----------------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -114,250 +112,268 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from basedet_b200 import _lib, ops, pipelines
-    from basedet_b200.layers import DefaultAnchorGenerator
-    from basedet_b200 import workloads as W
+    from basedet_b200 import _lib, benchmarks as BM, distributed as D, ops
 
     _lib.load()
-    gt_np, ng_np, sizes = make_inputs(rank)
-    B, G = gt_np.shape[0], gt_np.shape[1]
-    gen = DefaultAnchorGenerator(W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, W.RETINANET_OFFSET)
-    A = sum(h * w * 9 for h, w in sizes)
-    gt_d = torch.from_numpy(gt_np).to(dev)
-    ng_d = torch.from_numpy(ng_np).to(dev)
-    plan = ops.AssignPlan(A, G, B, dev)
-    iou_buf = ops._padded_rows((B, G), A, dev)[0] if args.path == "materialised" else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step(gt, ng):
-        anchors = gen.generate_all_level_anchors(sizes, dev)  # regenerated every step, as retinanet.py:116 does
-        if args.path == "fused":
-            return ops.assign_targets(anchors, gt, ng, THRESHOLDS, LABELS, ALLOW_LQ, True, plan=plan)
-        ops.pairwise_batched(gt, ng, anchors, out=iou_buf)
-        idx, lab = ops.match(iou_buf, THRESHOLDS, LABELS, ALLOW_LQ, num_g=ng)
-        offs = []
-        for b in range(B):  # BoxCoder.encode(anchors, gt[match_indices]) per image, as the reference loop does
-            offs.append(ops.box_encode(anchors, gt[b, :, :4], (0, 0, 0, 0), (1, 1, 1, 1), gather_idx=idx[b]))
-        return lab, idx, offs
+    peak, peak_src = measured_peak()
+    traffic = profile_traffic()
+    warm = max(args.warmup, 3)
+    windows = []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        step(gt_d, ng_d)
-    barrier()
+    def shard(name, scaling):
+        n = BM.CONFIG_BATCH[name]
+        if scaling == "weak" or n < world:
+            # weak: every rank runs the full batch (its own images); configs smaller than the world: one replica per rank
+            return list(range(rank * n, (rank + 1) * n)), n * world, ("weak" if scaling == "weak" else "replicas")
+        lo, hi = D.shard_range(n, rank, world)
+        return list(range(lo, hi)), n, "strong"
+
+    def measure(name, scaling, steps, profile=True):
+        images, total_images, mode = shard(name, scaling)
+        arm = BM.ARMS[name](images, dev)
+        if hasattr(arm, "finish_setup"):
+            arm.finish_setup()
+        graphed = arm.capture() if not args.eager else False
+        # ---- device-resident timing
+        for _ in range(warm):
+            arm.step()
+        barrier()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            arm.step()
+            e.record()
+            evs.append((s, e))
+        barrier()
+        t1 = time.perf_counter()
+        per_step = [s.elapsed_time(e) for s, e in evs]
+        dev_ms = float(sum(per_step))
+        # ---- end to end: pinned host inputs -> H2D -> step -> result summary -> D2H, every step
+        res_h = torch.empty((steps,) + tuple(arm.summary.shape), dtype=arm.summary.dtype).pin_memory()
+        for _ in range(3):
+            arm.e2e_step(res_h[0])
+        barrier()
+        te0 = time.perf_counter()
+        for i in range(steps):
+            arm.e2e_step(res_h[i])
+        barrier()
+        te1 = time.perf_counter()
+        windows.append((t0, te1))
+        e2e_ms = (te1 - te0) * 1e3
+        # ---- per-kernel durations: eager launches bracketed by the library's event hooks (outside the timed regions)
+        kernels, launches_per_step = {}, None
+        if profile:
+            n_prof = 3
+            arm.eager()
+            torch.cuda.synchronize()
+            ops.profile_begin()
+            for _ in range(n_prof):
+                flush.zero_()
+                arm.eager()
+            torch.cuda.synchronize()
+            rep = ops.profile_report()
+            ops.profile_end()
+            launches_per_step = sum(n for _, n in rep.values()) / n_prof
+            tot = sum(ms for ms, _ in rep.values()) or 1.0
+            for kname, (ms, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+                d = {"avg_us": ms / n * 1e3, "launches_per_step": n / n_prof, "share_of_kernel_time": ms / tot}
+                if kname in arm.kernel_bytes:
+                    gbs = arm.kernel_bytes[kname] / (ms / n * 1e-3) / 1e9
+                    d.update(algorithmic_bytes_per_launch=arm.kernel_bytes[kname], GBps=gbs, frac_of_peak=gbs / peak)
+                if kname in arm.kernel_units:
+                    unit, units = arm.kernel_units[kname]
+                    d[unit] = units / (ms / n * 1e-3)
+                kernels[kname] = d
+        # ---- max over ranks
+        times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
+        rec = {
+            "workload": arm.workload, "images_total": total_images, "images_this_rank": len(images), "scaling": mode,
+            "value": total_images * steps / (dev_ms_max * 1e-3), "unit": UNIT, "ms_per_step": dev_ms_max / steps,
+            "ms_per_step_min": float(min(per_step)), "cuda_graph": bool(graphed),
+            "e2e": {"value": total_images * steps / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": arm.h2d_bytes, "d2h_bytes_per_step": arm.d2h_bytes,
+                    "note": "pinned host inputs -> H2D -> step (CUDA graph replay) -> result summary -> D2H every step; wall "
+                            "clock between device syncs; " + arm.resident_note},
+            "gpu_launches_per_step": launches_per_step, "kernels": kernels,
+        }
+        if not graphed and getattr(arm, "capture_error", None):
+            rec["cuda_graph_error"] = arm.capture_error
+        dom = arm.dominant if arm.dominant in kernels else (next(iter(kernels)) if kernels else None)
+        if dom:
+            k = kernels[dom]
+            rec["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": k.get("GBps"), "peak": peak, "unit": "GB/s",
+                               "frac": k.get("frac_of_peak"), "traffic": traffic.get(dom),
+                               "traffic_source": "profiles/traffic.json (ncu --set full capture, not measured in this run)"
+                               if traffic.get(dom) is not None else None,
+                               "algorithmic_bytes_per_launch": k.get("algorithmic_bytes_per_launch"),
+                               "avg_launch_ms": k["avg_us"] / 1e3, "peak_source": peak_src}
+            for unit in ("pair-evaluations/s",):
+                if unit in k:
+                    rec["roofline"][unit] = k[unit]
+        if name == "c3":
+            rec["roi_level_histogram"] = arm.level_hist
+            rec["roi_footprint_union_bytes"] = arm.union_bytes
+            rec["pyramid_bytes"] = arm.pyramid_bytes
+        del arm
+        torch.cuda.empty_cache()
+        return rec
 
     sampler = ClockSampler(local) if rank == 0 else None
-    # ---- timed region: device-resident inputs, per-step CUDA events, L2 flushed between steps (outside the events)
-    dom = "assign_main_kernel" if args.path == "fused" else "pairwise_kernel"
-    ops.profile_begin(only=dom)  # event pairs around the dominant kernel only: bracketing every launch stretches the step
-    evs = []
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        step(gt_d, ng_d)
-        e.record()
-        evs.append((s, e))
-    barrier()
-    t1 = time.perf_counter()
-    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
-    dom_ms, dom_n = ops.profile_collect(dom)
-    _, launches = ops.profile_collect(None)
-    ops.profile_end()
-    # keep the same load running until the clock sampler has seen >= 0.5 s of it
-    t_tail = time.perf_counter()
-    while time.perf_counter() - t0 < 0.6:
-        step(gt_d, ng_d)
-    torch.cuda.synchronize()
-    t_end = time.perf_counter()
-    clocks = sampler.stop(t0, t_end) if sampler else None
-
-    # ---- end-to-end: host (pinned) gt -> H2D -> step -> label census -> D2H, every step, through the public pipeline
-    # object (pipelines.TargetAssigner: the same launches as step(), captured once into a CUDA graph and replayed)
-    gt_h = torch.from_numpy(gt_np).pin_memory()
-    ng_h = torch.from_numpy(ng_np).pin_memory()
-    res_h = torch.empty((args.steps, B, 3), dtype=torch.int32).pin_memory()
-    e2e_launches = 0
-    if args.path == "fused":
-        assigner = pipelines.TargetAssigner(gen, sizes, B, G, THRESHOLDS, LABELS, ALLOW_LQ, True, device=dev)
-
-        def e2e_step(i):
-            counts = assigner(gt_h, ng_h)[3]
-            res_h[i].copy_(counts, non_blocking=True)
-        e2e_launches = assigner.kernels_per_replay
-    else:
-        gt_in, ng_in = torch.empty_like(gt_d), torch.empty_like(ng_d)
-
-        def e2e_step(i):
-            gt_in.copy_(gt_h, non_blocking=True)
-            ng_in.copy_(ng_h, non_blocking=True)
-            lab = step(gt_in, ng_in)[0]
-            res_h[i].copy_(ops.count_labels(lab), non_blocking=True)
-    for i in range(3):
-        e2e_step(0)
-    barrier()
-    te0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    barrier()
-    te1 = time.perf_counter()
-    e2e_s = te1 - te0
-    num_fg = int(res_h[-1, :, 2].sum())
-
-    # ---- the memory-bound kernels of the drop-in (materialised) path, same inputs, same event hooks
-    mem_kernels = {}
-    if rank == 0:
-        iou_view = ops._padded_rows((B, G), A, dev)[0]
-        anchors_once = gen.generate_all_level_anchors(sizes, dev)
-        for it in range(3 + 20):  # 3 warm-up passes, then 20 measured ones
-            if it == 3:
-                torch.cuda.synchronize()
-                ops.profile_begin()
+    names = [n for n in ("c3", "c1", "c2", "c4", "c5") if not args.only or n in args.only.split(",")]
+    configs = {}
+    for n in names:
+        configs[n] = measure(n, args.scaling, args.steps)
+    weak = None
+    if world > 1 and args.scaling == "strong" and HEADLINE in configs:
+        w = measure(HEADLINE, "weak", args.steps, profile=False)
+        weak = {"value": w["value"], "unit": UNIT, "ms_per_step": w["ms_per_step"], "images_total": w["images_total"],
+                "e2e": w["e2e"]["value"]}
+    # keep a load running until the clock sampler has seen >= 0.5 s of it
+    if sampler is not None and windows and sum(b - a for a, b in windows) < 0.6:
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.6:
             flush.zero_()
-            ops.pairwise_batched(gt_d, ng_d, anchors_once, out=iou_view)
-            flush.zero_()
-            ops.match(iou_view, THRESHOLDS, LABELS, ALLOW_LQ, num_g=ng_d)
         torch.cuda.synchronize()
-        peak_, _src = measured_peak()
-        for name, nbytes in (("pairwise_kernel", algorithmic_bytes(A, B, G, "materialised")),
-                             ("match_colmax_kernel", B * (4 * G * A + 8 * A))):
-            ms, n = ops.profile_collect(name)
-            if n:
-                gbs = nbytes / (ms / n * 1e-3) / 1e9
-                mem_kernels[name] = {"achieved": gbs, "frac": gbs / peak_, "avg_launch_ms": ms / n,
-                                     "algorithmic_bytes_per_launch": nbytes}
-        ops.profile_end()
-        del iou_view
-
-    # ---- max over ranks
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
-    total_images = IMAGES_PER_GPU * world * args.steps
+        windows.append((t0, time.perf_counter()))
+    clocks = sampler.stop(windows) if sampler else None
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        abytes = algorithmic_bytes(A, B, G, args.path)
-        achieved = abytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_n else None
+        head = configs.get(HEADLINE) or next(iter(configs.values()))
         out = {
-            "metric": METRIC, "value": total_images / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "configs[1]: RetinaNet target assignment, batch %d per GPU, A=%d anchors (800x800), G=%d GT: "
-                            "anchors_grid + IoU + Matcher(.4/.5, low-quality) + class labels + BoxCoder.encode" % (B, A, G),
-                "path": args.path, "images_per_gpu": B, "anchors": A, "gt_per_image": G,
-                "sharding": "images across ranks, no collective on the data path",
-                "l2": "256 MB memset between timed steps (outside the per-step CUDA event pairs)",
-                "timing": "sum of per-step CUDA event intervals on the launching stream, max over ranks",
-            },
-            "e2e": {"value": total_images / (e2e_ms_max * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(gt_np.nbytes + ng_np.nbytes), "d2h_bytes_per_step": int(B * 3 * 4),
-                    "note": "pinned host gt -> H2D -> step -> per-image label census (num_fg normaliser) -> D2H; "
-                            "wall clock between device syncs; labels/offsets stay on the GPU as in the reference's loss; "
-                            + ("the step is pipelines.TargetAssigner: the same 3 kernels + census replayed as one CUDA graph "
-                               "(%d kernel nodes per step), two buffer sets so that the copies of step i+1 overlap step i, "
-                               "no L2 flush between steps" % e2e_launches if e2e_launches else
-                               "eager launches"),
-                    "num_fg_last_step": num_fg},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms / max(dom_n, 1),
-                         "launches_timed": dom_n, "peak_source": peak_src},
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": head["scaling"] if head["scaling"] != "replicas" else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": head["workload"], "images_total": head["images_total"],
+                       "images_per_gpu": head["images_this_rank"],
+                       "sharding": "images across ranks (distributed.shard_range), no collective on the data path",
+                       "l2": "256 MB memset between timed steps (outside the per-step CUDA event pairs)",
+                       "timing": "sum of per-step CUDA event intervals on the launching stream, max over ranks; the step is "
+                                 "one CUDA graph replay",
+                       "other_configs": "configs.c1 .. configs.c5 of this line"},
+            "e2e": head["e2e"],
+            "gpu_launches": int(round((head["gpu_launches_per_step"] or 0) * args.steps)),
+            "roofline": head.get("roofline"),
             "clocks": clocks,
-            "wall_ms_timed_region_incl_flush": (t1 - t0) * 1e3,
-            "roofline_memory_bound_kernels": mem_kernels,
+            "configs": configs,
         }
-        if args.path == "fused":
-            out["roofline"]["note"] = ("assign_main_kernel never materialises the (G, A) matrix: it is issue-bound on fp32 pair "
-                                       "tests (ncu: ~76-84 % issue-active, profiles/), so its HBM fraction is low by construction; "
-                                       "the HBM-bound kernels of the drop-in path are listed in roofline_memory_bound_kernels")
-            # the fused path is rated in pair evaluations per second, not in HBM %
-            pairs = float(IMAGES_PER_GPU) * G * A
-            out["roofline"]["pair_evaluations_per_s"] = pairs / (dom_ms / max(dom_n, 1) * 1e-3) if dom_ms else None
-            out["roofline"]["materialised_equivalent_GBps"] = (
-                algorithmic_bytes(A, B, G, "materialised") + B * (4 * G * A + 8 * A)) / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 \
-                if dom_ms else None
-        traffic = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic):
-            try:
-                out["roofline"]["traffic"] = json.load(open(traffic)).get(dom)
-            except Exception:
-                pass
-        out["cpu_baseline"] = cpu_baseline(gt_np, ng_np, sizes)
+        if weak is not None:
+            out["weak_scaling"] = weak
+        out["cpu_baseline"] = cpu_baseline(HEADLINE if HEADLINE in configs else names[0])
         emit(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
 class CpuArm:
-    """The reference path on the host cores.  BaseDet is pure Python over MegEngine, which cannot be installed
-    offline, so the timed code is oracle/c/oracle.c: a plain-C restatement (materialised (G, A) matrix, one pass per
-    reference op, pthread-parallel over all host cores) that tests/ pin to the reference's own source."""
+    """The reference path on the host cores.  BaseDet is pure Python over MegEngine, which cannot be installed offline,
+    so the timed code is oracle/cpu_arms.py: the numpy + C (oracle/c/oracle.c, pthread-parallel, materialised matrices,
+    one pass per reference op) restatement that tests/ pin to the reference's own source.  One call = ONE image."""
 
-    def __init__(self, sizes):
+    def __init__(self, name):
         from basedet_b200 import workloads as W
-        from oracle import c_oracle, ref_ops as R
-        self.C = c_oracle
-        self.anchors_fn = lambda: np.concatenate(R.default_anchors(sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS,
-                                                                   W.RETINANET_STRIDES, W.RETINANET_OFFSET))
-        A = sum(h * w * 9 for h, w in sizes)
-        self.scratch = c_oracle.TargetScratch(NUM_GT, A)
+        from oracle import c_oracle, cpu_arms, ref_ops as R
+        self.name, self.W, self.CA, self.R = name, W, cpu_arms, R
         self.cores = c_oracle.num_threads()
+        rng = np.random.default_rng(0)
+        if name == "c3":
+            fs = [(-(-W.FRCNN_HW[0] // s), -(-W.FRCNN_HW[1] // s)) for s in W.FRCNN_RCNN_STRIDES]
+            # one image's pyramid / dout (activation values do not steer control flow: reused for every sampled image)
+            self.feats = [rng.standard_normal((1, W.FRCNN_CHANNELS, h, w), dtype=np.float32) for h, w in fs]
+            self.dout = rng.standard_normal((W.FRCNN_NUM_ROIS, W.FRCNN_CHANNELS, 7, 7), dtype=np.float32)
+            self.inputs = lambda i: W.frcnn_image(i % 16)
+            self.what = "anchors + RPN proposals + RPN targets + RCNN targets + ROIAlign fwd + bwd (fp64-accumulated)"
+        elif name == "c2":
+            sizes = W.retinanet_level_sizes(800, 800)
+            self.sizes = sizes
+            self.scratch = c_oracle.TargetScratch(100, sum(h * w * 9 for h, w in sizes))
+            self.inputs = lambda i: W.target_assign_batch(1, 100, 800, 800, seed0=100 + i % 16)[0][0]
+            self.what = "anchors + materialised IoU + Matcher + class labels + BoxCoder.encode"
+        elif name == "c1":
+            self.sizes = W.retinanet_level_sizes(800, 800)
+            self.inputs = lambda i: W.retinanet_image(0)
+            self.what = "anchors + sigmoid filter + top-k + decode + batched NMS + scale / clip"
+        elif name == "c4":
+            self.sizes = W.retinanet_level_sizes(*W.FCOS_HW)
+            self.inputs = lambda i: W.fcos_image(i % 64)
+            self.what = "points + FCOS score filter + top-k + PointCoder.decode + batched NMS + scale / clip"
+        elif name == "c5":
+            self.inputs = lambda i: W.stress_image(i % 8)
+            self.what = "500 x 200k IoU + Matcher + single-class NMS over 100k boxes"
+        else:
+            raise ValueError(name)
 
-    def image(self, gt5):
-        anchors = self.anchors_fn()  # the reference regenerates anchors every forward (retinanet.py:116)
-        return self.C.retinanet_targets_one(anchors, gt5, THRESHOLDS, LABELS, ALLOW_LQ, scratch=self.scratch)
+    def image(self, inp):
+        W, CA, R = self.W, self.CA, self.R
+        if self.name == "c3":
+            return CA.frcnn_image_chain(inp, self.feats, self.dout)
+        if self.name == "c2":
+            anchors = np.concatenate(R.default_anchors(self.sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS,
+                                                       W.RETINANET_STRIDES, W.RETINANET_OFFSET))
+            return CA.retinanet_targets_image(anchors, inp, self.scratch)
+        if self.name == "c1":
+            anc = R.default_anchors(self.sizes, W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, W.RETINANET_OFFSET)
+            return CA.dense_image_postprocess(inp["logits"], inp["offsets"], anc, inp["im_info"])
+        if self.name == "c4":
+            pts = R.anchor_points(self.sizes, 1, W.RETINANET_STRIDES, 0.5)
+            return CA.dense_image_postprocess(inp["logits"], inp["offsets"], pts, inp["im_info"], 0.05, W.FCOS_NMS_THR, 100,
+                                              1000, ctrness_l=inp["ctrness"])
+        return CA.stress_image_ops(inp)
 
 
-def cpu_baseline(gt_np, ng_np, sizes, budget_s=12.0):
-    arm = CpuArm(sizes)
-    arm.image(gt_np[0, : ng_np[0]])
+def cpu_baseline(name, budget_s=15.0, max_images=64):
+    arm = CpuArm(name)
+    inputs = [arm.inputs(i) for i in range(4)]
+    arm.image(inputs[0])
     n_img, t0 = 0, time.perf_counter()
     while True:
-        b = n_img % gt_np.shape[0]
-        arm.image(gt_np[b, : ng_np[b]])
+        arm.image(inputs[n_img % len(inputs)])
         n_img += 1
-        if time.perf_counter() - t0 > budget_s or n_img >= 256:
+        if time.perf_counter() - t0 > budget_s or n_img >= max_images:
             break
     dt = time.perf_counter() - t0
-    return {"value": n_img / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
-            "sample": "%d images of the same workload, one at a time, C restatement of the reference op sequence on %d "
-                      "pthreads (MegEngine itself is not installable offline)" % (n_img, arm.cores)}
+    return {"value": n_img / dt, "unit": UNIT, "cores": arm.cores, "kind": "port", "config": name,
+            "sample": "%d images of the same workload, one at a time (%s); numpy + C restatement of the reference op sequence, "
+                      "C passes on %d pthreads (MegEngine itself is not installable offline)" % (n_img, arm.what, arm.cores)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    gt_np, ng_np, sizes = make_inputs(0)
-    arm = CpuArm(sizes)
+    name = (args.only or HEADLINE).split(",")[0]
+    arm = CpuArm(name)
+    inputs = [arm.inputs(i) for i in range(min(args.steps, 16))]
     for i in range(max(args.warmup, 1)):
-        arm.image(gt_np[0, : ng_np[0]])
+        arm.image(inputs[0])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        b = i % gt_np.shape[0]
-        arm.image(gt_np[b, : ng_np[b]])  # bounded sample: ONE image of the batch-16 step per step
+        arm.image(inputs[i % len(inputs)])  # bounded sample: ONE image of the config's batch per step
     dt = time.perf_counter() - t0
     val = args.steps / dt
-    A = sum(h * w * 9 for h, w in sizes)
-    sample = ("1 image per step; C restatement (oracle/c/oracle.c) of the reference's MegEngine op sequence on %d "
-              "pthreads; the reference is pure Python over MegEngine, not installable offline" % arm.cores)
+    sample = ("1 image per step (%s); numpy + C restatement (oracle/cpu_arms.py, oracle/c/oracle.c) of the reference's "
+              "MegEngine op sequence, C passes on %d pthreads; the reference is pure Python over MegEngine, not installable "
+              "offline; timed region %.1f s" % (arm.what, arm.cores, dt))
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: RetinaNet target assignment, A=%d anchors, G=%d GT; each step = 1 image "
-                               "(bounded sample of the batch-16 step)" % (A, NUM_GT), "path": "cpu-oracle"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[%d] (%s), each step = 1 image (bounded sample of the batch)"
+                               % (int(name[1]) - 1, name), "path": "cpu-oracle"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -381,11 +397,27 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--path", default="fused", choices=["fused", "materialised"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--only", default="", help="comma-separated subset of c1,c2,c3,c4,c5")
+    ap.add_argument("--eager", action="store_true", help="time eager launches instead of the CUDA graph replay")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # honour --gpus when started without torchrun: re-launch as one process per GPU
+            import socket
+            s = socket.socket()
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+            s.close()
+            os.dup2(_RESULT_FD, 1)
+            os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                       "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                                       "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     if args.impl == "reference":
         run_reference(args)
     else:

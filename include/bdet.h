@@ -349,6 +349,8 @@ int bdet_bw_probe(void* dst, const void* src, size_t bytes, int mode, int ctas_p
 int bdet_profile_begin(void);
 int bdet_profile_select(const char* name);
 int bdet_profile_collect(const char* name, float* total_ms_host, int* launches_host);
+/* "name total_ms launches\n" for every bracketed kernel since bdet_profile_begin(), into a host buffer */
+int bdet_profile_report(char* buf_host, size_t buf_bytes);
 int bdet_profile_end(void);
 
 #ifdef __cplusplus

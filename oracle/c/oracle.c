@@ -184,7 +184,7 @@ static void nms_range(int lo, int hi, void* p) {
     if (iou > c->thr) c->removed[j] = 1;
   }
 }
-int oracle_nms_sorted(const float* b, int n, float thr, int max_output, int* kept) {
+static int nms_sorted_simple(const float* b, int n, float thr, int max_output, int* kept) {
   uint8_t* removed = (uint8_t*)calloc((size_t)(n > 0 ? n : 1), 1);
   float* area = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
   for (int i = 0; i < n; ++i) area[i] = (b[4 * i + 2] - b[4 * i]) * (b[4 * i + 3] - b[4 * i + 1]);
@@ -202,13 +202,70 @@ int oracle_nms_sorted(const float* b, int n, float thr, int max_output, int* kep
   return cnt;
 }
 
-/* F.nn.roi_align(mode=average, aligned) (ASSUMED-6): feat (B,C,H,W), rois (K,5) -> out (K,C,PH,PW) */
-void oracle_roi_align_fwd(const float* feat, int B, int C, int H, int W, const float* rois, int K, int PH, int PW,
-                          int SH, int SW, float scale, float offset, float* out) {
-  (void)B;
-  for (int k = 0; k < K; ++k) {
-    const float* r = rois + 5 * (size_t)k;
-    const float* fm = feat + (size_t)((int)r[0]) * C * H * W;
+/* Same greedy result for large n, blocked so that the bulk of the pair tests runs on all cores: box j is removed iff a
+ * KEPT box i < j has IoU(i, j) > thr.  Per block of kNmsBlock sorted boxes: (1) in parallel, every box of the block is
+ * tested against the boxes kept in EARLIER blocks (that list is final); (2) the survivors are resolved sequentially
+ * inside the block.  Identical decisions, identical fp32 expression. */
+enum { kNmsBlock = 4096 };
+typedef struct { const float* b; const float* area; const int* kept; int n_kept; uint8_t* removed; int base; float thr; } nmsb_ctx;
+static inline int nms_hit(const float* a, float aa, const float* q, float qa, float thr) {
+  /* emax / emin: the same values as fmaxf / fminf on NaN-free boxes, without the libm call */
+  float w = emax(emin(a[2], q[2]) - emax(a[0], q[0]), 0.f);
+  float h = emax(emin(a[3], q[3]) - emax(a[1], q[1]), 0.f);
+  float inter = w * h;
+  if (!(inter > 0.f) && thr >= 0.f) return 0;
+  return inter / ((aa + qa) - inter) > thr;
+}
+static void nms_block_pull(int lo, int hi, void* p) {
+  nmsb_ctx* c = (nmsb_ctx*)p;
+  for (int jj = lo; jj < hi; ++jj) {
+    const int j = c->base + jj;
+    const float* q = c->b + 4 * (size_t)j;
+    const float qa = c->area[j];
+    for (int t = 0; t < c->n_kept; ++t) {
+      const int i = c->kept[t];
+      if (nms_hit(c->b + 4 * (size_t)i, c->area[i], q, qa, c->thr)) { c->removed[j] = 1; break; }
+    }
+  }
+}
+int oracle_nms_sorted(const float* b, int n, float thr, int max_output, int* kept) {
+  if (n <= 2 * kNmsBlock) return nms_sorted_simple(b, n, thr, max_output, kept);
+  uint8_t* removed = (uint8_t*)calloc((size_t)n, 1);
+  float* area = (float*)malloc(sizeof(float) * (size_t)n);
+  for (int i = 0; i < n; ++i) area[i] = (b[4 * i + 2] - b[4 * i]) * (b[4 * i + 3] - b[4 * i + 1]);
+  int cnt = 0, done = 0;
+  for (int base = 0; base < n && !done; base += kNmsBlock) {
+    const int m = n - base < kNmsBlock ? n - base : kNmsBlock;
+    nmsb_ctx c = {b, area, kept, cnt, removed, base, thr};
+    if (cnt > 0) parallel_for(m, nms_block_pull, &c);
+    const int first = cnt;
+    for (int j = base; j < base + m; ++j) {
+      if (removed[j]) continue;
+      int hit = 0;
+      for (int t = first; t < cnt && !hit; ++t) hit = nms_hit(b + 4 * (size_t)kept[t], area[kept[t]], b + 4 * (size_t)j, area[j], thr);
+      if (hit) continue;
+      kept[cnt++] = j;
+      if (max_output > 0 && cnt >= max_output) { done = 1; break; }
+    }
+  }
+  free(removed);
+  free(area);
+  return cnt;
+}
+
+/* F.nn.roi_align(mode=average, aligned) (ASSUMED-6): feat (B,C,H,W), rois (K,5) -> out (K,C,PH,PW).
+ * ROIs are independent: parallel over k. */
+typedef struct {
+  const float* feat; const float* rois; const float* dout; float* out; double* grad;
+  int C, H, W, K, PH, PW, SH, SW; float scale, offset;
+} roi_ctx;
+static void roi_fwd_range(int lo, int hi, void* p) {
+  roi_ctx* q = (roi_ctx*)p;
+  const int C = q->C, H = q->H, W = q->W, PH = q->PH, PW = q->PW, SH = q->SH, SW = q->SW;
+  const float scale = q->scale, offset = q->offset;
+  for (int k = lo; k < hi; ++k) {
+    const float* r = q->rois + 5 * (size_t)k;
+    const float* fm = q->feat + (size_t)((int)r[0]) * C * H * W;
     float sw_ = r[1] * scale - offset, sh_ = r[2] * scale - offset;
     float ew_ = r[3] * scale - offset, eh_ = r[4] * scale - offset;
     float rw = emax(ew_ - sw_, 0.f), rh = emax(eh_ - sh_, 0.f);
@@ -233,28 +290,36 @@ void oracle_roi_align_fwd(const float* feat, int B, int C, int H, int W, const f
               float bot = bl + (br - bl) * lw;
               acc = acc + (top + (bot - top) * lh);
             }
-          out[(((size_t)k * C + c) * PH + ph) * PW + pw] = acc / (float)(SH * SW);
+          q->out[(((size_t)k * C + c) * PH + ph) * PW + pw] = acc / (float)(SH * SW);
         }
     }
   }
 }
-
-/* backward w.r.t. feat, accumulated in double (order-independent reference); grad (B,C,H,W) must be zeroed */
-void oracle_roi_align_bwd(const float* dout, int B, int C, int H, int W, const float* rois, int K, int PH, int PW, int SH,
-                          int SW, float scale, float offset, double* grad) {
+void oracle_roi_align_fwd(const float* feat, int B, int C, int H, int W, const float* rois, int K, int PH, int PW,
+                          int SH, int SW, float scale, float offset, float* out) {
   (void)B;
-  for (int k = 0; k < K; ++k) {
-    const float* r = rois + 5 * (size_t)k;
-    double* gm = grad + (size_t)((int)r[0]) * C * H * W;
+  roi_ctx q = {feat, rois, NULL, out, NULL, C, H, W, K, PH, PW, SH, SW, scale, offset};
+  parallel_for(K, roi_fwd_range, &q);
+}
+
+/* backward w.r.t. feat, accumulated in double (order-independent reference); grad (B,C,H,W) must be zeroed.
+ * Parallel over channels: every thread walks all ROIs for its own channel range, so no two threads share an element. */
+static void roi_bwd_range(int lo, int hi, void* p) {
+  roi_ctx* q = (roi_ctx*)p;
+  const int C = q->C, H = q->H, W = q->W, PH = q->PH, PW = q->PW, SH = q->SH, SW = q->SW;
+  const float scale = q->scale, offset = q->offset;
+  for (int k = 0; k < q->K; ++k) {
+    const float* r = q->rois + 5 * (size_t)k;
+    double* gm = q->grad + (size_t)((int)r[0]) * C * H * W;
     float sw_ = r[1] * scale - offset, sh_ = r[2] * scale - offset;
     float ew_ = r[3] * scale - offset, eh_ = r[4] * scale - offset;
     float rw = emax(ew_ - sw_, 0.f), rh = emax(eh_ - sh_, 0.f);
     float bh = rh / (float)PH, bw = rw / (float)PW;
-    for (int c = 0; c < C; ++c) {
+    for (int c = lo; c < hi; ++c) {
       double* g = gm + (size_t)c * H * W;
       for (int ph = 0; ph < PH; ++ph)
         for (int pw = 0; pw < PW; ++pw) {
-          float gv = dout[(((size_t)k * C + c) * PH + ph) * PW + pw] / (float)(SH * SW);
+          float gv = q->dout[(((size_t)k * C + c) * PH + ph) * PW + pw] / (float)(SH * SW);
           for (int iy = 0; iy < SH; ++iy)
             for (int ix = 0; ix < SW; ++ix) {
               float hc = sh_ + bh * ((float)ph + ((float)iy + 0.5f) / (float)SH);
@@ -270,4 +335,10 @@ void oracle_roi_align_bwd(const float* dout, int B, int C, int H, int W, const f
         }
     }
   }
+}
+void oracle_roi_align_bwd(const float* dout, int B, int C, int H, int W, const float* rois, int K, int PH, int PW, int SH,
+                          int SW, float scale, float offset, double* grad) {
+  (void)B;
+  roi_ctx q = {NULL, rois, dout, NULL, grad, C, H, W, K, PH, PW, SH, SW, scale, offset};
+  parallel_for(C, roi_bwd_range, &q);
 }
