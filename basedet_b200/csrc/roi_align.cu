@@ -12,75 +12,9 @@
 //           with ONE red.global.add.f32 per touched pixel;
 //           (workspace given) atomics-free tile gather -- ROIs are binned per feature-map tile, one CTA accumulates its
 //           tile x channel chunk in shared memory and writes every dfeat element exactly once: bit-deterministic.
-#include "common.cuh"
+#include "roi_common.cuh"
 
 namespace bdet {
-
-constexpr int kRoiThreads = 256;
-constexpr int kMaxSamples = 256;  // P * S per axis
-
-struct RoiLevels {
-  const float* feat[BDET_MAX_LEVELS];
-  float* dfeat[BDET_MAX_LEVELS];
-  int H[BDET_MAX_LEVELS], W[BDET_MAX_LEVELS];
-  float scale[BDET_MAX_LEVELS];
-  int n_levels;
-};
-
-struct RoiArgs {
-  RoiLevels lv;
-  const float* rois;   // (K, 5)
-  const int* levels;   // (K) or nullptr
-  const float* dout;   // backward
-  float* out;          // forward
-  int B, C, K, PH, PW, SH, SW;
-  float offset;
-  int bwd_cap;         // floats of shared accumulation buffer (backward)
-};
-
-struct SampleTab {
-  int i0[kMaxSamples];
-  float frac[kMaxSamples];
-};
-
-// sample coordinate table for one axis: coord = start + bin * (p + (i + 0.5) / S)
-__device__ __forceinline__ void fill_axis(SampleTab& tab, int P, int S, float start, float bin) {
-  for (int s = threadIdx.x; s < P * S; s += kRoiThreads) {
-    int pidx = s / S, i = s - pidx * S;
-    float f = __fdiv_rn((float)i + 0.5f, (float)S);
-    float c = start + bin * ((float)pidx + f);
-    float fl = floorf(c);
-    tab.i0[s] = (int)fl;
-    tab.frac[s] = c - fl;
-  }
-}
-
-struct RoiGeom {
-  int n, lvl, H, W;
-  float start_w, start_h, bin_w, bin_h;
-  bool valid;
-};
-
-__device__ __forceinline__ RoiGeom roi_geom(const RoiArgs& p, int k) {
-  RoiGeom g;
-  const float* r = p.rois + (long long)k * 5;
-  g.n = (int)__ldg(r);
-  g.lvl = p.levels ? __ldg(p.levels + k) : 0;
-  g.valid = g.n >= 0 && g.n < p.B && g.lvl >= 0 && g.lvl < p.lv.n_levels;
-  if (!g.valid) g.lvl = 0;
-  g.H = p.lv.H[g.lvl];
-  g.W = p.lv.W[g.lvl];
-  const float sc = p.lv.scale[g.lvl];
-  g.start_w = __ldg(r + 1) * sc - p.offset;
-  g.start_h = __ldg(r + 2) * sc - p.offset;
-  float end_w = __ldg(r + 3) * sc - p.offset;
-  float end_h = __ldg(r + 4) * sc - p.offset;
-  float roi_w = fmaxf(end_w - g.start_w, 0.f);
-  float roi_h = fmaxf(end_h - g.start_h, 0.f);
-  g.bin_h = __fdiv_rn(roi_h, (float)p.PH);
-  g.bin_w = __fdiv_rn(roi_w, (float)p.PW);
-  return g;
-}
 
 template <int TPH, int TPW, int TS>
 __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArgs p) {
@@ -88,51 +22,15 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArg
   const int k = blockIdx.x, t = threadIdx.x;
   const int PH = TPH ? TPH : p.PH, PW = TPW ? TPW : p.PW, SH = TS ? TS : p.SH, SW = TS ? TS : p.SW;
   const RoiGeom g = roi_geom(p, k);
-  float* out = p.out + (long long)k * p.C * PH * PW;
-  const int total = p.C * PH * PW;
   if (!g.valid) {  // out-of-range batch / level index: defined as zeros (the reference would read out of bounds)
-    for (int o = t; o < total; o += kRoiThreads) out[o] = 0.f;
+    float* out = p.out + (long long)k * p.C * PH * PW;
+    for (int o = t; o < p.C * PH * PW; o += kRoiThreads) out[o] = 0.f;
     return;
   }
   fill_axis(ty, PH, SH, g.start_h, g.bin_h);
   fill_axis(tx, PW, SW, g.start_w, g.bin_w);
   __syncthreads();
-  const int H = g.H, W = g.W;
-  const float* feat = p.lv.feat[g.lvl] + (long long)g.n * p.C * H * W;
-  const float inv_cnt = (float)(SH * SW);
-  const int bins = PH * PW;
-  for (int o = t; o < total; o += kRoiThreads) {
-    const int c = o / bins, bin = o - c * bins;
-    const int ph = bin / PW, pw = bin - ph * PW;
-    const float* f = feat + (long long)c * H * W;
-    float acc = 0.f;
-#pragma unroll
-    for (int iy = 0; iy < (TS ? TS : 1); ++iy) {
-      for (int iy2 = 0; iy2 < (TS ? 1 : SH); ++iy2) {
-        const int sy = ph * SH + (TS ? iy : iy2);
-        const int y0 = ty.i0[sy], y1 = y0 + 1;
-        const float ly = ty.frac[sy];
-        const bool y0ok = y0 >= 0 && y0 < H, y1ok = y1 >= 0 && y1 < H;
-#pragma unroll
-        for (int ix = 0; ix < (TS ? TS : 1); ++ix) {
-          for (int ix2 = 0; ix2 < (TS ? 1 : SW); ++ix2) {
-            const int sx = pw * SW + (TS ? ix : ix2);
-            const int x0 = tx.i0[sx], x1 = x0 + 1;
-            const float lx = tx.frac[sx];
-            const bool x0ok = x0 >= 0 && x0 < W, x1ok = x1 >= 0 && x1 < W;
-            const float tl = (y0ok && x0ok) ? __ldg(f + y0 * W + x0) : 0.f;
-            const float tr = (y0ok && x1ok) ? __ldg(f + y0 * W + x1) : 0.f;
-            const float bl = (y1ok && x0ok) ? __ldg(f + y1 * W + x0) : 0.f;
-            const float br = (y1ok && x1ok) ? __ldg(f + y1 * W + x1) : 0.f;
-            const float top = tl + (tr - tl) * lx;
-            const float bot = bl + (br - bl) * lx;
-            acc += top + (bot - top) * ly;
-          }
-        }
-      }
-    }
-    out[o] = __fdiv_rn(acc, inv_cnt);
-  }
+  roi_fwd_direct<TPH, TPW, TS>(p, k, g, ty, tx, kRoiThreads);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -366,7 +264,7 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
 // no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
 constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
 
-__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p) {
+__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p, unsigned tma_level_mask) {
   extern __shared__ __align__(16) float bsm[];
   const int PH = p.PH, PW = p.PW;
   const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;  // table rows padded to 16 bytes (128-bit shared loads)
@@ -377,6 +275,10 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
   if (!g.valid) return;
+  if (tma_level_mask) {  // ROIs the TMA kernel (roi_tma.cu, launched just before) has taken
+    FwdPlan unused;
+    if (roi_bwd_takes_tma(p, g, tma_level_mask, &unused)) return;
+  }
   int y_lo, y_hi, x_lo, x_hi;
   if (!roi_footprint(p, g, y_lo, y_hi, x_lo, x_hi)) return;  // ROI entirely outside the map
   const int H = g.H, W = g.W;
@@ -611,6 +513,12 @@ extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, 
   BDET_REQUIRE(rois && out, "null argument");
   a.out = out;
   cudaStream_t st = as_stream(stream);
+  rc = roi_fwd_tma_launch(a, st);  // TMA kernel (roi_tma.cu) when the shape / alignment qualifies
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    BDET_LAUNCH_CHECK();
+    return BDET_OK;
+  }
   if (PH == 7 && PW == 7 && sample_h == 2 && sample_w == 2)
     BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a));
   else
@@ -682,7 +590,12 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a));
+  unsigned tma_mask = 0;
+  rc = roi_bwd_tma_launch(a, st, &tma_mask);  // smem accumulation + cp.reduce.async.bulk.tensor (roi_tma.cu)
+  if (rc < 0) return rc;
+  // the direct scatter kernel takes what is left (levels whose rows are not 16-byte multiples, oversized footprints);
+  // when every level has tensor maps it only finds work for ROIs wider than 64 feature pixels
+  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a, tma_mask));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }
