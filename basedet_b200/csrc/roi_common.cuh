@@ -127,11 +127,13 @@ constexpr int kBoxH = 8, kBoxC = 8;     // rows / channels of one TMA box
 constexpr int kWClasses = 7;            // box widths 8, 16, ..., 56 floats (4 levels x 7 maps + args < 4 KB of params)
 constexpr int kTmaLevels = 4;
 constexpr int kStageBytes = 40 * 1024;  // one pipeline stage of footprint boxes
+constexpr int kFwdMaxRows = 64;
+constexpr int kBwdMaxRows = 64;        // footprint rows of a forward stage at most
 constexpr int kMaxCCS = 64;             // channels per stage at most
 constexpr int kOutStageBytes = kMaxCCS * 49 * 4;
-constexpr int kFwdSmem = 2 * kStageBytes + 2 * kOutStageBytes + 1024;  // + alignment slack
+constexpr int kFwdSmem = 2 * kStageBytes + 2 * kOutStageBytes;
 
-constexpr int kBwdStageBytes = 40 * 1024;
+constexpr int kBwdStageBytes = 36 * 1024;
 
 struct FwdPlan {
   int xs, ys;       // footprint origin (may be negative / beyond the map: TMA fills zeros)
@@ -157,7 +159,7 @@ __device__ __forceinline__ int bwd_plan(const RoiArgs& p, const RoiGeom& g, unsi
   pl->ys = max(y_first, 0);
   const long long fw = (long long)x_last + 2 - pl->xs, fh = (long long)y_last + 2 - pl->ys;
   if (fw < 1 || fh < 1 || pl->xs >= g.W || pl->ys >= g.H) return 2;
-  if (fw > 8 * kWClasses) return 0;
+  if (fw > 8 * kWClasses || fh > kBwdMaxRows) return 0;
   const int cls = (int)((fw + 7) / 8) - 1;
   const int nrb = (int)((fh + kBoxH - 1) / kBoxH);
   const long long per_c = (long long)nrb * kBoxH * 8 * (cls + 1) * 4;
@@ -197,6 +199,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barriers: `n` threads in total (whole warps) take part, by bar_sync (waits) or bar_arrive (does not)
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"

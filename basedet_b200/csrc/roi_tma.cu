@@ -34,26 +34,73 @@ struct RoiTmaArgs {
   const RoiTmaMaps* gmaps;  // debug (BDET_ROI_TMA=2): descriptors read from global memory instead of the parameters
 };
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 2)
+// One forward task: (channel c of the stage, sample column sx), sample rows [SY0, SY1).  `tc` points at the channel's
+// first footprint row, column x0(sx); row offsets oA / oB (pixel rows r0 / r0 + 1 of every sample row) and the action
+// codes are CTA-uniform.  Writes bins ph = SY0/2 .. SY1/2 - 1 of column pw = sx / 2 (even sx lanes only).
+template <int SY0, int SY1>
+__device__ __forceinline__ void fwd_task(const float* __restrict__ tc, float lx, const int (&oA)[14], const int (&oB)[14],
+                                         const float (&fy)[14], unsigned act, bool store, float* __restrict__ oc) {
+  float ha = 0.f, hb = 0.f, vprev = 0.f;
+#pragma unroll
+  for (int sy = SY0; sy < SY1; ++sy) {
+    // action of this sample row (uniform): 0 = same pixel rows as the previous sample, 1 = one row further (the lower
+    // lerp becomes the upper one), 2 = both rows are new
+    const unsigned code = sy == SY0 ? 2u : ((act >> (2 * sy)) & 3u);
+    if (code != 0u) {
+      if (code == 1u) {
+        ha = hb;
+      } else {
+        const float l = tc[oA[sy]], r = tc[oA[sy] + 1];
+        ha = l + (r - l) * lx;
+      }
+      const float l = tc[oB[sy]], r = tc[oB[sy] + 1];
+      hb = l + (r - l) * lx;
+    }
+    const float v = ha + (hb - ha) * fy[sy];
+    if (sy & 1) {
+      // bin (ph, pw): ((v(0,0) + v(0,1)) + v(1,0)) + v(1,1), the reference's accumulation order from 0
+      const float p0 = __shfl_down_sync(0xffffffffu, vprev, 1);
+      const float p1 = __shfl_down_sync(0xffffffffu, v, 1);
+      float acc = 0.f + vprev;
+      acc = acc + p0;
+      acc = acc + v;
+      acc = acc + p1;
+      if (store) oc[(sy >> 1) * 7] = acc * 0.25f;  // == acc / 4 exactly
+    } else {
+      vprev = v;
+    }
+  }
+}
+
+// CTA = 8 compute warps + 1 DMA warp (lane 0 issues every bulk operation, so its per-thread bulk groups cover them all).
+constexpr int kComputeThreads = 256;
+constexpr int kTmaThreads = kComputeThreads + 32;
+// named barrier ids (0 = __syncthreads)
+constexpr int kBarReady0 = 1, kBarFree0 = 3;  // + stage
+
+__global__ void __launch_bounds__(kTmaThreads, 2)
 roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
-  extern __shared__ unsigned char smem_raw[];
+  // dynamic shared memory: [stage 0][stage 1][out stage 0][out stage 1]; 1024-byte aligned by declaration
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab ty, tx;
-  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
   __shared__ FwdPlan plan;
+  __shared__ int roff[kFwdMaxRows + 1];
   const RoiArgs& p = a.r;
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
   float* out = p.out + (long long)k * p.C * 49;
   if (!g.valid) {
-    for (int o = t; o < p.C * 49; o += kThreads) out[o] = 0.f;
+    for (int o = t; o < p.C * 49; o += kTmaThreads) out[o] = 0.f;
     return;
   }
-  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kThreads);
-  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kThreads);
+  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
+  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
   if (t == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], kComputeThreads / 32);
+    mbar_init(&empty_bar[1], kComputeThreads / 32);
     mbar_fence_init();
   }
   __syncthreads();
@@ -65,172 +112,177 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     // finite, ordered coordinates only (NaN / inf rois take the direct path, which tests every tap)
     const bool sane = fabsf(g.start_w) < 1e8f && fabsf(g.start_h) < 1e8f && g.bin_w < 1e7f && g.bin_h < 1e7f && fw >= 2 && fh >= 2;
     pl.cls = -1;
-    if (sane && ((a.level_mask >> g.lvl) & 1u) && fw <= 8 * kWClasses) {
+    pl.nrb = 0;
+    pl.ccs = 0;
+    if (sane && ((a.level_mask >> g.lvl) & 1u) && fw <= 8 * kWClasses && fh <= kFwdMaxRows) {
       pl.cls = (int)((fw + 7) / 8) - 1;
       pl.nrb = (int)((fh + kBoxH - 1) / kBoxH);
       const long long per_c = (long long)pl.nrb * kBoxH * 8 * (pl.cls + 1) * 4;  // bytes per channel
-      long long ccs = (kStageBytes / per_c) & ~7ll;
-      if (ccs > kMaxCCS) ccs = kMaxCCS;
+      const long long fit = kStageBytes / per_c;
+      // 14 tasks per channel on 256 threads: 16 / 32 / 48 / 64 channels fill 7 of 8 warps per pass, 8 channels run split
+      int ccs = fit >= 64 ? 64 : (fit >= 48 ? 48 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0))));
       if (ccs > p.C) ccs = p.C;
-      pl.ccs = (int)ccs;
-      if (ccs < kBoxC) pl.cls = -1;  // footprint too tall for one stage
+      pl.ccs = ccs;
+      if (ccs < kBoxC) pl.cls = -1;  // footprint too large for one stage
     }
     plan = pl;
   }
   __syncthreads();
   if (plan.cls < 0) {
-    roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kThreads);
+    roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kTmaThreads);
     return;
   }
   // ---- TMA path
-  const uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023;
-  auto stage = [&](int s) { return reinterpret_cast<float*>(base + (uintptr_t)s * kStageBytes); };
-  auto ostage = [&](int s) { return reinterpret_cast<float*>(base + 2 * kStageBytes + (uintptr_t)s * kOutStageBytes); };
+  float* const stage0 = reinterpret_cast<float*>(smem_raw);
+  float* const ostage0 = reinterpret_cast<float*>(smem_raw + 2 * kStageBytes);
   const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;                    // channel boxes per stage
-  const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 ch][8 rows][BW]
+  const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
   const int rb_stride = ncb * box_floats;         // floats between row boxes of a stage
   const int n_chunks = (p.C + CCS - 1) / CCS;
-  const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
   const int z0 = g.n * p.C;
+  for (int r = t; r <= nrb * kBoxH; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
+  __syncthreads();  // roff
 
-  // per-thread copies of the (CTA-uniform) sample-row program: relative pixel row and lerp fraction of the 14 sample rows
-  int yr[14];
-  float fy[14];
-#pragma unroll
-  for (int s = 0; s < 14; ++s) {
-    yr[s] = ty.i0[s] - ys;
-    fy[s] = ty.frac[s];
+  if (warp == kComputeThreads / 32) {
+    // ---------------- DMA warp: footprint boxes in, finished output chunks out
+    const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
+    auto load = [&](int chunk) {
+      const int s = chunk & 1, c0 = chunk * CCS;
+      if (chunk >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((chunk >> 1) - 1) & 1));  // the compute warps are done with it
+      if (lane == 0) {
+        const int cbs = min(ncb, (p.C - c0 + kBoxC - 1) / kBoxC);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_floats * 4);
+        for (int rb = 0; rb < nrb; ++rb)
+          for (int cb = 0; cb < cbs; ++cb)
+            tma_load_3d(stage0 + s * (kStageBytes / 4) + rb * rb_stride + cb * box_floats, map, xs, z0 + c0 + cb * kBoxC,
+                        ys + rb * kBoxH, &full_bar[s]);
+      }
+    };
+    load(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int s = chunk & 1, c0 = chunk * CCS;
+      if (chunk + 1 < n_chunks) load(chunk + 1);
+      bar_sync(kBarReady0 + s, kTmaThreads);  // the out stage holds chunk `chunk`
+      if (lane == 0) {
+        bulk_store(out + (size_t)c0 * 49, ostage0 + s * (kOutStageBytes / 4), (uint32_t)min(CCS, p.C - c0) * 49 * 4);
+        bulk_commit();
+        bulk_wait_read<0>();  // shared memory is read out: the stage may be rewritten (and must outlive the copy)
+      }
+      __syncwarp();
+      if (chunk + 2 < n_chunks) bar_arrive(kBarFree0 + s, kTmaThreads);
+    }
+    return;
   }
 
-  auto issue = [&](int chunk) {  // warp 0: one box per lane
-    const int s = chunk & 1, c0 = chunk * CCS;
-    const int cbs = min(ncb, (p.C - c0 + kBoxC - 1) / kBoxC);
-    const int nbox = nrb * cbs;
-    if (lane == 0) mbar_expect_tx(&full_bar[s], (uint32_t)nbox * box_floats * 4);
-    __syncwarp();
-    for (int b = lane; b < nbox; b += 32) {
-      const int rb = b / cbs, cb = b - rb * cbs;
-      tma_load_3d(stage(s) + rb * rb_stride + cb * box_floats, map, xs, ys + rb * kBoxH, z0 + c0 + cb * kBoxC,
-                  &full_bar[s]);
+  // ---------------- compute warps
+  // per-thread copies of the (CTA-uniform) sample-row program
+  int oA[14], oB[14];
+  float fy[14];
+  unsigned act = 0;
+#pragma unroll
+  for (int sy = 0; sy < 14; ++sy) {
+    const int r0 = ty.i0[sy] - ys;
+    oA[sy] = roff[r0];
+    oB[sy] = roff[r0 + 1];
+    fy[sy] = ty.frac[sy];
+    if (sy > 0) {
+      const int d = r0 - (ty.i0[sy - 1] - ys);
+      act |= (d == 0 ? 0u : (d == 1 ? 1u : 2u)) << (2 * sy);
     }
-  };
+  }
+  const bool split = CCS * 14 <= kComputeThreads / 2;  // 8 channels: two half-tasks per (channel, sample column)
 
-  if (warp == 0) issue(0);
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, p.C - c0);
-    if (t == 0) bulk_wait_read<1>();  // the bulk store that last read ostage[s] (chunk - 2) has drained
-    __syncthreads();                  // everyone is done with stage[s ^ 1] (chunk - 1) and may write ostage[s]
-    if (warp == 0 && chunk + 1 < n_chunks) issue(chunk + 1);
+    if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the bulk store of chunk - 2 has read the out stage
     mbar_wait(&full_bar[s], (uint32_t)((chunk >> 1) & 1));
-    const float* tile = stage(s);
-    float* os = ostage(s);
+    const float* tile = stage0 + s * (kStageBytes / 4);
+    float* os = ostage0 + s * (kOutStageBytes / 4);
     const int total = nc * 14;
-    for (int base_task = warp * 32; base_task < total; base_task += kThreads) {
-      const int task = base_task + lane;
+    if (split) {
+      const int half = warp / (kComputeThreads / 64);                // warps 0..3: sample rows 0..7, warps 4..7: 8..13
+      const int task = (warp - half * (kComputeThreads / 64)) * 32 + lane;
       const bool live = task < total;
       const int tk = live ? task : total - 1;
       const int c = tk / 14, sx = tk - c * 14;
-      const float* tc = tile + (c >> 3) * box_floats + (c & 7) * (kBoxH * BW) + (tx.i0[sx] - xs);
-      const float lx = tx.frac[sx];
-      auto hlerp = [&](int r) -> float {
-        const float* q = tc + (r >> 3) * rb_stride + (r & 7) * BW;
-        const float l = q[0], rr = q[1];
-        return l + (rr - l) * lx;
-      };
-      float v[14];
-      int rcur = -0x40000000;
-      float ha = 0.f, hb = 0.f;
-#pragma unroll
-      for (int sy = 0; sy < 14; ++sy) {
-        const int r0 = yr[sy];  // CTA-uniform: the branches below do not diverge
-        if (r0 != rcur) {
-          if (r0 == rcur + 1) {
-            ha = hb;
-          } else {
-            ha = hlerp(r0);
-          }
-          hb = hlerp(r0 + 1);
-          rcur = r0;
-        }
-        v[sy] = ha + (hb - ha) * fy[sy];
-      }
-      // bin (ph, pw): ((v(0,0) + v(0,1)) + v(1,0)) + v(1,1), the reference's accumulation order from 0
-      float o[7];
-#pragma unroll
-      for (int ph = 0; ph < 7; ++ph) {
-        const float p0 = __shfl_down_sync(0xffffffffu, v[2 * ph], 1);
-        const float p1 = __shfl_down_sync(0xffffffffu, v[2 * ph + 1], 1);
-        float acc = 0.f + v[2 * ph];
-        acc = acc + p0;
-        acc = acc + v[2 * ph + 1];
-        acc = acc + p1;
-        o[ph] = acc * 0.25f;  // == acc / 4 exactly
-      }
-      if (live && !(sx & 1)) {
-        float* oc = os + c * 49 + (sx >> 1);
-#pragma unroll
-        for (int ph = 0; ph < 7; ++ph) oc[ph * 7] = o[ph];
+      const float* tc = tile + (c >> 3) * box_floats + (c & 7) * BW + (tx.i0[sx] - xs);
+      float* oc = os + c * 49 + (sx >> 1);
+      if (half == 0)
+        fwd_task<0, 8>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), oc);
+      else
+        fwd_task<8, 14>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), oc);
+    } else {
+      for (int base_task = warp * 32; base_task < total; base_task += kComputeThreads) {
+        const int task = base_task + lane;
+        const bool live = task < total;
+        const int tk = live ? task : total - 1;
+        const int c = tk / 14, sx = tk - c * 14;
+        const float* tc = tile + (c >> 3) * box_floats + (c & 7) * BW + (tx.i0[sx] - xs);
+        fwd_task<0, 14>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), os + c * 49 + (sx >> 1));
       }
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (t == 0) {
-      bulk_store(out + (size_t)c0 * 49, os, (uint32_t)nc * 49 * 4);
-      bulk_commit();
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp no longer reads the stage
+    fence_proxy_async_smem();                   // its out-stage writes are visible to the bulk copy
+    bar_arrive(kBarReady0 + s, kTmaThreads);
   }
-  if (t == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk store's reads
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward.  Whether a ROI is taken by the TMA kernel is a pure function of its geometry and the level mask, so the
-// direct scatter kernel of roi_align.cu (launched right after with the same mask) skips exactly those ROIs.
-constexpr int kBwdRawBytes = kMaxCCS * 49 * 4;     // dout chunk as it lies in memory
-constexpr int kBwdPadBytes = kMaxCCS * 56 * 4;     // dout chunk / 4, rows padded to 8 floats
-constexpr int kBwdWxBytes = 8 * kWClasses * 8 * 4;  // Wx[x][pw]
-constexpr int kBwdSmem = 2 * kBwdStageBytes + kBwdRawBytes + kBwdPadBytes + kBwdWxBytes + 1024;
+// Backward.  Whether a ROI is taken by the TMA kernel is a pure function of its geometry and the level mask
+// (roi_bwd_takes_tma, roi_common.cuh), so the direct scatter kernel of roi_align.cu (launched right after with the same
+// mask) skips exactly those ROIs.
+//
+// Per channel chunk the gradient tile of the footprint is built in shared memory and added to dfeat with one
+// cp.reduce.async.bulk.tensor per [8 rows][8 channels][BW] box.  A lane owns one footprint column of one channel
+// (8 / 16 / 32 lanes per channel, so small footprints pack 4 / 2 channels into a warp): T[ph] = sum_pw Wx[x][pw] / 4 *
+// dout[ph][pw] in registers, then the transposed walk of the forward: every sample row adds (1 - ly) * T and ly * T
+// to the two pixel rows it touches, a finished pixel row is stored once.  No atomics inside the CTA.  The DMA warp brings
+// the dout chunks in (1-D bulk copies) and sends the finished tiles out.
+constexpr int kBwdRawBytes = kMaxCCS * 49 * 4;      // dout chunk as it lies in memory
+constexpr int kBwdWxBytes = 8 * kWClasses * 8 * 4;  // Wx[x][pw] / 4
+constexpr int kBwdSmem = 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes;
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kTmaThreads, 2)
 roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
-  extern __shared__ unsigned char smem_raw[];
+  // dynamic shared memory: [tile stage 0][tile stage 1][raw 0][raw 1][wx]; 1024-byte aligned by declaration
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab ty, tx;
-  __shared__ __align__(8) uint64_t raw_bar;
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
+  __shared__ int roff[kBwdMaxRows + 1];
   const RoiArgs& p = a.r;
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
   if (!g.valid) return;
   FwdPlan plan;
   if (roi_bwd_takes_tma(p, g, a.level_mask, &plan) != 1) return;  // the direct kernel takes this ROI, or nothing to do
-  const uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023;
-  auto stage = [&](int s) { return reinterpret_cast<float*>(base + (uintptr_t)s * kBwdStageBytes); };
-  float* raw = reinterpret_cast<float*>(base + 2 * kBwdStageBytes);
-  float* pad = reinterpret_cast<float*>(base + 2 * kBwdStageBytes + kBwdRawBytes);
-  float* wx = reinterpret_cast<float*>(base + 2 * kBwdStageBytes + kBwdRawBytes + kBwdPadBytes);
-  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kThreads);
-  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kThreads);
-  if (t == 0) {
-    mbar_init(&raw_bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
+  float* const stage0 = reinterpret_cast<float*>(smem_raw);
+  float* const raw0 = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes);
+  float* const wx = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes + 2 * kBwdRawBytes);
+  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
+  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
   const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;
-  const int box_floats = kBoxC * kBoxH * BW;
+  const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
   const int rb_stride = ncb * box_floats;
   const int n_chunks = (p.C + CCS - 1) / CCS;
   const int rows = nrb * kBoxH;
-  const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
   const int z0 = g.n * p.C;
   const float* dout = p.dout + (size_t)k * p.C * 49;
+  for (int r = t; r <= rows; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
   if (t == 0) {
-    mbar_expect_tx(&raw_bar, (uint32_t)min(CCS, p.C) * 196);
-    bulk_load(raw, dout, (uint32_t)min(CCS, p.C) * 196, &raw_bar);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], kComputeThreads / 32);
+    mbar_init(&empty_bar[1], kComputeThreads / 32);
+    mbar_fence_init();
   }
-  // Wx[x][pw]: summed tap weights of bin pw's two sample columns on footprint column x (zero beyond the footprint)
-  for (int i = t; i < BW * 8; i += kThreads) {
+  __syncthreads();  // tables, barriers
+  // Wx[x][pw] / 4: summed tap weights of bin pw's two sample columns on footprint column x (zero beyond the footprint);
+  // the factor 1 / (samples per bin) is folded in here (a power of two: the products are unchanged)
+  for (int i = t; i < BW * 8; i += kTmaThreads) {
     const int x = i >> 3, pw = i & 7;
     float w = 0.f;
     if (pw < 7) {
@@ -241,111 +293,132 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
         w += rel == x ? 1.f - fr : (rel + 1 == x ? fr : 0.f);
       }
     }
-    wx[i] = w;
+    wx[i] = w * 0.25f;
   }
-  int yr[14];
+  __syncthreads();
+
+  if (warp == kComputeThreads / 32) {
+    // ---------------- DMA warp: dout chunks in, finished tiles out (reduce-add into dfeat)
+    const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
+    auto load = [&](int chunk) {
+      const int s = chunk & 1;
+      if (chunk >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((chunk >> 1) - 1) & 1));
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)min(CCS, p.C - chunk * CCS) * 196;
+        mbar_expect_tx(&full_bar[s], bytes);
+        bulk_load(raw0 + s * (kBwdRawBytes / 4), dout + (size_t)chunk * CCS * 49, bytes, &full_bar[s]);
+      }
+    };
+    load(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int s = chunk & 1, c0 = chunk * CCS;
+      if (chunk + 1 < n_chunks) load(chunk + 1);
+      bar_sync(kBarReady0 + s, kTmaThreads);  // tile stage s holds chunk `chunk`
+      if (lane == 0) {
+        const int cbs = (min(CCS, p.C - c0) + kBoxC - 1) / kBoxC;
+        const float* tile = stage0 + s * (kBwdStageBytes / 4);
+        for (int rb = 0; rb < nrb; ++rb)
+          for (int cb = 0; cb < cbs; ++cb)
+            tma_reduce_add_3d(map, xs, z0 + c0 + cb * kBoxC, ys + rb * kBoxH, tile + rb * rb_stride + cb * box_floats);
+        bulk_commit();
+        bulk_wait_read<0>();  // the tile is read out: the stage may be rewritten (and must outlive the reduce)
+      }
+      __syncwarp();
+      if (chunk + 2 < n_chunks) bar_arrive(kBarFree0 + s, kTmaThreads);
+    }
+    return;
+  }
+
+  // ---------------- compute warps
+  // per-thread copies of the (CTA-uniform) sample-row program; offset -1 = pixel row above the map (dropped)
+  int oA[14], oB[14];
   float fy[14];
+  unsigned act = 0;
 #pragma unroll
-  for (int s = 0; s < 14; ++s) {
-    yr[s] = ty.i0[s] - ys;
-    fy[s] = ty.frac[s];
+  for (int sy = 0; sy < 14; ++sy) {
+    const int r0 = ty.i0[sy] - ys;
+    oA[sy] = r0 >= 0 ? roff[r0] : -1;
+    oB[sy] = r0 + 1 >= 0 ? roff[r0 + 1] : -1;
+    fy[sy] = ty.frac[sy];
+    if (sy > 0) {
+      const int d = r0 - (ty.i0[sy - 1] - ys);
+      act |= (d == 0 ? 0u : (d == 1 ? 1u : 2u)) << (2 * sy);
+    }
   }
+  const int r_last = ty.i0[13] - ys;
   // lanes per channel: 8 / 16 / 32 (two column passes when BW > 32)
   const int lpc = BW <= 8 ? 8 : (BW <= 16 ? 16 : 32);
   const int cpw = 32 / lpc;                       // channels per warp pass
   const int xl = lane & (lpc - 1), csub = lane / lpc;
   const int xpasses = (BW + 31) / 32;
-  __syncthreads();
 
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, p.C - c0);
-    mbar_wait(&raw_bar, (uint32_t)(chunk & 1));
-    for (int i = t; i < nc * 49; i += kThreads) {   // dout / 4 into rows of 8 floats
-      const int c = i / 49, j = i - c * 49;
-      const int ph = j / 7, pw = j - ph * 7;
-      pad[c * 56 + ph * 8 + pw] = raw[i] * 0.25f;
-    }
-    if (warp == 0) bulk_wait_read<1>();             // bulk groups are per thread: the lanes that issued the reduces of
-                                                    // chunk - 2 (from stage[s]) wait for their shared-memory reads
-    __syncthreads();
-    if (t == 0 && chunk + 1 < n_chunks) {
-      const int nn = min(CCS, p.C - c0 - CCS);
-      mbar_expect_tx(&raw_bar, (uint32_t)nn * 196);
-      bulk_load(raw, dout + (size_t)(c0 + CCS) * 49, (uint32_t)nn * 196, &raw_bar);
-    }
-    float* tile = stage(s);
-    for (int cb = warp * cpw; cb < nc; cb += (kThreads / 32) * cpw) {
+    if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the reduce of chunk - 2 has read tile stage s
+    mbar_wait(&full_bar[s], (uint32_t)((chunk >> 1) & 1));
+    float* tile = stage0 + s * (kBwdStageBytes / 4);
+    const float* raw = raw0 + s * (kBwdRawBytes / 4);
+    for (int cb = warp * cpw; cb < nc; cb += (kComputeThreads / 32) * cpw) {
       const int c = cb + csub;
       const bool cok = c < nc;
-      const float* dc = pad + (cok ? c : nc - 1) * 56;
+      const float* dc = raw + (cok ? c : nc - 1) * 49;
       for (int xp = 0; xp < xpasses; ++xp) {
         const int x = xp * 32 + xl;
-        const bool xok = x < BW;
+        const bool ok = cok && x < BW;
         float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-        if (xok) {
+        if (x < BW) {
           wa = *reinterpret_cast<const float4*>(wx + x * 8);
           wb = *reinterpret_cast<const float4*>(wx + x * 8 + 4);
         }
         float T[7];
 #pragma unroll
         for (int ph = 0; ph < 7; ++ph) {
-          const float4 u = *reinterpret_cast<const float4*>(dc + ph * 8);
-          const float4 w2 = *reinterpret_cast<const float4*>(dc + ph * 8 + 4);
-          float v = wa.x * u.x;
-          v = __fmaf_rn(wa.y, u.y, v);
-          v = __fmaf_rn(wa.z, u.z, v);
-          v = __fmaf_rn(wa.w, u.w, v);
-          v = __fmaf_rn(wb.x, w2.x, v);
-          v = __fmaf_rn(wb.y, w2.y, v);
-          v = __fmaf_rn(wb.z, w2.z, v);
+          const float* d = dc + ph * 7;
+          float v = wa.x * d[0];
+          v = __fmaf_rn(wa.y, d[1], v);
+          v = __fmaf_rn(wa.z, d[2], v);
+          v = __fmaf_rn(wa.w, d[3], v);
+          v = __fmaf_rn(wb.x, d[4], v);
+          v = __fmaf_rn(wb.y, d[5], v);
+          v = __fmaf_rn(wb.z, d[6], v);
           T[ph] = v;
         }
-        float* tcol = tile + (c >> 3) * box_floats + (c & 7) * (kBoxH * BW) + x;
-        auto put = [&](int r, float v) {
-          if (cok && xok && r >= 0) tcol[(r >> 3) * rb_stride + (r & 7) * BW] = v;  // r < 0: rows above the map
+        float* tcol = tile + (c >> 3) * box_floats + (c & 7) * BW + x;
+        auto put = [&](int off, float v) {
+          if (ok && off >= 0) tcol[off] = v;
         };
-        // walk the 14 sample rows (CTA-uniform program): rows r0, r0 + 1 accumulate in registers, finished rows are
-        // stored once, rows no sample touches are stored as zeros (the reduce adds the whole box)
-        int rcur = yr[0];
         float ra = 0.f, rb2 = 0.f;
 #pragma unroll
         for (int sy = 0; sy < 14; ++sy) {
-          const int r0 = yr[sy];
-          if (r0 != rcur) {
-            put(rcur, ra);
-            if (r0 == rcur + 1) {
+          const unsigned code = sy == 0 ? 0u : ((act >> (2 * sy)) & 3u);  // uniform
+          if (code != 0u) {
+            put(oA[sy - (sy > 0)], ra);            // the upper row of the previous sample is complete
+            if (code == 1u) {
               ra = rb2;
             } else {
-              put(rcur + 1, rb2);
-              for (int r = rcur + 2; r < r0; ++r) put(r, 0.f);
+              put(oB[sy - (sy > 0)], rb2);
+              for (int r = ty.i0[sy - (sy > 0)] - ys + 2; r < ty.i0[sy] - ys; ++r)   // rows no sample touches
+                if (r >= 0) put(roff[r], 0.f);
               ra = 0.f;
             }
             rb2 = 0.f;
-            rcur = r0;
           }
           const float tv = T[sy >> 1];
           ra = __fmaf_rn(1.f - fy[sy], tv, ra);
           rb2 = __fmaf_rn(fy[sy], tv, rb2);
         }
-        put(rcur, ra);
-        put(rcur + 1, rb2);
-        for (int r = rcur + 2; r < rows; ++r) put(r, 0.f);
+        put(oA[13], ra);
+        put(oB[13], rb2);
+        for (int r = r_last + 2; r < rows; ++r)    // the reduce adds whole boxes: rows below the footprint are zeros
+          if (r >= 0) put(roff[r], 0.f);
       }
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 0) {
-      const int cbs = (nc + kBoxC - 1) / kBoxC;
-      const int nbox = nrb * cbs;
-      for (int b = lane; b < nbox; b += 32) {
-        const int rb = b / cbs, cbx = b - rb * cbs;
-        tma_reduce_add_3d(map, xs, ys + rb * kBoxH, z0 + c0 + cbx * kBoxC, tile + rb * rb_stride + cbx * box_floats);
-      }
-      bulk_commit();
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp no longer reads raw stage s
+    fence_proxy_async_smem();                   // its tile writes are visible to the reduce
+    bar_arrive(kBarReady0 + s, kTmaThreads);
   }
-  if (warp == 0) bulk_wait_read<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -395,9 +468,11 @@ static bool level_maps(const void* ptr, int H, int W, long long BC, const CUtens
     if (cache->size() > 256) cache->clear();
     LevelMaps lm;
     for (int c = 0; c < kWClasses; ++c) {
-      cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BC};
-      cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-      cuuint32_t box[3] = {(cuuint32_t)(8 * (c + 1)), (cuuint32_t)kBoxH, (cuuint32_t)kBoxC};
+      // dimension order (x, channel, y): a box lands in shared memory as [8 rows][8 channels][BW], so the lanes of a
+      // warp, which read one pixel row of neighbouring channels, spread over the banks (channel stride = BW floats)
+      cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)BC, (cuuint64_t)H};
+      cuuint64_t strides[2] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4};
+      cuuint32_t box[3] = {(cuuint32_t)(8 * (c + 1)), (cuuint32_t)kBoxC, (cuuint32_t)kBoxH};
       cuuint32_t es[3] = {1, 1, 1};
       alignas(64) CUtensorMap m;
       CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
@@ -449,9 +524,9 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
   }
   if (!ta.level_mask) return 0;
   ta.gmaps = debug_global_maps(maps, st);
-  if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
+  if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_fwd: cannot reserve %d bytes of shared memory", kFwdSmem);
-  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<256><<<a.K, 256, kFwdSmem, st>>>(ta, *maps));
+  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K, kTmaThreads, kFwdSmem, st>>>(ta, *maps));
   return 1;
 }
 
@@ -476,9 +551,9 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
   }
   if (!ta.level_mask) return 0;
   ta.gmaps = debug_global_maps(maps, st);
-  if (cudaFuncSetAttribute(roi_align_bwd_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
+  if (cudaFuncSetAttribute(roi_align_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_bwd: cannot reserve %d bytes of shared memory", kBwdSmem);
-  BDET_KERNEL("roi_align_bwd_tma_kernel", st, roi_align_bwd_tma_kernel<256><<<a.K, 256, kBwdSmem, st>>>(ta, *maps));
+  BDET_KERNEL("roi_align_bwd_tma_kernel", st, roi_align_bwd_tma_kernel<<<a.K, kTmaThreads, kBwdSmem, st>>>(ta, *maps));
   *level_mask_out = ta.level_mask;
   return 1;
 }
