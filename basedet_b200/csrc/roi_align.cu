@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   const float cnt = (float)(p.SH * p.SW);
   float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
   const float* dout = p.dout + (long long)k * p.C * PH * PW;
-  float* sdw = sd + warp * PH * PWs;
+  float* sdw = sd + warp * (PH == 7 && PW == 7 ? 4 * 56 : PH * PWs);  // 7 x 7: up to 4 packed channels per warp
   for (int fy = y_lo; fy <= y_hi; fy += kFpChunk) {
     for (int fx = x_lo; fx <= x_hi; fx += kFpChunk) {
       const int nr = min(kFpChunk, y_hi - fy + 1), ncol = min(kFpChunk, x_hi - fx + 1);
@@ -329,38 +329,52 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
         // footprint column: T[ph] = sum_pw Wx[x][pw] * dout[ph][pw], then per footprint row (warp-uniform weights,
         // broadcast loads) sum_ph Wy[y][ph] * T[ph] and one coalesced red.  Dense 7-term sums: weights outside a
         // bin's range are zero, so there is no data-dependent branch.
+        // Narrow footprints pack G = 4 / 2 channels into a warp (8 / 16 lanes per channel), so that a 6-pixel-wide ROI
+        // does not leave 26 lanes idle; G consecutive channels are 49 * G contiguous floats of dout.
+        const int lpc = ncol <= 8 ? 8 : (ncol <= 16 ? 16 : 32);
+        const int G = 32 / lpc;
+        const int sub = lane / lpc, xl = lane - sub * lpc;
+        const int nd = 49 * G;                                   // dout floats per warp pass
+        float* sdg = sdw + sub * 56;
         for (int x0 = 0; x0 < ncol; x0 += 32) {
-          const int xx = x0 + lane;
+          const int xx = x0 + xl;
           const bool xok = xx < ncol;
           float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
           if (xok) {
             wa = *reinterpret_cast<const float4*>(wx + xx * 8);
             wb = *reinterpret_cast<const float4*>(wx + xx * 8 + 4);
           }
-          // dout of the next channel is fetched while the current one is processed (the load is the only long
+          // dout of the next channel group is fetched while the current one is processed (the load is the only long
           // latency of the loop)
-          const int i1 = lane + 32;
-          const int s0 = (lane / 7) * 8 + (lane % 7), s1 = (i1 / 7) * 8 + (i1 % 7);
-          float d0 = 0.f, d1 = 0.f;
-          if (warp < p.C) {
-            d0 = __ldg(dout + (long long)warp * 49 + lane);
-            if (i1 < 49) d1 = __ldg(dout + (long long)warp * 49 + i1);
-          }
-          for (int c = warp; c < p.C; c += kRoiThreads / 32) {
-            __syncwarp();
-            sdw[s0] = __fdiv_rn(d0, cnt);
-            if (i1 < 49) sdw[s1] = __fdiv_rn(d1, cnt);
-            __syncwarp();
-            const int cn = c + kRoiThreads / 32;
-            if (cn < p.C) {
-              d0 = __ldg(dout + (long long)cn * 49 + lane);
-              if (i1 < 49) d1 = __ldg(dout + (long long)cn * 49 + i1);
+          float dr[7];
+          auto fetch = [&](int c) {
+            const float* src = dout + (long long)c * 49;
+            const int n = min(nd, (p.C - c) * 49);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              const int i = lane + 32 * j;
+              dr[j] = (j * 32 < nd && i < n) ? __ldg(src + i) : 0.f;
             }
+          };
+          if (warp * G < p.C) fetch(warp * G);
+          for (int c = warp * G; c < p.C; c += (kRoiThreads / 32) * G) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              const int i = lane + 32 * j;
+              if (j * 32 < nd && i < nd) {
+                const int ch = i / 49, q = i - ch * 49;
+                sdw[ch * 56 + (q / 7) * 8 + (q % 7)] = __fdiv_rn(dr[j], cnt);
+              }
+            }
+            __syncwarp();
+            const int cn = c + (kRoiThreads / 32) * G;
+            if (cn < p.C) fetch(cn);
             float T[7];
 #pragma unroll
             for (int ph = 0; ph < 7; ++ph) {
-              const float4 a = *reinterpret_cast<const float4*>(sdw + ph * 8);
-              const float4 b = *reinterpret_cast<const float4*>(sdw + ph * 8 + 4);
+              const float4 a = *reinterpret_cast<const float4*>(sdg + ph * 8);
+              const float4 b = *reinterpret_cast<const float4*>(sdg + ph * 8 + 4);
               float v = wa.x * a.x;
               v = __fmaf_rn(wa.y, a.y, v);
               v = __fmaf_rn(wa.z, a.z, v);
@@ -370,7 +384,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
               v = __fmaf_rn(wb.z, b.z, v);
               T[ph] = v;
             }
-            float* gp = dfeat + (long long)c * H * W + (long long)fy * W + (fx + xx);
+            const bool ok = xok && c + sub < p.C;
+            float* gp = dfeat + (long long)(c + sub) * H * W + (long long)fy * W + (fx + xx);
 #pragma unroll 4
             for (int r = 0; r < nr; ++r, gp += W) {
               const float4 u = *reinterpret_cast<const float4*>(wy + r * 8);
@@ -382,7 +397,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
               sum = __fmaf_rn(w2.x, T[4], sum);
               sum = __fmaf_rn(w2.y, T[5], sum);
               sum = __fmaf_rn(w2.z, T[6], sum);
-              if (xok && sum != 0.f) atomicAdd(gp, sum);
+              if (ok && sum != 0.f) atomicAdd(gp, sum);
             }
           }
         }
@@ -586,7 +601,7 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
   }
   if (K == 0) return BDET_OK;
   const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;
-  const size_t smem = ((size_t)kFpChunk * (PHs + PWs) + (size_t)(kRoiThreads / 32) * PH * PWs) * 4;
+  const size_t smem = ((size_t)kFpChunk * (PHs + PWs) + (size_t)(kRoiThreads / 32) * (PH == 7 && PW == 7 ? 4 * 56 : PH * PWs)) * 4;
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -126,12 +126,14 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st);
 constexpr int kBoxH = 8, kBoxC = 8;     // rows / channels of one TMA box
 constexpr int kWClasses = 7;            // box widths 8, 16, ..., 56 floats (4 levels x 7 maps + args < 4 KB of params)
 constexpr int kTmaLevels = 4;
-constexpr int kStageBytes = 40 * 1024;  // one pipeline stage of footprint boxes
+constexpr int kRingBytes = 80 * 1024;   // forward: ring of footprint stages
+constexpr int kChunkBytes = 40 * 1024;  // stage size at most (small footprints: 64 channels per stage, all stages in flight)
+constexpr int kMaxSlots = 8;
 constexpr int kFwdMaxRows = 64;
 constexpr int kBwdMaxRows = 64;        // footprint rows of a forward stage at most
 constexpr int kMaxCCS = 64;             // channels per stage at most
 constexpr int kOutStageBytes = kMaxCCS * 49 * 4;
-constexpr int kFwdSmem = 2 * kStageBytes + 2 * kOutStageBytes;
+constexpr int kFwdSmem = kRingBytes + 2 * kOutStageBytes;
 
 constexpr int kBwdStageBytes = 36 * 1024;
 
@@ -148,6 +150,8 @@ struct FwdPlan {
 // to the map and the taps in front of it, which the reference drops anyway, never enter the tile.
 __device__ __forceinline__ int bwd_plan(const RoiArgs& p, const RoiGeom& g, unsigned level_mask, int x_first, int x_last,
                                         int y_first, int y_last, FwdPlan* pl) {
+  const int max_cls = (int)(level_mask >> 16);  // widest box class the TMA backward takes (bits 16..): tuned, see DESIGN.md
+  level_mask &= 0xffffu;
   pl->cls = -1;
   pl->nrb = 0;
   pl->ccs = 0;
@@ -159,7 +163,7 @@ __device__ __forceinline__ int bwd_plan(const RoiArgs& p, const RoiGeom& g, unsi
   pl->ys = max(y_first, 0);
   const long long fw = (long long)x_last + 2 - pl->xs, fh = (long long)y_last + 2 - pl->ys;
   if (fw < 1 || fh < 1 || pl->xs >= g.W || pl->ys >= g.H) return 2;
-  if (fw > 8 * kWClasses || fh > kBwdMaxRows) return 0;
+  if (fw > 8 * (max_cls + 1) || fw > 8 * kWClasses || fh > kBwdMaxRows) return 0;
   const int cls = (int)((fw + 7) / 8) - 1;
   const int nrb = (int)((fh + kBoxH - 1) / kBoxH);
   const long long per_c = (long long)nrb * kBoxH * 8 * (cls + 1) * 4;

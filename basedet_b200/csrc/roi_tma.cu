@@ -83,7 +83,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   // dynamic shared memory: [stage 0][stage 1][out stage 0][out stage 1]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab ty, tx;
-  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
   __shared__ FwdPlan plan;
   __shared__ int roff[kFwdMaxRows + 1];
   const RoiArgs& p = a.r;
@@ -97,10 +97,10 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
   fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
   if (t == 0) {
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
-    mbar_init(&empty_bar[0], kComputeThreads / 32);
-    mbar_init(&empty_bar[1], kComputeThreads / 32);
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kComputeThreads / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -118,8 +118,11 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       pl.cls = (int)((fw + 7) / 8) - 1;
       pl.nrb = (int)((fh + kBoxH - 1) / kBoxH);
       const long long per_c = (long long)pl.nrb * kBoxH * 8 * (pl.cls + 1) * 4;  // bytes per channel
-      const long long fit = kStageBytes / per_c;
-      // 14 tasks per channel on 256 threads: 16 / 32 / 48 / 64 channels fill 7 of 8 warps per pass, 8 channels run split
+      // chunks of <= kChunkBytes keep several stages of the ring in flight (the loads are latency bound); footprints too
+      // large for that take a whole half of the ring per chunk.  14 tasks per channel on 256 threads: 16 / 32 / 48 / 64
+      // channels fill 7 of 8 warps per pass, 8 channels run split
+      long long fit = kChunkBytes / per_c;
+      if (fit < 8) fit = (kRingBytes / 2) / per_c;
       int ccs = fit >= 64 ? 64 : (fit >= 48 ? 48 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0))));
       if (ccs > p.C) ccs = p.C;
       pl.ccs = ccs;
@@ -134,13 +137,16 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   }
   // ---- TMA path
   float* const stage0 = reinterpret_cast<float*>(smem_raw);
-  float* const ostage0 = reinterpret_cast<float*>(smem_raw + 2 * kStageBytes);
+  float* const ostage0 = reinterpret_cast<float*>(smem_raw + kRingBytes);
   const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;                    // channel boxes per stage
   const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
   const int rb_stride = ncb * box_floats;         // floats between row boxes of a stage
   const int n_chunks = (p.C + CCS - 1) / CCS;
   const int z0 = g.n * p.C;
+  // ring of footprint stages: slot = one chunk (rounded up to 1 KB), as many slots as fit (2 .. kMaxSlots)
+  const int slot_floats = ((nrb * rb_stride * 4 + 1023) & ~1023) / 4;
+  const int nslots = min(min(kMaxSlots, n_chunks), kRingBytes / (slot_floats * 4));
   for (int r = t; r <= nrb * kBoxH; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
   __syncthreads();  // roff
 
@@ -148,21 +154,21 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     // ---------------- DMA warp: footprint boxes in, finished output chunks out
     const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
     auto load = [&](int chunk) {
-      const int s = chunk & 1, c0 = chunk * CCS;
-      if (chunk >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((chunk >> 1) - 1) & 1));  // the compute warps are done with it
+      const int round = chunk / nslots, s = chunk - round * nslots, c0 = chunk * CCS;
+      if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));  // the compute warps are done with the slot
       if (lane == 0) {
         const int cbs = min(ncb, (p.C - c0 + kBoxC - 1) / kBoxC);
         mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_floats * 4);
         for (int rb = 0; rb < nrb; ++rb)
           for (int cb = 0; cb < cbs; ++cb)
-            tma_load_3d(stage0 + s * (kStageBytes / 4) + rb * rb_stride + cb * box_floats, map, xs, z0 + c0 + cb * kBoxC,
+            tma_load_3d(stage0 + s * slot_floats + rb * rb_stride + cb * box_floats, map, xs, z0 + c0 + cb * kBoxC,
                         ys + rb * kBoxH, &full_bar[s]);
       }
     };
-    load(0);
+    for (int c = 0; c < nslots - 1; ++c) load(c);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int s = chunk & 1, c0 = chunk * CCS;
-      if (chunk + 1 < n_chunks) load(chunk + 1);
+      if (chunk + nslots - 1 < n_chunks) load(chunk + nslots - 1);
       bar_sync(kBarReady0 + s, kTmaThreads);  // the out stage holds chunk `chunk`
       if (lane == 0) {
         bulk_store(out + (size_t)c0 * 49, ostage0 + s * (kOutStageBytes / 4), (uint32_t)min(CCS, p.C - c0) * 49 * 4);
@@ -197,8 +203,9 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, p.C - c0);
     if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the bulk store of chunk - 2 has read the out stage
-    mbar_wait(&full_bar[s], (uint32_t)((chunk >> 1) & 1));
-    const float* tile = stage0 + s * (kStageBytes / 4);
+    const int round = chunk / nslots, slot = chunk - round * nslots;
+    mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
+    const float* tile = stage0 + slot * slot_floats;
     float* os = ostage0 + s * (kOutStageBytes / 4);
     const int total = nc * 14;
     if (split) {
@@ -224,7 +231,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp no longer reads the stage
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp no longer reads the stage
     fence_proxy_async_smem();                   // its out-stage writes are visible to the bulk copy
     bar_arrive(kBarReady0 + s, kTmaThreads);
   }
@@ -238,20 +245,23 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
 // Per channel chunk the gradient tile of the footprint is built in shared memory and added to dfeat with one
 // cp.reduce.async.bulk.tensor per [8 rows][8 channels][BW] box.  A lane owns one footprint column of one channel
 // (8 / 16 / 32 lanes per channel, so small footprints pack 4 / 2 channels into a warp): T[ph] = sum_pw Wx[x][pw] / 4 *
-// dout[ph][pw] in registers, then the transposed walk of the forward: every sample row adds (1 - ly) * T and ly * T
-// to the two pixel rows it touches, a finished pixel row is stored once.  No atomics inside the CTA.  The DMA warp brings
-// the dout chunks in (1-D bulk copies) and sends the finished tiles out.
+// dout[ph][pw] in registers, then per box row the 7-term dot product with Wy[row][:] (the separable weights of the
+// direct kernel) and one store.  No atomics inside the CTA.  The DMA warp brings the dout chunks in (1-D bulk copies)
+// and sends the finished tiles out.
+constexpr int kBwdTmaDefaultCls = -1;  // measured (profiles/): the direct scatter kernel is faster on every ROI mix tried
 constexpr int kBwdRawBytes = kMaxCCS * 49 * 4;      // dout chunk as it lies in memory
 constexpr int kBwdWxBytes = 8 * kWClasses * 8 * 4;  // Wx[x][pw] / 4
-constexpr int kBwdSmem = 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes;
+constexpr int kBwdWyBytes = kBwdMaxRows * 8 * 4;   // Wy[row][ph]
+constexpr int kBwdSmem = 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes + kBwdWyBytes;
 
 __global__ void __launch_bounds__(kTmaThreads, 2)
 roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
-  // dynamic shared memory: [tile stage 0][tile stage 1][raw 0][raw 1][wx]; 1024-byte aligned by declaration
+  // dynamic shared memory: [tile stage 0][tile stage 1][raw 0][raw 1][wx][wy]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab ty, tx;
-  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
   __shared__ int roff[kBwdMaxRows + 1];
+  __shared__ float trash[32];  // lanes beyond the box width store here (keeps the stores branch-free)
   const RoiArgs& p = a.r;
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
@@ -261,6 +271,7 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   float* const stage0 = reinterpret_cast<float*>(smem_raw);
   float* const raw0 = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes);
   float* const wx = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes + 2 * kBwdRawBytes);
+  float* const wy = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes);
   fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
   fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
   const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
@@ -271,12 +282,15 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   const int rows = nrb * kBoxH;
   const int z0 = g.n * p.C;
   const float* dout = p.dout + (size_t)k * p.C * 49;
+  // ring of dout chunks (CCS * 196 bytes each): as many slots as fit, so that the loads run several chunks ahead
+  const int raw_floats = CCS * 49;
+  const int nslots = min(min(kMaxSlots, n_chunks), (2 * kBwdRawBytes) / (raw_floats * 4));
   for (int r = t; r <= rows; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
   if (t == 0) {
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
-    mbar_init(&empty_bar[0], kComputeThreads / 32);
-    mbar_init(&empty_bar[1], kComputeThreads / 32);
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kComputeThreads / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();  // tables, barriers
@@ -295,24 +309,39 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     }
     wx[i] = w * 0.25f;
   }
+  // Wy[r][ph]: the same for the rows; all `rows` rows of the boxes are filled, so rows no sample touches get zero weights
+  // and the tile needs no separate zero fill (the reduce adds whole boxes)
+  for (int i = t; i < rows * 8; i += kTmaThreads) {
+    const int r = i >> 3, ph = i & 7;
+    float w = 0.f;
+    if (ph < 7) {
+#pragma unroll
+      for (int iy = 0; iy < 2; ++iy) {
+        const int syi = 2 * ph + iy, rel = ty.i0[syi] - ys;
+        const float fr = ty.frac[syi];
+        w += rel == r ? 1.f - fr : (rel + 1 == r ? fr : 0.f);
+      }
+    }
+    wy[i] = w;
+  }
   __syncthreads();
 
   if (warp == kComputeThreads / 32) {
     // ---------------- DMA warp: dout chunks in, finished tiles out (reduce-add into dfeat)
     const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
     auto load = [&](int chunk) {
-      const int s = chunk & 1;
-      if (chunk >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((chunk >> 1) - 1) & 1));
+      const int round = chunk / nslots, s = chunk - round * nslots;
+      if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)min(CCS, p.C - chunk * CCS) * 196;
         mbar_expect_tx(&full_bar[s], bytes);
-        bulk_load(raw0 + s * (kBwdRawBytes / 4), dout + (size_t)chunk * CCS * 49, bytes, &full_bar[s]);
+        bulk_load(raw0 + s * raw_floats, dout + (size_t)chunk * CCS * 49, bytes, &full_bar[s]);
       }
     };
-    load(0);
+    for (int c = 0; c < nslots - 1; ++c) load(c);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int s = chunk & 1, c0 = chunk * CCS;
-      if (chunk + 1 < n_chunks) load(chunk + 1);
+      if (chunk + nslots - 1 < n_chunks) load(chunk + nslots - 1);
       bar_sync(kBarReady0 + s, kTmaThreads);  // tile stage s holds chunk `chunk`
       if (lane == 0) {
         const int cbs = (min(CCS, p.C - c0) + kBoxC - 1) / kBoxC;
@@ -330,22 +359,6 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   }
 
   // ---------------- compute warps
-  // per-thread copies of the (CTA-uniform) sample-row program; offset -1 = pixel row above the map (dropped)
-  int oA[14], oB[14];
-  float fy[14];
-  unsigned act = 0;
-#pragma unroll
-  for (int sy = 0; sy < 14; ++sy) {
-    const int r0 = ty.i0[sy] - ys;
-    oA[sy] = r0 >= 0 ? roff[r0] : -1;
-    oB[sy] = r0 + 1 >= 0 ? roff[r0 + 1] : -1;
-    fy[sy] = ty.frac[sy];
-    if (sy > 0) {
-      const int d = r0 - (ty.i0[sy - 1] - ys);
-      act |= (d == 0 ? 0u : (d == 1 ? 1u : 2u)) << (2 * sy);
-    }
-  }
-  const int r_last = ty.i0[13] - ys;
   // lanes per channel: 8 / 16 / 32 (two column passes when BW > 32)
   const int lpc = BW <= 8 ? 8 : (BW <= 16 ? 16 : 32);
   const int cpw = 32 / lpc;                       // channels per warp pass
@@ -356,9 +369,10 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, p.C - c0);
     if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the reduce of chunk - 2 has read tile stage s
-    mbar_wait(&full_bar[s], (uint32_t)((chunk >> 1) & 1));
+    const int round = chunk / nslots, slot = chunk - round * nslots;
+    mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
     float* tile = stage0 + s * (kBwdStageBytes / 4);
-    const float* raw = raw0 + s * (kBwdRawBytes / 4);
+    const float* raw = raw0 + slot * raw_floats;
     for (int cb = warp * cpw; cb < nc; cb += (kComputeThreads / 32) * cpw) {
       const int c = cb + csub;
       const bool cok = c < nc;
@@ -384,38 +398,30 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
           v = __fmaf_rn(wb.z, d[6], v);
           T[ph] = v;
         }
-        float* tcol = tile + (c >> 3) * box_floats + (c & 7) * BW + x;
-        auto put = [&](int off, float v) {
-          if (ok && off >= 0) tcol[off] = v;
-        };
-        float ra = 0.f, rb2 = 0.f;
+        // 32-bit shared addresses; a lane beyond the box width is redirected to its trash slot (branch-free stores)
+        const uint32_t tcol = smem_u32(tile + (c >> 3) * box_floats + (c & 7) * BW + x), tr = smem_u32(trash + lane);
+        const uint32_t row_pitch = ok ? (uint32_t)(kBoxC * BW) * 4u : 0u;
+        for (int rb = 0; rb < nrb; ++rb) {
+          uint32_t ad = ok ? tcol + (uint32_t)(rb * rb_stride) * 4u : tr;
+          const float* wr = wy + rb * (kBoxH * 8);
 #pragma unroll
-        for (int sy = 0; sy < 14; ++sy) {
-          const unsigned code = sy == 0 ? 0u : ((act >> (2 * sy)) & 3u);  // uniform
-          if (code != 0u) {
-            put(oA[sy - (sy > 0)], ra);            // the upper row of the previous sample is complete
-            if (code == 1u) {
-              ra = rb2;
-            } else {
-              put(oB[sy - (sy > 0)], rb2);
-              for (int r = ty.i0[sy - (sy > 0)] - ys + 2; r < ty.i0[sy] - ys; ++r)   // rows no sample touches
-                if (r >= 0) put(roff[r], 0.f);
-              ra = 0.f;
-            }
-            rb2 = 0.f;
+          for (int j = 0; j < kBoxH; ++j, ad += row_pitch) {
+            const float4 u = *reinterpret_cast<const float4*>(wr + j * 8);
+            const float4 w2 = *reinterpret_cast<const float4*>(wr + j * 8 + 4);
+            float sum = u.x * T[0];
+            sum = __fmaf_rn(u.y, T[1], sum);
+            sum = __fmaf_rn(u.z, T[2], sum);
+            sum = __fmaf_rn(u.w, T[3], sum);
+            sum = __fmaf_rn(w2.x, T[4], sum);
+            sum = __fmaf_rn(w2.y, T[5], sum);
+            sum = __fmaf_rn(w2.z, T[6], sum);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(sum) : "memory");
           }
-          const float tv = T[sy >> 1];
-          ra = __fmaf_rn(1.f - fy[sy], tv, ra);
-          rb2 = __fmaf_rn(fy[sy], tv, rb2);
         }
-        put(oA[13], ra);
-        put(oB[13], rb2);
-        for (int r = r_last + 2; r < rows; ++r)    // the reduce adds whole boxes: rows below the footprint are zeros
-          if (r >= 0) put(roff[r], 0.f);
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp no longer reads raw stage s
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp no longer reads its dout slot
     fence_proxy_async_smem();                   // its tile writes are visible to the reduce
     bar_arrive(kBarReady0 + s, kTmaThreads);
   }
@@ -496,6 +502,17 @@ static int tma_mode() {
   return on;
 }
 static bool tma_enabled() { return tma_mode() != 0; }
+// widest footprint class (box width 8 * (cls + 1)) the TMA backward takes; wider footprints go to the direct scatter
+// kernel.  BDET_ROI_BWD_TMA_CLS overrides (-1 = TMA backward off, 6 = every width).
+static int bwd_max_cls() {
+  static int v = -100;
+  if (v == -100) {
+    const char* e = getenv("BDET_ROI_BWD_TMA_CLS");
+    v = e ? atoi(e) : kBwdTmaDefaultCls;
+    if (v >= kWClasses) v = kWClasses - 1;
+  }
+  return v;
+}
 static const RoiTmaMaps* debug_global_maps(const RoiTmaMaps* host, cudaStream_t st) {
   if (tma_mode() != 2) return nullptr;
   RoiTmaMaps* d = nullptr;
@@ -550,6 +567,9 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
     }
   }
   if (!ta.level_mask) return 0;
+  const int max_cls = bwd_max_cls();
+  if (max_cls < 0) return 0;
+  ta.level_mask |= (unsigned)max_cls << 16;  // travels with the mask to both kernels (bwd_plan)
   ta.gmaps = debug_global_maps(maps, st);
   if (cudaFuncSetAttribute(roi_align_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_bwd: cannot reserve %d bytes of shared memory", kBwdSmem);

@@ -77,3 +77,19 @@ def test_tma_forward_many_rois_one_level_bit_exact():
     g = ops.roi_align_bwd(T(dout), [feat.shape], T(rois), None, [0.25], (7, 7))[0].cpu().numpy()
     gref = C.roi_align_bwd(dout, feat.shape, rois, (7, 7), 0.25)
     assert np.max(np.abs(g - gref)) / max(np.abs(gref).max(), 1.0) <= 1e-5
+
+
+def test_tma_backward_opt_in_path():
+    """The cp.reduce.async.bulk.tensor backward is opt-in (BDET_ROI_BWD_TMA_CLS, read once per process; the direct
+    scatter kernel measured faster): run this file's oracle comparison in a child process with it enabled for every
+    footprint width."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("BDET_ROI_BWD_TMA_CLS"):
+        pytest.skip("already inside the opt-in child")
+    env = dict(os.environ, BDET_ROI_BWD_TMA_CLS="6")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "vs_oracle or many_rois", "-x"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
