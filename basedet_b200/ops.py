@@ -53,7 +53,7 @@ def _rows(t, name="boxes"):
     """(N, >=4) fp32 view -> (tensor, ld): keeps row-strided views such as gt[:, :4] without a copy."""
     t = _f32(t, name)
     assert t.ndim == 2 and t.shape[1] >= 4
-    if t.shape[0] <= 1 or (t.stride(1) == 1 and t.stride(0) >= t.shape[1]):
+    if t.stride(1) == 1 and (t.shape[0] <= 1 or t.stride(0) >= t.shape[1]):
         return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 4))
     t = t.contiguous()
     return t, t.shape[1]

@@ -254,6 +254,16 @@ def roi_pool_forward_backward(features, rois, strides, pool_shape=(7, 7), dout=N
     return out, grads
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(torch.device("cuda", key))
+    return _SIDE_STREAMS[key]
+
+
 def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets, features, gt_boxes, num_gt, im_info,
                         noise_rpn, noise_rcnn, dout=None, rpn_strides=(4, 8, 16, 32, 64), rcnn_strides=(4, 8, 16, 32), prev_nms_topk=2000,
                         post_nms_topk=1000, nms_threshold=0.7, num_rois=512, pool_shape=(7, 7), plan=None, dfeats=None):
@@ -278,14 +288,25 @@ def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets
     # anchors: one launch for all levels; the per-level tensors are views of the flat buffer
     n_l = [int(s.shape[1]) for s in rpn_scores]
     anchors_all = anchor_generator.generate_all_level_anchors(feature_sizes, dev)
+    # Two branches of the step are independent of the proposal -> RCNN -> ROIAlign chain: the RPN targets (anchors and GT
+    # only) and the zero fill of dfeat.  Both go to a side stream (a second branch of the graph when captured): the chain
+    # is a sequence of short latency-bound launches that leaves most of the SMs and of the HBM bandwidth idle.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        rpn_labels, rpn_targets_ = rpn_targets(anchors_all, gt_boxes, num_gt, noise_rpn[:, 0], noise_rpn[:, 1], plan=plan)
+        if dout is not None:
+            if dfeats is None:
+                dfeats = [torch.empty_like(f) for f in features]
+            for d in dfeats:
+                d.zero_()
     offs = [0]
     for n in n_l:
         offs.append(offs[-1] + n)
     anchors_list = [anchors_all[offs[i]:offs[i + 1]] for i in range(len(n_l))]
     # RPN proposals (no gradient flows through them, rpn.py:186)
     rois, n_rois = rpn_proposals(rpn_scores, rpn_offsets, anchors_list, im_info, prev_nms_topk, post_nms_topk, nms_threshold)
-    # RPN targets
-    rpn_labels, rpn_targets_ = rpn_targets(anchors_all, gt_boxes, num_gt, noise_rpn[:, 0], noise_rpn[:, 1], plan=plan)
     # RCNN targets on the proposals
     s_rois, s_labels, s_targets, s_count = rcnn_targets(rois, n_rois, gt_boxes, num_gt, noise_rcnn[:, 0], noise_rcnn[:, 1],
                                                         num_rois=num_rois)
@@ -298,8 +319,8 @@ def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets
     pooled = ops.roi_align_fwd(features, flat_rois, levels, scales, pool_shape)
     out = dict(rois=rois, n_rois=n_rois, rpn_labels=rpn_labels, rpn_targets=rpn_targets_, rcnn_rois=s_rois,
                rcnn_labels=s_labels, rcnn_targets=s_targets, rcnn_count=s_count, pooled=pooled, levels=levels)
+    main.wait_stream(side)  # join: RPN targets done, dfeat zeroed
     if dout is not None:
-        out["dfeats"] = ops.roi_align_bwd(dout, [tuple(f.shape) for f in features], flat_rois, levels, scales, pool_shape,
-                                          dfeats=dfeats)
+        out["dfeats"] = ops.roi_align_bwd(dout, None, flat_rois, levels, scales, pool_shape, dfeats=dfeats, accumulate=True)
     return out
 

@@ -25,6 +25,18 @@ def _plain(t):
     return t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
 
 
+def _rescale_inplace(d, mean, std):
+    """deltas *= std; deltas += mean on the caller's tensor (two roundings, like the reference's two statements)."""
+    if not isinstance(d, torch.Tensor) or d.requires_grad or not d.is_floating_point():
+        return
+    if all(m == 0.0 for m in mean) and all(v == 1.0 for v in std):
+        return
+    k = d.shape[-1] // 4
+    with torch.no_grad():
+        d.mul_(torch.tensor(list(std) * k, dtype=d.dtype, device=d.device))
+        d.add_(torch.tensor(list(mean) * k, dtype=d.dtype, device=d.device))
+
+
 class BoxCoder(BoxCoderBase, metaclass=ABCMeta):
     def __init__(self, reg_mean=(0.0, 0.0, 0.0, 0.0), reg_std=(1.0, 1.0, 1.0, 1.0)):
         self.reg_mean = [float(v) for v in reg_mean]
@@ -37,9 +49,14 @@ class BoxCoder(BoxCoderBase, metaclass=ABCMeta):
         return ops.box_encode(_plain(bbox), _plain(gt), self.reg_mean, self.reg_std)
 
     def decode(self, anchors, deltas):
-        """boxcoder.py:75-98: (N,4),(N,4k) -> (N,4k).  Like the reference, ``deltas`` is rescaled IN PLACE
-        (deltas *= std; deltas += mean) when it is a contiguous fp32 tensor."""
-        return ops.box_decode(_plain(anchors), _plain(deltas), self.reg_mean, self.reg_std, writeback=True)
+        """boxcoder.py:75-98: (N,4),(N,4k) -> (N,4k).  Like the reference (:76-77), ``deltas`` is rescaled IN
+        PLACE (deltas *= std; deltas += mean) -- for any float dtype and layout, through torch in-place ops so that
+        autograd's version counter sees the write.  A tensor that is part of an autograd graph is left untouched (the
+        in-place write would corrupt the activations saved for backward); with the identity mean / std nothing is written."""
+        d = _plain(deltas)
+        out = ops.box_decode(_plain(anchors), d, self.reg_mean, self.reg_std, writeback=False)
+        _rescale_inplace(d, self.reg_mean, self.reg_std)
+        return out
 
 
 class SumBoxCoder(BoxCoderBase, metaclass=ABCMeta):
@@ -52,7 +69,10 @@ class SumBoxCoder(BoxCoderBase, metaclass=ABCMeta):
         return ops.sum_encode(_plain(anchors), _plain(gt), self.reg_mean, self.reg_std)
 
     def decode(self, anchors, deltas):
-        return ops.sum_decode(_plain(anchors), _plain(deltas), self.reg_mean, self.reg_std, writeback=True)
+        d = _plain(deltas)
+        out = ops.sum_decode(_plain(anchors), d, self.reg_mean, self.reg_std, writeback=False)
+        _rescale_inplace(d, self.reg_mean, self.reg_std)   # boxcoder.py:123-124, same rule as BoxCoder.decode
+        return out
 
 
 class PointCoder(BoxCoderBase, metaclass=ABCMeta):

@@ -15,8 +15,13 @@ def _pair(v):
 
 
 class Boxes(torch.Tensor):
-    """(N, 4) xyxy boxes.  Shares storage with the wrapped tensor (the reference shares ``__dict__``, boxes.py:26);
-    results of arithmetic are plain tensors, (N, 4) slices stay ``Boxes`` (boxes.py:214-219)."""
+    """(N, 4) xyxy boxes; results of arithmetic are plain tensors, (N, 4) slices stay ``Boxes`` (boxes.py:214-219).
+
+    Value semantics like the reference's: MegEngine tensors are values, ``Boxes(t)`` only shares ``__dict__`` (boxes.py:26),
+    and the in-place ``clip`` / ``scale`` (``self[:, 0::2] = ...``, boxes.py:170-177, 206-212) rebind the Boxes object --
+    the tensor it was built from keeps its values (``Boxes(proposals).clip(...)`` in rpn.py:168 leaves
+    ``proposals`` un-clipped, which is also what the fused ``pipelines.rpn_proposals`` does).  Construction is a
+    zero-copy alias; the first in-place operation detaches the Boxes onto private storage (copy on write)."""
 
     __torch_function__ = torch._C._disabled_torch_function_impl
 
@@ -64,13 +69,14 @@ class Boxes(torch.Tensor):
 
     def _apply(self, sw, sh, cw, ch, inplace):
         src = self._plain()
-        if inplace and src.is_contiguous() and src.dtype == torch.float32:
-            ops.boxes_scale_clip(src, sw, sh, cw, ch)
+        if inplace and getattr(self, "_owned", False) and src.is_contiguous() and src.dtype == torch.float32:
+            ops.boxes_scale_clip(src, sw, sh, cw, ch)  # already on private storage
             return self
         out = src.float().contiguous().clone()
         ops.boxes_scale_clip(out, sw, sh, cw, ch)
         if inplace:
-            src.copy_(out)
+            self.set_(out)  # rebinds THIS object only; the tensor it was built from is untouched
+            self._owned = True
             return self
         return out
 

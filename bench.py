@@ -128,6 +128,10 @@ def run_b200(args):
 
     def shard(name, scaling):
         n = BM.CONFIG_BATCH[name]
+        if args.simulate_world > 1 and world == 1:
+            # analysis aid: run rank 0's shard of a `simulate_world`-rank strong-scaling job on this one GPU
+            lo, hi = D.shard_range(n, 0, args.simulate_world)
+            return list(range(lo, max(hi, lo + 1))), max(hi - lo, 1), "strong-shard-of-%d" % args.simulate_world
         if scaling == "weak" or n < world:
             # weak: every rank runs the full batch (its own images); configs smaller than the world: one replica per rank
             return list(range(rank * n, (rank + 1) * n)), n * world, ("weak" if scaling == "weak" else "replicas")
@@ -403,6 +407,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--only", default="", help="comma-separated subset of c1,c2,c3,c4,c5")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of the CUDA graph replay")
+    ap.add_argument("--simulate-world", type=int, default=1,
+                    help="analysis aid (1 GPU): time rank 0's shard of an N-rank strong-scaling run")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and args.gpus != world:

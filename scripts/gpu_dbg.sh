@@ -1,12 +1,11 @@
 mkdir -p gpurun_out
-for cls in -1 0 1 2 3 6; do
-  BDET_ROI_BWD_TMA_CLS=$cls timeout 300 python bench.py --steps 10 --warmup 3 --only c3 > gpurun_out/bench_c3_cls$cls.json 2> gpurun_out/bench_c3_cls$cls.err
-  python - <<PY
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -q -m gpu -x -k "config3" 2>&1 | tail -3
+timeout 600 python bench.py --steps 20 --warmup 5 --only c3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -2 gpurun_out/bench_c3.err
+timeout 600 python bench.py --steps 20 --warmup 5 --only c3 --simulate-world 8 > gpurun_out/bench_sim8.json 2> gpurun_out/bench_sim8.err; tail -2 gpurun_out/bench_sim8.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_c3_cls$cls.json').read().strip().splitlines()[-1])
-k=d['configs']['c3']['kernels']
-print('cls $cls ms/step %.3f'%d['ms_per_step'], {n:round(v['avg_us']) for n,v in k.items() if 'roi_align' in n})
+for f in ('bench_c3','bench_sim8'):
+    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
+    c=d['configs']['c3']
+    print(f, c['images_total'],'img/s %.1f'%c['value'],'ms %.4f'%c['ms_per_step'],'e2e %.1f'%c['e2e']['value'])
 PY
-done
-BDET_ROI_BWD_TMA_CLS=1 timeout 300 python scripts/perf_roi.py 2>&1 | grep bwd
-BDET_ROI_BWD_TMA_CLS=2 timeout 300 python scripts/perf_roi.py 2>&1 | grep bwd

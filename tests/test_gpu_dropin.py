@@ -66,8 +66,14 @@ class TestBoxes:  # tests/structures/test_boxes.py
         assert np.allclose(b2.width.cpu().numpy(), [1, 0.5, 1, 0.5, 0.5, 1.0])
         raw = torch.tensor([[-5.0, 2.0, 50.0, 80.0]], device=cuda)
         bx = Boxes(raw)
-        bx.clip((60, 40))
-        assert raw.cpu().numpy().tolist() == [[0.0, 2.0, 40.0, 60.0]]  # storage shared with the wrapped tensor
+        assert bx.data_ptr() == raw.data_ptr()                          # construction is a zero-copy alias ...
+        out = bx.clip((60, 40))
+        assert out is bx and bx.cpu().numpy().tolist() == [[0.0, 2.0, 40.0, 60.0]]
+        # ... and the in-place op detaches: MegEngine tensors are values, the wrapped tensor keeps its coordinates
+        # (SURVEY N3 / rpn.py:168: Boxes(proposals).clip(...) leaves `proposals` un-clipped)
+        assert raw.cpu().numpy().tolist() == [[-5.0, 2.0, 50.0, 80.0]]
+        bx.scale((2.0, 0.5))
+        assert bx.cpu().numpy().tolist() == [[0.0, 4.0, 20.0, 120.0]] and raw[0, 0].item() == -5.0
         assert bx.filter_by_size().cpu().numpy().tolist() == [True]
 
 
@@ -252,3 +258,40 @@ def test_sample_labels_dropin(cuda):
     t3 = torch.from_numpy(lab.copy()).to(cuda)
     sample_labels(t3, 10 ** 6, 0)
     assert np.array_equal(t3.cpu().numpy(), lab)
+
+
+def test_dropin_find_top_rpn_proposals_equals_fused_pipeline(cuda):
+    """models/det/rpn.py:141-186 written against the drop-in layer (Boxes.clip / filter_by_size / BoxCoder.decode /
+    batched_nms), line for line, equals pipelines.rpn_proposals: same rois in the same order, un-clipped coordinates
+    (the two paths must agree on the Boxes in-place semantics)."""
+    from basedet_b200 import pipelines
+
+    rng = np.random.default_rng(9)
+    hw, B, pre_k, post_k, thr = (128, 160), 2, 300, 100, 0.7
+    sizes = W.frcnn_level_sizes(*hw)
+    gen = DefaultAnchorGenerator(W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, 0.5)
+    anchors_list = gen.generate_anchors_by_features(sizes, cuda)
+    n_l = [a.shape[0] for a in anchors_list]
+    scores = [torch.from_numpy(np.stack([W.distinct_scores(rng, n, -9.0, 3.0) for _ in range(B)])).to(cuda) for n in n_l]
+    deltas = [torch.from_numpy(rng.normal(0, 0.5, (B, n, 4)).astype(np.float32)).to(cuda) for n in n_l]   # wide: many clip
+    im_info = torch.tensor([[hw[0], hw[1], hw[0], hw[1], 0.0]] * B, device=cuda)
+    rois, cnt = pipelines.rpn_proposals(scores, deltas, anchors_list, im_info, pre_k, post_k, thr)
+    box_coder = BoxCoder((0.0, 0.0, 0.0, 0.0), (1.0, 1.0, 1.0, 1.0))
+    for bid in range(B):
+        props, scs, lvls = [], [], []
+        for level, (s, d, a) in enumerate(zip(scores, deltas, anchors_list)):
+            proposals = box_coder.decode(a, d[bid].clone())
+            k = min(pre_k, s.shape[1])
+            sc, order = torch.topk(s[bid], k)                      # F.topk(descending=True); scores are distinct
+            props.append(proposals[order]); scs.append(sc); lvls.append(torch.full_like(sc, level))
+        proposals, sc, levels = torch.cat(props), torch.cat(scs), torch.cat(lvls)
+        proposal_boxes = Boxes(proposals).clip(im_info[bid][:2])    # rpn.py:168
+        keep_mask = proposal_boxes.filter_by_size()
+        proposals, sc, levels = proposals[keep_mask], sc[keep_mask], levels[keep_mask]
+        keep = batched_nms(proposals, sc, levels, thr, post_k).long()
+        ref = proposals[keep]
+        n = int(cnt[bid])
+        assert n == ref.shape[0]
+        assert (rois[bid, :n, 0] == bid).all()
+        assert torch.equal(rois[bid, :n, 1:], ref)                  # same kernels underneath: bit-identical, un-clipped
+        assert (ref[:, 0] < 0).any() or (ref[:, 2] > hw[1]).any()   # the case is exercised: some rois stick out
