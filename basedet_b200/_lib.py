@@ -82,6 +82,13 @@ SIGNATURES = {
                                         fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_ota_topk_match_workspace": (c_size_t, [c_int]),
     "bdet_ota_topk_match": (c_int, [vp, c_int, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]),
+    "bdet_ota_cost_workspace": (c_size_t, [c_int]),
+    "bdet_ota_cost": (c_int, [vp, vp, c_int, vp, c_int, vp, c_int, vp, c_double, c_double, c_double, vp, vp, vp, c_size_t, vp]),
+    "bdet_ota_collect": (c_int, [vp, vp, c_int, vp, c_int, vp, vp, vp, vp, vp]),
+    "bdet_free_anchor_box_prob_workspace": (c_size_t, [c_int]),
+    "bdet_free_anchor_box_prob": (c_int, [vp, c_int, vp, c_int, c_int, c_float, c_float, c_float, vp, vp, c_size_t, vp]),
+    "bdet_free_anchor_bags": (c_int, [vp, c_int, c_int, vp, vp, vp, c_int, fp, fp, vp, vp, vp]),
+    "bdet_coco_format": (c_int, [vp, vp, c_int, c_int, vp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_select_decode_workspace": (c_size_t, [c_int, c_int, c_int]),
     "bdet_select_decode_ws": (c_int, [POINTER(vp), POINTER(vp), ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,
                                       fp, fp, vp, c_int, vp, vp, vp, vp, vp, vp, c_size_t, vp]),

@@ -852,6 +852,86 @@ def ota_topk_match(cost, ious, candidate_k=10):
     return out
 
 
+def ota_cost(points, radius, gt5, cls_logits, pred_deltas, alpha=0.25, gamma=2.0, reg_weight=1.5):
+    """OTA cost construction (models/det/ota.py:91-152) for one image: points (A,2), radius (A) = stride * 2.5 of each
+    point's level, gt5 (G,5), cls_logits (A,C), pred_deltas (A,4) ltrb -> cost (G,A), ious (G,A)."""
+    lib = _lib.load()
+    pts, rad, gt = _f32c(points, "points"), _f32c(radius, "radius"), _f32c(gt5, "gt")
+    lg, dl = _f32c(cls_logits, "cls_logits"), _f32c(pred_deltas, "pred_deltas")
+    A, G, C = pts.shape[0], gt.shape[0], lg.shape[1]
+    assert pts.shape == (A, 2) and rad.shape == (A,) and lg.shape[0] == A and dl.shape == (A, 4) and gt.shape[1] == 5
+    cost = torch.empty((G, A), dtype=torch.float32, device=pts.device)
+    ious = torch.empty((G, A), dtype=torch.float32, device=pts.device)
+    ws = _workspace(lib.bdet_ota_cost_workspace(A), pts.device)
+    with _guard(pts):
+        check(lib.bdet_ota_cost(_p(pts), _p(rad), A, _p(gt), G, _p(lg), C, _p(dl), float(alpha), float(gamma), float(reg_weight),
+                                _p(cost), _p(ious), _p(ws), ws.numel(), _stream(pts)))
+    return cost, ious
+
+
+def ota_collect(matched, points, gt5, ious):
+    """Targets of the matched points (ota.py:160-175): -> gt_classes (A,) fp32, box_targets (A,4), iou_targets (A,)."""
+    lib = _lib.load()
+    m, pts, gt, io = _i32c(matched, "matched"), _f32c(points, "points"), _f32c(gt5, "gt"), _f32c(ious, "ious")
+    A, G = pts.shape[0], gt.shape[0]
+    cls_t = torch.empty((A,), dtype=torch.float32, device=pts.device)
+    box_t = torch.empty((A, 4), dtype=torch.float32, device=pts.device)
+    iou_t = torch.empty((A,), dtype=torch.float32, device=pts.device)
+    with _guard(pts):
+        check(lib.bdet_ota_collect(_p(m), _p(pts), A, _p(gt), G, _p(io), _p(cls_t), _p(box_t), _p(iou_t), _stream(pts)))
+    return cls_t, box_t, iou_t
+
+
+def free_anchor_box_prob(pred_boxes, gt5, num_classes, box_iou_thresh=0.6, clamp_eps=1e-7):
+    """FreeAnchor box-probability scatter (free_anchor.py:54-86): pred_boxes (A,4) decoded, gt5 (G,5) -> (A,C)."""
+    import numpy as np
+
+    lib = _lib.load()
+    pb, gt = _f32c(pred_boxes, "pred_boxes"), _f32c(gt5, "gt")
+    A, G = pb.shape[0], gt.shape[0]
+    out = torch.empty((A, int(num_classes)), dtype=torch.float32, device=pb.device)
+    ws = _workspace(lib.bdet_free_anchor_box_prob_workspace(G), pb.device)
+    lower = float(np.float32(float(box_iou_thresh) + float(clamp_eps)))  # thresh1 + clamp_eps in Python floats, then fp32
+    with _guard(pb):
+        check(lib.bdet_free_anchor_box_prob(_p(pb), A, _p(gt), G, int(num_classes), float(box_iou_thresh), lower,
+                                            float(clamp_eps), _p(out), _p(ws), ws.numel(), _stream(pb)))
+    return out
+
+
+def free_anchor_bags(matched_idx, anchors, gt5, pred_scores, mean=(0, 0, 0, 0), std=(0.1, 0.1, 0.2, 0.2)):
+    """Bag scores / BoxCoder targets (free_anchor.py:95-113): matched_idx (G,K) int32 -> (G,K), (G*K,4)."""
+    lib = _lib.load()
+    mi, an, gt, sc = _i32c(matched_idx, "matched_idx"), _f32c(anchors, "anchors"), _f32c(gt5, "gt"), _f32c(pred_scores, "scores")
+    G, K = mi.shape
+    ms = torch.empty((G, K), dtype=torch.float32, device=an.device)
+    mo = torch.empty((G * K, 4), dtype=torch.float32, device=an.device)
+    with _guard(an):
+        check(lib.bdet_free_anchor_bags(_p(mi), G, K, _p(an), _p(gt), _p(sc), sc.shape[1], farr(mean), farr(std), _p(ms), _p(mo),
+                                        _stream(an)))
+    return ms, mo
+
+
+def coco_format(dets, counts, image_ids, category_ids=None):
+    """COCOEvaluator.format on the device (coco_eval.py:111-138): dets (B,K,6) + counts (B,) + image_ids (B,) int32
+    [+ category_ids (C,) int32 = classes_originID] -> (image_id (N,), bbox_xywh (N,4) f64, score (N,) f64, category_id (N,)),
+    N = counts.sum() (one D2H read of the total: the result is variable-length)."""
+    lib = _lib.load()
+    d, c, ids = _f32c(dets, "dets"), _i32c(counts, "counts"), _i32c(image_ids, "image_ids")
+    B, K = d.shape[0], d.shape[1]
+    cat = _i32c(category_ids, "category_ids") if category_ids is not None else None
+    dev = d.device
+    ri = torch.empty((B * K,), dtype=torch.int32, device=dev)
+    rb = torch.empty((B * K, 4), dtype=torch.float64, device=dev)
+    rs = torch.empty((B * K,), dtype=torch.float64, device=dev)
+    rc = torch.empty((B * K,), dtype=torch.int32, device=dev)
+    tot = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with _guard(d):
+        check(lib.bdet_coco_format(_p(d), _p(c), B, K, _p(ids), _p(cat), cat.numel() if cat is not None else 0, _p(ri), _p(rb),
+                                   _p(rs), _p(rc), _p(tot), _stream(d)))
+    n = int(tot.item())
+    return ri[:n], rb[:n], rs[:n], rc[:n]
+
+
 # ----------------------------------------------------------------------------- measurement hooks
 def profile_begin(only=None):
     """Bracket kernel launches with CUDA events; ``only`` = time just that kernel (the rest are counted)."""

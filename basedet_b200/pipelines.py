@@ -132,6 +132,37 @@ def atss_targets(points_list, gt_boxes, num_gt, strides=(8, 16, 32, 64, 128), an
     return lab, off, ctr
 
 
+def free_anchor_targets(anchors, pred_offsets, pred_scores, gt_boxes, num_classes, box_iou_thresh=0.6, bucket_size=50,
+                        reg_mean=(0, 0, 0, 0), reg_std=(0.1, 0.1, 0.2, 0.2)):
+    """The box ops of one image of FreeAnchor.get_losses, models/det/free_anchor.py:48-113 (defaults:
+    configs/det_model/freeanchor_cfg.py): anchors (A,4), pred_offsets (A,4), pred_scores (A,C) = sigmoid(logits),
+    gt_boxes (G,5).  -> box_prob (A,C), matched_idx (G,bucket) [sorted by (IoU desc, index asc); the reference's
+    F.topk(no_sort=True) leaves the order inside a bag unspecified], matched_score (G,bucket), matched_offsets (G*bucket,4)."""
+    pred_box = ops.box_decode(anchors, pred_offsets, reg_mean, reg_std)                   # :55 (no in-place rescale: detached)
+    box_prob = ops.free_anchor_box_prob(pred_box, gt_boxes, num_classes, box_iou_thresh)  # :57-86
+    quality = ops.pairwise(gt_boxes[:, :4], anchors)                                      # :91
+    G, A = quality.shape
+    k = min(int(bucket_size), A)
+    q = quality.contiguous() if quality.stride(0) != A else quality
+    _, idx, _ = ops.topk_segments(q.reshape(-1), [A] * G, k)                              # :93-95
+    ms, mo = ops.free_anchor_bags(idx, anchors, gt_boxes, pred_scores, reg_mean, reg_std)  # :99-114
+    return box_prob, idx, ms, mo
+
+
+def ota_targets(points_list, strides, gt_boxes, cls_logits, pred_deltas, candidate_k=10, alpha=0.25, gamma=2.0,
+                reg_weight=1.5, center_sampling_radius=2.5):
+    """One image of OTA.get_ground_truth with the top-k matcher, models/det/ota.py:91-175: points_list[l] (n_l,2),
+    gt_boxes (G,5), cls_logits (A,C), pred_deltas (A,4) ltrb.  -> gt_classes (A,) fp32 (0 = background), box_targets
+    (A,4), iou_targets (A,), matched (A,) int32 (G = background), cost (G,A), ious (G,A)."""
+    pts = torch.cat([p.reshape(-1, 2) for p in points_list]) if len(points_list) > 1 else points_list[0]
+    radius = torch.cat([torch.full((p.shape[0],), float(s * center_sampling_radius), dtype=torch.float32, device=pts.device)
+                        for p, s in zip(points_list, strides)])
+    cost, ious = ops.ota_cost(pts, radius, gt_boxes, cls_logits, pred_deltas, alpha, gamma, reg_weight)   # :91-152
+    matched = ops.ota_topk_match(cost, ious, candidate_k)                                                 # :158
+    cls_t, box_t, iou_t = ops.ota_collect(matched, pts, gt_boxes, ious)                                   # :160-175
+    return cls_t, box_t, iou_t, matched, cost, ious
+
+
 class _AssignSlot:
     """One set of static input / output buffers of TargetAssigner with its captured graph."""
 

@@ -200,6 +200,43 @@ size_t bdet_ota_topk_match_workspace(int A);
 int bdet_ota_topk_match(const float* cost, int ldc, const float* ious, int ldi, int G, int A, int candidate_k,
                         int* matched_gt, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
+/* OTA cost construction, models/det/ota.py:91-152 with layers/losses/sigmoid_focal_loss.py:30-36 and iou_loss.py:9-43,96:
+ * per (GT g, point a)  cost = (sum_c focal(logit[a,c], onehot_g) + reg_weight * -log(max(iou_ltrb(pred[a], enc(a, g)), eps)))
+ * + 1e6 * !(a inside box g and inside its centre box of radius[a]),  ious = that ltrb IoU.  points (A,2); radius (A) =
+ * stride * 2.5 of the point's level; gt (G,5) classes 1..C; cls_logits (A,C); pred_deltas (A,4) ltrb; cost, ious (G,A).
+ * Floating point through logf / expf: tolerance-gated (1e-5), feed bdet_ota_topk_match; bdet_ota_collect then writes the
+ * targets of ota.py:160-175: gt_classes (A) fp32 (0 = background), box_targets (A,4), iou_targets (A). */
+size_t bdet_ota_cost_workspace(int A);
+int bdet_ota_cost(const float* points, const float* radius, int A, const float* gt, int G, const float* cls_logits,
+                  int num_classes, const float* pred_deltas, double alpha, double gamma, double reg_weight, float* cost,
+                  float* ious, void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+int bdet_ota_collect(const int* matched_gt, const float* points, int A, const float* gt, int G, const float* ious,
+                     float* gt_classes, float* box_targets, float* iou_targets, bdet_stream_t stream);
+
+/* FreeAnchor box ops, models/det/free_anchor.py:48-113 (one image).
+ * bdet_free_anchor_box_prob (:54-86): box_prob (A,C) = scatter of clip((IoU(gt g, pred a) - t1) / (t2[g] - t1), 0, 1) to
+ * [a, class(g) - 1] over the non-zero entries in ascending (g, a) order (the last GT of a class wins), t2[g] =
+ * clip(max_a IoU, thresh2_lower, 1), thresh2_lower = fp32(t1 + clamp_eps) summed in double by the caller; includes the
+ * reference's empty-set workaround (:71-73, :85-86).  pred_boxes (A,4) = BoxCoder.decode(anchors, pred_offsets).
+ * bdet_free_anchor_bags (:95-113): for matched_idx (G,K) (the per-GT top-K anchors by IoU: bdet_pairwise + bdet_topk)
+ * matched_score (G,K) = pred_scores[idx, class(g) - 1] and matched_offsets (G*K,4) = BoxCoder.encode(anchors[idx], gt g). */
+size_t bdet_free_anchor_box_prob_workspace(int G);
+int bdet_free_anchor_box_prob(const float* pred_boxes, int A, const float* gt, int G, int num_classes,
+                              float box_iou_thresh, float thresh2_lower, float clamp_eps, float* box_prob,
+                              void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+int bdet_free_anchor_bags(const int* matched_idx, int G, int K, const float* anchors, const float* gt,
+                          const float* pred_scores, int num_classes, const float* mean_host, const float* std_host,
+                          float* matched_score, float* matched_offsets, bdet_stream_t stream);
+
+/* ------------------------------------------------------------------ 8(f)-4: COCO result records on the device
+ * COCOEvaluator.format  evaluators/coco_eval.py:111-138.  dets (B,K,6) rows [x1,y1,x2,y2,score,label] with counts (B)
+ * valid rows (bdet_finalize_detections' layout) -> compact records in image order: image id, bbox [x, y, w, h] and score
+ * as float64 (the reference converts to float64 before the subtraction), category id = category_ids[label]
+ * (classes_originID; -1 if the label is out of range) or label + 1 when category_ids is NULL; *total = record count. */
+int bdet_coco_format(const float* dets, const int* counts, int B, int K, const int* image_ids, const int* category_ids,
+                     int num_classes, int* rec_image_id, double* rec_bbox_xywh, double* rec_score, int* rec_category_id,
+                     int* total, bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ a10: score filter + top-k
  * F.topk(scores, k, descending=True) as used in models/det/rpn.py:155 and retinanet.py:189-190.
  * Segmented: segment s covers scores[seg_start[s] .. seg_start[s] + seg_len[s]) (element offsets from `scores`;

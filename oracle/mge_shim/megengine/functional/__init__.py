@@ -218,6 +218,20 @@ def indexing_one_hot(src, index, axis=1, keepdims=False):
     return Tensor(np.take_along_axis(_a(src), np.expand_dims(_a(index).astype(np.int64), axis), axis).squeeze(axis))
 
 
+def one_hot(inp, num_classes):
+    """F.one_hot: int labels (...,) -> int32 (..., num_classes)."""
+    a = _a(inp).astype(np.int64)
+    return Tensor((a[..., None] == np.arange(num_classes)).astype(np.int32))
+
+
+def logsigmoid(x):
+    """F.logsigmoid = -softplus(-x), evaluated in the numerically stable form MegEngine uses:
+    min(x, 0) - log1p(exp(-|x|)) (ASSUMED-12; fp32 throughout)."""
+    a = _a(_t(x)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        return Tensor((np.minimum(a, f32(0)) - np.log1p(np.exp(-np.abs(a)).astype(f32)).astype(f32)).astype(f32))
+
+
 def where(mask, x, y):
     return Tensor(np.where(_a(mask), _a(x), _a(y)))
 

@@ -25,6 +25,9 @@ reference's own tests.
              (value desc, index asc).  ``sample_labels`` (sampling.py:27) relies on it.
   ASSUMED-9  ``x ** 2`` on a tensor is ``x * x`` (one rounding); F.topk(descending=False) orders by
              (value asc, index asc); argmin returns the FIRST index among equal minima.
+  ASSUMED-11 Advanced-index assignment ``t[i, j] = v`` with repeated (i, j) pairs keeps the LAST value in index
+             order (FreeAnchor's box-probability scatter, free_anchor.py:78).
+  ASSUMED-12 F.logsigmoid(x) = min(x, 0) - log1p(exp(-|x|)) in fp32; ``x ** gamma`` with gamma = 2 is x * x.
 """
 import math
 
@@ -517,6 +520,155 @@ def ota_topk_match(cost, ious, candidate_k=10):
         matching[cost_argmin, multi] = 1.0
     full = np.concatenate([matching * 2, np.ones((1, A), f32)], axis=0)         # :160-161
     return np.argmax(full, axis=0).astype(np.int32)                             # first index (ASSUMED-2)
+
+
+# --------------------------------------------------------------------------- FreeAnchor (8(f)-3)
+def free_anchor_targets(anchors, pred_offsets, pred_scores, gt5, num_classes, box_iou_thresh=0.6, bucket_size=50,
+                        reg_mean=(0, 0, 0, 0), reg_std=(0.1, 0.1, 0.2, 0.2), clamp_eps=1e-7):
+    """The box ops of one image of FreeAnchor.get_losses, basedet/models/det/free_anchor.py:48-113 (defaults:
+    configs/det_model/freeanchor_cfg.py:15-24).  anchors (A,4); pred_offsets (A,4); pred_scores (A,C) = sigmoid(logits);
+    gt5 (G,5) with classes 1..C.  Returns
+      box_prob (A,C)           the box-probability scatter (:54-84), including the reference's empty-set workaround,
+      matched_idx (G,bucket)   the bag of every GT: its `bucket_size` best anchors by IoU (:87-92; F.topk(no_sort=True):
+                               the order inside a bag is unspecified -- this restatement returns (IoU desc, index asc)),
+      matched_score (G,bucket) pred_scores[bag anchor, class of the GT] (:95-101),
+      matched_offsets (G*bucket,4) BoxCoder.encode(bag anchors, GT) (:103-110)."""
+    anchors = np.asarray(anchors, f32)
+    gt5 = np.asarray(gt5, f32)
+    A, G = anchors.shape[0], gt5.shape[0]
+    labels = gt5[:, 4].astype(np.int32) - 1                                     # :52
+    pred_box, _ = boxcoder_decode(anchors, np.array(pred_offsets, f32, copy=True), reg_mean, reg_std)   # :55
+    overlaps = box_iou(gt5[:, :4], pred_box)                                    # :57
+    thresh1 = f32(box_iou_thresh)
+    thresh2 = np.minimum(np.maximum(overlaps.max(axis=1, keepdims=True), f32(box_iou_thresh + clamp_eps)), f32(1.0))   # :60-64
+    with np.errstate(all="ignore"):
+        prob = ((overlaps - thresh1).astype(f32) / (thresh2 - thresh1).astype(f32)).astype(f32)
+    prob = np.minimum(np.maximum(prob, f32(0)), f32(1.0))                       # :65-66
+    fill = bool(prob.max() <= f32(clamp_eps))                                   # :71
+    if fill:
+        prob[0, 0] = f32(0.001)                                                 # :73
+    nz = np.flatnonzero(prob.reshape(-1) != 0)                                  # :75 ascending flat indices (ASSUMED-4)
+    a_idx, g_idx = nz % A, nz // A                                              # :79-80
+    box_prob = np.zeros((A, num_classes), f32)
+    for a, g in zip(a_idx.tolist(), g_idx.tolist()):                            # :83 last write wins (ASSUMED-11)
+        box_prob[a, labels[g]] = prob[g, a]
+    if fill:
+        box_prob[0, 0] = 0.0                                                    # :85-86
+    quality = box_iou(gt5[:, :4], anchors)                                      # :91
+    k = min(int(bucket_size), A)
+    matched_idx = np.argsort(-quality, axis=1, kind="stable")[:, :k].astype(np.int32)   # :93-95
+    matched_score = np.asarray(pred_scores, f32)[matched_idx, labels[:, None]]  # :99-106
+    flat = matched_idx.reshape(-1)
+    gt_b = np.broadcast_to(gt5[:, None, :4], (G, k, 4)).reshape(-1, 4)          # :108-110
+    matched_offsets = boxcoder_encode(anchors[flat], gt_b, reg_mean, reg_std)   # :111-114
+    return box_prob, matched_idx, matched_score, matched_offsets, fill
+
+
+# --------------------------------------------------------------------------- OTA (8(f)-3)
+def logsigmoid_f32(x):
+    """F.logsigmoid (ASSUMED-12)."""
+    x = np.asarray(x, f32)
+    with np.errstate(all="ignore"):
+        return (np.minimum(x, f32(0)) - np.log1p(np.exp(-np.abs(x)).astype(f32)).astype(f32)).astype(f32)
+
+
+def sigmoid_focal_loss(logits, targets, alpha=-1.0, gamma=0.0):
+    """basedet/layers/losses/sigmoid_focal_loss.py:30-36 over cross_entropy.py:24-27, fp32."""
+    logits, targets = np.asarray(logits, f32), np.asarray(targets, f32)
+    scores = sigmoid_f32(logits)
+    loss = (-((targets * logsigmoid_f32(logits)).astype(f32)
+              + ((f32(1) - targets) * logsigmoid_f32(-logits)).astype(f32)).astype(f32)).astype(f32)
+    if gamma != 0:
+        base = ((targets * (f32(1) - scores)).astype(f32) + ((f32(1) - targets) * scores).astype(f32)).astype(f32)
+        loss = (loss * np.power(base, f32(gamma)).astype(f32)).astype(f32)
+    if alpha >= 0:
+        loss = (loss * ((targets * f32(alpha)).astype(f32) + ((f32(1) - targets) * f32(1 - alpha)).astype(f32)).astype(f32)).astype(f32)
+    return loss
+
+
+def ltrb_iou(b1, b2, eps):
+    """get_ltrb_boxes_iou(iou_type="iou"), basedet/layers/losses/iou_loss.py:9-43."""
+    b1, b2 = np.asarray(b1, f32), np.asarray(b2, f32)
+    b1 = np.concatenate([-b1[..., :2], b1[..., 2:]], axis=-1)
+    b2 = np.concatenate([-b2[..., :2], b2[..., 2:]], axis=-1)
+    a1 = (np.maximum(b1[..., 2] - b1[..., 0], f32(0)) * np.maximum(b1[..., 3] - b1[..., 1], f32(0))).astype(f32)
+    a2 = (np.maximum(b2[..., 2] - b2[..., 0], f32(0)) * np.maximum(b2[..., 3] - b2[..., 1], f32(0))).astype(f32)
+    w = np.maximum(np.minimum(b1[..., 2], b2[..., 2]) - np.maximum(b1[..., 0], b2[..., 0]), f32(0))
+    h = np.maximum(np.minimum(b1[..., 3], b2[..., 3]) - np.maximum(b1[..., 1], b2[..., 1]), f32(0))
+    inter = (w * h).astype(f32)
+    union = ((a1 + a2).astype(f32) - inter).astype(f32)
+    with np.errstate(all="ignore"):
+        return (inter / np.maximum(union, f32(eps))).astype(f32)
+
+
+def ota_cost(points_list, strides, gt5, cls_logits, pred_deltas, num_classes, alpha=0.25, gamma=2.0, reg_weight=1.5,
+             center_sampling_radius=2.5):
+    """The cost / IoU matrices of one image of OTA.get_ground_truth, basedet/models/det/ota.py:91-145.
+    points_list[l] (n_l, 2); gt5 (G, 5) classes 1..C; cls_logits (A, C); pred_deltas (A, 4) ltrb.
+    -> cost (G, A), ious (G, A), is_in_boxes (G, A) bool, gt_deltas (G, A, 4), loss_cls_bg (A,)."""
+    gt5 = np.asarray(gt5, f32)
+    pts = np.concatenate([np.asarray(p, f32) for p in points_list], axis=0)
+    G, A = gt5.shape[0], pts.shape[0]
+    deltas = pointcoder_encode(pts, gt5[:, None, :4])                           # :92  (G, A, 4)
+    is_in_boxes = deltas.min(axis=-1) > f32(0.01)                               # :93
+    gt_centers = ((gt5[:, :2] + gt5[:, 2:4]).astype(f32) / f32(2)).astype(f32)  # :97
+    in_centers = []
+    for stride, lp in zip(strides, points_list):                                # :99-109
+        radius = f32(stride * center_sampling_radius)
+        cb = np.concatenate([np.maximum((gt_centers - radius).astype(f32), gt5[:, :2]),
+                             np.minimum((gt_centers + radius).astype(f32), gt5[:, 2:4])], axis=-1)
+        cd = pointcoder_encode(np.asarray(lp, f32), cb[:, None, :])
+        in_centers.append(cd.min(axis=-1) > 0)
+    is_in_boxes = is_in_boxes & np.concatenate(in_centers, axis=1)              # :110-112
+    onehot = (np.arange(num_classes)[None, :] == (gt5[:, 4].astype(np.int32) - 1)[:, None]).astype(f32)   # :115-117
+    logits = np.asarray(cls_logits, f32)
+    loss_cls = seq_sum_f32(sigmoid_focal_loss(np.broadcast_to(logits[None], (G, A, num_classes)),
+                                              np.broadcast_to(onehot[:, None, :], (G, A, num_classes)), alpha, gamma), 2)   # :122-127
+    loss_cls_bg = seq_sum_f32(sigmoid_focal_loss(logits, np.zeros_like(logits), alpha, gamma), 1)   # :129-134
+    gt_delta = pointcoder_encode(pts, gt5[:, None, :4])                         # :136-138
+    ious = ltrb_iou(np.broadcast_to(np.asarray(pred_deltas, f32)[None], (G, A, 4)), gt_delta, np.finfo(np.float32).eps)
+    with np.errstate(all="ignore"):
+        loss_delta = (-np.log(np.maximum(ious, f32(np.finfo(np.float32).eps)))).astype(f32)   # iou_loss.py:96
+    cost = ((loss_cls + (f32(reg_weight) * loss_delta).astype(f32)).astype(f32)
+            + (f32(1e6) * (~is_in_boxes).astype(f32)).astype(f32)).astype(f32)  # :152
+    return cost, ious, is_in_boxes, gt_delta, loss_cls_bg
+
+
+def ota_targets(points_list, strides, gt5, cls_logits, pred_deltas, num_classes, candidate_k=10, **kw):
+    """One image of OTA.get_ground_truth with matching == "topk", ota.py:91-172.
+    -> gt_classes (A,) fp32 (0 = background), box targets (A, 4), ious (A,), matched (A,) int32 (G = background)."""
+    cost, ious, _, gt_delta, _ = ota_cost(points_list, strides, gt5, cls_logits, pred_deltas, num_classes, **kw)
+    G, A = cost.shape
+    matched = ota_topk_match(cost, ious, candidate_k)                           # :158
+    fg = matched != G                                                           # :161
+    cls_t = np.zeros(A, f32)
+    cls_t[fg] = np.asarray(gt5, f32)[:, 4][matched[fg]]                         # :162
+    box_t = np.zeros((A, 4), f32)
+    box_t[fg] = gt_delta[matched[fg], np.arange(A)[fg]]                         # :165-168
+    iou_t = np.zeros(A, f32)
+    iou_t[fg] = ious[matched[fg], np.arange(A)[fg]]                             # :171-175
+    return cls_t, box_t, iou_t, matched
+
+
+# --------------------------------------------------------------------------- COCO result records (8(f)-4)
+def coco_format(dets, counts, image_ids, category_ids=None):
+    """COCOEvaluator.format, basedet/evaluators/coco_eval.py:111-138, for padded detections (B, K, 6) rows
+    [x1, y1, x2, y2, score, label] with `counts[b]` valid rows.  -> image_id (N,), bbox xywh (N, 4), score (N,),
+    category_id (N,): `category_ids[label]` (classes_originID) when given, else label + 1; images without detections
+    contribute nothing (:123-124)."""
+    dets = np.asarray(dets, f32)
+    img, box, sc, cat = [], [], [], []
+    for b, n in enumerate(np.asarray(counts).tolist()):
+        if n <= 0:
+            continue
+        d = dets[b, :n].astype(np.float64)                                      # np.array(..., dtype=np.float) (:107)
+        d[:, 2:4] = d[:, 2:4] - d[:, 0:2]                                       # :125
+        for row in d:
+            img.append(int(image_ids[b]))
+            box.append(row[:4])
+            sc.append(row[4])
+            cat.append(int(category_ids[int(row[5])]) if category_ids is not None else int(row[5]) + 1)
+    return (np.array(img, np.int32), np.array(box, np.float64).reshape(-1, 4), np.array(sc, np.float64), np.array(cat, np.int32))
 
 
 def _ctrness(offsets):
