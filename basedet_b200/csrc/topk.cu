@@ -354,6 +354,12 @@ struct FilterArgs {
   int n_seg, C, mode;
   int na;                     // anchors per position (NCHW segments only)
   float thr, pre;             // pre: raw-logit pre-filter (sigmoid mode)
+  // sampled per-segment thresholds (filter_sample_kernel): seg_thr[s] >= thr is a score bound that still leaves >= k
+  // candidates with overwhelming probability; seg_redo[s] = 1 marks a segment whose bound turned out too tight and is
+  // swept again with the plain threshold (redo_pass).
+  float* seg_thr;
+  int* seg_redo;              // [n_seg] flags, [n_seg] = "any segment flagged"
+  int k, redo_pass;
 };
 
 // Candidate index reported for element e of a segment, and the index of its centerness value.
@@ -378,7 +384,7 @@ constexpr int kFiltVec = 4;                               // float4 per thread p
 constexpr int kFiltTile = 32 * kFiltVec * 4;              // 512 elements: one WARP iteration
 
 // Exact fp32 score of one candidate (same expressions as scores_kernel, so a dense bdet_scores tensor is bit-identical).
-__device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long long ci, float& s) {
+__device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long long ci, float& s, float thr) {
   if (p.mode == BDET_SCORE_SIGMOID) {
     s = sigmoid_f(x);
   } else if (p.mode == BDET_SCORE_FCOS) {
@@ -386,7 +392,101 @@ __device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long l
   } else {
     s = x;
   }
-  return s > p.thr;
+  return s > thr;
+}
+__device__ __forceinline__ bool exact_score(const FilterArgs& p, float x, long long ci, float& s) {
+  return exact_score(p, x, ci, s, p.thr);
+}
+
+// ---- stage 0: sampled threshold ---------------------------------------------------------------------------------
+// With thousands of candidates per anchor level and only k = 1000 wanted (FCOS at the 0.05 threshold: ~28 % of all logits
+// pass), exact-scoring every candidate is the cost of the filter.  One CTA per segment scores a strided sample of kFSample
+// elements exactly, takes the r-th largest sample score t (r = 2 * k * sample / n + kFMargin, a CTA-wide radix select over
+// the fp32 bits) and publishes seg_thr = max(thr, t): the expected number of elements above t is r * n / sample >= 2 k, so
+// the sweep exact-scores a few thousand elements per segment instead of hundreds of thousands.  The final top-k is
+// unchanged as long as >= k elements pass; filter_check_kernel verifies that and flags the (rare) segment that has to be
+// swept again with the plain threshold, so the result is exact either way.
+constexpr int kFSample = 8192;
+constexpr int kFSampleMin = 16 * kFSample;  // shorter segments are not sampled
+constexpr int kFMargin = 16;
+constexpr int kFSThreads = 512;             // each thread scores kFSample / kFSThreads elements and keeps their maximum
+
+__global__ void __launch_bounds__(kFSThreads) filter_sample_kernel(const FilterArgs p) {
+  __shared__ float gmax[kFSThreads];
+  __shared__ int s_above;
+  const int s = blockIdx.x, t = threadIdx.x;
+  const SegDesc sd = p.seg[s];
+  if (t == 0) {
+    p.seg_redo[s] = 0;
+    if (s == 0) {
+      p.seg_redo[p.n_seg] = 0;
+      p.seg_redo[p.n_seg + 1] = 0;  // arrival ticket of the sweep (the last warp runs the check)
+    }
+  }
+  const long long want = sd.len >= kFSampleMin ? (2ll * p.k * kFSample + sd.len - 1) / sd.len + kFMargin : 0;
+  if (sd.len < kFSampleMin || p.k <= 0 || p.mode == BDET_SCORE_RAW || want > kFSThreads / 2) {
+    if (t == 0) p.seg_thr[s] = p.thr;
+    return;
+  }
+  const int stride = sd.len / kFSample;
+  if (t == 0) s_above = 0;
+  __syncthreads();
+  int above = 0;
+  float mx = 0.f;  // scores are >= 0; elements at or below the threshold can never be the bound
+  constexpr int kPer = kFSample / kFSThreads;
+  float xs[kPer], cs[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {  // all the (strided, uncached) loads first: one round trip instead of kPer
+    const int i = t + j * kFSThreads;
+    const int e = i * stride + (i & 7);  // a little jitter so that a stride that is a multiple of C still visits every class
+    int idx;
+    long long ci;
+    if (sd.hw > 0) key_index<true>(p, sd, e, idx, ci);
+    else key_index<false>(p, sd, e, idx, ci);
+    xs[j] = __ldg(p.logits + sd.start + e);
+    cs[j] = p.mode == BDET_SCORE_FCOS ? __ldg(p.ctr + ci) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    float sc;
+    if (p.mode == BDET_SCORE_SIGMOID) sc = sigmoid_f(xs[j]);
+    else sc = sqrtf(sigmoid_f(xs[j]) * sigmoid_f(cs[j]));  // fcos.py:194, the same expression as exact_score
+    if (sc > p.thr) {
+      mx = fmaxf(mx, sc);
+      ++above;
+    }
+  }
+  gmax[t] = mx;
+  atomicAdd(&s_above, above);
+  __syncthreads();
+  // Too few sample elements above the threshold for the bound to pay: keep the plain threshold.
+  if (want > s_above || (long long)s_above * stride < 8ll * p.k) {
+    if (t == 0) p.seg_thr[s] = p.thr;
+    return;
+  }
+  // The `want`-th largest of the per-thread maxima: >= `want` distinct sample elements are at or above it, so it is a
+  // (slightly conservative) stand-in for the `want`-th largest sample.  Rank by counting (ties broken by thread index).
+  int rank = 0;
+  for (int j = 0; j < kFSThreads; ++j) {
+    const float o = gmax[j];
+    rank += (o > mx) || (o == mx && j < t);
+  }
+  if (rank == (int)want - 1) p.seg_thr[s] = fmaxf(p.thr, mx);
+}
+
+// Run by the last warp of the sweep to finish (arrival ticket): a sampled bound that left fewer than k candidates is
+// withdrawn and the segment flagged for the second sweep.
+__device__ __forceinline__ void filter_check(const FilterArgs& p, int lane) {
+  int any = 0;
+  for (int s = lane; s < p.n_seg; s += 32) {
+    if (p.seg_thr[s] > p.thr && atomicAdd(p.cand_count + s, 0) < p.k) {
+      p.seg_thr[s] = p.thr;
+      p.cand_count[s] = 0;
+      p.seg_redo[s] = 1;
+      any = 1;
+    }
+  }
+  if (__any_sync(0xffffffffu, any) && lane == 0) p.seg_redo[p.n_seg] = 1;
 }
 
 // ---- stage 1: warp-autonomous streaming filter --------------------------------------------------------------
@@ -440,6 +540,21 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
   while (s + 1 < p.n_seg && p.seg[s + 1].tile_start <= tile) ++s;
   SegDesc sd = p.seg[s];
   const bool tab_mode = !NCHW && p.mode == BDET_SCORE_FCOS && (kFiltTile / p.C + 2) <= kWTab;
+  if (p.redo_pass && p.seg_redo[p.n_seg] == 0) return;  // the usual case: no segment was flagged
+  // per-segment score bound and the raw-logit pre-filter that goes with it (sigmoid(x) > t  <=>  x > logit(t))
+  float thr_s = p.thr, pre_s = p.pre;
+  auto seg_bounds = [&]() {
+    thr_s = p.seg_thr ? p.seg_thr[s] : p.thr;
+    pre_s = p.pre;
+    if (thr_s > p.thr && p.mode != BDET_SCORE_RAW) {
+      const float q = p.mode == BDET_SCORE_FCOS ? thr_s * thr_s : thr_s;
+      if (q < 1.f) {
+        const float l = logf(__fdiv_rn(q, 1.f - q));
+        pre_s = fmaxf(p.pre, l - 1e-3f * fmaxf(fabsf(l), 1.f));
+      }
+    }
+  };
+  seg_bounds();
 
   auto flush_keys = [&]() {  // warp-uniform
     if (nk == 0) return;
@@ -460,7 +575,7 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
       if (i < count) {
         long long ci;
         key_index<NCHW>(p, sd, L.se[i], e, ci);
-        ok = exact_score(p, L.sx[i], ci, sc);
+        ok = exact_score(p, L.sx[i], ci, sc, thr_s);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
       if (ok) L.keys[nk + __popc(m & lt)] = make_key(sc, (uint32_t)e);
@@ -487,16 +602,17 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
   while (true) {
     const int e0 = (tile - sd.tile_start) * kFiltTile;
     const int pos0 = e0 / p.C;
+    const bool skip = p.redo_pass && p.seg_redo[s] == 0;  // second pass: only the flagged segments
     // this tile's loads first (latency is hidden by the other ~32 resident warps, each with 2 KB in flight)
     float4 cur[kFiltVec];
-    load_tile<VEC>(p.logits + sd.start, sd.len, e0, lane, cur);
-    if (tab_mode) {
+    if (!skip) load_tile<VEC>(p.logits + sd.start, sd.len, e0, lane, cur);
+    if (tab_mode && !skip) {
       const int npos = min((min(e0 + kFiltTile, sd.len) - 1) / p.C - pos0 + 1, kWTab);
       for (int i = lane; i < npos; i += 32) {
         const float sc = sigmoid_f(__ldg(p.ctr + sd.ctr_start + pos0 + i));
-        const float q = __fdiv_rn(p.thr * p.thr, sc);  // need sigmoid(x) > q
+        const float q = __fdiv_rn(thr_s * thr_s, sc);  // need sigmoid(x) > q
         float bound = CUDART_INF_F;
-        if (!(p.thr > 0.f)) bound = -CUDART_INF_F;
+        if (!(thr_s > 0.f)) bound = -CUDART_INF_F;
         else if (q < 1.f) bound = logf(__fdiv_rn(q, 1.f - q)) - 0.01f;  // generous margin: survivors are re-tested exactly
         L.tab[i] = bound;
       }
@@ -509,9 +625,10 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
       while (ns + 1 < p.n_seg && p.seg[ns + 1].tile_start <= next) ++ns;
 #pragma unroll
     for (int j = 0; j < kFiltVec; ++j) {
+      if (skip) break;
       const int e = e0 + (j * 32 + lane) * 4;
       const float xs[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
-      float bd[4] = {p.pre, p.pre, p.pre, p.pre};
+      float bd[4] = {pre_s, pre_s, pre_s, pre_s};
       if (tab_mode) {
         const int q0 = e / p.C - pos0;
         const int r0 = e - (q0 + pos0) * p.C;
@@ -543,6 +660,17 @@ __global__ void __launch_bounds__(kFiltThreads, 4) score_filter_kernel(const Fil
     if (ns != s) {
       s = ns;
       sd = p.seg[s];
+      seg_bounds();
+    }
+  }
+  if (p.seg_thr && !p.redo_pass) {  // the last warp to finish the first sweep verifies the sampled bounds
+    __threadfence();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(p.seg_redo + p.n_seg + 1, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket == min(nwarps, total_tiles) - 1) {
+      __threadfence();
+      filter_check(p, lane);
     }
   }
 }
@@ -562,6 +690,8 @@ __global__ void __launch_bounds__(256) scores_kernel(const float* __restrict__ l
 struct TopkWs {
   SegDesc* seg;
   int* cand_count;
+  float* seg_thr;
+  int* seg_redo;
   uint64_t* keys;
   size_t bytes;
 };
@@ -573,6 +703,10 @@ static TopkWs carve_ws(void* base, int64_t total, int n_seg, bool with_keys) {
   o += align_up((size_t)(n_seg + 1) * sizeof(SegDesc), 256);
   w.cand_count = reinterpret_cast<int*>(p + o);
   o += align_up((size_t)n_seg * 4, 256);
+  w.seg_thr = reinterpret_cast<float*>(p + o);
+  o += align_up((size_t)n_seg * 4, 256);
+  w.seg_redo = reinterpret_cast<int*>(p + o);
+  o += align_up((size_t)(n_seg + 2) * 4, 256);
   w.keys = reinterpret_cast<uint64_t*>(p + o);
   if (with_keys) o += align_up((size_t)total * 8, 256);
   w.bytes = o + 256;
@@ -934,6 +1068,17 @@ static int score_filter_topk_impl(const float* logits, const float* ctrness, int
   f.mode = mode;
   f.na = seg_hw_host ? na : 0;
   f.thr = threshold;
+  f.seg_thr = nullptr;
+  f.seg_redo = w.seg_redo;
+  f.k = k;
+  f.redo_pass = 0;
+  bool sampled = false;
+  // The sampled bound pays when candidates outnumber k by far: by construction in FCOS mode (sqrt(sigmoid * sigmoid) lifts
+  // ~30 % of all logits over 0.05), and for very long segments in any mode.  It costs two short extra launches, so plain
+  // sigmoid heads (~1 % candidates, the single-image RetinaNet case) skip it.  The result is exact either way.
+  if (mode != BDET_SCORE_RAW && k > 0)
+    for (int s = 0; s < n_seg; ++s)
+      sampled = sampled || (seg_len_host[s] >= kFSampleMin && (mode == BDET_SCORE_FCOS || seg_len_host[s] >= (1 << 23)));
   // raw-logit pre-filter: sigmoid(x) > q  needs  x > logit(q); keep a safety margin for fp32 rounding.
   f.pre = -std::numeric_limits<float>::infinity();
   if (mode != BDET_SCORE_RAW) {
@@ -947,15 +1092,22 @@ static int score_filter_topk_impl(const float* logits, const float* ctrness, int
   }
   if (tiles > 0) {
     const int grid = min(ceil_div(tiles, kFiltThreads / 32), sm_count() * 4);  // persistent warps, 4 CTAs / SM
-    if (f.na > 0) {  // NCHW head outputs: survivors are re-indexed (two integer divisions each)
-      if (vec)
-        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
-      else
-        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
-    } else if (vec) {
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
-    } else {
-      BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+    if (sampled) {
+      f.seg_thr = w.seg_thr;
+      BDET_KERNEL("filter_sample_kernel", st, filter_sample_kernel<<<n_seg, kFSThreads, 0, st>>>(f));
+    }
+    for (int pass = 0; pass < (sampled ? 2 : 1); ++pass) {
+      f.redo_pass = pass;
+      if (f.na > 0) {  // NCHW head outputs: survivors are re-indexed (two integer divisions each)
+        if (vec)
+          BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+        else
+          BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, true><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+      } else if (vec) {
+        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<true, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+      } else {
+        BDET_KERNEL("score_filter_kernel", st, score_filter_kernel<false, false><<<grid, kFiltThreads, 0, st>>>(f, tiles));
+      }
     }
   }
   SelArgs a{nullptr, w.keys, w.cand_count, w.seg, out_scores, out_idx, out_count, k, next_pow2(k < 2 ? 2 : k)};
