@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
 // no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
 constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
 
-__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p, unsigned tma_level_mask) {
+__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p, unsigned tma_level_mask, int csplit) {
   extern __shared__ __align__(16) float bsm[];
   const int PH = p.PH, PW = p.PW;
   const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;  // table rows padded to 16 bytes (128-bit shared loads)
@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   float* wx = wy + kFpChunk * PHs;              // kFpChunk * PWs
   float* sd = wx + kFpChunk * PWs;              // (warps) * PH * PWs: dout / S^2 of the warp's current channel
   __shared__ int rlo[kFpChunk], rhi[kFpChunk], clo[kFpChunk], chi[kFpChunk];
-  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int k, quarter;
+  roi_cta_map(blockIdx.x, p.K, csplit, &k, &quarter);
+  const int Cn = p.C / csplit, cbeg = quarter * Cn;  // this CTA's channels (roi_common.cuh: channel-quarter-major order)
   const RoiGeom g = roi_geom(p, k);
   if (!g.valid) return;
   if (tma_level_mask) {  // ROIs the TMA kernel (roi_tma.cu, launched just before) has taken
@@ -283,8 +286,11 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   if (!roi_footprint(p, g, y_lo, y_hi, x_lo, x_hi)) return;  // ROI entirely outside the map
   const int H = g.H, W = g.W;
   const float cnt = (float)(p.SH * p.SW);
-  float* dfeat = p.lv.dfeat[g.lvl] + (long long)g.n * p.C * H * W;
-  const float* dout = p.dout + (long long)k * p.C * PH * PW;
+  const int icnt = p.SH * p.SW;
+  const bool cnt_pow2 = (icnt & (icnt - 1)) == 0;  // x / 2^k == x * 2^-k exactly: skips the IEEE division routine
+  const float inv_cnt = __fdiv_rn(1.f, cnt);
+  float* dfeat = p.lv.dfeat[g.lvl] + ((long long)g.n * p.C + cbeg) * H * W;
+  const float* dout = p.dout + ((long long)k * p.C + cbeg) * PH * PW;
   float* sdw = sd + warp * (PH == 7 && PW == 7 ? 4 * 56 : PH * PWs);  // 7 x 7: up to 4 packed channels per warp
   for (int fy = y_lo; fy <= y_hi; fy += kFpChunk) {
     for (int fx = x_lo; fx <= x_hi; fx += kFpChunk) {
@@ -349,27 +355,27 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
           float dr[7];
           auto fetch = [&](int c) {
             const float* src = dout + (long long)c * 49;
-            const int n = min(nd, (p.C - c) * 49);
+            const int n = min(nd, (Cn - c) * 49);
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
               const int i = lane + 32 * j;
               dr[j] = (j * 32 < nd && i < n) ? __ldg(src + i) : 0.f;
             }
           };
-          if (warp * G < p.C) fetch(warp * G);
-          for (int c = warp * G; c < p.C; c += (kRoiThreads / 32) * G) {
+          if (warp * G < Cn) fetch(warp * G);
+          for (int c = warp * G; c < Cn; c += (kRoiThreads / 32) * G) {
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
               const int i = lane + 32 * j;
               if (j * 32 < nd && i < nd) {
                 const int ch = i / 49, q = i - ch * 49;
-                sdw[ch * 56 + (q / 7) * 8 + (q % 7)] = __fdiv_rn(dr[j], cnt);
+                sdw[ch * 56 + (q / 7) * 8 + (q % 7)] = cnt_pow2 ? dr[j] * inv_cnt : __fdiv_rn(dr[j], cnt);
               }
             }
             __syncwarp();
             const int cn = c + (kRoiThreads / 32) * G;
-            if (cn < p.C) fetch(cn);
+            if (cn < Cn) fetch(cn);
             float T[7];
 #pragma unroll
             for (int ph = 0; ph < 7; ++ph) {
@@ -384,7 +390,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
               v = __fmaf_rn(wb.z, b.z, v);
               T[ph] = v;
             }
-            const bool ok = xok && c + sub < p.C;
+            const bool ok = xok && c + sub < Cn;
             float* gp = dfeat + (long long)(c + sub) * H * W + (long long)fy * W + (fx + xx);
 #pragma unroll 4
             for (int r = 0; r < nr; ++r, gp += W) {
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
               sum = __fmaf_rn(w2.x, T[4], sum);
               sum = __fmaf_rn(w2.y, T[5], sum);
               sum = __fmaf_rn(w2.z, T[6], sum);
-              if (ok && sum != 0.f) atomicAdd(gp, sum);
+              red_add_if(gp, sum, ok && sum != 0.f);  // predicated: no divergent branch around the reduction
             }
           }
         }
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
       while ((1 << wshift) < wcols) ++wshift;  // lanes: x = lane & (2^wshift - 1), row sub-index = lane >> wshift
       const int rows_per_it = 32 >> wshift;
       const int lx = lane & ((1 << wshift) - 1), lr = lane >> wshift;
-      for (int c = warp; c < p.C; c += kRoiThreads / 32) {
+      for (int c = warp; c < Cn; c += kRoiThreads / 32) {
         __syncwarp();
         for (int i = lane; i < PH * PW; i += 32)
           sdw[(i / PW) * PWs + (i % PW)] = __fdiv_rn(__ldg(dout + (long long)c * PH * PW + i), cnt);
@@ -605,12 +611,13 @@ extern "C" int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int csplit = roi_channel_split(C);
   unsigned tma_mask = 0;
   rc = roi_bwd_tma_launch(a, st, &tma_mask);  // smem accumulation + cp.reduce.async.bulk.tensor (roi_tma.cu)
   if (rc < 0) return rc;
   // the direct scatter kernel takes what is left (levels whose rows are not 16-byte multiples, oversized footprints);
   // when every level has tensor maps it only finds work for ROIs wider than 64 feature pixels
-  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a, tma_mask));
+  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K * csplit, kRoiThreads, smem, st>>>(a, tma_mask, csplit));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

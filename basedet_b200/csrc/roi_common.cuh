@@ -121,6 +121,28 @@ __device__ __forceinline__ void roi_fwd_direct(const RoiArgs& p, int k, const Ro
 // roi_tma.cu: launches the TMA forward when the call qualifies (returns 1), 0 = use the direct kernel, < 0 = error
 int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st);
 
+// ---- CTA order.  A ROI reads (or updates) its footprint in every channel plane, so ROIs processed at the same time
+// spread their working set over the whole pyramid of their image (91 MB for config 3) and evict each other from L2: the
+// forward re-read the features 2.5 x from DRAM (ncu).  CTAs are therefore ordered channel-quarter-major inside groups of
+// kRoiGroup consecutive ROIs: (group, quarter, roi in group).  While one quarter of the channels of a group is in flight
+// the working set is a quarter of the planes, which stays in L2, and overlapping footprints are fetched once.
+constexpr int kRoiGroup = 512;
+__device__ __forceinline__ void roi_cta_map(int bid, int K, int Q, int* roi, int* quarter) {
+  const int g = bid / (kRoiGroup * Q);
+  const int base = g * kRoiGroup;
+  const int rsize = min(kRoiGroup, K - base);
+  const int rem = bid - g * kRoiGroup * Q;
+  *quarter = rem / rsize;
+  *roi = base + rem - *quarter * rsize;
+}
+// channel split of a call: quarters when that leaves multiples of 8 channels with enough work each
+// Measured on B200 (profiles/r02_roi_align.md): the split costs more in per-CTA set-up (4 x the tables, barriers and
+// pipeline fill) than the L2 locality returns -- forward 0.75 -> 0.98 ms, backward 1.27 -> 1.40 ms -- so it is off.
+static inline int roi_channel_split(int C) {
+  (void)C;
+  return 1;
+}
+
 // ---- which ROIs the TMA kernels (roi_tma.cu) take: a pure function of the ROI geometry, shared with the direct
 // backward kernel, which skips exactly those ROIs -----------------------------------------------------------------
 constexpr int kBoxH = 8, kBoxC = 8;     // rows / channels of one TMA box
@@ -193,6 +215,11 @@ __device__ __forceinline__ int roi_bwd_takes_tma(const RoiArgs& p, const RoiGeom
 }
 
 int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_out);
+
+// non-returning fp32 reduction under a predicate (no branch)
+__device__ __forceinline__ void red_add_if(float* addr, float v, bool pred) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p red.global.add.f32 [%0], %1;\n}\n" ::"l"(addr), "f"(v), "r"((int)pred) : "memory");
+}
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UTMAREDG / UBLKCP / SYNCS) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

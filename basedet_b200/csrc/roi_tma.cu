@@ -30,6 +30,7 @@ struct alignas(64) RoiTmaMaps {
 
 struct RoiTmaArgs {
   RoiArgs r;
+  int csplit;           // channel quarters per ROI (roi_cta_map): 1 or 4
   unsigned level_mask;  // levels that have tensor maps
   const RoiTmaMaps* gmaps;  // debug (BDET_ROI_TMA=2): descriptors read from global memory instead of the parameters
 };
@@ -87,11 +88,14 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   __shared__ FwdPlan plan;
   __shared__ int roff[kFwdMaxRows + 1];
   const RoiArgs& p = a.r;
-  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int k, quarter;
+  roi_cta_map(blockIdx.x, p.K, a.csplit, &k, &quarter);
+  const int Cn = p.C / a.csplit, cbeg = quarter * Cn;  // this CTA's channels
   const RoiGeom g = roi_geom(p, k);
-  float* out = p.out + (long long)k * p.C * 49;
+  float* out = p.out + ((long long)k * p.C + cbeg) * 49;
   if (!g.valid) {
-    for (int o = t; o < p.C * 49; o += kTmaThreads) out[o] = 0.f;
+    for (int o = t; o < Cn * 49; o += kTmaThreads) out[o] = 0.f;
     return;
   }
   fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
@@ -124,7 +128,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       long long fit = kChunkBytes / per_c;
       if (fit < 8) fit = (kRingBytes / 2) / per_c;
       int ccs = fit >= 64 ? 64 : (fit >= 48 ? 48 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0))));
-      if (ccs > p.C) ccs = p.C;
+      if (ccs > Cn) ccs = Cn;
       pl.ccs = ccs;
       if (ccs < kBoxC) pl.cls = -1;  // footprint too large for one stage
     }
@@ -132,7 +136,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   }
   __syncthreads();
   if (plan.cls < 0) {
-    roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kTmaThreads);
+    if (quarter == 0) roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kTmaThreads);  // all channels of the ROI, once
     return;
   }
   // ---- TMA path
@@ -142,8 +146,8 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   const int ncb = CCS / kBoxC;                    // channel boxes per stage
   const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
   const int rb_stride = ncb * box_floats;         // floats between row boxes of a stage
-  const int n_chunks = (p.C + CCS - 1) / CCS;
-  const int z0 = g.n * p.C;
+  const int n_chunks = (Cn + CCS - 1) / CCS;
+  const int z0 = g.n * p.C + cbeg;
   // ring of footprint stages: slot = one chunk (rounded up to 1 KB), as many slots as fit (2 .. kMaxSlots)
   const int slot_floats = ((nrb * rb_stride * 4 + 1023) & ~1023) / 4;
   const int nslots = min(min(kMaxSlots, n_chunks), kRingBytes / (slot_floats * 4));
@@ -157,7 +161,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       const int round = chunk / nslots, s = chunk - round * nslots, c0 = chunk * CCS;
       if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));  // the compute warps are done with the slot
       if (lane == 0) {
-        const int cbs = min(ncb, (p.C - c0 + kBoxC - 1) / kBoxC);
+        const int cbs = min(ncb, (Cn - c0 + kBoxC - 1) / kBoxC);
         mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_floats * 4);
         for (int rb = 0; rb < nrb; ++rb)
           for (int cb = 0; cb < cbs; ++cb)
@@ -171,7 +175,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       if (chunk + nslots - 1 < n_chunks) load(chunk + nslots - 1);
       bar_sync(kBarReady0 + s, kTmaThreads);  // the out stage holds chunk `chunk`
       if (lane == 0) {
-        bulk_store(out + (size_t)c0 * 49, ostage0 + s * (kOutStageBytes / 4), (uint32_t)min(CCS, p.C - c0) * 49 * 4);
+        bulk_store(out + (size_t)c0 * 49, ostage0 + s * (kOutStageBytes / 4), (uint32_t)min(CCS, Cn - c0) * 49 * 4);
         bulk_commit();
         bulk_wait_read<0>();  // shared memory is read out: the stage may be rewritten (and must outlive the copy)
       }
@@ -201,7 +205,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
 
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     const int s = chunk & 1, c0 = chunk * CCS;
-    const int nc = min(CCS, p.C - c0);
+    const int nc = min(CCS, Cn - c0);
     if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the bulk store of chunk - 2 has read the out stage
     const int round = chunk / nslots, slot = chunk - round * nslots;
     mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
@@ -540,10 +544,11 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
     }
   }
   if (!ta.level_mask) return 0;
+  ta.csplit = roi_channel_split(a.C);
   ta.gmaps = debug_global_maps(maps, st);
   if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_fwd: cannot reserve %d bytes of shared memory", kFwdSmem);
-  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K, kTmaThreads, kFwdSmem, st>>>(ta, *maps));
+  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K * ta.csplit, kTmaThreads, kFwdSmem, st>>>(ta, *maps));
   return 1;
 }
 
@@ -569,6 +574,7 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
   if (!ta.level_mask) return 0;
   const int max_cls = bwd_max_cls();
   if (max_cls < 0) return 0;
+  ta.csplit = 1;
   ta.level_mask |= (unsigned)max_cls << 16;  // travels with the mask to both kernels (bwd_plan)
   ta.gmaps = debug_global_maps(maps, st);
   if (cudaFuncSetAttribute(roi_align_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
