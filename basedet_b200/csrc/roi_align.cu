@@ -12,6 +12,8 @@
 //           with ONE red.global.add.f32 per touched pixel;
 //           (workspace given) atomics-free tile gather -- ROIs are binned per feature-map tile, one CTA accumulates its
 //           tile x channel chunk in shared memory and writes every dfeat element exactly once: bit-deterministic.
+#include <algorithm>
+
 #include "roi_common.cuh"
 
 namespace bdet {
@@ -442,6 +444,65 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Max ROI pooling, layers/common/roi_pool.py:62-63 -> F.nn.roi_pooling(mode="max", scale) (MegDNN ROIPooling, the Caffe
+// rule, oracle ASSUMED-13, pinned by the reference's known-answer test tests/layers/test_roi_pool.py:48-61): roi corners
+// rounded to pixels, size = end - start + 1 (>= 1), bin [floor(p * size / P), ceil((p + 1) * size / P)) clipped to the
+// map, maximum over the bin (0 for an empty bin); the argmax is kept for the backward.
+__global__ void __launch_bounds__(256) roi_maxpool_fwd_kernel(const RoiArgs p, int* __restrict__ argmax) {
+  const long long total = (long long)p.K * p.C * p.PH * p.PW;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int pw = (int)(o % p.PW), ph = (int)((o / p.PW) % p.PH);
+    const int c = (int)((o / ((long long)p.PW * p.PH)) % p.C), k = (int)(o / ((long long)p.PW * p.PH * p.C));
+    const float* r = p.rois + (long long)k * 5;
+    const int n = (int)__ldg(r);
+    const int lvl = p.levels ? __ldg(p.levels + k) : 0;
+    float best = 0.f;
+    int bi = -1;
+    if (n >= 0 && n < p.B && lvl >= 0 && lvl < p.lv.n_levels) {
+      const int H = p.lv.H[lvl], W = p.lv.W[lvl];
+      const float sc = p.lv.scale[lvl];
+      const int x0 = (int)roundf(__ldg(r + 1) * sc), y0 = (int)roundf(__ldg(r + 2) * sc);
+      const int x1 = (int)roundf(__ldg(r + 3) * sc), y1 = (int)roundf(__ldg(r + 4) * sc);
+      const int rw = max(x1 - x0 + 1, 1), rh = max(y1 - y0 + 1, 1);
+      const float bh = __fdiv_rn((float)rh, (float)p.PH), bw = __fdiv_rn((float)rw, (float)p.PW);
+      int hs = (int)floorf((float)ph * bh), he = (int)ceilf((float)(ph + 1) * bh);
+      int ws = (int)floorf((float)pw * bw), we = (int)ceilf((float)(pw + 1) * bw);
+      hs = min(max(hs + y0, 0), H);
+      he = min(max(he + y0, 0), H);
+      ws = min(max(ws + x0, 0), W);
+      we = min(max(we + x0, 0), W);
+      if (he > hs && we > ws) {
+        const float* f = p.lv.feat[lvl] + ((long long)n * p.C + c) * H * W;
+        best = -3.402823466e+38f;
+        for (int y = hs; y < he; ++y)
+          for (int x = ws; x < we; ++x) {
+            const float v = __ldg(f + y * W + x);
+            if (v > best) {
+              best = v;
+              bi = y * W + x;
+            }
+          }
+      }
+    }
+    p.out[o] = best;
+    if (argmax) argmax[o] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_maxpool_bwd_kernel(const RoiArgs p, const int* __restrict__ argmax) {
+  const long long total = (long long)p.K * p.C * p.PH * p.PW;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int a = argmax[o];
+    if (a < 0) continue;
+    const int c = (int)((o / ((long long)p.PW * p.PH)) % p.C), k = (int)(o / ((long long)p.PW * p.PH * p.C));
+    const int n = (int)__ldg(p.rois + (long long)k * 5);
+    const int lvl = p.levels ? __ldg(p.levels + k) : 0;
+    if (n < 0 || n >= p.B || lvl < 0 || lvl >= p.lv.n_levels) continue;
+    atomicAdd(p.lv.dfeat[lvl] + ((long long)n * p.C + c) * p.lv.H[lvl] * p.lv.W[lvl] + a, __ldg(p.dout + o));
+  }
+}
+
 static void make_tile_grid(TileGrid* g, int n_levels, const int* hw, int B, int* max_per_image) {
   int base = 0, mx = 1;
   for (int l = 0; l < n_levels; ++l) {
@@ -544,6 +605,50 @@ extern "C" int bdet_roi_align_fwd(const float* const* feats_host, int n_levels, 
     BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<7, 7, 2><<<K, kRoiThreads, 0, st>>>(a));
   else
     BDET_KERNEL("roi_align_fwd_kernel", st, roi_align_fwd_kernel<0, 0, 0><<<K, kRoiThreads, 0, st>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_roi_maxpool_fwd(const float* const* feats_host, int n_levels, const int* hw_host, const float* scale_host,
+                                    int B, int C, const float* rois, const int* levels, int K, int PH, int PW, float* out,
+                                    int* argmax, bdet_stream_t stream) {
+  BDET_REQUIRE(feats_host && hw_host && scale_host, "null argument");
+  RoiArgs a;
+  int rc = fill_roi_args(&a, reinterpret_cast<const void* const*>(feats_host), false, n_levels, hw_host, scale_host, B, C, rois,
+                         levels, K, PH, PW, 1, 1, 0);
+  if (rc) return rc;
+  if (K == 0 || C == 0) return BDET_OK;
+  BDET_REQUIRE(rois && out, "null argument");
+  a.out = out;
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)K * C * PH * PW;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+  BDET_KERNEL("roi_maxpool_fwd_kernel", st, roi_maxpool_fwd_kernel<<<grid, 256, 0, st>>>(a, argmax));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" int bdet_roi_maxpool_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, int B, int C, const float* rois,
+                                    const int* levels, int K, int PH, int PW, const float* dout, const int* argmax,
+                                    int accumulate, bdet_stream_t stream) {
+  BDET_REQUIRE(dfeats_host && hw_host, "null argument");
+  float ones[BDET_MAX_LEVELS];
+  for (int l = 0; l < BDET_MAX_LEVELS; ++l) ones[l] = 1.f;
+  RoiArgs a;
+  int rc = fill_roi_args(&a, reinterpret_cast<const void* const*>(dfeats_host), true, n_levels, hw_host, ones, B, C, rois, levels,
+                         K, PH, PW, 1, 1, 0);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (B == 0 || C == 0) return BDET_OK;
+  if (!accumulate)
+    for (int l = 0; l < n_levels; ++l)
+      BDET_CUDA(cudaMemsetAsync(dfeats_host[l], 0, (size_t)B * C * hw_host[2 * l] * hw_host[2 * l + 1] * 4, st));
+  if (K == 0) return BDET_OK;
+  BDET_REQUIRE(rois && dout && argmax, "null argument");
+  a.dout = dout;
+  const long long total = (long long)K * C * PH * PW;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+  BDET_KERNEL("roi_maxpool_bwd_kernel", st, roi_maxpool_bwd_kernel<<<grid, 256, 0, st>>>(a, argmax));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

@@ -39,13 +39,29 @@ class _RoiAlignFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+class _RoiMaxPoolFn(torch.autograd.Function):
+    """F.nn.roi_pooling(mode="max") (roi_pool.py:62-63): the gradient goes to the argmax pixel of every bin."""
+
+    @staticmethod
+    def forward(ctx, rois, levels, scales, pool_shape, *features):
+        out, argmax = ops.roi_maxpool_fwd(list(features), rois, levels, scales, pool_shape)
+        ctx.save_for_backward(rois, levels, argmax)
+        ctx.pool_shape = pool_shape
+        ctx.shapes = [tuple(f.shape) for f in features]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rois, levels, argmax = ctx.saved_tensors
+        grads = ops.roi_maxpool_bwd(dout.contiguous(), argmax, ctx.shapes, rois, levels, ctx.pool_shape)
+        return (None, None, None, None) + tuple(grads)
+
+
 def roi_pool(features: List[torch.Tensor], rois: torch.Tensor, strides: List[int], pool_shape,
              pooler_type: str = "roi_align") -> torch.Tensor:
     """features: list of (B, C, H_l, W_l); rois (K, 5) [batch, x1, y1, x2, y2] -> (K, C, PH, PW) in roi order."""
     assert pooler_type in ("roi_align", "roi_pool")
     assert len(strides) == len(features)
-    if pooler_type == "roi_pool":
-        raise NotImplementedError("max roi_pooling is outside the B200 hot path (SURVEY 8a); use roi_align")
     if isinstance(pool_shape, int):
         pool_shape = (pool_shape, pool_shape)
     rois = rois.detach().float().contiguous()
@@ -54,4 +70,5 @@ def roi_pool(features: List[torch.Tensor], rois: torch.Tensor, strides: List[int
         levels = ops.roi_assign_levels(rois, int(math.log2(strides[0])), int(math.log2(strides[-1])))
     scales = tuple(1.0 / s for s in strides)
     feats = [f.float().contiguous() for f in features]
-    return _RoiAlignFn.apply(rois, levels, scales, tuple(pool_shape), *feats)
+    fn = _RoiMaxPoolFn if pooler_type == "roi_pool" else _RoiAlignFn
+    return fn.apply(rois, levels, scales, tuple(pool_shape), *feats)

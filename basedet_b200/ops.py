@@ -724,6 +724,37 @@ def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample
     return dfeats
 
 
+def roi_maxpool_fwd(features, rois, levels, scales, pool_shape):
+    """F.nn.roi_pooling(mode="max") over all levels: -> (out (K,C,PH,PW), argmax (K,C,PH,PW) int32)."""
+    lib = _lib.load()
+    feats = [_f32c(f, "feature") for f in features]
+    B, C = feats[0].shape[:2]
+    r = _f32c(rois, "rois")
+    K = r.shape[0]
+    lv = _i32c(levels) if levels is not None else None
+    PH, PW = pool_shape
+    out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=r.device)
+    am = torch.empty((K, C, PH, PW), dtype=torch.int32, device=r.device)
+    n, ptrs, hw = _level_args(feats)
+    with _guard(r):
+        check(lib.bdet_roi_maxpool_fwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, _p(out), _p(am), _stream(r)))
+    return out, am
+
+
+def roi_maxpool_bwd(dout, argmax, feature_shapes, rois, levels, pool_shape):
+    lib = _lib.load()
+    d = _f32c(dout, "dout")
+    r = _f32c(rois, "rois")
+    lv = _i32c(levels) if levels is not None else None
+    dfeats = [torch.empty(tuple(s), dtype=torch.float32, device=d.device) for s in feature_shapes]
+    B, C = dfeats[0].shape[:2]
+    n, ptrs, hw = _level_args(dfeats)
+    with _guard(d):
+        check(lib.bdet_roi_maxpool_bwd(ptrs, n, hw, B, C, _p(r), _p(lv), r.shape[0], pool_shape[0], pool_shape[1], _p(d),
+                                       _p(_i32c(argmax)), 0, _stream(d)))
+    return dfeats
+
+
 # ----------------------------------------------------------------------------- small Boxes / glue ops
 def box_props(boxes, mode):
     """mode 0 width, 1 height, 2 area (structures/boxes.py:36-52)."""

@@ -359,6 +359,18 @@ int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_ho
                        int sample_h, int sample_w, int aligned, const float* dout, int accumulate,
                        void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
+/* Max ROI pooling: roi_pool(..., pooler_type="roi_pool"), layers/common/roi_pool.py:62-63 -> F.nn.roi_pooling(mode="max").
+ * Caffe / MegDNN rule (pinned by the reference's test tests/layers/test_roi_pool.py:48-61): corners rounded to pixels,
+ * size = end - start + 1 (>= 1), bin [floor(p*size/P), ceil((p+1)*size/P)) clipped to the map, 0 for an empty bin.
+ * argmax (K,C,PH,PW) int32 (optional in the forward) = flat y*W+x index of the maximum, -1 for an empty bin; the backward
+ * adds dout to dfeat at it (fp32 atomics; dfeats zeroed first unless accumulate). */
+int bdet_roi_maxpool_fwd(const float* const* feats_host, int n_levels, const int* hw_host, const float* scale_host, int B,
+                         int C, const float* rois, const int* levels, int K, int PH, int PW, float* out, int* argmax,
+                         bdet_stream_t stream);
+int bdet_roi_maxpool_bwd(float* const* dfeats_host, int n_levels, const int* hw_host, int B, int C, const float* rois,
+                         const int* levels, int K, int PH, int PW, const float* dout, const int* argmax, int accumulate,
+                         bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ small Boxes / glue ops
  * Boxes.width / height / area  structures/boxes.py:36-52 (mode 0 / 1 / 2) -> out (N) */
 int bdet_box_props(const float* boxes, int ld, int N, int mode, float* out, bdet_stream_t stream);

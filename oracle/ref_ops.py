@@ -27,6 +27,8 @@ reference's own tests.
              (value asc, index asc); argmin returns the FIRST index among equal minima.
   ASSUMED-11 Advanced-index assignment ``t[i, j] = v`` with repeated (i, j) pairs keeps the LAST value in index
              order (FreeAnchor's box-probability scatter, free_anchor.py:78).
+  ASSUMED-13 F.nn.roi_pooling(mode="max") is MegDNN ROIPooling = the Caffe rule (rounded corners, size = end - start + 1,
+             floor / ceil bin edges, 0 for empty bins); pinned by tests/layers/test_roi_pool.py:48-61.
   ASSUMED-12 F.logsigmoid(x) = min(x, 0) - log1p(exp(-|x|)) in fp32; ``x ** gamma`` with gamma = 2 is x * x.
 """
 import math
@@ -1079,14 +1081,41 @@ def roi_align_backward(dout, feat_shape, rois, pool_shape, spatial_scale, sample
     return grad.reshape(B, C, H, W)
 
 
+def roi_max_pooling(feat, rois, pool_shape, spatial_scale):
+    """megengine.functional.nn.roi_pooling(mode="max") (ASSUMED-13: MegDNN ROIPooling = the Caffe rule; pinned by the
+    reference's own known-answer test, tests/layers/test_roi_pool.py:48-61).  feat (B,C,H,W); rois (K,5)."""
+    feat = np.asarray(feat, f32)
+    rois = np.asarray(rois, f32)
+    B, C, H, W = feat.shape
+    PH, PW = pool_shape
+    out = np.zeros((rois.shape[0], C, PH, PW), f32)
+    rnd = lambda v: int(math.floor(abs(float(v)) + 0.5) * (1 if v >= 0 else -1))   # C roundf: half away from zero
+    for k, r in enumerate(rois):
+        n = int(r[0])
+        x0, y0, x1, y1 = (rnd(f32(r[i]) * f32(spatial_scale)) for i in (1, 2, 3, 4))
+        rw, rh = max(x1 - x0 + 1, 1), max(y1 - y0 + 1, 1)
+        bh, bw = f32(rh) / f32(PH), f32(rw) / f32(PW)
+        for ph in range(PH):
+            hs = min(max(int(math.floor(f32(ph) * bh)) + y0, 0), H)
+            he = min(max(int(math.ceil(f32(ph + 1) * bh)) + y0, 0), H)
+            for pw in range(PW):
+                ws = min(max(int(math.floor(f32(pw) * bw)) + x0, 0), W)
+                we = min(max(int(math.ceil(f32(pw + 1) * bw)) + x0, 0), W)
+                if he > hs and we > ws:
+                    out[k, :, ph, pw] = feat[n, :, hs:he, ws:we].reshape(C, -1).max(axis=1)
+    return out
+
+
 def roi_pool(features, rois, strides, pool_shape, pooler_type="roi_align"):
-    """basedet/layers/common/roi_pool.py:35-78 ("roi_align" branch only).
+    """basedet/layers/common/roi_pool.py:35-78.
 
     Follows the reference literally: dummy ROI per level (:28-31), per-level pooling,
     argsort re-ordering, dummies dropped (:74-76).
     """
-    assert pooler_type == "roi_align"
+    assert pooler_type in ("roi_align", "roi_pool")
     assert len(strides) == len(features)
+    if isinstance(pool_shape, int):
+        pool_shape = (pool_shape, pool_shape)
     rois = np.asarray(rois, dtype=f32)
     num_fms = len(strides)
     lvl = np.concatenate([assign_levels(rois, strides), np.arange(num_fms, dtype=np.int32)])
@@ -1094,7 +1123,10 @@ def roi_pool(features, rois, strides, pool_shape, pooler_type="roi_align"):
     pool_list, inds_list = [], []
     for i, (feat, stride) in enumerate(zip(features, strides)):
         inds = np.flatnonzero(lvl == i)
-        pool_list.append(roi_align(feat, rois_d[inds], pool_shape, 1.0 / stride, 2, True))
+        if pooler_type == "roi_pool":
+            pool_list.append(roi_max_pooling(feat, rois_d[inds], pool_shape, 1.0 / stride))
+        else:
+            pool_list.append(roi_align(feat, rois_d[inds], pool_shape, 1.0 / stride, 2, True))
         inds_list.append(inds)
     fm_order = np.argsort(np.concatenate(inds_list), kind="stable")
     pooled = np.concatenate(pool_list, axis=0)

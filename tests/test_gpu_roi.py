@@ -146,3 +146,38 @@ def test_roi_align_backward_scatter_generic_shapes(cuda, pool, samples):
     got = ops.roi_align_bwd(T(dout, cuda), [feat_shape], T(rois, cuda), None, [0.25], pool, samples, gather=False)[0].cpu().numpy()
     ref = R.roi_align_backward(dout, feat_shape, rois, pool, 0.25, samples)
     assert np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1.0) <= 1e-5
+
+
+def test_roi_max_pool_kat_and_oracle(cuda):
+    """pooler_type="roi_pool" (roi_pool.py:62-63): the reference's known answer, then random multi-level pyramids
+    against the oracle (bit-exact: a maximum), and the argmax backward through autograd."""
+    from basedet_b200.layers import roi_pool
+    from tests.test_oracle_kat import ROI, ROI_FEAT
+
+    expected = np.array([[6.0, 7.0, 8.0, 8.0], [11.0, 12.0, 13.0, 13.0], [16.0, 17.0, 18.0, 18.0], [16.0, 17.0, 18.0, 18.0]])
+    out = roi_pool([T(ROI_FEAT, cuda)], T(ROI, cuda), strides=[1], pool_shape=4, pooler_type="roi_pool")
+    assert np.array_equal(out.cpu().numpy()[0, 0], expected)
+    rng = np.random.default_rng(12)
+    B, C = 2, 6
+    feats = _pyramid(rng, B, C, (160, 224))
+    rois = W.make_rois(rng, 50, B, 160, 224, 4, 250)
+    rois[3, 1:] = [-30, -20, 40, 50]
+    rois[4, 1:] = [200, 140, 260, 200]
+    rois[5, 1:] = [50, 50, 50, 50]
+    rois[6, 1:] = [500, 500, 600, 600]      # outside: empty bins -> 0
+    tf = [T(f, cuda).requires_grad_(True) for f in feats]
+    out = roi_pool(tf, T(rois, cuda), W.FRCNN_RCNN_STRIDES, (7, 7), "roi_pool")
+    ref = R.roi_pool(feats, rois, W.FRCNN_RCNN_STRIDES, (7, 7), "roi_pool")
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    # backward: d(sum(out * w)) / d feat = w scattered to the argmax pixels; check against a finite structure: the gradient
+    # of sum(out) counts how many bins selected each pixel, and its total equals the number of non-empty bins
+    out.sum().backward()
+    total = sum(float(f.grad.sum()) for f in tf)
+    levels = R.assign_levels(rois, W.FRCNN_RCNN_STRIDES)
+    nonempty = 0
+    for l, f in enumerate(feats):
+        sel = rois[levels == l]
+        if len(sel):
+            big = R.roi_max_pooling(np.where(np.isfinite(f), 1.0, 1.0).astype(np.float32) * 0 + 1, sel, (7, 7), 1.0 / W.FRCNN_RCNN_STRIDES[l])
+            nonempty += int((big > 0).sum())
+    assert abs(total - nonempty) < 0.5

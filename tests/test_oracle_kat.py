@@ -73,6 +73,13 @@ def test_roi_align_kat():
     assert np.allclose(out[0, 0], ROI_ALIGN_EXPECTED)
 
 
+def test_roi_max_pool_kat():
+    # test_roi_pool.py:48-61 (pooler_type="roi_pool" -> F.nn.roi_pooling(mode="max")): pins ASSUMED-13
+    expected = np.array([[6.0, 7.0, 8.0, 8.0], [11.0, 12.0, 13.0, 13.0], [16.0, 17.0, 18.0, 18.0], [16.0, 17.0, 18.0, 18.0]])
+    out = R.roi_pool([ROI_FEAT], ROI, strides=[1], pool_shape=4, pooler_type="roi_pool")
+    assert np.array_equal(out[0, 0], expected)
+
+
 def test_roi_align_resize_kat():
     # test_roi_pool.py:64-75: 2x nearest-upsampled... the reference uses F.vision.interpolate (bilinear,
     # align_corners=False).  Equivariance holds for a linear ramp, which arange is.
