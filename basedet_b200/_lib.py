@@ -42,6 +42,8 @@ SIGNATURES = {
     "bdet_assign_targets_workspace": (c_size_t, [c_int, c_int, c_int]),
     "bdet_assign_targets": (c_int, [vp, c_int, vp, c_int, vp, c_int, fp, ip, c_int, c_int, c_int, fp, fp,
                                     vp, vp, vp, vp, c_size_t, vp]),
+    "bdet_assign_targets_grid": (c_int, [c_int, ip, dp, dp, ip, fp, vp, c_int, vp, c_int, fp, ip, c_int, c_int, c_int, fp, fp,
+                                         vp, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),
     "bdet_topk": (c_int, [vp, lp, lp, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]),
     "bdet_score_filter_topk_workspace": (c_size_t, [c_int64, c_int, c_int]),

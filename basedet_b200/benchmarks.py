@@ -129,7 +129,8 @@ class RetinaNetPostprocess(Arm):
 # ------------------------------------------------------------------------------------------------------ config 2
 class RetinaNetTargets(Arm):
     """configs[1]: RetinaNet training target assignment: anchors (regenerated per forward, retinanet.py:116) x GT IoU
-    + Matcher(.4/.5, low-quality) + class labels + BoxCoder.encode (models/det/retinanet.py:211-232), fused."""
+    + Matcher(.4/.5, low-quality) + class labels + BoxCoder.encode + label census (models/det/retinanet.py:211-232,
+    142-146), fused (bdet_assign_targets; bdet_assign_targets_grid for <= 4 images per GPU)."""
     name = "c2_retinanet_targets"
     dominant = "assign_main_kernel"
 
@@ -154,11 +155,19 @@ class RetinaNetTargets(Arm):
                              % (self.B * self.A * 24 / 1e6)
 
     def eager(self):
-        anchors = self.gen.generate_all_level_anchors(self.sizes, self.dev)
+        # anchors are regenerated per forward in the reference (retinanet.py:116)
         m = W.RETINANET_MATCHER
-        out = ops.assign_targets(anchors, self.gt, self.ng, m["thresholds"], m["labels"], m["allow_low_quality"], True,
-                                 plan=self.plan)
-        ops.count_labels(self.plan.labels, out=self.summary)
+        if self.B <= pipelines.GRID_ASSIGN_MAX_BATCH:
+            # few images per GPU (the strong-scaling regime): the step is launch bound, so the anchors are generated in
+            # registers inside the assignment kernels together with the label census -- two launches instead of four
+            out = ops.assign_targets_grid(self.gen._plan(self.sizes), self.gt, self.ng, m["thresholds"], m["labels"],
+                                          m["allow_low_quality"], True, plan=self.plan, counts=self.summary)
+        else:
+            # larger batches are issue bound: one anchor tensor shared by all images is cheaper than regenerating it per image
+            anchors = self.gen.generate_all_level_anchors(self.sizes, self.dev)
+            out = ops.assign_targets(anchors, self.gt, self.ng, m["thresholds"], m["labels"], m["allow_low_quality"], True,
+                                     plan=self.plan)
+            ops.count_labels(self.plan.labels, out=self.summary)
         self.out = out
         return out
 

@@ -2,39 +2,16 @@
 // Reference: basedet/layers/common/anchor_generator.py:23-30 (create_anchor_grid),
 // :111-122 (DefaultAnchorGenerator), :152-165 (AnchorPointGenerator), :175-182 (FastPointGenerator).
 // Pure write kernel: one thread per output box (128-bit store) / point (64-bit store).
-#include "common.cuh"
+#include "anchor_levels.cuh"
 
 namespace bdet {
-
-constexpr int kMaxBase = 64;
-
-struct AnchorLevels {
-  int n_levels;
-  int H[BDET_MAX_LEVELS], W[BDET_MAX_LEVELS], n_base[BDET_MAX_LEVELS], base_off[BDET_MAX_LEVELS];
-  double stride[BDET_MAX_LEVELS], shift[BDET_MAX_LEVELS];
-  long long out_off[BDET_MAX_LEVELS];    // in boxes / points
-  long long start[BDET_MAX_LEVELS + 1];  // prefix of per-level work items
-  float base[kMaxBase * 4];
-};
 
 __global__ void __launch_bounds__(256) anchors_grid_kernel(float4* __restrict__ out, const __grid_constant__ AnchorLevels p) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= p.start[p.n_levels]) return;
-  int l = 0;
-#pragma unroll
-  for (int k = 1; k < BDET_MAX_LEVELS; ++k)
-    if (k < p.n_levels && i >= p.start[k]) l = k;
-  long long r = i - p.start[l];
-  int nb = p.n_base[l];
-  int a = (int)(r % nb);
-  long long pos = r / nb;
-  int w = (int)(pos % p.W[l]);
-  int h = (int)(pos / p.W[l]);
-  // F.arange(shift, n*stride + shift, stride): fp32(start + i*step) evaluated in fp64 (oracle ASSUMED-7)
-  float x = (float)(p.shift[l] + (double)w * p.stride[l]);
-  float y = (float)(p.shift[l] + (double)h * p.stride[l]);
-  const float* b = p.base + (p.base_off[l] + a) * 4;
-  out[p.out_off[l] + r] = make_float4(x + b[0], y + b[1], x + b[2], y + b[3]);
+  long long slot;
+  const float4 v = anchor_at(p, i, &slot);
+  out[slot] = v;
 }
 
 // mode 0: AnchorPointGenerator -- (x, y) for (h, w) row-major, each repeated num_anchors times.
@@ -62,33 +39,6 @@ __global__ void __launch_bounds__(256) points_grid_kernel(float2* __restrict__ o
     v.y = (float)jj * s;
   }
   out[p.out_off[l] + r] = v;
-}
-
-static int fill_levels(AnchorLevels* p, int n_levels, const int* hw, const double* stride, const double* shift,
-                       const int* n_base, int num_anchors, const float* base, const int64_t* out_off) {
-  if (n_levels < 1 || n_levels > BDET_MAX_LEVELS)
-    return set_error(BDET_EINVAL, "anchors: n_levels must be in [1, %d]", BDET_MAX_LEVELS);
-  p->n_levels = n_levels;
-  p->start[0] = 0;
-  int boff = 0;
-  for (int l = 0; l < n_levels; ++l) {
-    p->H[l] = hw[2 * l];
-    p->W[l] = hw[2 * l + 1];
-    if (p->H[l] < 0 || p->W[l] < 0) return set_error(BDET_EINVAL, "anchors: negative feature size");
-    p->n_base[l] = n_base ? n_base[l] : num_anchors;
-    if (p->n_base[l] < 1) return set_error(BDET_EINVAL, "anchors: need >= 1 anchor per cell");
-    p->base_off[l] = boff;
-    boff += p->n_base[l];
-    p->stride[l] = stride[l];
-    p->shift[l] = shift ? shift[l] : 0.0;
-    p->out_off[l] = out_off[l];
-    p->start[l + 1] = p->start[l] + (long long)p->H[l] * p->W[l] * p->n_base[l];
-  }
-  if (base) {
-    if (boff > kMaxBase) return set_error(BDET_EUNSUPPORTED, "anchors: more than %d base anchors", kMaxBase);
-    for (int i = 0; i < boff * 4; ++i) p->base[i] = base[i];
-  }
-  return BDET_OK;
 }
 
 }  // namespace bdet

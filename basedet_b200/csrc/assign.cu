@@ -15,7 +15,7 @@
 // assign_lq_kernel -- one CTA per (image, GT): finds the tiles whose maximum equals the row maximum and
 //   re-evaluates only those 512-anchor segments (matcher.py:47-49), including rows whose maximum is 0.
 // HBM traffic: 16 B/anchor read + 24 B/anchor written (labels, indices, offsets) per image.
-#include "common.cuh"
+#include "anchor_levels.cuh"
 
 namespace bdet {
 
@@ -33,12 +33,19 @@ struct AssignArgs {
   float* offsets;
   uint32_t* rowmax;  // (B, Gmax) fp32 bits (IoU >= 0, so uint order == float order); zero-initialised
   uint32_t* blkmax;  // (B, Gmax, tiles)
+  int* counts;       // optional (B, 3): labels < 0, == 0, > 0 (the census retinanet.py:142-146 / rpn.py:231 needs)
   int A, Gmax, tiles, allow_lq, apply_class, unit_coder;
   MatchCfg cfg;
   Vec4 mean, stdv;
 };
 
-__global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
+// anchors == nullptr: the anchors are generated in registers from the grid description (the same expression as
+// anchors_grid_kernel, bit for bit) -- no anchor tensor, no separate launch.
+__device__ __forceinline__ float4 assign_anchor(const AssignArgs& p, const AnchorLevels& lv, long long c) {
+  return p.anchors ? ldg4(p.anchors + c * 4) : anchor_at(lv, c, nullptr);
+}
+
+__global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p, const __grid_constant__ AnchorLevels lv) {
   extern __shared__ __align__(16) unsigned char raw[];
   float4* sbox = reinterpret_cast<float4*>(raw);
   float* sarea = reinterpret_cast<float*>(sbox + p.Gmax);
@@ -61,8 +68,8 @@ __global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
   const long long c0 = (long long)tile * kATile + warp * kAPW + lane;
   const long long c1 = c0 + 32;
   const bool ok0 = c0 < p.A, ok1 = c1 < p.A;
-  const float4 an0 = ok0 ? ldg4(p.anchors + c0 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 an1 = ok1 ? ldg4(p.anchors + c1 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 an0 = ok0 ? assign_anchor(p, lv, c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 an1 = ok1 ? assign_anchor(p, lv, c1) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float aa0 = box_area(an0), aa1 = box_area(an1);
   // warp bounding box (NaN coordinates are ignored by fmin/fmax; such anchors give IoU 0 against everything)
   float mnx = CUDART_INF_F, mny = CUDART_INF_F, mxx = -CUDART_INF_F, mxy = -CUDART_INF_F;
@@ -121,6 +128,7 @@ __global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
     }
   }
 
+  int n_neg = 0, n_zero = 0, n_pos = 0;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const bool ok = j ? ok1 : ok0;
@@ -138,6 +146,19 @@ __global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
     p.labels[o] = label;
     p.idx[o] = bi;
     reinterpret_cast<float4*>(p.offsets)[o] = off;
+    n_neg += label < 0;
+    n_zero += label == 0;
+    n_pos += label > 0;
+  }
+  if (p.counts) {  // per-warp totals, three atomics per warp
+    n_neg = __reduce_add_sync(0xffffffffu, n_neg);
+    n_zero = __reduce_add_sync(0xffffffffu, n_zero);
+    n_pos = __reduce_add_sync(0xffffffffu, n_pos);
+    if (lane == 0) {
+      if (n_neg) atomicAdd(p.counts + b * 3, n_neg);
+      if (n_zero) atomicAdd(p.counts + b * 3 + 1, n_zero);
+      if (n_pos) atomicAdd(p.counts + b * 3 + 2, n_pos);
+    }
   }
 
   if (p.allow_lq) {
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(kAT) assign_main_kernel(const AssignArgs p) {
 
 // allow_low_quality_matches, matcher.py:47-49: every anchor whose IoU with g equals the row maximum of g gets
 // label 1 (then the class of ITS OWN matched GT, retinanet.py:222-223).
-__global__ void __launch_bounds__(kLqThreads) assign_lq_kernel(const AssignArgs p) {
+__global__ void __launch_bounds__(kLqThreads) assign_lq_kernel(const AssignArgs p, const __grid_constant__ AnchorLevels lv) {
   extern __shared__ int stiles[];  // tiles
   __shared__ int nhit;
   const int g = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
@@ -179,11 +200,21 @@ __global__ void __launch_bounds__(kLqThreads) assign_lq_kernel(const AssignArgs 
     for (int i = t; i < kATile; i += kLqThreads) {
       const long long c = base + i;
       if (c >= p.A) break;
-      const float4 an = ldg4(p.anchors + c * 4);
+      const float4 an = assign_anchor(p, lv, c);
       const float v = iou_pair(a, ga, an, box_area(an));
       if (__float_as_uint(v) == rm) {
         const long long o = (long long)b * p.A + c;
-        p.labels[o] = p.apply_class ? (int)__ldg(gtb + p.idx[o] * 5 + 4) : 1;
+        const int nl = p.apply_class ? (int)__ldg(gtb + p.idx[o] * 5 + 4) : 1;
+        if (p.counts) {  // several GT rows may promote the same anchor: the exchange tells who changed the census
+          const int old = atomicExch(p.labels + o, nl);
+          const int oc = old < 0 ? 0 : (old == 0 ? 1 : 2), nc = nl < 0 ? 0 : (nl == 0 ? 1 : 2);
+          if (oc != nc) {
+            atomicSub(p.counts + b * 3 + oc, 1);
+            atomicAdd(p.counts + b * 3 + nc, 1);
+          }
+        } else {
+          p.labels[o] = nl;
+        }
       }
     }
   }
@@ -199,19 +230,19 @@ extern "C" size_t bdet_assign_targets_workspace(int Gmax, int A, int B) {
   return align_up((size_t)B * Gmax * 4, 256) + (size_t)B * Gmax * tiles * 4 + 256;
 }
 
-extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, const int* num_gt_dev, int B,
-                                   const float* thresholds_host, const int* labels_host, int n_labels,
-                                   int allow_low_quality, int apply_class, const float* mean_host,
-                                   const float* std_host, int* labels, int* match_idx, float* offsets,
-                                   void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+static int assign_targets_impl(const float* anchors, const AnchorLevels* grid, int A, const float* gt, int Gmax,
+                               const int* num_gt_dev, int B, const float* thresholds_host, const int* labels_host, int n_labels,
+                               int allow_low_quality, int apply_class, const float* mean_host, const float* std_host,
+                               int* labels, int* match_idx, float* offsets, int* counts, void* workspace,
+                               size_t workspace_bytes, bdet_stream_t stream) {
   BDET_REQUIRE(A >= 0 && Gmax >= 0 && B >= 0, "negative size");
   AssignArgs a;
   int rc = make_match_cfg(&a.cfg, thresholds_host, labels_host, n_labels);
   if (rc) return rc;
   if (A == 0 || B == 0) return BDET_OK;
-  BDET_REQUIRE(anchors && labels && match_idx && offsets && num_gt_dev, "null argument");
+  BDET_REQUIRE((anchors || grid) && labels && match_idx && offsets && num_gt_dev, "null argument");
   BDET_REQUIRE(Gmax == 0 || gt, "null gt");
-  BDET_REQUIRE(aligned16(anchors) && aligned16(offsets), "anchors/offsets must be 16-byte aligned");
+  BDET_REQUIRE((!anchors || aligned16(anchors)) && aligned16(offsets), "anchors/offsets must be 16-byte aligned");
   BDET_REQUIRE(B <= 65535 && Gmax <= 65535, "B / Gmax > 65535");
   const size_t smem = (size_t)max(Gmax, 1) * (24 + 4 * (kAT / 32));
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_assign_targets: Gmax > 3600 does not fit shared memory");
@@ -234,7 +265,11 @@ extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt,
   }
   a.rowmax = nullptr;
   a.blkmax = nullptr;
+  a.counts = counts;
   cudaStream_t st = as_stream(stream);
+  if (counts) BDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * 3 * 4, st));
+  static const AnchorLevels kNoGrid = {};
+  const AnchorLevels& lv = grid ? *grid : kNoGrid;
   if (a.allow_lq) {
     const size_t need = bdet_assign_targets_workspace(Gmax, A, B);
     if (!workspace || workspace_bytes < need)
@@ -247,13 +282,46 @@ extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt,
   }
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(assign_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<<<dim3(a.tiles, B), kAT, smem, st>>>(a));
+  BDET_KERNEL("assign_main_kernel", st, assign_main_kernel<<<dim3(a.tiles, B), kAT, smem, st>>>(a, lv));
   if (a.allow_lq) {
     const size_t lq_smem = (size_t)a.tiles * 4;
     if (lq_smem > 40 * 1024)
       BDET_CUDA(cudaFuncSetAttribute(assign_lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lq_smem));
-    BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<<<dim3(Gmax, B), kLqThreads, lq_smem, st>>>(a));
+    BDET_KERNEL("assign_lq_kernel", st, assign_lq_kernel<<<dim3(Gmax, B), kLqThreads, lq_smem, st>>>(a, lv));
   }
   BDET_LAUNCH_CHECK();
   return BDET_OK;
+}
+
+extern "C" int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, const int* num_gt_dev, int B,
+                                   const float* thresholds_host, const int* labels_host, int n_labels,
+                                   int allow_low_quality, int apply_class, const float* mean_host,
+                                   const float* std_host, int* labels, int* match_idx, float* offsets,
+                                   void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  return assign_targets_impl(anchors, nullptr, A, gt, Gmax, num_gt_dev, B, thresholds_host, labels_host, n_labels,
+                             allow_low_quality, apply_class, mean_host, std_host, labels, match_idx, offsets, nullptr, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int bdet_assign_targets_grid(int n_levels, const int* hw_host, const double* stride_host, const double* shift_host,
+                                        const int* n_base_host, const float* base_host, const float* gt, int Gmax,
+                                        const int* num_gt_dev, int B, const float* thresholds_host, const int* labels_host,
+                                        int n_labels, int allow_low_quality, int apply_class, const float* mean_host,
+                                        const float* std_host, int* labels, int* match_idx, float* offsets, int* counts,
+                                        void* workspace, size_t workspace_bytes, bdet_stream_t stream) {
+  BDET_REQUIRE(hw_host && stride_host && n_base_host && base_host, "null argument");
+  static thread_local AnchorLevels lv;
+  static thread_local int64_t off[BDET_MAX_LEVELS];
+  if (n_levels < 1 || n_levels > BDET_MAX_LEVELS) return set_error(BDET_EINVAL, "bdet_assign_targets_grid: n_levels must be in [1, %d]", BDET_MAX_LEVELS);
+  int64_t o = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    off[l] = o;
+    o += (int64_t)hw_host[2 * l] * hw_host[2 * l + 1] * n_base_host[l];
+  }
+  int rc = fill_levels(&lv, n_levels, hw_host, stride_host, shift_host, n_base_host, 0, base_host, off);
+  if (rc) return rc;
+  if (o > 0x7fffffffLL) return set_error(BDET_EUNSUPPORTED, "bdet_assign_targets_grid: more than 2^31 anchors");
+  return assign_targets_impl(nullptr, &lv, (int)o, gt, Gmax, num_gt_dev, B, thresholds_host, labels_host, n_labels,
+                             allow_low_quality, apply_class, mean_host, std_host, labels, match_idx, offsets, counts, workspace,
+                             workspace_bytes, stream);
 }

@@ -391,6 +391,30 @@ def assign_targets(anchors, gt_boxes, num_gt, thresholds, labels, allow_low_qual
     return plan.labels, plan.idx, plan.offsets
 
 
+def assign_targets_grid(anchor_plan, gt_boxes, num_gt, thresholds, labels, allow_low_quality=True, apply_class=True,
+                        mean=(0, 0, 0, 0), std=(1, 1, 1, 1), plan=None, counts=None):
+    """``assign_targets`` with the anchors generated inside the kernels from an ``AnchorPlan`` (the generator's grid
+    description) instead of read from a tensor; ``counts`` (B,3) int32, optional, receives the label census.
+    -> (labels (B,A), match_idx (B,A), offsets (B,A,4))."""
+    lib = _lib.load()
+    gt = _f32c(gt_boxes, "gt_boxes")
+    assert gt.ndim == 3 and gt.shape[2] == 5, "gt_boxes must be (B, Gmax, 5)"
+    B, Gmax, _ = gt.shape
+    A = anchor_plan.offs[-1]
+    ng = _i32c(num_gt, "num_gt")
+    if plan is None:
+        plan = AssignPlan(A, Gmax, B, gt.device)
+    assert (plan.A, plan.Gmax, plan.B) == (A, Gmax, B)
+    assert counts is None or (counts.shape == (B, 3) and counts.dtype == torch.int32 and counts.is_contiguous())
+    with _guard(gt):
+        check(lib.bdet_assign_targets_grid(anchor_plan.n, anchor_plan.hw, anchor_plan.strides, anchor_plan.shifts,
+                                           anchor_plan.n_base, anchor_plan.base, _p(gt), Gmax, _p(ng), B, farr(thresholds),
+                                           iarr(labels), len(labels), int(bool(allow_low_quality)), int(bool(apply_class)),
+                                           farr(mean), farr(std), _p(plan.labels), _p(plan.idx), _p(plan.offsets), _p(counts),
+                                           _p(plan.ws), plan.ws.numel(), _stream(gt)))
+    return plan.labels, plan.idx, plan.offsets
+
+
 class DensePlan:
     """Pre-allocated outputs (+ ATSS workspace) of the anchor-free target assignment, reused across steps."""
 

@@ -163,6 +163,12 @@ def ota_targets(points_list, strides, gt_boxes, cls_logits, pred_deltas, candida
     return cls_t, box_t, iou_t, matched, cost, ious
 
 
+# Measured on B200 (profiles/r02_strong_scaling.md): generating the anchors in registers and folding the census into the
+# assignment kernels wins while the step is launch bound (2 images: 61 -> 54 us) and loses once it is issue bound
+# (16 images: 112 -> 131 us: the integer divisions and fp64 grid arithmetic are paid per image instead of once).
+GRID_ASSIGN_MAX_BATCH = 4
+
+
 class _AssignSlot:
     """One set of static input / output buffers of TargetAssigner with its captured graph."""
 
@@ -178,9 +184,13 @@ class _AssignSlot:
 
     def step(self, owner):
         thr, lab, lq, cls, mean, std = owner.cfg
-        anchors = owner.gen.generate_all_level_anchors(owner.sizes, owner.device)
-        ops.assign_targets(anchors, self.gt, self.num_gt, thr, lab, lq, cls, mean, std, plan=self.plan)
-        ops.count_labels(self.plan.labels, out=self.counts)
+        if self.gt.shape[0] <= GRID_ASSIGN_MAX_BATCH:
+            ops.assign_targets_grid(owner.gen._plan(owner.sizes), self.gt, self.num_gt, thr, lab, lq, cls, mean, std,
+                                    plan=self.plan, counts=self.counts)
+        else:
+            anchors = owner.gen.generate_all_level_anchors(owner.sizes, owner.device)
+            ops.assign_targets(anchors, self.gt, self.num_gt, thr, lab, lq, cls, mean, std, plan=self.plan)
+            ops.count_labels(self.plan.labels, out=self.counts)
 
 
 class TargetAssigner:
@@ -217,7 +227,7 @@ class TargetAssigner:
                     slot.step(self)
                 slot.done.record()
         self.turn = 0
-        self.kernels_per_replay = 4  # anchors_grid, assign_main, assign_lq, count_labels
+        self.kernels_per_replay = 2 if batch <= GRID_ASSIGN_MAX_BATCH else 4
 
     def __call__(self, gt_boxes, num_gt):
         """gt_boxes (B, max_gt, 5) fp32 and num_gt (B,) int32, host (pinned) or device."""

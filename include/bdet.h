@@ -139,6 +139,16 @@ int bdet_assign_targets(const float* anchors, int A, const float* gt, int Gmax, 
                         int allow_low_quality, int apply_class, const float* mean_host,
                         const float* std_host, int* labels, int* match_idx, float* offsets,
                         void* workspace, size_t workspace_bytes, bdet_stream_t stream);
+/* The same with the anchors generated in registers from the grid description of bdet_anchors_grid (bit-identical
+ * anchors; level l holds H*W*n_base[l] anchors in (h, w, base) order, levels concatenated): no anchor tensor, no separate
+ * launch -- models/det/retinanet.py:116 regenerates the anchors every forward.  counts (B,3) int32, optional: the census
+ * of the final labels (< 0, == 0, > 0) that retinanet.py:142-146 / rpn.py:231 needs, accumulated by the same kernels. */
+int bdet_assign_targets_grid(int n_levels, const int* hw_host, const double* stride_host, const double* shift_host,
+                             const int* n_base_host, const float* base_host, const float* gt, int Gmax,
+                             const int* num_gt_dev, int B, const float* thresholds_host, const int* labels_host,
+                             int n_labels, int allow_low_quality, int apply_class, const float* mean_host,
+                             const float* std_host, int* labels, int* match_idx, float* offsets, int* counts,
+                             void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
 /* ------------------------------------------------------------------ 8(f)-1: anchor-free dense-head target assignment
  * points (A,2) = all levels concatenated (level l owns [level_start[l], level_start[l+1])), gt (B,Gmax,5) rows

@@ -422,3 +422,26 @@ def test_ota_topk_match_vs_oracle(cuda, G, A, q, kc):
     ref = R.ota_topk_match(cost, ious, kc)
     assert np.array_equal(got, ref)
     assert (ref < G).sum() >= 1
+
+
+def test_assign_targets_grid_equals_tensor_path(cuda):
+    """bdet_assign_targets_grid (anchors generated in registers + label census folded into the kernels) is bit-identical
+    to bdet_assign_targets on the materialised anchors, for RetinaNet (class labels) and RPN (no class) settings, ragged
+    GT counts and an image without GT; the census equals count_labels."""
+    from basedet_b200.layers import DefaultAnchorGenerator
+
+    for scales, ratios, strides, sizes, thr, cls in (
+            (W.RETINANET_SCALES, W.RETINANET_RATIOS, W.RETINANET_STRIDES, W.retinanet_level_sizes(256, 320), [0.4, 0.5], True),
+            (W.FRCNN_SCALES, W.FRCNN_RATIOS, W.FRCNN_RPN_STRIDES, W.frcnn_level_sizes(192, 256), [0.3, 0.7], False)):
+        gen = DefaultAnchorGenerator(scales, ratios, strides, 0.5)
+        anchors = gen.generate_all_level_anchors(sizes, cuda)
+        gt, ng = W.target_assign_batch(5, num_gt=20, img_h=sizes[0][0] * strides[0], img_w=sizes[0][1] * strides[0], ragged=True)
+        ng[3] = 0
+        gt_d, ng_d = torch.from_numpy(gt).to(cuda), torch.from_numpy(ng).to(cuda)
+        ref = [t.clone() for t in ops.assign_targets(anchors, gt_d, ng_d, thr, [0, -1, 1], True, cls)]
+        counts = torch.full((5, 3), -7, dtype=torch.int32, device=cuda)
+        got = ops.assign_targets_grid(gen._plan(sizes), gt_d, ng_d, thr, [0, -1, 1], True, cls, counts=counts)
+        for g_, r_ in zip(got, ref):
+            assert torch.equal(g_, r_)
+        assert torch.equal(counts, ops.count_labels(ref[0]))
+        assert int(counts.sum()) == 5 * anchors.shape[0]
