@@ -92,6 +92,9 @@ SIGNATURES = {
     "bdet_free_anchor_box_prob_workspace": (c_size_t, [c_int]),
     "bdet_free_anchor_box_prob": (c_int, [vp, c_int, vp, c_int, c_int, c_float, c_float, c_float, vp, vp, c_size_t, vp]),
     "bdet_free_anchor_bags": (c_int, [vp, c_int, c_int, vp, vp, vp, c_int, fp, fp, vp, vp, vp]),
+    "bdet_dense_tail_smem": (c_size_t, [c_int, c_int, c_int]),
+    "bdet_dense_tail": (c_int, [POINTER(vp), POINTER(vp), ip, ip, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, fp, fp, vp,
+                                c_int, c_float, c_int, vp, vp, vp]),
     "bdet_coco_format": (c_int, [vp, vp, c_int, c_int, vp, vp, c_int, vp, vp, vp, vp, vp, vp]),
     "bdet_select_decode_workspace": (c_size_t, [c_int, c_int, c_int]),
     "bdet_select_decode_ws": (c_int, [POINTER(vp), POINTER(vp), ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, vp, vp, vp,

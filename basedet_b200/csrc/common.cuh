@@ -78,6 +78,16 @@ __device__ __forceinline__ float iou_pair(float4 a, float area_a, float4 b, floa
   return r;
 }
 
+// NMS overlap predicate (oracle ASSUMED-5): IoU = inter / (Sa + Sb - inter); suppress iff IoU > thr.  inter == 0 can only
+// exceed a negative threshold, so the division is skipped for it when thr >= 0.
+__device__ __forceinline__ bool nms_overlap(float4 a, float sa, float4 b, float sb, float thr) {
+  float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
+  float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
+  float inter = w * h;
+  if (!(inter > 0.f) && thr >= 0.f) return false;
+  return __fdiv_rn(inter, (sa + sb) - inter) > thr;
+}
+
 // Order-preserving float <-> uint32 map (ascending).
 __device__ __forceinline__ uint32_t f2ord(float f) {
   uint32_t u = __float_as_uint(f);

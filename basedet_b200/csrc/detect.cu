@@ -7,6 +7,7 @@
 // Only the <= k selected candidates per (image, level) are decoded -- the reference decodes every anchor and then
 // gathers.  One CTA per image keeps the reference's ordering (levels in order, score-descending inside).
 #include "common.cuh"
+#include "sortnet.cuh"
 
 namespace bdet {
 
@@ -288,6 +289,215 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense tail: select_decode -> sort -> class-aware NMS -> finalize of a dense head (RetinaNet / FCOS inference,
+// retinanet.py:193-209, fcos.py:204-221, post_processing.py:17-47,78-103) as ONE kernel, one CTA per image.
+// The four launches it replaces are single-CTA, latency-bound kernels (7-17 us each); here their intermediates never
+// leave shared memory:
+//   (1) the per-level top-k runs (already score-sorted) are merged by ranking -- own position + a binary search in every
+//       other run over the scores staged in shared memory -- and every candidate is decoded straight into its sorted slot;
+//   (2) the class offset `label * (max(boxes) + 1)` (post_processing.py:44-46) is applied on the fly;
+//   (3) keep-driven NMS over 64-box blocks against the kept list (the nms_fused_kernel scheme), stopping at max_out;
+//   (4) the kept boxes are scaled / clipped and written as (max_out, 6) rows, zero padded.
+// Decisions are the same predicates on the same fp32 values as the separate kernels: identical detections.
+struct TailArgs {
+  SelectArgs s;
+  float thr;
+  int max_out;
+  float* dets;     // (B, max_out, 6)
+  int* det_count;  // (B)
+};
+
+__global__ void __launch_bounds__(kDetThreads) dense_tail_kernel(const TailArgs q) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const SelectArgs& p = q.s;
+  const int cap = p.L * p.k;
+  float4* sbox = reinterpret_cast<float4*>(raw);                 // cap: decoded boxes in sorted order
+  float* sscore = reinterpret_cast<float*>(sbox + cap);          // cap: sorted scores
+  int* slabel = reinterpret_cast<int*>(sscore + cap);            // cap: sorted labels
+  float* rscore = reinterpret_cast<float*>(slabel + cap);        // cap: the runs' scores, level-major (for the ranking)
+  float4* kbox = reinterpret_cast<float4*>(rscore + cap);        // max_out: shifted boxes kept so far
+  float* karea = reinterpret_cast<float*>(kbox + q.max_out);     // max_out
+  int* kidx = reinterpret_cast<int*>(karea + q.max_out);         // max_out: sorted position of the kept boxes
+  __shared__ int rend[BDET_MAX_LEVELS + 1];
+  __shared__ uint32_t smax;
+  __shared__ float4 srow[64];
+  __shared__ float sarea[64];
+  __shared__ uint64_t sdiag[64];
+  __shared__ int skept[64];
+  __shared__ int snk;
+  __shared__ uint32_t srem[2];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) {
+    int s = 0;
+    rend[0] = 0;
+    for (int l = 0; l < p.L; ++l) {
+      s += min(p.topk_cnt[b * p.L + l], p.k);
+      rend[l + 1] = s;
+    }
+    smax = 0u;
+  }
+  __syncthreads();
+  const int n = rend[p.L];
+  for (int l = 0; l < p.L; ++l) {
+    const int cnt = rend[l + 1] - rend[l];
+    const float* v = p.topk_val + (long long)(b * p.L + l) * p.k;
+    for (int j = t; j < cnt; j += kDetThreads) rscore[rend[l] + j] = __ldg(v + j);
+  }
+  __syncthreads();
+  // (1) rank + decode.  Order = (score desc, position in the level-major concatenation asc), the key of nms_sort_small.
+  float m = -CUDART_INF_F;
+  for (int i = t; i < n; i += kDetThreads) {
+    int l = 0;
+    while (rend[l + 1] <= i) ++l;
+    const uint64_t key = make_key(rscore[i], (uint32_t)i);
+    int rank = 0;
+    for (int r = 0; r < p.L; ++r) {
+      int lo = rend[r], hi = rend[r + 1];
+      if (r == l) {
+        rank += i - lo;
+      } else {
+        const int start = lo;
+        while (lo < hi) {  // lower bound among unique keys
+          const int mid = (lo + hi) >> 1;
+          if (make_key(rscore[mid], (uint32_t)mid) < key) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += lo - start;
+      }
+    }
+    const int idx = __ldg(p.topk_idx + (long long)(b * p.L + l) * p.k + (i - rend[l]));
+    const float4 bx = decode_one(p, l, b, idx / p.div);
+    sbox[rank] = bx;
+    sscore[rank] = rscore[i];
+    slabel[rank] = idx % p.div;                                   // retinanet.py:194
+    m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  }
+  {
+    const uint32_t w = __reduce_max_sync(0xffffffffu, f2ord(m));
+    if (lane == 0 && n > 0) atomicMax(&smax, w);
+  }
+  __syncthreads();
+  const float shift_unit = ord2f(smax) + 1.f;                     // post_processing.py:45: max_coordinate + 1
+  auto shifted = [&](int i) {                                     // :46 boxes + offsets
+    float4 bx = sbox[i];
+    const float off = (float)slabel[i] * shift_unit;
+    bx.x += off;
+    bx.y += off;
+    bx.z += off;
+    bx.w += off;
+    return bx;
+  };
+  // (3) keep-driven NMS (see nms_fused_kernel)
+  const int max_out = min(q.max_out, cap);
+  const int nblk = (n + 63) >> 6;
+  int count = 0;
+  for (int blk = 0; blk < nblk && count < max_out; ++blk) {
+    __syncthreads();
+    const int r0 = blk * 64;
+    const int nv = min(64, n - r0);
+    const uint64_t valid = nv >= 64 ? ~0ull : ((1ull << nv) - 1ull);
+    if (t < 64) {
+      const float4 bx = t < nv ? shifted(r0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      srow[t] = bx;
+      sarea[t] = box_area(bx);
+      sdiag[t] = 0ull;
+    }
+    if (t < 2) srem[t] = 0u;
+    __syncthreads();
+    {
+      const int col = ((warp & 1) << 5) | lane, slice = warp >> 1;
+      bool sup = false;
+      if (col < nv) {
+        const float4 c = srow[col];
+        const float ca = sarea[col];
+        for (int k2 = slice; k2 < count && !sup; k2 += kDetThreads / 64) sup = nms_overlap(kbox[k2], karea[k2], c, ca, q.thr);
+      }
+      const uint32_t mm = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && mm) atomicOr(&srem[warp & 1], mm);
+    }
+    __syncthreads();
+    const uint64_t alive = ~(((uint64_t)srem[1] << 32) | srem[0]) & valid;
+    if (alive == 0ull) continue;
+    {
+      const float4 c0 = srow[lane], c1 = srow[lane + 32];
+      const float a0 = sarea[lane], a1 = sarea[lane + 32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = warp + 32 * h;
+        if (!((alive >> i) & 1ull)) continue;
+        const float4 a = srow[i];
+        const float sa = sarea[i];
+        const bool p0 = (lane > i) && (lane < nv) && nms_overlap(a, sa, c0, a0, q.thr);
+        const bool p1 = (lane + 32 > i) && (lane + 32 < nv) && nms_overlap(a, sa, c1, a1, q.thr);
+        const uint32_t lo = __ballot_sync(0xffffffffu, p0);
+        const uint32_t hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == 0) sdiag[i] = ((uint64_t)hi << 32) | lo;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t cand = alive;
+      int nk = 0;
+      while (cand != 0ull && count + nk < max_out) {
+        const int i = __ffsll((long long)cand) - 1;
+        if (lane == 0) skept[nk] = i;
+        ++nk;
+        cand &= ~sdiag[i];
+        cand &= ~(1ull << i);
+      }
+      if (lane == 0) snk = nk;
+    }
+    __syncthreads();
+    const int nk = snk;
+    if (t < nk) {
+      const int i = skept[t];
+      kbox[count + t] = srow[i];
+      karea[count + t] = sarea[i];
+      kidx[count + t] = r0 + i;
+    }
+    count += nk;
+  }
+  __syncthreads();
+  // (4) finalize, post_processing.py:96-101
+  float sh = 1.f, sw = 1.f, ch = 0.f, cw = 0.f;
+  if (p.im_info) {
+    const float* info = p.im_info + (long long)b * p.info_ld;
+    sh = __fdiv_rn(info[2], info[0]);
+    sw = __fdiv_rn(info[3], info[1]);
+    ch = info[2];
+    cw = info[3];
+  }
+  for (int j = t; j < q.max_out; j += kDetThreads) {
+    float* o = q.dets + ((long long)b * q.max_out + j) * 6;
+    if (j >= count) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o[c] = 0.f;
+      continue;
+    }
+    const int i = kidx[j];
+    float4 bx = sbox[i];
+    if (p.im_info) {
+      bx.x *= sw;
+      bx.y *= sh;
+      bx.z *= sw;
+      bx.w *= sh;
+      bx.x = fminf(fmaxf(bx.x, 0.f), cw);
+      bx.y = fminf(fmaxf(bx.y, 0.f), ch);
+      bx.z = fminf(fmaxf(bx.z, 0.f), cw);
+      bx.w = fminf(fmaxf(bx.w, 0.f), ch);
+    }
+    o[0] = bx.x;
+    o[1] = bx.y;
+    o[2] = bx.z;
+    o[3] = bx.w;
+    o[4] = sscore[i];
+    o[5] = (float)slabel[i];
+  }
+  if (t == 0) q.det_count[b] = count;
+}
+
 }  // namespace bdet
 
 using namespace bdet;
@@ -402,6 +612,69 @@ extern "C" int bdet_finalize_detections(const float* boxes, const float* scores,
   FinalArgs a{boxes, scores, labels, keep, keep_count, im_info, info_ld, N, keep_ld, max_out, mode, labels_is_float, B, out};
   BDET_KERNEL("finalize_kernel", as_stream(stream),
               finalize_kernel<<<dim3(ceil_div(max_out, 256), B), 256, 0, as_stream(stream)>>>(a));
+  BDET_LAUNCH_CHECK();
+  return BDET_OK;
+}
+
+extern "C" size_t bdet_dense_tail_smem(int L, int k, int max_out) {
+  const size_t cap = (size_t)L * k;
+  return cap * (16 + 4 + 4 + 4) + (size_t)max_out * (16 + 4 + 4);
+}
+
+extern "C" int bdet_dense_tail(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host,
+                               const int* hw_host, int L, int B, int k, int div, int coder, const int* topk_idx,
+                               const float* topk_val, const int* topk_cnt, const float* mean_host, const float* std_host,
+                               const float* im_info, int info_ld, float iou_thresh, int max_out, float* dets, int* det_count,
+                               bdet_stream_t stream) {
+  BDET_REQUIRE(L >= 1 && L <= BDET_MAX_LEVELS && B >= 0 && B <= 65535 && k >= 1 && div >= 1 && max_out >= 1, "bad sizes");
+  BDET_REQUIRE(coder == 0 || coder == 1, "coder must be 0 (BoxCoder) or 1 (PointCoder)");
+  if (B == 0) return BDET_OK;
+  BDET_REQUIRE(anchors_host && deltas_host && n_l_host && topk_idx && topk_val && topk_cnt && dets && det_count, "null argument");
+  BDET_REQUIRE(!im_info || info_ld >= 4, "im_info rows need [h, w, orig_h, orig_w]");
+  const size_t smem = bdet_dense_tail_smem(L, k, max_out);
+  if (smem > 200 * 1024)
+    return set_error(BDET_EUNSUPPORTED, "bdet_dense_tail: L * k = %d candidates do not fit shared memory (use the separate kernels)", L * k);
+  TailArgs q;
+  SelectArgs& a = q.s;
+  for (int l = 0; l < L; ++l) {
+    const int hw = hw_host ? hw_host[l] : 0;
+    BDET_REQUIRE(anchors_host[l] && deltas_host[l] && (hw > 0 || aligned16(deltas_host[l])), "null / unaligned level pointer");
+    BDET_REQUIRE(hw >= 0 && (hw == 0 || n_l_host[l] % hw == 0), "NCHW level: n_l must be H*W*A");
+    a.anchors[l] = anchors_host[l];
+    a.deltas[l] = deltas_host[l];
+    a.n_l[l] = n_l_host[l];
+    a.hw[l] = hw;
+  }
+  a.L = L;
+  a.B = B;
+  a.k = k;
+  a.div = div;
+  a.coder = coder;
+  a.label_mode = 0;
+  a.filter = 0;
+  a.topk_idx = topk_idx;
+  a.topk_val = topk_val;
+  a.topk_cnt = topk_cnt;
+  a.im_info = im_info;
+  a.info_ld = info_ld;
+  for (int i = 0; i < 4; ++i) {
+    a.mean.v[i] = mean_host ? mean_host[i] : 0.f;
+    a.stdv.v[i] = std_host ? std_host[i] : 1.f;
+  }
+  a.boxes = nullptr;
+  a.scores = nullptr;
+  a.labels = nullptr;
+  a.count = nullptr;
+  a.run_end = nullptr;
+  a.flagw = nullptr;
+  a.blkcnt = nullptr;
+  q.thr = iou_thresh;
+  q.max_out = max_out;
+  q.dets = dets;
+  q.det_count = det_count;
+  cudaStream_t st = as_stream(stream);
+  BDET_CUDA(cudaFuncSetAttribute(dense_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BDET_KERNEL("dense_tail_kernel", st, dense_tail_kernel<<<B, kDetThreads, smem, st>>>(q));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

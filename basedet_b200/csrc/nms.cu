@@ -220,16 +220,7 @@ __global__ void __launch_bounds__(256) nms_gather_kernel(const NmsArgs p) {
   p.sboxes[base + i] = shifted_box(p, base + src, mc);
 }
 
-// ---- suppression mask ----------------------------------------------------------------------------------
-// oracle ASSUMED-5: IoU = inter / (Sa + Sb - inter); suppress iff IoU > thr.  inter == 0 can only exceed a
-// negative threshold, so the division is skipped for it when thr >= 0.
-__device__ __forceinline__ bool nms_overlap(float4 a, float sa, float4 b, float sb, float thr) {
-  float w = fmaxf(fminf(a.z, b.z) - fmaxf(a.x, b.x), 0.f);
-  float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.y, b.y), 0.f);
-  float inter = w * h;
-  if (!(inter > 0.f) && thr >= 0.f) return false;
-  return __fdiv_rn(inter, (sa + sb) - inter) > thr;
-}
+// ---- suppression mask: nms_overlap (common.cuh) ----------------------------------------------------------------
 
 // One launch per row chunk [blk0, blk0 + cb_n) x 64 sorted boxes, two kinds of CTAs (blockIdx.y):
 //   y <  cb_n : PULL  -- column block blk0 + x of the chunk against a slice of the boxes kept by the EARLIER chunks

@@ -636,6 +636,31 @@ def select_decode(anchors, deltas, topk, k, div, coder=0, label_mode=0, mean=(0,
     return boxes, sc, labels, count
 
 
+def dense_tail(anchors, deltas, topk, k, div, coder, iou_thresh, max_out, im_info, mean=(0, 0, 0, 0), std=(1, 1, 1, 1), nchw=False):
+    """select_decode -> NMS -> finalize of a dense head in one kernel (one CTA per image); returns None when the candidate
+    set does not fit shared memory (callers then use the separate kernels).  -> dets (B, max_out, 6), count (B,)."""
+    lib = _lib.load()
+    L = len(anchors)
+    if lib.bdet_dense_tail_smem(L, int(k), int(max_out)) > 200 * 1024:
+        return None
+    anc = [_f32c(a) for a in anchors]
+    dl = [_f32c(d) for d in deltas]
+    B = dl[0].shape[0]
+    vals, idx, cnt = topk
+    dev = dl[0].device
+    dets = torch.empty((B, int(max_out), 6), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    ap = (ctypes.c_void_p * L)(*[a.data_ptr() for a in anc])
+    dp_ = (ctypes.c_void_p * L)(*[d.data_ptr() for d in dl])
+    info = _f32c(im_info) if im_info is not None else None
+    hw = iarr([d.shape[2] * d.shape[3] for d in dl]) if nchw else None
+    with _guard(dets):
+        check(lib.bdet_dense_tail(ap, dp_, iarr([a.shape[0] for a in anc]), hw, L, B, int(k), int(div), int(coder), _p(idx),
+                                  _p(vals), _p(cnt), farr(mean), farr(std), _p(info), info.shape[1] if info is not None else 0,
+                                  float(iou_thresh), int(max_out), _p(dets), _p(count), _stream(dets)))
+    return dets, count
+
+
 def finalize_detections(boxes, scores_, labels, keep, keep_count, max_out, im_info=None, mode=0):
     """mode 0 -> (B, max_out, 6) [x1,y1,x2,y2,score,label] scaled/clipped by im_info; mode 1 -> (B, max_out, 5) rois."""
     lib = _lib.load()

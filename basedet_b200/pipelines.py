@@ -24,14 +24,17 @@ def _flat_levels(tensors):
 
 
 def dense_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_threshold=0.05, iou_threshold=0.5,
-                      max_detections=100, topk=1000, ctrness_list=None, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1)):
+                      max_detections=100, topk=1000, ctrness_list=None, reg_mean=(0, 0, 0, 0), reg_std=(1, 1, 1, 1),
+                      fused_tail=True):
     """RetinaNet.inference / FCOS.inference minus the network, for a whole batch.
 
     models/det/retinanet.py:181-209 (ctrness_list None: sigmoid scores, BoxCoder) or models/det/fcos.py:191-221
     (ctrness_list given: sqrt(sigmoid(cls)*sigmoid(ctr)), PointCoder) + layers/common/post_processing.py:50-103.
     logits_list[l] (B, n_l, C); offsets_list[l] (B, n_l, 4); anchors_list[l] (n_l, 4) boxes or (n_l, 2) points;
     img_info (B, >=4) rows [h, w, orig_h, orig_w].
-    Returns dets (B, max_detections, 6) rows [x1, y1, x2, y2, score, label] (zero padded) and counts (B,)."""
+    Returns dets (B, max_detections, 6) rows [x1, y1, x2, y2, score, label] (zero padded) and counts (B,).
+    ``fused_tail``: decode + NMS + finalize as one kernel per image (bdet_dense_tail) when the candidates fit shared memory;
+    False keeps the four separate launches (identical detections)."""
     L = len(logits_list)
     C = logits_list[0].shape[-1]
     lg = [t.float().contiguous() for t in logits_list]
@@ -44,6 +47,11 @@ def dense_postprocess(logits_list, offsets_list, anchors_list, img_info, cls_thr
     else:
         top = ops.score_filter_topk_raw(base, starts, lens, cls_threshold, topk, _lib.SCORE_SIGMOID, None, None, C)
         coder = 0
+    if fused_tail:
+        out = ops.dense_tail(anchors_list, offsets_list, top, topk, C, coder, iou_threshold, max_detections, img_info, reg_mean,
+                             reg_std)
+        if out is not None:
+            return out
     boxes, scores, labels, count, runs = ops.select_decode(anchors_list, offsets_list, top, topk, C, coder, 0, reg_mean,
                                                            reg_std, with_runs=True)
     # every level's candidates arrive score-sorted from the top-k: NMS merges the L runs instead of re-sorting
@@ -61,6 +69,10 @@ def dense_postprocess_nchw(head_logits, head_offsets, anchors_list, img_info, nu
     the NCHW memory linearly and re-indexes only the survivors; results are identical to permuting first."""
     mode = _lib.SCORE_FCOS if head_ctrness is not None else _lib.SCORE_SIGMOID
     top = ops.score_filter_topk_nchw(head_logits, cls_threshold, topk, num_classes, mode, head_ctrness)
+    out = ops.dense_tail(anchors_list, head_offsets, top, topk, num_classes, 1 if head_ctrness is not None else 0, iou_threshold,
+                         max_detections, img_info, reg_mean, reg_std, nchw=True)
+    if out is not None:
+        return out
     boxes, scores, labels, count, runs = ops.select_decode(anchors_list, head_offsets, top, topk, num_classes,
                                                            1 if head_ctrness is not None else 0, 0, reg_mean, reg_std,
                                                            with_runs=True, nchw=True)

@@ -238,6 +238,18 @@ int bdet_free_anchor_bags(const int* matched_idx, int G, int K, const float* anc
                           const float* pred_scores, int num_classes, const float* mean_host, const float* std_host,
                           float* matched_score, float* matched_offsets, bdet_stream_t stream);
 
+/* Dense tail: bdet_select_decode -> bdet_nms_runs -> bdet_finalize_detections of a dense head in ONE kernel (one CTA per
+ * image; RetinaNet / FCOS inference, retinanet.py:193-209, fcos.py:204-221, post_processing.py:17-47,78-103).  Arguments
+ * as bdet_select_decode_ws (label = idx % div, no size filter) plus the NMS threshold, max_out and im_info rows
+ * [h, w, orig_h, orig_w] for the final scale / clip; dets (B, max_out, 6) rows [x1,y1,x2,y2,score,label] zero padded,
+ * det_count (B).  Needs bdet_dense_tail_smem(L, k, max_out) <= 200 KB (5 levels x 1000 candidates: 142 KB); identical
+ * detections to the separate kernels. */
+size_t bdet_dense_tail_smem(int L, int k, int max_out);
+int bdet_dense_tail(const float* const* anchors_host, const float* const* deltas_host, const int* n_l_host, const int* hw_host,
+                    int L, int B, int k, int div, int coder, const int* topk_idx, const float* topk_val, const int* topk_cnt,
+                    const float* mean_host, const float* std_host, const float* im_info, int info_ld, float iou_thresh,
+                    int max_out, float* dets, int* det_count, bdet_stream_t stream);
+
 /* ------------------------------------------------------------------ 8(f)-4: COCO result records on the device
  * COCOEvaluator.format  evaluators/coco_eval.py:111-138.  dets (B,K,6) rows [x1,y1,x2,y2,score,label] with counts (B)
  * valid rows (bdet_finalize_detections' layout) -> compact records in image order: image id, bbox [x, y, w, h] and score
