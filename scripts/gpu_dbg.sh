@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_targets.py tests/test_gpu_fullsize.py tests/test_gpu_pipelines.py -q -m gpu -x 2>&1 | tail -5
-timeout 600 python bench.py --steps 50 --warmup 5 --only c2 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -2 gpurun_out/bench_c2.err
-timeout 600 python bench.py --steps 50 --warmup 5 --only c2 --simulate-world 8 > gpurun_out/bench_c2s8.json 2> gpurun_out/bench_c2s8.err
+timeout 1500 python -m pytest tests/test_gpu_pipelines.py tests/test_gpu_postprocess.py tests/test_gpu_fullsize.py tests/test_gpu_golden.py tests/test_gpu_dropin.py -q -m gpu -x 2>&1 | tail -6
+timeout 600 python bench.py --steps 20 --warmup 5 --only c1,c4 > gpurun_out/bench_c14.json 2> gpurun_out/bench_c14.err; tail -2 gpurun_out/bench_c14.err
 python - <<PY
 import json
-for f in ('bench_c2','bench_c2s8'):
-    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
-    c=d['configs']['c2']
-    print(f, c['images_total'],'img/s %.1f'%c['value'],'ms %.4f'%c['ms_per_step'],'e2e %.1f'%c['e2e']['value'], {k:round(v['avg_us'],1) for k,v in c['kernels'].items()})
+d=json.loads(open('gpurun_out/bench_c14.json').read().strip().splitlines()[-1])
+for n,c in d['configs'].items():
+    print('==',n,c['images_total'],'img/s %.1f'%c['value'],'ms %.4f'%c['ms_per_step'],'launches',c['gpu_launches_per_step'], {k:round(v['avg_us'],1) for k,v in c['kernels'].items()})
 PY

@@ -18,7 +18,8 @@ cap() {  # name, kernel regex, config, count
   ncu -i /tmp/$1.ncu-rep --page raw --csv > $O/r02_ncu_$1_raw.csv 2>/dev/null
   echo "cap $1 rc=$? $(wc -l < $O/r02_ncu_$1_raw.csv) rows"
 }
-cap c3 'roi_align_fwd_tma|roi_align_bwd_kernel|assign_main|select_sort|sample_labels|nms_chunk|nms_sweep|rcnn_match' c3 16
+cap roi 'roi_align_fwd_tma|roi_align_bwd_kernel' c3 2
+cap c3 'assign_main|select_sort|sample_labels|nms_chunk|nms_sweep|rcnn_match' c3 16
 cap c4 'score_filter|filter_sample|select_sort|nms_fused|nms_sort_small|select_decode' c4 12
 cap c2 'assign_main|assign_lq|anchors_grid|count_labels' c2 8
 cap c5 'pairwise|match_colmax|nms_chunk|nms_sweep|nms_tile_sort' c5 10
