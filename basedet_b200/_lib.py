@@ -66,6 +66,11 @@ SIGNATURES = {
     "bdet_roi_align_bwd_workspace": (c_size_t, [c_int, ip, c_int, c_int]),
     "bdet_roi_align_bwd": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
                                    c_int, c_int, c_int, vp, c_int, vp, c_size_t, vp]),
+    "bdet_roi_order": (c_int, [c_int, ip, fp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
+    "bdet_roi_align_fwd_perm": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, vp, vp, vp]),
+    "bdet_roi_align_bwd_perm": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, vp, c_int, vp, vp, c_size_t, vp]),
     "bdet_roi_maxpool_fwd": (c_int, [POINTER(vp), c_int, ip, fp, c_int, c_int, vp, vp, c_int, c_int, c_int, vp, vp, vp]),
     "bdet_roi_maxpool_bwd": (c_int, [POINTER(vp), c_int, ip, c_int, c_int, vp, vp, c_int, c_int, c_int, vp, vp, c_int, vp]),
     "bdet_box_props": (c_int, [vp, c_int, c_int, c_int, vp, vp]),

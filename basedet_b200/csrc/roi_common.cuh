@@ -25,7 +25,9 @@ struct RoiArgs {
   int B, C, K, PH, PW, SH, SW;
   float offset;
   int bwd_cap;         // floats of shared accumulation buffer (backward)
+  const int* perm;     // optional (K): CTA i works on ROI perm[i] (roi_order_kernel: image / level / tile order for L2)
 };
+__device__ __forceinline__ int roi_of_cta(const RoiArgs& p, int i) { return p.perm ? __ldg(p.perm + i) : i; }
 
 struct SampleTab {
   int i0[kMaxSamples];

@@ -91,6 +91,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int k, quarter;
   roi_cta_map(blockIdx.x, p.K, a.csplit, &k, &quarter);
+  k = roi_of_cta(p, k);
   const int Cn = p.C / a.csplit, cbeg = quarter * Cn;  // this CTA's channels
   const RoiGeom g = roi_geom(p, k);
   float* out = p.out + ((long long)k * p.C + cbeg) * 49;
@@ -267,7 +268,7 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   __shared__ int roff[kBwdMaxRows + 1];
   __shared__ float trash[32];  // lanes beyond the box width store here (keeps the stores branch-free)
   const RoiArgs& p = a.r;
-  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int k = roi_of_cta(p, blockIdx.x), t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const RoiGeom g = roi_geom(p, k);
   if (!g.valid) return;
   FwdPlan plan;

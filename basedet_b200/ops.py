@@ -725,8 +725,29 @@ def _level_args(features):
     return n, ptrs, iarr(hw)
 
 
-def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True):
-    """features: list of (B,C,H_l,W_l) fp32 contiguous; rois (K,5); levels (K,) int32 or None -> (K,C,PH,PW)."""
+ROI_ORDER_MIN, ROI_ORDER_MAX = 1024, 16384
+
+
+def roi_order(feature_shapes, rois, levels, scales, pool_shape, aligned=True):
+    """Processing order of the ROI kernels (bdet_roi_order): rois sorted by (image, level, tile) so that concurrently
+    processed rois share feature planes in L2.  -> perm (K,) int32, or None when K is outside [1024, 16384]."""
+    lib = _lib.load()
+    r = _f32c(rois, "rois")
+    K = r.shape[0]
+    if K < ROI_ORDER_MIN or K > ROI_ORDER_MAX:
+        return None
+    lv = _i32c(levels) if levels is not None else None
+    hw = iarr([int(v) for s in feature_shapes for v in s[-2:]])
+    perm = torch.empty((K,), dtype=torch.int32, device=r.device)
+    with _guard(r):
+        check(lib.bdet_roi_order(len(feature_shapes), hw, farr(scales), int(feature_shapes[0][0]), _p(r), _p(lv), K,
+                                 pool_shape[0], pool_shape[1], int(bool(aligned)), _p(perm), _stream(r)))
+    return perm
+
+
+def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True, perm=None):
+    """features: list of (B,C,H_l,W_l) fp32 contiguous; rois (K,5); levels (K,) int32 or None -> (K,C,PH,PW).
+    perm: optional processing order from ``roi_order`` (results are in roi order either way)."""
     lib = _lib.load()
     feats = [_f32c(f, "feature") for f in features]
     B, C = feats[0].shape[:2]
@@ -740,13 +761,13 @@ def roi_align_fwd(features, rois, levels, scales, pool_shape, sample_points=(2, 
     out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=r.device)
     n, ptrs, hw = _level_args(feats)
     with _guard(r):
-        check(lib.bdet_roi_align_fwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
-                                     int(sample_points[1]), int(bool(aligned)), _p(out), _stream(r)))
+        check(lib.bdet_roi_align_fwd_perm(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
+                                          int(sample_points[1]), int(bool(aligned)), _p(out), _p(perm), _stream(r)))
     return out
 
 
 def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample_points=(2, 2), aligned=True,
-                  dfeats=None, accumulate=False, gather=False, workspace=None):
+                  dfeats=None, accumulate=False, gather=False, workspace=None, perm=None):
     """Gradient w.r.t. the features.  ``dfeats`` (list) are written (accumulate=False) or added to (True);
     allocated when None.  gather=False (default, currently the faster one) is the shared-memory scatter kernel;
     gather=True the atomics-free, run-to-run deterministic tile-gather kernel."""
@@ -767,9 +788,9 @@ def roi_align_bwd(dout, feature_shapes, rois, levels, scales, pool_shape, sample
         need = lib.bdet_roi_align_bwd_workspace(n, hw, B, max(K, 1))
         ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, d.device)
     with _guard(d):
-        check(lib.bdet_roi_align_bwd(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
-                                     int(sample_points[1]), int(bool(aligned)), _p(d), int(bool(accumulate)), _p(ws),
-                                     ws.numel() if ws is not None else 0, _stream(d)))
+        check(lib.bdet_roi_align_bwd_perm(ptrs, n, hw, farr(scales), B, C, _p(r), _p(lv), K, PH, PW, int(sample_points[0]),
+                                          int(sample_points[1]), int(bool(aligned)), _p(d), int(bool(accumulate)), _p(perm),
+                                          _p(ws), ws.numel() if ws is not None else 0, _stream(d)))
     return dfeats
 
 

@@ -322,7 +322,8 @@ def _side_stream(dev):
 
 def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets, features, gt_boxes, num_gt, im_info,
                         noise_rpn, noise_rcnn, dout=None, rpn_strides=(4, 8, 16, 32, 64), rcnn_strides=(4, 8, 16, 32), prev_nms_topk=2000,
-                        post_nms_topk=1000, nms_threshold=0.7, num_rois=512, pool_shape=(7, 7), plan=None, dfeats=None):
+                        post_nms_topk=1000, nms_threshold=0.7, num_rois=512, pool_shape=(7, 7), plan=None, dfeats=None,
+                        roi_order=True):
     """Every box op of one Faster R-CNN FPN training step, for the whole batch (BASELINE configs[2]):
 
       FasterRCNN.get_losses, models/det/faster_rcnn.py:73-94
@@ -372,11 +373,14 @@ def frcnn_train_box_ops(anchor_generator, feature_sizes, rpn_scores, rpn_offsets
     flat_rois = s_rois.reshape(B * num_rois, 5)
     levels = ops.roi_assign_levels(flat_rois, int(math.log2(rcnn_strides[0])), int(math.log2(rcnn_strides[-1])))
     scales = [1.0 / s for s in rcnn_strides]
-    pooled = ops.roi_align_fwd(features, flat_rois, levels, scales, pool_shape)
+    # one processing order for the forward and the backward: rois sorted by (image, level, tile) keep the planes in L2
+    perm = ops.roi_order([tuple(f.shape) for f in features], flat_rois, levels, scales, pool_shape) if roi_order else None
+    pooled = ops.roi_align_fwd(features, flat_rois, levels, scales, pool_shape, perm=perm)
     out = dict(rois=rois, n_rois=n_rois, rpn_labels=rpn_labels, rpn_targets=rpn_targets_, rcnn_rois=s_rois,
                rcnn_labels=s_labels, rcnn_targets=s_targets, rcnn_count=s_count, pooled=pooled, levels=levels)
     main.wait_stream(side)  # join: RPN targets done, dfeat zeroed
     if dout is not None:
-        out["dfeats"] = ops.roi_align_bwd(dout, None, flat_rois, levels, scales, pool_shape, dfeats=dfeats, accumulate=True)
+        out["dfeats"] = ops.roi_align_bwd(dout, None, flat_rois, levels, scales, pool_shape, dfeats=dfeats, accumulate=True,
+                                          perm=perm)
     return out
 

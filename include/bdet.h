@@ -381,6 +381,22 @@ int bdet_roi_align_bwd(float* const* dfeats_host, int n_levels, const int* hw_ho
                        int sample_h, int sample_w, int aligned, const float* dout, int accumulate,
                        void* workspace, size_t workspace_bytes, bdet_stream_t stream);
 
+/* Processing order for the ROI kernels: perm (K) int32 = the rois sorted by (image, level, 32 x 32-pixel tile of the roi
+ * centre).  A roi touches its footprint in all C planes of its level, so rois that run at the same time should be
+ * neighbours: with the permutation the planes stay in L2 instead of being re-read from HBM (K <= 16 384; one CTA per
+ * image).
+ * bdet_roi_align_fwd_perm / _bwd_perm = the calls above with CTA i working on roi perm[i] (perm NULL = identity); results
+ * are in the original roi order either way (the backward's fp32 reductions in a different order: same 1e-5 gate). */
+int bdet_roi_order(int n_levels, const int* hw_host, const float* scale_host, int B, const float* rois, const int* levels,
+                   int K, int PH, int PW, int aligned, int* perm, bdet_stream_t stream);
+int bdet_roi_align_fwd_perm(const float* const* feats_host, int n_levels, const int* hw_host, const float* scale_host,
+                            int B, int C, const float* rois, const int* levels, int K, int PH, int PW, int sample_h,
+                            int sample_w, int aligned, float* out, const int* perm, bdet_stream_t stream);
+int bdet_roi_align_bwd_perm(float* const* dfeats_host, int n_levels, const int* hw_host, const float* scale_host, int B,
+                            int C, const float* rois, const int* levels, int K, int PH, int PW, int sample_h, int sample_w,
+                            int aligned, const float* dout, int accumulate, const int* perm, void* workspace,
+                            size_t workspace_bytes, bdet_stream_t stream);
+
 /* Max ROI pooling: roi_pool(..., pooler_type="roi_pool"), layers/common/roi_pool.py:62-63 -> F.nn.roi_pooling(mode="max").
  * Caffe / MegDNN rule (pinned by the reference's test tests/layers/test_roi_pool.py:48-61): corners rounded to pixels,
  * size = end - start + 1 (>= 1), bin [floor(p*size/P), ceil((p+1)*size/P)) clipped to the map, 0 for an empty bin.

@@ -18,8 +18,13 @@ for name, lo, hi in (("logU_8_600", 8, 600), ("small_8_64", 8, 64)):
     dout = torch.randn((K, Cn, 7, 7), device=dev, generator=g)
     lv = ops.roi_assign_levels(rois, 2, 5)
     sc = [1 / s for s in W.FRCNN_RCNN_STRIDES]
+    shapes = [tuple(f.shape) for f in feats]
+    perm = ops.roi_order(shapes, rois, lv, sc, (7, 7))
     for what, fn in (("fwd", lambda: ops.roi_align_fwd(feats, rois, lv, sc, (7, 7))),
-                     ("bwd", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe))):
+                     ("bwd", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe)),
+                     ("order", lambda: ops.roi_order(shapes, rois, lv, sc, (7, 7))),
+                     ("fwd_ordered", lambda: ops.roi_align_fwd(feats, rois, lv, sc, (7, 7), perm=perm)),
+                     ("bwd_ordered", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe, perm=perm))):
         for _ in range(3): fn()
         torch.cuda.synchronize()
         ops.profile_begin()

@@ -79,6 +79,39 @@ def test_tma_forward_many_rois_one_level_bit_exact():
     assert np.max(np.abs(g - gref)) / max(np.abs(gref).max(), 1.0) <= 1e-5
 
 
+def test_roi_processing_order_is_a_permutation_and_changes_no_result():
+    """bdet_roi_order: a permutation of 0..K-1 sorted by (image, level, tile); the forward with it is bit-identical to the
+    forward without it, the backward (fp32 reductions in another order) stays within 1e-5 of the oracle."""
+    rng = np.random.default_rng(41)
+    B, C_, hw = 3, 24, (256, 320)
+    sizes = [(-(-hw[0] // s), -(-hw[1] // s)) for s in STRIDES]
+    feats = [rng.normal(0, 1, (B, C_, h, w)).astype(np.float32) for h, w in sizes]
+    rois = W.make_rois(rng, 500, B, hw[0], hw[1], 4, 300)
+    rois = rois[rng.permutation(len(rois))]          # images interleaved, as no caller would hand them over
+    rois[:8] = special_rois(rng, B, hw, 20)[:8]
+    levels = R.assign_levels(rois, STRIDES)
+    K = rois.shape[0]
+    scales = [1.0 / s for s in STRIDES]
+    tf, tr, tl = [T(f) for f in feats], T(rois), T(levels)
+    shapes = [f.shape for f in feats]
+    perm = ops.roi_order(shapes, tr, tl, scales, (7, 7))
+    assert perm is not None
+    pn = perm.cpu().numpy()
+    assert np.array_equal(np.sort(pn), np.arange(K))
+    key = rois[pn, 0].astype(np.int64) * len(STRIDES) + levels[pn]
+    assert np.all(np.diff(key) >= 0)
+    plain = ops.roi_align_fwd(tf, tr, tl, scales, (7, 7))
+    ordered = ops.roi_align_fwd(tf, tr, tl, scales, (7, 7), perm=perm)
+    assert torch.equal(plain, ordered)
+    dout = rng.normal(0, 1, (K, C_, 7, 7)).astype(np.float32)
+    grads = ops.roi_align_bwd(T(dout), shapes, tr, tl, scales, (7, 7), perm=perm)
+    for l, f in enumerate(feats):
+        sel = np.flatnonzero(levels == l)
+        gref = C.roi_align_bwd(dout[sel], f.shape, rois[sel], (7, 7), scales[l])
+        assert np.max(np.abs(grads[l].cpu().numpy() - gref)) / max(np.abs(gref).max(), 1.0) <= 1e-5, l
+    assert ops.roi_order(shapes, tr[:100], tl[:100], scales, (7, 7)) is None     # below the size where it pays
+
+
 def test_tma_backward_opt_in_path():
     """The cp.reduce.async.bulk.tensor backward is opt-in (BDET_ROI_BWD_TMA_CLS, read once per process; the direct
     scatter kernel measured faster): run this file's oracle comparison in a child process with it enabled for every
