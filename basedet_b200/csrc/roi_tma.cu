@@ -32,61 +32,85 @@ struct RoiTmaArgs {
   RoiArgs r;
   int csplit;           // channel quarters per ROI (roi_cta_map): 1 or 4
   unsigned level_mask;  // levels that have tensor maps
+  int chunk_bytes;      // forward: target size of a footprint stage
   const RoiTmaMaps* gmaps;  // debug (BDET_ROI_TMA=2): descriptors read from global memory instead of the parameters
 };
 
-// One forward task: (channel c of the stage, sample column sx), sample rows [SY0, SY1).  `tc` points at the channel's
-// first footprint row, column x0(sx); row offsets oA / oB (pixel rows r0 / r0 + 1 of every sample row) and the action
-// codes are CTA-uniform.  Writes bins ph = SY0/2 .. SY1/2 - 1 of column pw = sx / 2 (even sx lanes only).
-template <int SY0, int SY1>
-__device__ __forceinline__ void fwd_task(const float* __restrict__ tc, float lx, const int (&oA)[14], const int (&oB)[14],
-                                         const float (&fy)[14], unsigned act, bool store, float* __restrict__ oc) {
-  float ha = 0.f, hb = 0.f, vprev = 0.f;
+// Sample-row program of one bin row (CTA-uniform, shared memory): for each of its two sample rows the byte offset of
+// pixel row r0 inside a channel's footprint (row pitch 8 * BW floats) with the action in the low two bits
+// (0 = both pixel rows are new, 1 = one row further: the lower lerp becomes the upper one, 2 = same rows as the previous
+// sample) and the vertical fraction.
+struct __align__(16) RowProg {
+  int o0;
+  float f0;
+  int o1;
+  float f1;
+};
+
+__device__ __forceinline__ float lerp_at(const char* q, float t) {
+  const float l = *reinterpret_cast<const float*>(q), r = *reinterpret_cast<const float*>(q + 4);
+  return l + (r - l) * t;
+}
+
+// One forward task: channel c of the stage, bin column pw, bin rows [ph0, ph1).  ta / tb point at the channel's first
+// footprint row, columns x0(2 pw) / x0(2 pw + 1).  The thread keeps the horizontal lerps of the current two pixel rows of
+// both sample columns in registers, so a tap is read once per pixel row; the 2 x 2 samples of a bin are combined in the
+// reference's order: ((v(0,0) + v(0,1)) + v(1,0)) + v(1,1), accumulated from 0.
+__device__ __forceinline__ void fwd_task(const char* __restrict__ ta, const char* __restrict__ tb, float lxa, float lxb, int pitch,
+                                         const RowProg* __restrict__ prog, int ph0, int ph1, float* __restrict__ oc) {
+  float ua = 0.f, la = 0.f, ub = 0.f, lb = 0.f;  // upper / lower pixel row, sample columns a / b
+  for (int ph = ph0; ph < ph1; ++ph) {
+    const int4 pr = *reinterpret_cast<const int4*>(prog + ph);
+    float v[2][2];
 #pragma unroll
-  for (int sy = SY0; sy < SY1; ++sy) {
-    // action of this sample row (uniform): 0 = same pixel rows as the previous sample, 1 = one row further (the lower
-    // lerp becomes the upper one), 2 = both rows are new
-    const unsigned code = sy == SY0 ? 2u : ((act >> (2 * sy)) & 3u);
-    if (code != 0u) {
-      if (code == 1u) {
-        ha = hb;
-      } else {
-        const float l = tc[oA[sy]], r = tc[oA[sy] + 1];
-        ha = l + (r - l) * lx;
+    for (int iy = 0; iy < 2; ++iy) {
+      const int o = iy ? pr.z : pr.x;
+      const float fy = __int_as_float(iy ? pr.w : pr.y);
+      const int mode = (iy == 0 && ph == ph0) ? 0 : (o & 3);
+      if (mode != 2) {
+        const int off = o & ~3;
+        if (mode == 1) {
+          ua = la;
+          ub = lb;
+        } else {
+          ua = lerp_at(ta + off, lxa);
+          ub = lerp_at(tb + off, lxb);
+        }
+        la = lerp_at(ta + off + pitch, lxa);
+        lb = lerp_at(tb + off + pitch, lxb);
       }
-      const float l = tc[oB[sy]], r = tc[oB[sy] + 1];
-      hb = l + (r - l) * lx;
+      v[iy][0] = ua + (la - ua) * fy;
+      v[iy][1] = ub + (lb - ub) * fy;
     }
-    const float v = ha + (hb - ha) * fy[sy];
-    if (sy & 1) {
-      // bin (ph, pw): ((v(0,0) + v(0,1)) + v(1,0)) + v(1,1), the reference's accumulation order from 0
-      const float p0 = __shfl_down_sync(0xffffffffu, vprev, 1);
-      const float p1 = __shfl_down_sync(0xffffffffu, v, 1);
-      float acc = 0.f + vprev;
-      acc = acc + p0;
-      acc = acc + v;
-      acc = acc + p1;
-      if (store) oc[(sy >> 1) * 7] = acc * 0.25f;  // == acc / 4 exactly
-    } else {
-      vprev = v;
-    }
+    float acc = 0.f + v[0][0];
+    acc = acc + v[0][1];
+    acc = acc + v[1][0];
+    acc = acc + v[1][1];
+    oc[ph * 7] = acc * 0.25f;  // == acc / 4 exactly
   }
 }
 
-// CTA = 8 compute warps + 1 DMA warp (lane 0 issues every bulk operation, so its per-thread bulk groups cover them all).
+// Forward CTA = 2 groups of 7 compute warps + 1 DMA warp (lane 0 issues every bulk operation, so its per-thread bulk groups
+// cover them all).  A group's 224 lanes = 32 channels x 7 bin columns: a pass over a 32-channel stage leaves no lane idle;
+// stages of 16 / 8 channels are split into 2 / 4 runs of bin rows.  Group g computes the chunks = g (mod 2) into out
+// stage g: the kernel is bound by the latency of a chunk's load -> lerp -> store chain, so two chunks are in progress.
+constexpr int kFwdLanes = 224;
+constexpr int kFwdGroups = 2;
+constexpr int kFwdThreads = kFwdGroups * kFwdLanes + 32;
+// Backward (opt-in) CTA = 8 compute warps + 1 DMA warp.
 constexpr int kComputeThreads = 256;
 constexpr int kTmaThreads = kComputeThreads + 32;
 // named barrier ids (0 = __syncthreads)
 constexpr int kBarReady0 = 1, kBarFree0 = 3;  // + stage
 
-__global__ void __launch_bounds__(kTmaThreads, 2)
+__global__ void __launch_bounds__(kFwdThreads, 2)
 roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
-  // dynamic shared memory: [stage 0][stage 1][out stage 0][out stage 1]; 1024-byte aligned by declaration
+  // dynamic shared memory: [ring of footprint stages][out stage 0][out stage 1]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab ty, tx;
   __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
   __shared__ FwdPlan plan;
-  __shared__ int roff[kFwdMaxRows + 1];
+  __shared__ RowProg prog[8];
   const RoiArgs& p = a.r;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int k, quarter;
@@ -96,15 +120,15 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   const RoiGeom g = roi_geom(p, k);
   float* out = p.out + ((long long)k * p.C + cbeg) * 49;
   if (!g.valid) {
-    for (int o = t; o < Cn * 49; o += kTmaThreads) out[o] = 0.f;
+    for (int o = t; o < Cn * 49; o += kFwdThreads) out[o] = 0.f;
     return;
   }
-  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
-  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
-  if (t == 0) {
+  fill_axis(ty, 7, 2, g.start_h, g.bin_h, kFwdThreads);
+  fill_axis(tx, 7, 2, g.start_w, g.bin_w, kFwdThreads);
+  if (t == 32) {  // (a slot is consumed by one group: kFwdLanes / 32 arrivals free it)
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kComputeThreads / 32);
+      mbar_init(&empty_bar[i], kFwdLanes / 32);
     }
     mbar_fence_init();
   }
@@ -124,12 +148,11 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       pl.nrb = (int)((fh + kBoxH - 1) / kBoxH);
       const long long per_c = (long long)pl.nrb * kBoxH * 8 * (pl.cls + 1) * 4;  // bytes per channel
       // chunks of <= kChunkBytes keep several stages of the ring in flight (the loads are latency bound); footprints too
-      // large for that take a whole half of the ring per chunk.  14 tasks per channel on 256 threads: 16 / 32 / 48 / 64
-      // channels fill 7 of 8 warps per pass, 8 channels run split
-      long long fit = kChunkBytes / per_c;
+      // large for that take a whole half of the ring per chunk
+      long long fit = a.chunk_bytes / per_c;
       if (fit < 8) fit = (kRingBytes / 2) / per_c;
-      int ccs = fit >= 64 ? 64 : (fit >= 48 ? 48 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0))));
-      if (ccs > Cn) ccs = Cn;
+      int ccs = fit >= 64 ? 64 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0)));
+      while (ccs > 8 && ccs > Cn) ccs >>= 1;  // 8 <= Cn (multiple of 8); a tail chunk may still be partial
       pl.ccs = ccs;
       if (ccs < kBoxC) pl.cls = -1;  // footprint too large for one stage
     }
@@ -137,25 +160,35 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   }
   __syncthreads();
   if (plan.cls < 0) {
-    if (quarter == 0) roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kTmaThreads);  // all channels of the ROI, once
+    if (quarter == 0) roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kFwdThreads);  // all channels of the ROI, once
     return;
   }
   // ---- TMA path
-  float* const stage0 = reinterpret_cast<float*>(smem_raw);
+  unsigned char* const stage0 = smem_raw;
   float* const ostage0 = reinterpret_cast<float*>(smem_raw + kRingBytes);
   const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;                    // channel boxes per stage
-  const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
-  const int rb_stride = ncb * box_floats;         // floats between row boxes of a stage
+  const int box_bytes = kBoxC * kBoxH * BW * 4;   // one box: [8 rows][8 channels][BW]
+  // a stage is [channel box][row box][8 rows][8 channels][BW]: footprint rows of a channel are 8 * BW floats apart
+  const int cb_bytes = nrb * box_bytes, pitch = kBoxC * BW * 4;
   const int n_chunks = (Cn + CCS - 1) / CCS;
   const int z0 = g.n * p.C + cbeg;
   // ring of footprint stages: slot = one chunk (rounded up to 1 KB), as many slots as fit (2 .. kMaxSlots)
-  const int slot_floats = ((nrb * rb_stride * 4 + 1023) & ~1023) / 4;
-  const int nslots = min(min(kMaxSlots, n_chunks), kRingBytes / (slot_floats * 4));
-  for (int r = t; r <= nrb * kBoxH; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
-  __syncthreads();  // roff
+  const int slot_bytes = (ncb * cb_bytes + 1023) & ~1023;
+  const int nslots = min(min(kMaxSlots, n_chunks), kRingBytes / slot_bytes);
+  if (t < 7) {
+    RowProg rp;
+    const int ra = ty.i0[2 * t] - ys, rb = ty.i0[2 * t + 1] - ys;
+    const int da = t > 0 ? ra - (ty.i0[2 * t - 1] - ys) : 2, db = rb - ra;
+    rp.o0 = ra * pitch | (da == 0 ? 2 : (da == 1 ? 1 : 0));
+    rp.o1 = rb * pitch | (db == 0 ? 2 : (db == 1 ? 1 : 0));
+    rp.f0 = ty.frac[2 * t];
+    rp.f1 = ty.frac[2 * t + 1];
+    prog[t] = rp;
+  }
+  __syncthreads();  // prog
 
-  if (warp == kComputeThreads / 32) {
+  if (warp == kFwdGroups * kFwdLanes / 32) {
     // ---------------- DMA warp: footprint boxes in, finished output chunks out
     const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
     auto load = [&](int chunk) {
@@ -163,82 +196,58 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));  // the compute warps are done with the slot
       if (lane == 0) {
         const int cbs = min(ncb, (Cn - c0 + kBoxC - 1) / kBoxC);
-        mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_floats * 4);
-        for (int rb = 0; rb < nrb; ++rb)
-          for (int cb = 0; cb < cbs; ++cb)
-            tma_load_3d(stage0 + s * slot_floats + rb * rb_stride + cb * box_floats, map, xs, z0 + c0 + cb * kBoxC,
-                        ys + rb * kBoxH, &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_bytes);
+        for (int cb = 0; cb < cbs; ++cb)
+          for (int rb = 0; rb < nrb; ++rb)
+            tma_load_3d(stage0 + s * slot_bytes + cb * cb_bytes + rb * box_bytes, map, xs, z0 + c0 + cb * kBoxC, ys + rb * kBoxH,
+                        &full_bar[s]);
       }
     };
     for (int c = 0; c < nslots - 1; ++c) load(c);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int s = chunk & 1, c0 = chunk * CCS;
       if (chunk + nslots - 1 < n_chunks) load(chunk + nslots - 1);
-      bar_sync(kBarReady0 + s, kTmaThreads);  // the out stage holds chunk `chunk`
+      bar_sync(kBarReady0 + s, kFwdLanes + 32);  // the out stage holds chunk `chunk`
       if (lane == 0) {
         bulk_store(out + (size_t)c0 * 49, ostage0 + s * (kOutStageBytes / 4), (uint32_t)min(CCS, Cn - c0) * 49 * 4);
         bulk_commit();
         bulk_wait_read<0>();  // shared memory is read out: the stage may be rewritten (and must outlive the copy)
       }
       __syncwarp();
-      if (chunk + 2 < n_chunks) bar_arrive(kBarFree0 + s, kTmaThreads);
+      if (chunk + 2 < n_chunks) bar_arrive(kBarFree0 + s, kFwdLanes + 32);
     }
     return;
   }
 
-  // ---------------- compute warps
-  // per-thread copies of the (CTA-uniform) sample-row program
-  int oA[14], oB[14];
-  float fy[14];
-  unsigned act = 0;
-#pragma unroll
-  for (int sy = 0; sy < 14; ++sy) {
-    const int r0 = ty.i0[sy] - ys;
-    oA[sy] = roff[r0];
-    oB[sy] = roff[r0 + 1];
-    fy[sy] = ty.frac[sy];
-    if (sy > 0) {
-      const int d = r0 - (ty.i0[sy - 1] - ys);
-      act |= (d == 0 ? 0u : (d == 1 ? 1u : 2u)) << (2 * sy);
-    }
-  }
-  const bool split = CCS * 14 <= kComputeThreads / 2;  // 8 channels: two half-tasks per (channel, sample column)
+  // ---------------- compute warps: lane -> (channel, run of bin rows, bin column), the same for every chunk
+  const int nseg = CCS >= 32 ? 1 : (CCS >= 16 ? 2 : 4);
+  const int per_c = 7 * nseg;
+  const int grp = warp / (kFwdLanes / 32), tg = t - grp * kFwdLanes;
+  const int c_l = tg / per_c, rem = tg - c_l * per_c, seg = rem / 7, pw = rem - seg * 7;
+  const int ph0 = nseg == 1 ? 0 : (nseg == 2 ? seg * 4 : seg * 2), ph1 = nseg == 1 ? 7 : min(7, ph0 + (nseg == 2 ? 4 : 2));
+  const float lxa = tx.frac[2 * pw], lxb = tx.frac[2 * pw + 1];
+  const int xa = (tx.i0[2 * pw] - xs) * 4, xb = (tx.i0[2 * pw + 1] - xs) * 4;
+  const int passes = CCS > 32 ? 2 : 1;
 
-  for (int chunk = 0; chunk < n_chunks; ++chunk) {
-    const int s = chunk & 1, c0 = chunk * CCS;
+  for (int chunk = grp; chunk < n_chunks; chunk += kFwdGroups) {
+    const int s = grp, c0 = chunk * CCS;
     const int nc = min(CCS, Cn - c0);
-    if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the bulk store of chunk - 2 has read the out stage
+    if (chunk >= 2) bar_sync(kBarFree0 + s, kFwdLanes + 32);  // the bulk store of chunk - 2 has read the out stage
     const int round = chunk / nslots, slot = chunk - round * nslots;
     mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
-    const float* tile = stage0 + slot * slot_floats;
+    const char* tile = reinterpret_cast<const char*>(stage0 + slot * slot_bytes);
     float* os = ostage0 + s * (kOutStageBytes / 4);
-    const int total = nc * 14;
-    if (split) {
-      const int half = warp / (kComputeThreads / 64);                // warps 0..3: sample rows 0..7, warps 4..7: 8..13
-      const int task = (warp - half * (kComputeThreads / 64)) * 32 + lane;
-      const bool live = task < total;
-      const int tk = live ? task : total - 1;
-      const int c = tk / 14, sx = tk - c * 14;
-      const float* tc = tile + (c >> 3) * box_floats + (c & 7) * BW + (tx.i0[sx] - xs);
-      float* oc = os + c * 49 + (sx >> 1);
-      if (half == 0)
-        fwd_task<0, 8>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), oc);
-      else
-        fwd_task<8, 14>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), oc);
-    } else {
-      for (int base_task = warp * 32; base_task < total; base_task += kComputeThreads) {
-        const int task = base_task + lane;
-        const bool live = task < total;
-        const int tk = live ? task : total - 1;
-        const int c = tk / 14, sx = tk - c * 14;
-        const float* tc = tile + (c >> 3) * box_floats + (c & 7) * BW + (tx.i0[sx] - xs);
-        fwd_task<0, 14>(tc, tx.frac[sx], oA, oB, fy, act, live && !(sx & 1), os + c * 49 + (sx >> 1));
+    for (int ps = 0; ps < passes; ++ps) {
+      const int c = c_l + ps * 32;
+      if (c < nc) {
+        const char* tc = tile + (c >> 3) * cb_bytes + (c & 7) * (BW * 4);
+        fwd_task(tc + xa, tc + xb, lxa, lxb, pitch, prog, ph0, ph1, os + c * 49 + pw);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp no longer reads the stage
     fence_proxy_async_smem();                   // its out-stage writes are visible to the bulk copy
-    bar_arrive(kBarReady0 + s, kTmaThreads);
+    bar_arrive(kBarReady0 + s, kFwdLanes + 32);
   }
 }
 
@@ -546,10 +555,12 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
   }
   if (!ta.level_mask) return 0;
   ta.csplit = roi_channel_split(a.C);
+  static const int chunk_kb = getenv("BDET_ROI_CHUNK_KB") ? atoi(getenv("BDET_ROI_CHUNK_KB")) : kChunkBytes / 1024;
+  ta.chunk_bytes = chunk_kb * 1024;
   ta.gmaps = debug_global_maps(maps, st);
   if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_fwd: cannot reserve %d bytes of shared memory", kFwdSmem);
-  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K * ta.csplit, kTmaThreads, kFwdSmem, st>>>(ta, *maps));
+  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K * ta.csplit, kFwdThreads, kFwdSmem, st>>>(ta, *maps));
   return 1;
 }
 
