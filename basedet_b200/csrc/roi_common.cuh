@@ -29,13 +29,17 @@ struct RoiArgs {
 };
 __device__ __forceinline__ int roi_of_cta(const RoiArgs& p, int i) { return p.perm ? __ldg(p.perm + i) : i; }
 
-struct SampleTab {
-  int i0[kMaxSamples];
-  float frac[kMaxSamples];
+template <int N>
+struct SampleTabT {
+  int i0[N];
+  float frac[N];
 };
+using SampleTab = SampleTabT<kMaxSamples>;
+using SampleTab14 = SampleTabT<16>;  // 7 bins x 2 samples (the TMA kernels: 4 CTAs / SM need the shared memory)
 
 // sample coordinate table for one axis: coord = start + bin * (p + (i + 0.5) / S)
-__device__ __forceinline__ void fill_axis(SampleTab& tab, int P, int S, float start, float bin, int nthreads = kRoiThreads) {
+template <class Tab>
+__device__ __forceinline__ void fill_axis(Tab& tab, int P, int S, float start, float bin, int nthreads = kRoiThreads) {
   for (int s = threadIdx.x; s < P * S; s += nthreads) {
     int pidx = s / S, i = s - pidx * S;
     float f = __fdiv_rn((float)i + 0.5f, (float)S);
@@ -75,8 +79,8 @@ __device__ __forceinline__ RoiGeom roi_geom(const RoiArgs& p, int k) {
 
 // Direct-load forward of one ROI (all channels) by the calling CTA: every tap is a predicated __ldg (used for pool
 // shapes / levels / ROIs the TMA kernel does not take).  ty / tx must hold the sample tables of the ROI.
-template <int TPH, int TPW, int TS>
-__device__ __forceinline__ void roi_fwd_direct(const RoiArgs& p, int k, const RoiGeom& g, const SampleTab& ty, const SampleTab& tx,
+template <int TPH, int TPW, int TS, class Tab>
+__device__ __forceinline__ void roi_fwd_direct(const RoiArgs& p, int k, const RoiGeom& g, const Tab& ty, const Tab& tx,
                                                int nthreads) {
   const int t = threadIdx.x;
   const int PH = TPH ? TPH : p.PH, PW = TPW ? TPW : p.PW, SH = TS ? TS : p.SH, SW = TS ? TS : p.SW;
@@ -148,22 +152,25 @@ static inline int roi_channel_split(int C) {
 // ---- which ROIs the TMA kernels (roi_tma.cu) take: a pure function of the ROI geometry, shared with the direct
 // backward kernel, which skips exactly those ROIs -----------------------------------------------------------------
 constexpr int kBoxH = 8, kBoxC = 8;     // rows / channels of one TMA box
-constexpr int kWClasses = 7;            // box widths 8, 16, ..., 56 floats (4 levels x 7 maps + args < 4 KB of params)
+constexpr int kWClasses = 7;            // box widths 12, 20, ..., 60 floats (4 levels x 7 maps + args < 4 KB of params)
+// Box width of class c.  Odd multiples of 4 floats: a box is [8 rows][8 channels][BW], so the 8 channels of a box row start
+// BW floats apart = 8 different bank groups (12 c mod 32 = 0, 12, 24, 4, 16, 28, 8, 20); with multiples of 8 floats the
+// channels c and c + 4 (or c + 2, or all of them) shared their banks and 60% of the shared-memory wavefronts were replays
+// (profiles/r02_notes.md).
+__host__ __device__ constexpr int box_width(int cls) { return 8 * cls + 12; }
+__host__ __device__ constexpr int width_class(long long fw) { return fw <= 12 ? 0 : (int)((fw - 12 + 7) / 8); }
+constexpr int kMaxBoxWidth = box_width(kWClasses - 1);
 constexpr int kTmaLevels = 4;
-constexpr int kRingBytes = 80 * 1024;   // forward: ring of footprint stages
-constexpr int kChunkBytes = 40 * 1024;  // stage size at most (small footprints: 64 channels per stage, all stages in flight)
 constexpr int kMaxSlots = 8;
 constexpr int kFwdMaxRows = 64;
 constexpr int kBwdMaxRows = 64;        // footprint rows of a forward stage at most
 constexpr int kMaxCCS = 64;             // channels per stage at most
-constexpr int kOutStageBytes = kMaxCCS * 49 * 4;
-constexpr int kFwdSmem = kRingBytes + 2 * kOutStageBytes;
 
 constexpr int kBwdStageBytes = 36 * 1024;
 
 struct FwdPlan {
   int xs, ys;       // footprint origin (may be negative / beyond the map: TMA fills zeros)
-  int cls;          // width class: BW = 8 * (cls + 1)
+  int cls;          // width class: BW = box_width(cls)
   int nrb;          // row boxes
   int ccs;          // channels per stage (multiple of 8)
 };
@@ -187,10 +194,10 @@ __device__ __forceinline__ int bwd_plan(const RoiArgs& p, const RoiGeom& g, unsi
   pl->ys = max(y_first, 0);
   const long long fw = (long long)x_last + 2 - pl->xs, fh = (long long)y_last + 2 - pl->ys;
   if (fw < 1 || fh < 1 || pl->xs >= g.W || pl->ys >= g.H) return 2;
-  if (fw > 8 * (max_cls + 1) || fw > 8 * kWClasses || fh > kBwdMaxRows) return 0;
-  const int cls = (int)((fw + 7) / 8) - 1;
+  if (fw > box_width(max_cls) || fw > kMaxBoxWidth || fh > kBwdMaxRows) return 0;
+  const int cls = width_class(fw);
   const int nrb = (int)((fh + kBoxH - 1) / kBoxH);
-  const long long per_c = (long long)nrb * kBoxH * 8 * (cls + 1) * 4;
+  const long long per_c = (long long)nrb * kBoxH * box_width(cls) * 4;
   long long ccs = (kBwdStageBytes / per_c) & ~7ll;
   if (ccs > kMaxCCS) ccs = kMaxCCS;
   if (ccs > p.C) ccs = p.C;
@@ -249,6 +256,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
+      : "memory");
+}
+// the same with a suspend-time hint: a warp that waits for data sleeps in the barrier unit instead of spinning through the
+// issue slots the working warps need (the spin loop was 17% of the forward kernel's instructions)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 // box load of a rank-3 tensor map: coordinates (x, y, z) = (fastest, ..., slowest); out-of-bounds elements arrive as 0

@@ -3,15 +3,17 @@
 // Reference: basedet/layers/common/roi_pool.py:35-78 -> F.nn.roi_align(mode="average", sample_points=2, aligned=True)
 // (MegDNN semantics restated in oracle ASSUMED-6: taps outside the map read 0, lerp as a + (b - a) * t, mean of 4).
 //
-// forward : one CTA per ROI.  The ROI's footprint (rows / columns floor(first sample) .. floor(last sample) + 1) is
-//           fetched per channel chunk as [8 channels x 8 rows x BW columns] boxes with cp.async.bulk.tensor (BW = the
-//           footprint width rounded up to 8; one tensor map per (level, BW)), double-buffered behind an mbarrier while
-//           the previous chunk is computed.  Out-of-bounds box elements arrive as zeros -- exactly the reference's
-//           border rule, so the inner loop has no bounds tests.  A thread owns (channel, sample column): it walks the 14
-//           sample rows, keeps the two horizontal lerps of the current pixel rows in registers and never re-reads a tap
-//           (2 shared loads per footprint row); the 2x2 samples of a bin are combined in the reference's order with one
-//           shuffle.  Outputs are staged in shared memory and leave as one bulk copy per chunk (49 * channels floats are
-//           contiguous in (K, C, 7, 7)).
+// forward : one CTA per ROI (7 compute warps + 1 DMA warp, 4 CTAs per SM).  The ROI's footprint (rows / columns
+//           floor(first sample) .. floor(last sample) + 1) is fetched per channel chunk as [rows x 8 channels x BW columns]
+//           boxes with cp.async.bulk.tensor (BW = 12, 20, ..., 60 floats; boxes of 8 / 4 / 2 rows; one tensor map per
+//           (level, BW, rows)) into a ring of stages behind full / empty mbarriers.  Out-of-bounds box elements arrive as
+//           zeros -- exactly the reference's border rule, so the inner loop has no bounds tests.  A thread owns (channel,
+//           bin column): it walks the bin rows, keeps the horizontal lerps of the current two pixel rows of both sample
+//           columns in registers and combines the 2x2 samples of a bin in the reference's order.  Outputs are staged in
+//           shared memory and leave as one bulk copy per chunk (49 * channels floats are contiguous in (K, C, 7, 7)).
+//           What bounds it (measured, profiles/r02_notes.md): NOT HBM -- the time is the same with the whole pyramid
+//           resident in L2 -- but the latency of each CTA's load -> lerp -> store chain; hence 4 small CTAs per SM rather
+//           than 2 large ones (-20% on small ROIs), and the op-by-op variants that cut instructions but also ILP lost.
 // backward: same footprint boxes in the other direction: per chunk the footprint gradient tile is accumulated in
 //           shared memory (no atomics inside the CTA: one thread owns a pixel) and flushed with
 //           cp.reduce.async.bulk.tensor (element-wise fp32 add in L2, out-of-bounds elements dropped).
@@ -27,6 +29,14 @@ namespace bdet {
 struct alignas(64) RoiTmaMaps {
   CUtensorMap m[kTmaLevels][kWClasses];
 };
+// Forward: boxes of 8, 4 and 2 rows per (level, width), so that a footprint of fh rows is fetched as fh rounded up to even
+// rows (8 + 2 for 10 rows, not 16): less shared memory per channel, so more channels per stage and fewer stages per ROI.
+// 10.5 KB of kernel parameters (CUDA >= 12.1: up to 32 KB).
+constexpr int kHClasses = 3;
+__host__ __device__ constexpr int box_height(int hc) { return kBoxH >> hc; }
+struct alignas(64) RoiFwdMaps {
+  CUtensorMap m[kTmaLevels][kWClasses][kHClasses];
+};
 
 struct RoiTmaArgs {
   RoiArgs r;
@@ -36,10 +46,13 @@ struct RoiTmaArgs {
   const RoiTmaMaps* gmaps;  // debug (BDET_ROI_TMA=2): descriptors read from global memory instead of the parameters
 };
 
-// Sample-row program of one bin row (CTA-uniform, shared memory): for each of its two sample rows the byte offset of
-// pixel row r0 inside a channel's footprint (row pitch 8 * BW floats) with the action in the low two bits
+// Sample-row program of one bin row (CTA-uniform, shared memory): for each of its two sample rows the footprint row r0 of
+// the upper tap (<< 2; rows are `pitch` bytes apart) with the action in the low two bits
 // (0 = both pixel rows are new, 1 = one row further: the lower lerp becomes the upper one, 2 = same rows as the previous
 // sample) and the vertical fraction.
+// (An op-list formulation -- ADVANCE row / EMIT sample, visiting every pixel row once -- executes 40% fewer instructions
+// and measured 25% SLOWER: one op at a time leaves a warp a single dependent LDS -> FADD -> FMUL -> FADD chain, while this
+// loop keeps the four lerps of a bin row's two sample rows in flight.)
 struct __align__(16) RowProg {
   int o0;
   float f0;
@@ -68,7 +81,7 @@ __device__ __forceinline__ void fwd_task(const char* __restrict__ ta, const char
       const float fy = __int_as_float(iy ? pr.w : pr.y);
       const int mode = (iy == 0 && ph == ph0) ? 0 : (o & 3);
       if (mode != 2) {
-        const int off = o & ~3;
+        const int off = (o >> 2) * pitch;
         if (mode == 1) {
           ua = la;
           ub = lb;
@@ -90,35 +103,36 @@ __device__ __forceinline__ void fwd_task(const char* __restrict__ ta, const char
   }
 }
 
-// Forward CTA = 2 groups of 7 compute warps + 1 DMA warp (lane 0 issues every bulk operation, so its per-thread bulk groups
-// cover them all).  A group's 224 lanes = 32 channels x 7 bin columns: a pass over a 32-channel stage leaves no lane idle;
-// stages of 16 / 8 channels are split into 2 / 4 runs of bin rows.  Group g computes the chunks = g (mod 2) into out
-// stage g: the kernel is bound by the latency of a chunk's load -> lerp -> store chain, so two chunks are in progress.
+// Forward CTA = 7 compute warps + 1 DMA warp (lane 0 issues every bulk operation, so its per-thread bulk groups cover them
+// all).  224 compute lanes = 32 channels x 7 bin columns: a pass over a 32-channel stage leaves no lane idle; stages of
+// 16 / 8 channels are split into 2 / 4 runs of bin rows.
 constexpr int kFwdLanes = 224;
-constexpr int kFwdGroups = 2;
-constexpr int kFwdThreads = kFwdGroups * kFwdLanes + 32;
 // Backward (opt-in) CTA = 8 compute warps + 1 DMA warp.
 constexpr int kComputeThreads = 256;
 constexpr int kTmaThreads = kComputeThreads + 32;
 // named barrier ids (0 = __syncthreads)
 constexpr int kBarReady0 = 1, kBarFree0 = 3;  // + stage
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
-roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
+constexpr int kFwdThreads = kFwdLanes + 32;
+constexpr int kRingBytes = 36 * 1024;              // ring of footprint stages
+constexpr int kFwdChunkBytes = 18 * 1024;          // stage size at most when the footprint allows: >= 2 stages in the ring
+constexpr int kMaxC = 32;                          // channels per stage at most (= one pass of the 224 lanes)
+constexpr int kOutStageBytes = kMaxC * 49 * 4;     // two out stages
+constexpr int kFwdSmem = kRingBytes + 2 * kOutStageBytes;
+__global__ void __launch_bounds__(kFwdThreads, 4)
+roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiFwdMaps maps) {
   // dynamic shared memory: [ring of footprint stages][out stage 0][out stage 1]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ SampleTab ty, tx;
+  __shared__ SampleTab14 ty, tx;
   __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
   __shared__ FwdPlan plan;
   __shared__ RowProg prog[8];
   const RoiArgs& p = a.r;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int k, quarter;
-  roi_cta_map(blockIdx.x, p.K, a.csplit, &k, &quarter);
-  k = roi_of_cta(p, k);
-  const int Cn = p.C / a.csplit, cbeg = quarter * Cn;  // this CTA's channels
+  const int k = roi_of_cta(p, blockIdx.x);
+  const int Cn = p.C;
   const RoiGeom g = roi_geom(p, k);
-  float* out = p.out + ((long long)k * p.C + cbeg) * 49;
+  float* out = p.out + (long long)k * p.C * 49;
   if (!g.valid) {
     for (int o = t; o < Cn * 49; o += kFwdThreads) out[o] = 0.f;
     return;
@@ -143,67 +157,79 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     pl.cls = -1;
     pl.nrb = 0;
     pl.ccs = 0;
-    if (sane && ((a.level_mask >> g.lvl) & 1u) && fw <= 8 * kWClasses && fh <= kFwdMaxRows) {
-      pl.cls = (int)((fw + 7) / 8) - 1;
-      pl.nrb = (int)((fh + kBoxH - 1) / kBoxH);
-      const long long per_c = (long long)pl.nrb * kBoxH * 8 * (pl.cls + 1) * 4;  // bytes per channel
-      // chunks of <= kChunkBytes keep several stages of the ring in flight (the loads are latency bound); footprints too
-      // large for that take a whole half of the ring per chunk
-      long long fit = a.chunk_bytes / per_c;
-      if (fit < 8) fit = (kRingBytes / 2) / per_c;
-      int ccs = fit >= 64 ? 64 : (fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0)));
+    if (sane && ((a.level_mask >> g.lvl) & 1u) && fw <= kMaxBoxWidth && fh <= kFwdMaxRows) {
+      pl.cls = width_class(fw);
+      pl.nrb = (int)((fh + 1) & ~1ll);  // (forward: ROWS fetched, boxes of 8 / 4 / 2)
+      const int per_c = pl.nrb * box_width(pl.cls) * 4;  // bytes per channel
+      // stages of <= chunk_bytes keep two or more of them in the ring; footprints too large for that take the whole ring
+      // per stage (load and compute alternate; the SM's other three CTAs fill the gaps)
+      int fit = a.chunk_bytes / per_c;
+      if (fit < 8) fit = kRingBytes / per_c;  // (a single stage may fill the ring: load and compute alternate)
+      int ccs = fit >= 32 ? 32 : (fit >= 16 ? 16 : (fit >= 8 ? 8 : 0));
       while (ccs > 8 && ccs > Cn) ccs >>= 1;  // 8 <= Cn (multiple of 8); a tail chunk may still be partial
       pl.ccs = ccs;
       if (ccs < kBoxC) pl.cls = -1;  // footprint too large for one stage
     }
     plan = pl;
   }
+  if (t >= 32 && t < 39) {
+    // row program (offsets in ROWS here; scaled by the pitch once the width class is known)
+    const int b = t - 32, ys = ty.i0[0];
+    RowProg rp;
+    const int ra = ty.i0[2 * b] - ys, rb = ty.i0[2 * b + 1] - ys;
+    const int da = b > 0 ? ra - (ty.i0[2 * b - 1] - ys) : 2, db = rb - ra;
+    rp.o0 = ra << 2 | (da == 0 ? 2 : (da == 1 ? 1 : 0));
+    rp.o1 = rb << 2 | (db == 0 ? 2 : (db == 1 ? 1 : 0));
+    rp.f0 = ty.frac[2 * b];
+    rp.f1 = ty.frac[2 * b + 1];
+    prog[b] = rp;
+  }
   __syncthreads();
   if (plan.cls < 0) {
-    if (quarter == 0) roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kFwdThreads);  // all channels of the ROI, once
+    roi_fwd_direct<7, 7, 2>(p, k, g, ty, tx, kFwdThreads);
     return;
   }
   // ---- TMA path
   unsigned char* const stage0 = smem_raw;
   float* const ostage0 = reinterpret_cast<float*>(smem_raw + kRingBytes);
-  const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
+  const int BW = box_width(plan.cls), rows = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;                    // channel boxes per stage
-  const int box_bytes = kBoxC * kBoxH * BW * 4;   // one box: [8 rows][8 channels][BW]
-  // a stage is [channel box][row box][8 rows][8 channels][BW]: footprint rows of a channel are 8 * BW floats apart
-  const int cb_bytes = nrb * box_bytes, pitch = kBoxC * BW * 4;
+  // a stage is [channel box][row][8 channels][BW]: footprint rows of a channel are 8 * BW floats apart (a multiple of
+  // 128 bytes: every row is a legal TMA destination), whatever boxes brought them
+  const int pitch = kBoxC * BW * 4, cb_bytes = rows * pitch;
   const int n_chunks = (Cn + CCS - 1) / CCS;
-  const int z0 = g.n * p.C + cbeg;
+  const int z0 = g.n * p.C;
   // ring of footprint stages: slot = one chunk (rounded up to 1 KB), as many slots as fit (2 .. kMaxSlots)
-  const int slot_bytes = (ncb * cb_bytes + 1023) & ~1023;
-  const int nslots = min(min(kMaxSlots, n_chunks), kRingBytes / slot_bytes);
-  if (t < 7) {
-    RowProg rp;
-    const int ra = ty.i0[2 * t] - ys, rb = ty.i0[2 * t + 1] - ys;
-    const int da = t > 0 ? ra - (ty.i0[2 * t - 1] - ys) : 2, db = rb - ra;
-    rp.o0 = ra * pitch | (da == 0 ? 2 : (da == 1 ? 1 : 0));
-    rp.o1 = rb * pitch | (db == 0 ? 2 : (db == 1 ? 1 : 0));
-    rp.f0 = ty.frac[2 * t];
-    rp.f1 = ty.frac[2 * t + 1];
-    prog[t] = rp;
-  }
-  __syncthreads();  // prog
-
-  if (warp == kFwdGroups * kFwdLanes / 32) {
+  const int slot_bytes = min((ncb * cb_bytes + 1023) & ~1023, kRingBytes);
+  const int nslots = min(kMaxSlots, kRingBytes / slot_bytes);
+  if (warp == kFwdLanes / 32) {
     // ---------------- DMA warp: footprint boxes in, finished output chunks out
-    const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
+    const CUtensorMap* map = &maps.m[g.lvl][plan.cls][0];  // + height class
+    int ld_slot = 0, ld_round = 0;  // slot / round of the next chunk to load (chunks are loaded in order)
     auto load = [&](int chunk) {
-      const int round = chunk / nslots, s = chunk - round * nslots, c0 = chunk * CCS;
-      if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));  // the compute warps are done with the slot
+      const int s = ld_slot, c0 = chunk * CCS;
+      if (ld_round >= 1) mbar_wait_sleep(&empty_bar[s], (uint32_t)((ld_round - 1) & 1));  // the compute warps are done with the slot
       if (lane == 0) {
         const int cbs = min(ncb, (Cn - c0 + kBoxC - 1) / kBoxC);
-        mbar_expect_tx(&full_bar[s], (uint32_t)(nrb * cbs) * box_bytes);
-        for (int cb = 0; cb < cbs; ++cb)
-          for (int rb = 0; rb < nrb; ++rb)
-            tma_load_3d(stage0 + s * slot_bytes + cb * cb_bytes + rb * box_bytes, map, xs, z0 + c0 + cb * kBoxC, ys + rb * kBoxH,
-                        &full_bar[s]);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(cbs * cb_bytes));
+        for (int cb = 0; cb < cbs; ++cb) {
+          unsigned char* dst = stage0 + s * slot_bytes + cb * cb_bytes;
+          const int z = z0 + c0 + cb * kBoxC;
+          int r = 0;
+          for (; r + 8 <= rows; r += 8) tma_load_3d(dst + r * pitch, map, xs, z, ys + r, &full_bar[s]);
+          if (rows - r >= 4) {
+            tma_load_3d(dst + r * pitch, map + 1, xs, z, ys + r, &full_bar[s]);
+            r += 4;
+          }
+          if (rows - r >= 2) tma_load_3d(dst + r * pitch, map + 2, xs, z, ys + r, &full_bar[s]);
+        }
+      }
+      if (++ld_slot == nslots) {
+        ld_slot = 0;
+        ++ld_round;
       }
     };
-    for (int c = 0; c < nslots - 1; ++c) load(c);
+    for (int c = 0; c < nslots - 1 && c < n_chunks; ++c) load(c);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int s = chunk & 1, c0 = chunk * CCS;
       if (chunk + nslots - 1 < n_chunks) load(chunk + nslots - 1);
@@ -220,34 +246,42 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   }
 
   // ---------------- compute warps: lane -> (channel, run of bin rows, bin column), the same for every chunk
-  const int nseg = CCS >= 32 ? 1 : (CCS >= 16 ? 2 : 4);
-  const int per_c = 7 * nseg;
-  const int grp = warp / (kFwdLanes / 32), tg = t - grp * kFwdLanes;
-  const int c_l = tg / per_c, rem = tg - c_l * per_c, seg = rem / 7, pw = rem - seg * 7;
-  const int ph0 = nseg == 1 ? 0 : (nseg == 2 ? seg * 4 : seg * 2), ph1 = nseg == 1 ? 7 : min(7, ph0 + (nseg == 2 ? 4 : 2));
+  const int tg = t;
+  int c_l, seg, pw, ph0, ph1;  // (divisions by constants)
+  if (CCS >= 32) {
+    c_l = tg / 7, pw = tg - c_l * 7, seg = 0, ph0 = 0, ph1 = 7;
+  } else if (CCS >= 16) {
+    c_l = tg / 14;
+    const int rem = tg - c_l * 14;
+    seg = rem / 7, pw = rem - seg * 7, ph0 = seg * 4, ph1 = min(7, ph0 + 4);
+  } else {
+    c_l = tg / 28;
+    const int rem = tg - c_l * 28;
+    seg = rem / 7, pw = rem - seg * 7, ph0 = seg * 2, ph1 = min(7, ph0 + 2);
+  }
   const float lxa = tx.frac[2 * pw], lxb = tx.frac[2 * pw + 1];
   const int xa = (tx.i0[2 * pw] - xs) * 4, xb = (tx.i0[2 * pw + 1] - xs) * 4;
-  const int passes = CCS > 32 ? 2 : 1;
 
-  for (int chunk = grp; chunk < n_chunks; chunk += kFwdGroups) {
-    const int s = grp, c0 = chunk * CCS;
+  int slot = 0, round = 0;
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, Cn - c0);
     if (chunk >= 2) bar_sync(kBarFree0 + s, kFwdLanes + 32);  // the bulk store of chunk - 2 has read the out stage
-    const int round = chunk / nslots, slot = chunk - round * nslots;
-    mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
+    mbar_wait_sleep(&full_bar[slot], (uint32_t)(round & 1));
     const char* tile = reinterpret_cast<const char*>(stage0 + slot * slot_bytes);
     float* os = ostage0 + s * (kOutStageBytes / 4);
-    for (int ps = 0; ps < passes; ++ps) {
-      const int c = c_l + ps * 32;
-      if (c < nc) {
-        const char* tc = tile + (c >> 3) * cb_bytes + (c & 7) * (BW * 4);
-        fwd_task(tc + xa, tc + xb, lxa, lxb, pitch, prog, ph0, ph1, os + c * 49 + pw);
-      }
+    if (c_l < nc) {
+      const char* tc = tile + (c_l >> 3) * cb_bytes + (c_l & 7) * (BW * 4);
+      fwd_task(tc + xa, tc + xb, lxa, lxb, pitch, prog, ph0, ph1, os + c_l * 49 + pw);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp no longer reads the stage
     fence_proxy_async_smem();                   // its out-stage writes are visible to the bulk copy
     bar_arrive(kBarReady0 + s, kFwdLanes + 32);
+    if (++slot == nslots) {
+      slot = 0;
+      ++round;
+    }
   }
 }
 
@@ -264,7 +298,7 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
 // and sends the finished tiles out.
 constexpr int kBwdTmaDefaultCls = -1;  // measured (profiles/): the direct scatter kernel is faster on every ROI mix tried
 constexpr int kBwdRawBytes = kMaxCCS * 49 * 4;      // dout chunk as it lies in memory
-constexpr int kBwdWxBytes = 8 * kWClasses * 8 * 4;  // Wx[x][pw] / 4
+constexpr int kBwdWxBytes = kMaxBoxWidth * 8 * 4;  // Wx[x][pw] / 4
 constexpr int kBwdWyBytes = kBwdMaxRows * 8 * 4;   // Wy[row][ph]
 constexpr int kBwdSmem = 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes + kBwdWyBytes;
 
@@ -272,7 +306,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
 roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
   // dynamic shared memory: [tile stage 0][tile stage 1][raw 0][raw 1][wx][wy]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ SampleTab ty, tx;
+  __shared__ SampleTab14 ty, tx;
   __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
   __shared__ int roff[kBwdMaxRows + 1];
   __shared__ float trash[32];  // lanes beyond the box width store here (keeps the stores branch-free)
@@ -288,7 +322,7 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   float* const wy = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes);
   fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
   fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
-  const int BW = 8 * (plan.cls + 1), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
+  const int BW = box_width(plan.cls), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
   const int ncb = CCS / kBoxC;
   const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
   const int rb_stride = ncb * box_floats;
@@ -472,11 +506,11 @@ struct MapKeyHash {
   }
 };
 struct LevelMaps {
-  CUtensorMap m[kWClasses];
+  CUtensorMap m[kWClasses][kHClasses];
 };
 
 // Builds (or finds) the kWClasses maps of one level.  Returns false when the level cannot be described (alignment).
-static bool level_maps(const void* ptr, int H, int W, long long BC, const CUtensorMap** out) {
+static bool level_maps(const void* ptr, int H, int W, long long BC, const LevelMaps** out) {
   static thread_local std::unordered_map<MapKey, LevelMaps, MapKeyHash>* cache = nullptr;
   if (!cache) cache = new std::unordered_map<MapKey, LevelMaps, MapKeyHash>();
   if ((W & 3) || (reinterpret_cast<uintptr_t>(ptr) & 15u) || BC < 1 || BC > 0x7fffffffll) return false;
@@ -487,23 +521,24 @@ static bool level_maps(const void* ptr, int H, int W, long long BC, const CUtens
   if (it == cache->end()) {
     if (cache->size() > 256) cache->clear();
     LevelMaps lm;
-    for (int c = 0; c < kWClasses; ++c) {
-      // dimension order (x, channel, y): a box lands in shared memory as [8 rows][8 channels][BW], so the lanes of a
-      // warp, which read one pixel row of neighbouring channels, spread over the banks (channel stride = BW floats)
-      cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)BC, (cuuint64_t)H};
-      cuuint64_t strides[2] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4};
-      cuuint32_t box[3] = {(cuuint32_t)(8 * (c + 1)), (cuuint32_t)kBoxC, (cuuint32_t)kBoxH};
-      cuuint32_t es[3] = {1, 1, 1};
-      alignas(64) CUtensorMap m;
-      CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return false;
-      lm.m[c] = m;
-    }
+    for (int c = 0; c < kWClasses; ++c)
+      for (int h = 0; h < kHClasses; ++h) {
+        // dimension order (x, channel, y): a box lands in shared memory as [rows][8 channels][BW], so the lanes of a
+        // warp, which read one pixel row of neighbouring channels, spread over the banks (channel stride = BW floats)
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)BC, (cuuint64_t)H};
+        cuuint64_t strides[2] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4};
+        cuuint32_t box[3] = {(cuuint32_t)box_width(c), (cuuint32_t)kBoxC, (cuuint32_t)box_height(h)};
+        cuuint32_t es[3] = {1, 1, 1};
+        alignas(64) CUtensorMap m;
+        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+        lm.m[c][h] = m;
+      }
     it = cache->emplace(key, lm).first;
   }
-  *out = it->second.m;
+  *out = &it->second;
   return true;
 }
 
@@ -516,7 +551,7 @@ static int tma_mode() {
   return on;
 }
 static bool tma_enabled() { return tma_mode() != 0; }
-// widest footprint class (box width 8 * (cls + 1)) the TMA backward takes; wider footprints go to the direct scatter
+// widest footprint class (box width box_width(cls)) the TMA backward takes; wider footprints go to the direct scatter
 // kernel.  BDET_ROI_BWD_TMA_CLS overrides (-1 = TMA backward off, 6 = every width).
 static int bwd_max_cls() {
   static int v = -100;
@@ -541,26 +576,26 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
   if (!tma_enabled() || a.PH != 7 || a.PW != 7 || a.SH != 2 || a.SW != 2) return 0;
   if (a.lv.n_levels > kTmaLevels || (a.C & 7) || a.C < 8) return 0;
   if ((reinterpret_cast<uintptr_t>(a.out) & 15u)) return 0;
-  static thread_local RoiTmaMaps* maps = nullptr;  // 4 KB: filled per call, passed by value
-  if (!maps) maps = new RoiTmaMaps();
+  static thread_local RoiFwdMaps* maps = nullptr;  // filled per call, passed by value
+  if (!maps) maps = new RoiFwdMaps();
   RoiTmaArgs ta;
   ta.r = a;
   ta.level_mask = 0;
   for (int l = 0; l < a.lv.n_levels; ++l) {
-    const CUtensorMap* lm = nullptr;
+    const LevelMaps* lm = nullptr;
     if (level_maps(a.lv.feat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, &lm)) {
-      for (int c = 0; c < kWClasses; ++c) maps->m[l][c] = lm[c];
+      for (int c = 0; c < kWClasses; ++c)
+        for (int h = 0; h < kHClasses; ++h) maps->m[l][c][h] = lm->m[c][h];
       ta.level_mask |= 1u << l;
     }
   }
   if (!ta.level_mask) return 0;
-  ta.csplit = roi_channel_split(a.C);
-  static const int chunk_kb = getenv("BDET_ROI_CHUNK_KB") ? atoi(getenv("BDET_ROI_CHUNK_KB")) : kChunkBytes / 1024;
-  ta.chunk_bytes = chunk_kb * 1024;
-  ta.gmaps = debug_global_maps(maps, st);
+  ta.csplit = 1;
+  ta.chunk_bytes = kFwdChunkBytes;
+  ta.gmaps = nullptr;
   if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_fwd: cannot reserve %d bytes of shared memory", kFwdSmem);
-  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K * ta.csplit, kFwdThreads, kFwdSmem, st>>>(ta, *maps));
+  BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K, kFwdThreads, kFwdSmem, st>>>(ta, *maps));
   return 1;
 }
 
@@ -577,9 +612,9 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
   ta.r = a;
   ta.level_mask = 0;
   for (int l = 0; l < a.lv.n_levels; ++l) {
-    const CUtensorMap* lm = nullptr;
+    const LevelMaps* lm = nullptr;
     if (level_maps(a.lv.dfeat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, &lm)) {
-      for (int c = 0; c < kWClasses; ++c) maps->m[l][c] = lm[c];
+      for (int c = 0; c < kWClasses; ++c) maps->m[l][c] = lm->m[c][0];
       ta.level_mask |= 1u << l;
     }
   }

@@ -6,14 +6,15 @@ import numpy as np, torch
 from basedet_b200 import ops, workloads as W
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-B, Cn = 16, 256
+B, Cn = int(os.environ.get("PERF_B", "16")), 256
+NOFLUSH = os.environ.get("PERF_NOFLUSH") == "1"  # with PERF_B=1 the pyramid (91 MB) stays in L2: separates DRAM from SM limits
 fs = [(-(-800 // s), -(-1344 // s)) for s in W.FRCNN_RCNN_STRIDES]
 g = torch.Generator(device=dev); g.manual_seed(3)
 feats = [torch.randn((B, Cn, h, w), device=dev, generator=g) for h, w in fs]
 dfe = [torch.empty_like(f) for f in feats]
-res = {"tma": os.environ.get("BDET_ROI_TMA", "1")}
+res = {"tma": os.environ.get("BDET_ROI_TMA", "1"), "B": B, "noflush": NOFLUSH}
 for name, lo, hi in (("logU_8_600", 8, 600), ("small_8_64", 8, 64)):
-    rois = torch.from_numpy(W.make_rois(np.random.default_rng(0), 512, B, 800, 1344, lo, hi)).to(dev)
+    rois = torch.from_numpy(W.make_rois(np.random.default_rng(0), 8192 // B, B, 800, 1344, lo, hi)).to(dev)
     K = rois.shape[0]
     dout = torch.randn((K, Cn, 7, 7), device=dev, generator=g)
     lv = ops.roi_assign_levels(rois, 2, 5)
@@ -30,7 +31,7 @@ for name, lo, hi in (("logU_8_600", 8, 600), ("small_8_64", 8, 64)):
         ops.profile_begin()
         ts = []
         for _ in range(8):
-            flush.zero_()
+            if not NOFLUSH: flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
         rep = ops.profile_report(); ops.profile_end()
