@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_kernel(const RoiArg
 // with the same products as the scatter form (oracle: g * ((1-ly)(1-lx)) ...); only the summation order differs.
 constexpr int kTH = 16, kTW = 32, kCC = 32;
 constexpr int kGatherThreads = 256;
-constexpr int kMaxList = 1024;
+constexpr int kMaxList = 384;  // (static shared memory: 3 CTAs of the gather kernel per SM)
 
 struct TileGrid {
   int tiles_y[BDET_MAX_LEVELS], tiles_x[BDET_MAX_LEVELS];
@@ -133,14 +133,25 @@ __device__ __forceinline__ float tap_weight(float c, int pix) {
   return i0 == pix ? 1.f - fr : (i0 + 1 == pix ? fr : 0.f);
 }
 
-__global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(const BinArgs b, int accumulate) {
+// FAST: 7 x 7 bins, 2 x 2 samples (every shipped config).  The ROI's contribution is computed as in the scatter kernel --
+// a lane owns one tile column of one channel (narrow footprints pack 4 / 2 channels into a warp), T[ph] = sum_pw Wx[x][pw]
+// dout[ph][pw] / 4 in registers, then one 7-term dot product with Wy[row][:] per footprint row -- and added to the
+// shared-memory tile by its owner lane (no atomics: a warp works on its own channels, ROIs are visited one after another).
+// Tables are padded to 8 floats per row (128-bit shared loads); the tile columns are XOR-swizzled by the channel so that
+// the channels packed into a warp fall on different banks.
+__device__ __forceinline__ int gather_col(int c, int x) { return x ^ ((c & 3) << 3); }
+
+template <bool FAST>
+__global__ void __launch_bounds__(kGatherThreads, FAST ? 3 : 1) roi_align_bwd_gather_kernel(const BinArgs b, int accumulate) {
   extern __shared__ __align__(16) float gsm[];
   const RoiArgs& p = b.r;
   const int PH = p.PH, PW = p.PW, bins = PH * PW;
+  const int PHs = FAST ? 8 : PH, PWs = FAST ? 8 : PW;  // table row pitch
   float* acc = gsm;                          // kCC * kTH * kTW
-  float* sdout = acc + kCC * kTH * kTW;      // kCC * bins      (dout / S^2 of the current ROI)
-  float* wy = sdout + kCC * bins;            // kTH * PH        Wy[r][ph] = sum of the bin's sample weights on row r
-  float* wx = wy + kTH * PH;                 // kTW * PW
+  float* sdout = acc + kCC * kTH * kTW;      // kCC * PH * PWs  (dout / S^2 of the current ROI)
+  float* wy = sdout + kCC * PH * PWs;        // kTH * PHs       Wy[r][ph] = sum of the bin's sample weights on row r
+  float* wx = wy + kTH * PHs;                // kTW * PWs
+  __shared__ int rng[4];                     // FAST: rows / columns of the tile the current ROI touches
   __shared__ int rlo[kTH], rhi[kTH], clo[kTW], chi[kTW];
   __shared__ int sids[kMaxList];
   const int tile = blockIdx.x, c0 = blockIdx.y * kCC, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -174,6 +185,80 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
     __syncthreads();  // previous ROI's tables are free; (first iteration) acc zero-fill and sids are complete
     const int k = sorted ? sids[e - beg] : b.list[e];
     const RoiGeom g = roi_geom(p, k);
+    if (FAST) {
+      // warp 0: Wy of the 16 tile rows, warp 1: Wx of the 32 tile columns; zero outside the map / the ROI's footprint
+      if (warp < 2) {
+        const bool rows = warp == 0;
+        const int pix = rows ? y0t + lane : x0t + lane;
+        const bool live = rows ? (lane < kTH && pix < H) : pix < W;
+        const float start = rows ? g.start_h : g.start_w, bin = rows ? g.bin_h : g.bin_w;
+        float* tab = rows ? wy : wx;
+        bool nz = false;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          float w = 0.f;
+          if (live) w = tap_weight(start + bin * ((float)q + 0.25f), pix) + tap_weight(start + bin * ((float)q + 0.75f), pix);
+          if (rows ? lane < kTH : true) tab[lane * 8 + q] = w;
+          nz |= w != 0.f;
+        }
+        if (rows ? lane < kTH : true) tab[lane * 8 + 7] = 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) {
+          rng[rows ? 0 : 2] = m ? __ffs(m) - 1 : 0;
+          rng[rows ? 1 : 3] = m ? 31 - __clz(m) : -1;
+        }
+      }
+      const float* dk = p.dout + ((long long)k * p.C + c0) * 49;
+      for (int i = t; i < nc * 49; i += kGatherThreads) {
+        const int c = i / 49, q = i - c * 49, ph = q / 7;
+        sdout[c * 56 + ph * 8 + (q - ph * 7)] = __ldg(dk + i) * 0.25f;  // / (2 * 2) exactly
+      }
+      __syncthreads();
+      const int fr0 = rng[0], fr1 = rng[1], fc0 = rng[2], fc1 = rng[3];
+      if (fr1 < fr0 || fc1 < fc0) continue;  // CTA-uniform
+      const int ncol = fc1 - fc0 + 1;
+      const int lpc = ncol <= 8 ? 8 : (ncol <= 16 ? 16 : 32), G = 32 / lpc;
+      const int sub = lane / lpc, xl = lane - sub * lpc, x = fc0 + xl;
+      const bool xok = xl < ncol;
+      float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+      if (xok) {
+        wa = *reinterpret_cast<const float4*>(wx + x * 8);
+        wb = *reinterpret_cast<const float4*>(wx + x * 8 + 4);
+      }
+      for (int cb = warp * G; cb < nc; cb += (kGatherThreads / 32) * G) {
+        const int c = cb + sub;
+        const bool ok = xok && c < nc;
+        const float* dc = sdout + (c < nc ? c : nc - 1) * 56;
+        float T[7];
+#pragma unroll
+        for (int ph = 0; ph < 7; ++ph) {
+          const float4 a = *reinterpret_cast<const float4*>(dc + ph * 8);
+          const float4 d2 = *reinterpret_cast<const float4*>(dc + ph * 8 + 4);
+          float v = wa.x * a.x;
+          v = __fmaf_rn(wa.y, a.y, v);
+          v = __fmaf_rn(wa.z, a.z, v);
+          v = __fmaf_rn(wa.w, a.w, v);
+          v = __fmaf_rn(wb.x, d2.x, v);
+          v = __fmaf_rn(wb.y, d2.y, v);
+          v = __fmaf_rn(wb.z, d2.z, v);
+          T[ph] = v;
+        }
+        float* ac = acc + c * (kTH * kTW) + gather_col(c, x);
+        for (int r = fr0; r <= fr1; ++r) {
+          const float4 u = *reinterpret_cast<const float4*>(wy + r * 8);
+          const float4 w2 = *reinterpret_cast<const float4*>(wy + r * 8 + 4);
+          float sum = u.x * T[0];
+          sum = __fmaf_rn(u.y, T[1], sum);
+          sum = __fmaf_rn(u.z, T[2], sum);
+          sum = __fmaf_rn(u.w, T[3], sum);
+          sum = __fmaf_rn(w2.x, T[4], sum);
+          sum = __fmaf_rn(w2.y, T[5], sum);
+          sum = __fmaf_rn(w2.z, T[6], sum);
+          if (ok) ac[r * kTW] += sum;
+        }
+      }
+      continue;
+    }
     // rows: thread r < kTH builds Wy[r][:] and its non-zero bin range; columns: threads 32 .. 32 + kTW
     if (t < kTH) {
       const int y = y0t + t;
@@ -255,7 +340,8 @@ __global__ void __launch_bounds__(kGatherThreads) roi_align_bwd_gather_kernel(co
     const int y = y0t + rem / kTW, x = x0t + rem % kTW;
     if (y < H && x < W) {
       float* o = df + ((long long)c * H + y) * W + x;
-      *o = accumulate ? (*o + acc[i]) : acc[i];
+      const float v = FAST ? acc[c * (kTH * kTW) + (rem / kTW) * kTW + gather_col(c, rem % kTW)] : acc[i];
+      *o = accumulate ? (*o + v) : v;
     }
   }
 }
@@ -776,13 +862,15 @@ extern "C" int bdet_roi_align_bwd_perm(float* const* dfeats_host, int n_levels, 
     if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<false><<<ceil_div(K, 256), 256, 0, st>>>(b));
     BDET_KERNEL("roi_bin_scan_kernel", st, roi_bin_scan_kernel<<<1, 1024, 0, st>>>(b));
     if (K > 0) BDET_KERNEL("roi_bin_kernel", st, roi_bin_kernel<true><<<ceil_div(K, 256), 256, 0, st>>>(b));
-    const size_t smem = ((size_t)kCC * kTH * kTW + (size_t)kCC * PH * PW + (size_t)kTH * PH + (size_t)kTW * PW) * 4;
+    const bool fast = PH == 7 && PW == 7 && sample_h == 2 && sample_w == 2;
+    const int PHs = fast ? 8 : PH, PWs = fast ? 8 : PW;
+    const size_t smem = ((size_t)kCC * kTH * kTW + (size_t)kCC * PH * PWs + (size_t)kTH * PHs + (size_t)kTW * PWs) * 4;
     if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large for the gather kernel");
-    BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = fast ? roi_align_bwd_gather_kernel<true> : roi_align_bwd_gather_kernel<false>;
+    BDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int chunks = ceil_div(C, kCC);
     if (chunks > 65535) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: too many channels");
-    BDET_KERNEL("roi_align_bwd_gather_kernel", st,
-                roi_align_bwd_gather_kernel<<<dim3(n_tiles, chunks), kGatherThreads, smem, st>>>(b, accumulate));
+    BDET_KERNEL("roi_align_bwd_gather_kernel", st, kern<<<dim3(n_tiles, chunks), kGatherThreads, smem, st>>>(b, accumulate));
     BDET_LAUNCH_CHECK();
     return BDET_OK;
   }

@@ -23,6 +23,7 @@ for name, lo, hi in (("logU_8_600", 8, 600), ("small_8_64", 8, 64)):
     perm = ops.roi_order(shapes, rois, lv, sc, (7, 7))
     for what, fn in (("fwd", lambda: ops.roi_align_fwd(feats, rois, lv, sc, (7, 7))),
                      ("bwd", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe)),
+                     ("bwd_gather", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe, gather=True)),
                      ("order", lambda: ops.roi_order(shapes, rois, lv, sc, (7, 7))),
                      ("fwd_ordered", lambda: ops.roi_align_fwd(feats, rois, lv, sc, (7, 7), perm=perm)),
                      ("bwd_ordered", lambda: ops.roi_align_bwd(dout, None, rois, lv, sc, (7, 7), dfeats=dfe, perm=perm))):
