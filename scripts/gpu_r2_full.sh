@@ -12,6 +12,9 @@ timeout 600 python bench.py --steps 20 --warmup 5 --simulate-world 8 > $O/r02_be
 BDET_ROI_TMA=0 timeout 300 python scripts/perf_roi.py > $O/r02_perf_roi_direct.log 2>&1
 BDET_ROI_TMA=1 timeout 300 python scripts/perf_roi.py > $O/r02_perf_roi_tma.log 2>&1
 BDET_ROI_TMA=1 BDET_ROI_BWD_TMA_CLS=6 timeout 300 python scripts/perf_roi.py > $O/r02_perf_roi_tma_bwd.log 2>&1
+# is it HBM?  the same 8192 rois on ONE image whose 91 MB pyramid stays in L2, no flush between iterations
+PERF_B=1 PERF_NOFLUSH=1 timeout 300 python scripts/perf_roi.py > $O/r02_perf_roi_l2resident.log 2>&1
+timeout 120 scripts/tma_probe/red_probe > $O/r02_red_probe.log 2>&1
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 > /dev/null 2> $O/r02_launches_bench.err; echo "launch list rc=$?"
 cap() {  # name, kernel regex, config, count
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$2" -c $4 -o /tmp/$1 -f python bench.py --steps 1 --warmup 3 --only $3 --eager > $O/r02_ncu_$1.log 2>&1
