@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kGatherThreads, FAST ? 3 : 1) roi_align_bwd_ga
 // no zero / flush passes.  Accumulation order across ROIs is arbitrary (fp32, 1e-5 gate).
 constexpr int kFpChunk = 64;  // footprint rows / cols tabulated at a time
 
-__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p, unsigned tma_level_mask, int csplit) {
+__global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArgs p, unsigned tma_level_mask) {
   extern __shared__ __align__(16) float bsm[];
   const int PH = p.PH, PW = p.PW;
   const int PHs = (PH + 3) & ~3, PWs = (PW + 3) & ~3;  // table rows padded to 16 bytes (128-bit shared loads)
@@ -362,10 +362,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
   float* sd = wx + kFpChunk * PWs;              // (warps) * PH * PWs: dout / S^2 of the warp's current channel
   __shared__ int rlo[kFpChunk], rhi[kFpChunk], clo[kFpChunk], chi[kFpChunk];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int k, quarter;
-  roi_cta_map(blockIdx.x, p.K, csplit, &k, &quarter);
-  k = roi_of_cta(p, k);
-  const int Cn = p.C / csplit, cbeg = quarter * Cn;  // this CTA's channels (roi_common.cuh: channel-quarter-major order)
+  const int k = roi_of_cta(p, blockIdx.x);
+  const int Cn = p.C, cbeg = 0;
   const RoiGeom g = roi_geom(p, k);
   if (!g.valid) return;
   if (tma_level_mask) {  // ROIs the TMA kernel (roi_tma.cu, launched just before) has taken
@@ -885,13 +883,12 @@ extern "C" int bdet_roi_align_bwd_perm(float* const* dfeats_host, int n_levels, 
   if (smem > 200 * 1024) return set_error(BDET_EUNSUPPORTED, "bdet_roi_align_bwd: pool shape too large");
   if (smem > 40 * 1024)
     BDET_CUDA(cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int csplit = roi_channel_split(C);
   unsigned tma_mask = 0;
   rc = roi_bwd_tma_launch(a, st, &tma_mask);  // smem accumulation + cp.reduce.async.bulk.tensor (roi_tma.cu)
   if (rc < 0) return rc;
   // the direct scatter kernel takes what is left (levels whose rows are not 16-byte multiples, oversized footprints);
   // when every level has tensor maps it only finds work for ROIs wider than 64 feature pixels
-  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K * csplit, kRoiThreads, smem, st>>>(a, tma_mask, csplit));
+  BDET_KERNEL("roi_align_bwd_kernel", st, roi_align_bwd_kernel<<<K, kRoiThreads, smem, st>>>(a, tma_mask));
   BDET_LAUNCH_CHECK();
   return BDET_OK;
 }

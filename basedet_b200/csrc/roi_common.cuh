@@ -128,26 +128,9 @@ __device__ __forceinline__ void roi_fwd_direct(const RoiArgs& p, int k, const Ro
 int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st);
 
 // ---- CTA order.  A ROI reads (or updates) its footprint in every channel plane, so ROIs processed at the same time
-// spread their working set over the whole pyramid of their image (91 MB for config 3) and evict each other from L2: the
-// forward re-read the features 2.5 x from DRAM (ncu).  CTAs are therefore ordered channel-quarter-major inside groups of
-// kRoiGroup consecutive ROIs: (group, quarter, roi in group).  While one quarter of the channels of a group is in flight
-// the working set is a quarter of the planes, which stays in L2, and overlapping footprints are fetched once.
-constexpr int kRoiGroup = 512;
-__device__ __forceinline__ void roi_cta_map(int bid, int K, int Q, int* roi, int* quarter) {
-  const int g = bid / (kRoiGroup * Q);
-  const int base = g * kRoiGroup;
-  const int rsize = min(kRoiGroup, K - base);
-  const int rem = bid - g * kRoiGroup * Q;
-  *quarter = rem / rsize;
-  *roi = base + rem - *quarter * rsize;
-}
-// channel split of a call: quarters when that leaves multiples of 8 channels with enough work each
-// Measured on B200 (profiles/r02_roi_align.md): the split costs more in per-CTA set-up (4 x the tables, barriers and
-// pipeline fill) than the L2 locality returns -- forward 0.75 -> 0.98 ms, backward 1.27 -> 1.40 ms -- so it is off.
-static inline int roi_channel_split(int C) {
-  (void)C;
-  return 1;
-}
+// should be neighbours: the kernels take ROI perm[blockIdx.x] when the caller passes the permutation of bdet_roi_order
+// (roi_of_cta).  (A channel-quarter-major order with 4 CTAs per ROI was measured and dropped: the 4 x per-CTA set-up cost
+// more than the locality returned -- forward 0.75 -> 0.98 ms, backward 1.27 -> 1.40 ms; profiles/r02_notes.md.)
 
 // ---- which ROIs the TMA kernels (roi_tma.cu) take: a pure function of the ROI geometry, shared with the direct
 // backward kernel, which skips exactly those ROIs -----------------------------------------------------------------

@@ -40,10 +40,8 @@ struct alignas(64) RoiFwdMaps {
 
 struct RoiTmaArgs {
   RoiArgs r;
-  int csplit;           // channel quarters per ROI (roi_cta_map): 1 or 4
   unsigned level_mask;  // levels that have tensor maps
   int chunk_bytes;      // forward: target size of a footprint stage
-  const RoiTmaMaps* gmaps;  // debug (BDET_ROI_TMA=2): descriptors read from global memory instead of the parameters
 };
 
 // Sample-row program of one bin row (CTA-uniform, shared memory): for each of its two sample rows the footprint row r0 of
@@ -308,7 +306,6 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab14 ty, tx;
   __shared__ __align__(8) uint64_t full_bar[kMaxSlots], empty_bar[kMaxSlots];
-  __shared__ int roff[kBwdMaxRows + 1];
   __shared__ float trash[32];  // lanes beyond the box width store here (keeps the stores branch-free)
   const RoiArgs& p = a.r;
   const int k = roi_of_cta(p, blockIdx.x), t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -333,7 +330,6 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   // ring of dout chunks (CCS * 196 bytes each): as many slots as fit, so that the loads run several chunks ahead
   const int raw_floats = CCS * 49;
   const int nslots = min(min(kMaxSlots, n_chunks), (2 * kBwdRawBytes) / (raw_floats * 4));
-  for (int r = t; r <= rows; r += kTmaThreads) roff[r] = (r >> 3) * rb_stride + (r & 7) * (kBoxC * BW);
   if (t == 0) {
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -376,7 +372,7 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
 
   if (warp == kComputeThreads / 32) {
     // ---------------- DMA warp: dout chunks in, finished tiles out (reduce-add into dfeat)
-    const CUtensorMap* map = a.gmaps ? &a.gmaps->m[g.lvl][plan.cls] : &maps.m[g.lvl][plan.cls];
+    const CUtensorMap* map = &maps.m[g.lvl][plan.cls];
     auto load = [&](int chunk) {
       const int round = chunk / nslots, s = chunk - round * nslots;
       if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));
@@ -562,14 +558,6 @@ static int bwd_max_cls() {
   }
   return v;
 }
-static const RoiTmaMaps* debug_global_maps(const RoiTmaMaps* host, cudaStream_t st) {
-  if (tma_mode() != 2) return nullptr;
-  RoiTmaMaps* d = nullptr;
-  if (cudaMalloc(&d, sizeof(RoiTmaMaps)) != cudaSuccess) return nullptr;  // debug only: leaked
-  cudaMemcpyAsync(d, host, sizeof(RoiTmaMaps), cudaMemcpyHostToDevice, st);
-  return d;
-}
-
 // Forward launch through the TMA kernel when at least one level qualifies.  Returns 1 if launched, 0 if the caller
 // should use the direct kernel, < 0 on error.
 int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
@@ -590,9 +578,7 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
     }
   }
   if (!ta.level_mask) return 0;
-  ta.csplit = 1;
   ta.chunk_bytes = kFwdChunkBytes;
-  ta.gmaps = nullptr;
   if (cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_fwd: cannot reserve %d bytes of shared memory", kFwdSmem);
   BDET_KERNEL("roi_align_fwd_tma_kernel", st, roi_align_fwd_tma_kernel<<<a.K, kFwdThreads, kFwdSmem, st>>>(ta, *maps));
@@ -621,9 +607,7 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
   if (!ta.level_mask) return 0;
   const int max_cls = bwd_max_cls();
   if (max_cls < 0) return 0;
-  ta.csplit = 1;
   ta.level_mask |= (unsigned)max_cls << 16;  // travels with the mask to both kernels (bwd_plan)
-  ta.gmaps = debug_global_maps(maps, st);
   if (cudaFuncSetAttribute(roi_align_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem) != cudaSuccess)
     return set_error(BDET_ECUDA, "roi_align_bwd: cannot reserve %d bytes of shared memory", kBwdSmem);
   BDET_KERNEL("roi_align_bwd_tma_kernel", st, roi_align_bwd_tma_kernel<<<a.K, kTmaThreads, kBwdSmem, st>>>(ta, *maps));
