@@ -149,12 +149,13 @@ constexpr int kFwdMaxRows = 64;
 constexpr int kBwdMaxRows = 64;        // footprint rows of a forward stage at most
 constexpr int kMaxCCS = 64;             // channels per stage at most
 
-constexpr int kBwdStageBytes = 36 * 1024;
+constexpr int kBwdStageBytes = 24 * 1024;  // one gradient tile stage (two per CTA; 3 CTAs per SM)
+constexpr int kBwdMaxC = 32;                // channels per stage at most
 
 struct FwdPlan {
   int xs, ys;       // footprint origin (may be negative / beyond the map: TMA fills zeros)
   int cls;          // width class: BW = box_width(cls)
-  int nrb;          // row boxes
+  int nrb;          // rows fetched / reduced (rounded up to even: boxes of 8 / 4 / 2 rows)
   int ccs;          // channels per stage (multiple of 8)
 };
 
@@ -177,12 +178,14 @@ __device__ __forceinline__ int bwd_plan(const RoiArgs& p, const RoiGeom& g, unsi
   pl->ys = max(y_first, 0);
   const long long fw = (long long)x_last + 2 - pl->xs, fh = (long long)y_last + 2 - pl->ys;
   if (fw < 1 || fh < 1 || pl->xs >= g.W || pl->ys >= g.H) return 2;
-  if (fw > box_width(max_cls) || fw > kMaxBoxWidth || fh > kBwdMaxRows) return 0;
-  const int cls = width_class(fw);
-  const int nrb = (int)((fh + kBoxH - 1) / kBoxH);
-  const long long per_c = (long long)nrb * kBoxH * box_width(cls) * 4;
+  // the backward has its own box widths, 8, 16, ..., 56 floats: its lanes are footprint columns, and 8 / 16 lanes per channel
+  // pack 4 / 2 channels into a warp; rows: the footprint rounded up to even (boxes of 8 / 4 / 2 rows)
+  if (fw > 8 * (max_cls + 1) || fw > 8 * kWClasses || fh > kBwdMaxRows) return 0;
+  const int cls = (int)((fw + 7) / 8) - 1;
+  const int nrb = (int)((fh + 1) & ~1ll);  // ROWS
+  const long long per_c = (long long)nrb * 8 * (cls + 1) * 4;
   long long ccs = (kBwdStageBytes / per_c) & ~7ll;
-  if (ccs > kMaxCCS) ccs = kMaxCCS;
+  if (ccs > kBwdMaxC) ccs = kBwdMaxC;
   if (ccs > p.C) ccs = p.C;
   if (ccs < kBoxC) return 0;
   pl->cls = cls;

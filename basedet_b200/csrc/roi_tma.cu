@@ -26,9 +26,6 @@
 
 namespace bdet {
 
-struct alignas(64) RoiTmaMaps {
-  CUtensorMap m[kTmaLevels][kWClasses];
-};
 // Forward: boxes of 8, 4 and 2 rows per (level, width), so that a footprint of fh rows is fetched as fh rounded up to even
 // rows (8 + 2 for 10 rows, not 16): less shared memory per channel, so more channels per stage and fewer stages per ROI.
 // 10.5 KB of kernel parameters (CUDA >= 12.1: up to 32 KB).
@@ -295,13 +292,17 @@ roi_align_fwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiFwdMaps 
 // direct kernel) and one store.  No atomics inside the CTA.  The DMA warp brings the dout chunks in (1-D bulk copies)
 // and sends the finished tiles out.
 constexpr int kBwdTmaDefaultCls = -1;  // measured (profiles/): the direct scatter kernel is faster on every ROI mix tried
-constexpr int kBwdRawBytes = kMaxCCS * 49 * 4;      // dout chunk as it lies in memory
-constexpr int kBwdWxBytes = kMaxBoxWidth * 8 * 4;  // Wx[x][pw] / 4
+constexpr int kBwdRawBytes = kBwdMaxC * 49 * 4;    // dout chunk as it lies in memory
+constexpr int kBwdWxBytes = 8 * kWClasses * 8 * 4;  // Wx[x][pw] / 4
 constexpr int kBwdWyBytes = kBwdMaxRows * 8 * 4;   // Wy[row][ph]
 constexpr int kBwdSmem = 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes + kBwdWyBytes;
+// the backward's tensor maps: box widths 8, 16, ..., 56 floats x box heights 8 / 4 / 2 rows
+struct alignas(64) RoiBwdMaps {
+  CUtensorMap m[kTmaLevels][kWClasses][kHClasses];
+};
 
-__global__ void __launch_bounds__(kTmaThreads, 2)
-roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps maps) {
+__global__ void __launch_bounds__(kTmaThreads, 3)
+roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiBwdMaps maps) {
   // dynamic shared memory: [tile stage 0][tile stage 1][raw 0][raw 1][wx][wy]; 1024-byte aligned by declaration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ SampleTab14 ty, tx;
@@ -319,12 +320,11 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   float* const wy = reinterpret_cast<float*>(smem_raw + 2 * kBwdStageBytes + 2 * kBwdRawBytes + kBwdWxBytes);
   fill_axis(ty, 7, 2, g.start_h, g.bin_h, kTmaThreads);
   fill_axis(tx, 7, 2, g.start_w, g.bin_w, kTmaThreads);
-  const int BW = box_width(plan.cls), nrb = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
-  const int ncb = CCS / kBoxC;
-  const int box_floats = kBoxC * kBoxH * BW;      // one box: [8 rows][8 channels][BW]
-  const int rb_stride = ncb * box_floats;
+  const int BW = 8 * (plan.cls + 1), rows = plan.nrb, CCS = plan.ccs, xs = plan.xs, ys = plan.ys;
+  // a tile stage is [channel box][row][8 channels][BW]: rows are 8 * BW floats apart (a multiple of 128 bytes, so any row
+  // can start a box of 8 / 4 / 2 rows)
+  const int pitch = kBoxC * BW, cb_floats = rows * pitch;
   const int n_chunks = (p.C + CCS - 1) / CCS;
-  const int rows = nrb * kBoxH;
   const int z0 = g.n * p.C;
   const float* dout = p.dout + (size_t)k * p.C * 49;
   // ring of dout chunks (CCS * 196 bytes each): as many slots as fit, so that the loads run several chunks ahead
@@ -353,8 +353,8 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     }
     wx[i] = w * 0.25f;
   }
-  // Wy[r][ph]: the same for the rows; all `rows` rows of the boxes are filled, so rows no sample touches get zero weights
-  // and the tile needs no separate zero fill (the reduce adds whole boxes)
+  // Wy[r][ph]: the same for the rows; every row of the tile is filled, so a row no sample touches gets zero weights and the
+  // tile needs no separate zero fill (the reduce adds whole boxes)
   for (int i = t; i < rows * 8; i += kTmaThreads) {
     const int r = i >> 3, ph = i & 7;
     float w = 0.f;
@@ -372,14 +372,19 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
 
   if (warp == kComputeThreads / 32) {
     // ---------------- DMA warp: dout chunks in, finished tiles out (reduce-add into dfeat)
-    const CUtensorMap* map = &maps.m[g.lvl][plan.cls];
+    const CUtensorMap* map = &maps.m[g.lvl][plan.cls][0];  // + height class
+    int ld_slot = 0, ld_round = 0;
     auto load = [&](int chunk) {
-      const int round = chunk / nslots, s = chunk - round * nslots;
-      if (round >= 1) mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1));
+      const int s = ld_slot;
+      if (ld_round >= 1) mbar_wait_sleep(&empty_bar[s], (uint32_t)((ld_round - 1) & 1));
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)min(CCS, p.C - chunk * CCS) * 196;
         mbar_expect_tx(&full_bar[s], bytes);
         bulk_load(raw0 + s * raw_floats, dout + (size_t)chunk * CCS * 49, bytes, &full_bar[s]);
+      }
+      if (++ld_slot == nslots) {
+        ld_slot = 0;
+        ++ld_round;
       }
     };
     for (int c = 0; c < nslots - 1; ++c) load(c);
@@ -390,9 +395,17 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
       if (lane == 0) {
         const int cbs = (min(CCS, p.C - c0) + kBoxC - 1) / kBoxC;
         const float* tile = stage0 + s * (kBwdStageBytes / 4);
-        for (int rb = 0; rb < nrb; ++rb)
-          for (int cb = 0; cb < cbs; ++cb)
-            tma_reduce_add_3d(map, xs, z0 + c0 + cb * kBoxC, ys + rb * kBoxH, tile + rb * rb_stride + cb * box_floats);
+        for (int cb = 0; cb < cbs; ++cb) {
+          const float* src = tile + cb * cb_floats;
+          const int z = z0 + c0 + cb * kBoxC;
+          int r = 0;
+          for (; r + 8 <= rows; r += 8) tma_reduce_add_3d(map, xs, z, ys + r, src + r * pitch);
+          if (rows - r >= 4) {
+            tma_reduce_add_3d(map + 1, xs, z, ys + r, src + r * pitch);
+            r += 4;
+          }
+          if (rows - r >= 2) tma_reduce_add_3d(map + 2, xs, z, ys + r, src + r * pitch);
+        }
         bulk_commit();
         bulk_wait_read<0>();  // the tile is read out: the stage may be rewritten (and must outlive the reduce)
       }
@@ -408,13 +421,13 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
   const int cpw = 32 / lpc;                       // channels per warp pass
   const int xl = lane & (lpc - 1), csub = lane / lpc;
   const int xpasses = (BW + 31) / 32;
+  int slot = 0, round = 0;
 
   for (int chunk = 0; chunk < n_chunks; ++chunk) {
     const int s = chunk & 1, c0 = chunk * CCS;
     const int nc = min(CCS, p.C - c0);
     if (chunk >= 2) bar_sync(kBarFree0 + s, kTmaThreads);  // the reduce of chunk - 2 has read tile stage s
-    const int round = chunk / nslots, slot = chunk - round * nslots;
-    mbar_wait(&full_bar[slot], (uint32_t)(round & 1));
+    mbar_wait_sleep(&full_bar[slot], (uint32_t)(round & 1));
     float* tile = stage0 + s * (kBwdStageBytes / 4);
     const float* raw = raw0 + slot * raw_floats;
     for (int cb = warp * cpw; cb < nc; cb += (kComputeThreads / 32) * cpw) {
@@ -443,24 +456,20 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
           T[ph] = v;
         }
         // 32-bit shared addresses; a lane beyond the box width is redirected to its trash slot (branch-free stores)
-        const uint32_t tcol = smem_u32(tile + (c >> 3) * box_floats + (c & 7) * BW + x), tr = smem_u32(trash + lane);
-        const uint32_t row_pitch = ok ? (uint32_t)(kBoxC * BW) * 4u : 0u;
-        for (int rb = 0; rb < nrb; ++rb) {
-          uint32_t ad = ok ? tcol + (uint32_t)(rb * rb_stride) * 4u : tr;
-          const float* wr = wy + rb * (kBoxH * 8);
-#pragma unroll
-          for (int j = 0; j < kBoxH; ++j, ad += row_pitch) {
-            const float4 u = *reinterpret_cast<const float4*>(wr + j * 8);
-            const float4 w2 = *reinterpret_cast<const float4*>(wr + j * 8 + 4);
-            float sum = u.x * T[0];
-            sum = __fmaf_rn(u.y, T[1], sum);
-            sum = __fmaf_rn(u.z, T[2], sum);
-            sum = __fmaf_rn(u.w, T[3], sum);
-            sum = __fmaf_rn(w2.x, T[4], sum);
-            sum = __fmaf_rn(w2.y, T[5], sum);
-            sum = __fmaf_rn(w2.z, T[6], sum);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(sum) : "memory");
-          }
+        uint32_t ad = ok ? smem_u32(tile + (c >> 3) * cb_floats + (c & 7) * BW + x) : smem_u32(trash + lane);
+        const uint32_t row_pitch = ok ? (uint32_t)pitch * 4u : 0u;
+#pragma unroll 2
+        for (int r = 0; r < rows; ++r, ad += row_pitch) {
+          const float4 u = *reinterpret_cast<const float4*>(wy + r * 8);
+          const float4 w2 = *reinterpret_cast<const float4*>(wy + r * 8 + 4);
+          float sum = u.x * T[0];
+          sum = __fmaf_rn(u.y, T[1], sum);
+          sum = __fmaf_rn(u.z, T[2], sum);
+          sum = __fmaf_rn(u.w, T[3], sum);
+          sum = __fmaf_rn(w2.x, T[4], sum);
+          sum = __fmaf_rn(w2.y, T[5], sum);
+          sum = __fmaf_rn(w2.z, T[6], sum);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(sum) : "memory");
         }
       }
     }
@@ -468,6 +477,10 @@ roi_align_bwd_tma_kernel(const RoiTmaArgs a, const __grid_constant__ RoiTmaMaps 
     if (lane == 0) mbar_arrive(&empty_bar[slot]);  // this warp no longer reads its dout slot
     fence_proxy_async_smem();                   // its tile writes are visible to the reduce
     bar_arrive(kBarReady0 + s, kTmaThreads);
+    if (++slot == nslots) {
+      slot = 0;
+      ++round;
+    }
   }
 }
 
@@ -494,7 +507,8 @@ struct MapKey {
   const void* ptr;
   int H, W;
   long long BC;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && H == o.H && W == o.W && BC == o.BC; }
+  int bwd;  // width family: forward 12, 20, ..., backward 8, 16, ...
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && H == o.H && W == o.W && BC == o.BC && bwd == o.bwd; }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
@@ -506,13 +520,13 @@ struct LevelMaps {
 };
 
 // Builds (or finds) the kWClasses maps of one level.  Returns false when the level cannot be described (alignment).
-static bool level_maps(const void* ptr, int H, int W, long long BC, const LevelMaps** out) {
+static bool level_maps(const void* ptr, int H, int W, long long BC, bool bwd, const LevelMaps** out) {
   static thread_local std::unordered_map<MapKey, LevelMaps, MapKeyHash>* cache = nullptr;
   if (!cache) cache = new std::unordered_map<MapKey, LevelMaps, MapKeyHash>();
   if ((W & 3) || (reinterpret_cast<uintptr_t>(ptr) & 15u) || BC < 1 || BC > 0x7fffffffll) return false;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return false;
-  MapKey key{ptr, H, W, BC};
+  MapKey key{ptr, H, W, BC, bwd ? 1 : 0};
   auto it = cache->find(key);
   if (it == cache->end()) {
     if (cache->size() > 256) cache->clear();
@@ -523,7 +537,7 @@ static bool level_maps(const void* ptr, int H, int W, long long BC, const LevelM
         // warp, which read one pixel row of neighbouring channels, spread over the banks (channel stride = BW floats)
         cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)BC, (cuuint64_t)H};
         cuuint64_t strides[2] = {(cuuint64_t)W * H * 4, (cuuint64_t)W * 4};
-        cuuint32_t box[3] = {(cuuint32_t)box_width(c), (cuuint32_t)kBoxC, (cuuint32_t)box_height(h)};
+        cuuint32_t box[3] = {(cuuint32_t)(bwd ? 8 * (c + 1) : box_width(c)), (cuuint32_t)kBoxC, (cuuint32_t)box_height(h)};
         cuuint32_t es[3] = {1, 1, 1};
         alignas(64) CUtensorMap m;
         CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
@@ -547,7 +561,7 @@ static int tma_mode() {
   return on;
 }
 static bool tma_enabled() { return tma_mode() != 0; }
-// widest footprint class (box width box_width(cls)) the TMA backward takes; wider footprints go to the direct scatter
+// widest footprint class (box width 8 * (cls + 1)) the TMA backward takes; wider footprints go to the direct scatter
 // kernel.  BDET_ROI_BWD_TMA_CLS overrides (-1 = TMA backward off, 6 = every width).
 static int bwd_max_cls() {
   static int v = -100;
@@ -571,7 +585,7 @@ int roi_fwd_tma_launch(const RoiArgs& a, cudaStream_t st) {
   ta.level_mask = 0;
   for (int l = 0; l < a.lv.n_levels; ++l) {
     const LevelMaps* lm = nullptr;
-    if (level_maps(a.lv.feat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, &lm)) {
+    if (level_maps(a.lv.feat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, false, &lm)) {
       for (int c = 0; c < kWClasses; ++c)
         for (int h = 0; h < kHClasses; ++h) maps->m[l][c][h] = lm->m[c][h];
       ta.level_mask |= 1u << l;
@@ -592,15 +606,16 @@ int roi_bwd_tma_launch(const RoiArgs& a, cudaStream_t st, unsigned* level_mask_o
   if (!tma_enabled() || a.PH != 7 || a.PW != 7 || a.SH != 2 || a.SW != 2) return 0;
   if (a.lv.n_levels > kTmaLevels || (a.C & 7) || a.C < 8) return 0;
   if ((reinterpret_cast<uintptr_t>(a.dout) & 15u)) return 0;
-  static thread_local RoiTmaMaps* maps = nullptr;
-  if (!maps) maps = new RoiTmaMaps();
+  static thread_local RoiBwdMaps* maps = nullptr;
+  if (!maps) maps = new RoiBwdMaps();
   RoiTmaArgs ta;
   ta.r = a;
   ta.level_mask = 0;
   for (int l = 0; l < a.lv.n_levels; ++l) {
     const LevelMaps* lm = nullptr;
-    if (level_maps(a.lv.dfeat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, &lm)) {
-      for (int c = 0; c < kWClasses; ++c) maps->m[l][c] = lm->m[c][0];
+    if (level_maps(a.lv.dfeat[l], a.lv.H[l], a.lv.W[l], (long long)a.B * a.C, true, &lm)) {
+      for (int c = 0; c < kWClasses; ++c)
+        for (int h = 0; h < kHClasses; ++h) maps->m[l][c][h] = lm->m[c][h];
       ta.level_mask |= 1u << l;
     }
   }
