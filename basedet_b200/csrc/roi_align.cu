@@ -430,6 +430,14 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
         const int sub = lane / lpc, xl = lane - sub * lpc;
         const int nd = 49 * G;                                   // dout floats per warp pass
         float* sdg = sdw + sub * 56;
+        // where this lane's j-th dout float of a pass goes in the padded table (the same for every pass): -1 = none
+        int dofs[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int i = lane + 32 * j;
+          const int ch = i / 49, q = i - ch * 49;
+          dofs[j] = i < nd ? ch * 56 + (q / 7) * 8 + (q % 7) : -1;
+        }
         for (int x0 = 0; x0 < ncol; x0 += 32) {
           const int xx = x0 + xl;
           const bool xok = xx < ncol;
@@ -454,13 +462,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_kernel(const RoiArg
           for (int c = warp * G; c < Cn; c += (kRoiThreads / 32) * G) {
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-              const int i = lane + 32 * j;
-              if (j * 32 < nd && i < nd) {
-                const int ch = i / 49, q = i - ch * 49;
-                sdw[ch * 56 + (q / 7) * 8 + (q % 7)] = cnt_pow2 ? dr[j] * inv_cnt : __fdiv_rn(dr[j], cnt);
-              }
-            }
+            for (int j = 0; j < 7; ++j)
+              if (dofs[j] >= 0) sdw[dofs[j]] = cnt_pow2 ? dr[j] * inv_cnt : __fdiv_rn(dr[j], cnt);
             __syncwarp();
             const int cn = c + (kRoiThreads / 32) * G;
             if (cn < Cn) fetch(cn);
