@@ -71,7 +71,9 @@ def main():
         d["rois"] = out["rois"][j, :, 1:]
         return d
 
-    for name, arm_cls, n_img, keys in (("c2", BM.RetinaNetTargets, 8, c2_keys), ("c3", BM.FasterRCNNTrainBoxOps, 4, c3_keys)):
+    # at least one image per rank (8 ranks: 8 images)
+    for name, arm_cls, n_img, keys in (("c2", BM.RetinaNetTargets, max(8, world), c2_keys),
+                                       ("c3", BM.FasterRCNNTrainBoxOps, max(4, world), c3_keys)):
         lo, hi = D.shard_range(n_img, rank, world)
         mine, arm, out = image_digests(arm_cls, list(range(lo, hi)), keys)
         dfe = None
